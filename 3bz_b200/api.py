@@ -1,0 +1,307 @@
+"""Host-side mirror of 3bz's public API (package.lisp:13-27, api.lisp) over libthreebz_cuda.so.
+
+The reference's host language is Common Lisp; no Lisp implementation exists in this image, so
+lisp/ holds the real CFFI shim (unrunnable here) and this module issues the SAME call
+sequences through ctypes, with the same names, argument meaning and error behaviour:
+
+    decompress_vector(compressed, format=:zlib, start=0, end=None, output=None) -> (buffer, count)
+    make_deflate_state / make_zlib_state / make_gzip_state (output_buffer=...)
+    make_octet_vector_context(vector, start=0, offset=start, end=len)
+    with_octet_pointer(pointer, size) + make_octet_pointer_context(op, start=0, offset=0, end=size)
+    decompress(context, state) -> offset ; finished / input_underrun / output_overflow
+    replace_output_buffer(state, buffer)
+    decompress_batch(members, format, capacities) -> [(buffer, count, verdict)]   (new entry point)
+
+Everything runs on the GPU engine; nothing here falls back to a CPU decoder.
+"""
+import ctypes as C
+import threading
+
+from . import _ffi
+from ._ffi import EngineError, check, fmt_code, lib
+
+
+class ThreeBzError(Exception):
+    """Stands for the plain Lisp `error` / `assert` / `ecase` conditions the reference signals."""
+
+    def __init__(self, message, verdict=None):
+        super().__init__(message)
+        self.verdict = verdict
+
+
+_tls = threading.local()
+
+
+def default_ctx(device=0):
+    """One engine context per (thread, device), created on first use."""
+    key = "ctx%d" % device
+    ctx = getattr(_tls, key, None)
+    if ctx is None:
+        ctx = Ctx(device)
+        setattr(_tls, key, ctx)
+    return ctx
+
+
+class Ctx:
+    def __init__(self, device=0):
+        self.L = lib()
+        h = C.c_void_p()
+        check(self.L.tbz_ctx_create(device, 0, C.byref(h)))
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if self.h:
+            self.L.tbz_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def launches(self):
+        n = C.c_uint64()
+        check(self.L.tbz_ctx_launch_count(self.h, C.byref(n)), self.h)
+        return n.value
+
+
+def _addr(buf):
+    """Address of a writable/readable bytes-like without copying (bytes are copied once)."""
+    if isinstance(buf, bytes):
+        keep = (C.c_uint8 * max(1, len(buf))).from_buffer_copy(buf if buf else b"\0")
+        return keep, C.addressof(keep)
+    if isinstance(buf, (bytearray, memoryview)):
+        mv = memoryview(buf)
+        if mv.readonly:
+            keep = (C.c_uint8 * max(1, len(mv))).from_buffer_copy(bytes(mv) if len(mv) else b"\0")
+        else:
+            keep = (C.c_uint8 * len(mv)).from_buffer(mv) if len(mv) else (C.c_uint8 * 1)()
+        return keep, C.addressof(keep)
+    if isinstance(buf, C.Array):
+        return buf, C.addressof(buf)
+    raise TypeError("expected an octet vector (bytes / bytearray / ctypes array), got %r" % type(buf))
+
+
+# ---- contexts (io-common.lisp:36-45, io-mmap.lisp:21-54) -----------------------------------
+class OctetVectorContext:
+    def __init__(self, vector, start=0, offset=None, end=None):
+        self.vector = vector
+        self.start = start
+        self.offset = start if offset is None else offset
+        self.end = len(vector) if end is None else end
+        self._keep, self._base = _addr(vector)
+
+    def _unread(self):
+        return self._base + self.offset, self.end - self.offset
+
+
+def make_octet_vector_context(vector, start=0, offset=None, end=None):
+    return OctetVectorContext(vector, start, offset, end)
+
+
+class OctetPointer:
+    """with-octet-pointer (io-mmap.lisp:26-40): valid only inside the `with` block.  The range is
+    registered with the driver so the engine DMAs straight from it."""
+
+    def __init__(self, pointer, size):
+        self.base, self.size, self.valid, self._registered = int(pointer), int(size), False, False
+
+    def __enter__(self):
+        self.valid = True
+        if self.size > 0 and lib().tbz_host_register(self.base, self.size, 0) == 0:
+            self._registered = True
+        return self
+
+    def __exit__(self, *a):
+        self.valid = False
+        if self._registered:
+            lib().tbz_host_unregister(self.base)
+            self._registered = False
+
+
+def with_octet_pointer(pointer, size):
+    return OctetPointer(pointer, size)
+
+
+class OctetPointerContext:
+    def __init__(self, op, start=0, offset=0, end=None):
+        self.op, self.start, self.offset = op, start, offset
+        self.end = op.size if end is None else end
+
+    def _unread(self):
+        if not (self.op.valid and self.op.base and self.op.size > 0):   # io-mmap.lisp:36-40,64
+            raise ThreeBzError("octet-pointer used outside its dynamic extent")
+        return self.op.base + self.offset, self.end - self.offset
+
+
+def make_octet_pointer_context(octet_pointer, start=0, offset=0, end=None):
+    return OctetPointerContext(octet_pointer, start, offset, end)
+
+
+def make_octet_stream_context(*a, **k):
+    raise NotImplementedError("octet-stream-context is out of scope for the device engine (SURVEY.md §8f.4)")
+
+
+# ---- states (deflate.lisp:4-62, zlib.lisp:3-12, gzip.lisp:3-28) ------------------------------
+class _State:
+    format = None
+
+    def __init__(self, output_buffer=None, ctx=None):
+        self.ctx = ctx or default_ctx()
+        self.L = lib()
+        h = C.c_void_p()
+        check(self.L.tbz_session_create(self.ctx.h, fmt_code(self.format), C.byref(h)), self.ctx.h)
+        self.h = h
+        self.output_buffer = None
+        self._keep = None
+        self.output_offset = 0
+        if output_buffer is not None:
+            self._set(output_buffer)
+
+    def _set(self, buf):
+        self._keep, addr = _addr(buf)
+        check(self.L.tbz_session_set_output(self.h, addr, len(buf)), self.ctx.h)
+        self.output_buffer = buf
+        self.output_offset = 0
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.L.tbz_session_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def _flags(self):
+        f, u, o = C.c_int32(), C.c_int32(), C.c_int32()
+        check(self.L.tbz_session_flags(self.h, C.byref(f), C.byref(u), C.byref(o)), self.ctx.h)
+        return bool(f.value), bool(u.value), bool(o.value)
+
+
+class DeflateState(_State):
+    format = "deflate"
+
+
+class ZlibState(_State):
+    format = "zlib"
+
+
+class GzipState(_State):
+    format = "gzip"
+
+
+def make_deflate_state(output_buffer=None, ctx=None):
+    return DeflateState(output_buffer, ctx)
+
+
+def make_zlib_state(output_buffer=None, ctx=None):
+    return ZlibState(output_buffer, ctx)
+
+
+def make_gzip_state(output_buffer=None, ctx=None):
+    return GzipState(output_buffer, ctx)
+
+
+def decompress(context, state):
+    """api.lisp:3-10.  Returns the current offset into the output buffer."""
+    addr, n = context._unread()
+    ret, verdict = C.c_int64(), C.c_int32()
+    if state.output_buffer is None:
+        state._set(bytearray(0))               # (make-array 0), deflate.lisp:47
+    rc = state.L.tbz_session_decompress(state.h, addr if n else None, n, C.byref(ret), C.byref(verdict))
+    context.offset = context.end               # the session now owns every unread octet
+    if rc == _ffi.E_STATE:
+        raise ThreeBzError("decompress called on a finished or failed state", verdict.value)
+    check(rc, state.ctx.h)
+    if verdict.value >= 16:
+        raise ThreeBzError(_ffi.verdict_name(verdict.value), verdict.value)
+    state.output_offset = ret.value
+    return ret.value
+
+
+def replace_output_buffer(state, buffer):
+    """api.lisp:12-21."""
+    keep, addr = _addr(buffer)
+    rc = state.L.tbz_session_replace_output(state.h, addr, len(buffer))
+    if rc == _ffi.E_BUFFER_SWITCH:
+        raise ThreeBzError("can't switch buffers without filling old one yet.")
+    check(rc, state.ctx.h)
+    state._keep, state.output_buffer, state.output_offset = keep, buffer, 0
+
+
+def finished(state):
+    return state._flags()[0]
+
+
+def input_underrun(state):
+    return state._flags()[1]
+
+
+def output_overflow(state):
+    return state._flags()[2]
+
+
+# ---- decompress-vector (api.lisp:23-65) ---------------------------------------------------------
+def _fmt_name(format):
+    return format.lstrip(":") if isinstance(format, str) else {0: "deflate", 1: "zlib", 2: "gzip"}[format]
+
+
+def decompress_vector(compressed, format="zlib", start=0, end=None, output=None, ctx=None):
+    """Returns (buffer, count).  With OUTPUT: one decode into it, errors as the Lisp words them.
+    Without: the engine sizes the result (the Lisp's doubling-buffer loop collapses to one
+    device-side growth loop; the returned vector and length are the same)."""
+    ctx = ctx or default_ctx()
+    L = lib()
+    end = len(compressed) if end is None else end
+    keep, base = _addr(compressed)
+    res = _ffi.Result()
+    name = _fmt_name(format)
+    if output is not None:
+        okeep, oaddr = _addr(output)
+        check(L.tbz_inflate_single(ctx.h, fmt_code(format), base + start, end - start, oaddr, len(output),
+                                   C.byref(res), 0, None), ctx.h)
+        if isinstance(output, bytes):
+            raise TypeError("output must be writable")
+        if res.verdict != _ffi.FINISHED:
+            if res.verdict == _ffi.INPUT_UNDERRUN:
+                raise ThreeBzError("incomplete %s stream" % name, res.verdict)
+            if res.verdict == _ffi.OUTPUT_OVERFLOW:
+                raise ThreeBzError("not enough space to decompress %s stream" % name, res.verdict)
+            raise ThreeBzError(_ffi.verdict_name(res.verdict), res.verdict)
+        return output, res.out_len
+    p = C.c_void_p()
+    check(L.tbz_inflate_alloc(ctx.h, fmt_code(format), base + start, end - start, C.byref(p), C.byref(res)), ctx.h)
+    try:
+        if res.verdict != _ffi.FINISHED:
+            if res.verdict == _ffi.INPUT_UNDERRUN:       # (assert (not (ds-input-underrun state)))
+                raise ThreeBzError("incomplete %s stream" % name, res.verdict)
+            raise ThreeBzError(_ffi.verdict_name(res.verdict), res.verdict)
+        buf = bytearray(C.string_at(p, res.out_len)) if res.out_len else bytearray()
+    finally:
+        L.tbz_free(p)
+    return buf, len(buf)
+
+
+# ---- decompress-batch: the new entry point for many independent members -------------------------
+def decompress_batch(members, format="zlib", capacities=None, ctx=None, flags=0):
+    """members: sequence of octet vectors; capacities: per-member output size (int or sequence).
+    Returns a list of (buffer, count, verdict_code); a bad member never poisons the batch."""
+    ctx = ctx or default_ctx()
+    L = lib()
+    n = len(members)
+    if capacities is None:
+        raise ValueError("capacities (one :output size per member) are required")
+    caps = [capacities] * n if isinstance(capacities, int) else list(capacities)
+    outs = [bytearray(c) for c in caps]
+    marr = (_ffi.Member * max(1, n))()
+    keep = []
+    for i, (m, o) in enumerate(zip(members, outs)):
+        k1, a1 = _addr(m)
+        k2, a2 = _addr(o)
+        keep += [k1, k2]
+        marr[i] = _ffi.Member(a1, len(m), a2, len(o))
+    rarr = (_ffi.Result * max(1, n))()
+    check(L.tbz_inflate_batch(ctx.h, fmt_code(format), marr, n, rarr, flags, None), ctx.h)
+    return [(outs[i], rarr[i].out_len, rarr[i].verdict) for i in range(n)]

@@ -1,0 +1,686 @@
+// runtime.cu — host runtime of libthreebz_cuda.so: contexts, memory, batches, sessions,
+// multi-GPU partitioning.  The only translation unit; kernels live in the .cuh files.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <atomic>
+#include <functional>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "threebz_cuda.h"
+#include "tbz_device.cuh"
+#include "inflate_seq.cuh"
+
+// =============================================================================================
+// kernels
+// =============================================================================================
+#define SEQ_WARPS 4
+
+__global__ void __launch_bounds__(SEQ_WARPS * 32)
+k_inflate_seq(const DMember *members, tbz_result *results, uint32_t n, int fmt,
+              const uint32_t *todo, const uint32_t *todo_count) {
+  __shared__ tbzseq::WarpSmem sm[SEQ_WARPS];
+  __shared__ uint32_t crc_tab[256];
+  crc_table_init(crc_tab, threadIdx.x, blockDim.x);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t i = blockIdx.x * SEQ_WARPS + warp;
+  if (todo_count) n = *todo_count;
+  if (i >= n) return;
+  if (todo) i = todo[i];
+  tbzseq::inflate_member(members[i], fmt, results[i], sm[warp], crc_tab, lane);
+}
+
+// =============================================================================================
+// host objects
+// =============================================================================================
+struct DevBlock { void *p; size_t size; bool used; };
+
+struct tbz_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, tev0 = nullptr, tev1 = nullptr;
+  std::vector<DevBlock> pool;
+  void *stage_in = nullptr;  size_t stage_in_cap = 0;    // pinned staging
+  void *stage_out = nullptr; size_t stage_out_cap = 0;
+  std::string last_error;
+  uint64_t launches = 0;
+  int sm_count = 0;
+};
+
+static thread_local std::string g_last_error;
+
+static int32_t fail(tbz_ctx *ctx, int32_t code, const char *what, cudaError_t e = cudaSuccess) {
+  char buf[512];
+  if (e != cudaSuccess) snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(e));
+  else snprintf(buf, sizeof buf, "%s", what);
+  if (ctx) ctx->last_error = buf;
+  g_last_error = buf;
+  return code;
+}
+#define CK(ctx, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail((ctx), TBZ_E_CUDA, #call, e_); } while (0)
+
+static int32_t dev_alloc(tbz_ctx *ctx, size_t n, void **p) {
+  if (n == 0) n = 256;
+  n = (n + 255) & ~(size_t)255;
+  int best = -1;
+  for (size_t i = 0; i < ctx->pool.size(); i++) {
+    DevBlock &b = ctx->pool[i];
+    if (!b.used && b.size >= n && (best < 0 || b.size < ctx->pool[best].size)) best = (int)i;
+  }
+  if (best >= 0 && ctx->pool[best].size <= 2 * n + (1 << 20)) {
+    ctx->pool[best].used = true; *p = ctx->pool[best].p; return TBZ_OK;
+  }
+  void *q = nullptr;
+  cudaError_t e = cudaMalloc(&q, n);
+  if (e != cudaSuccess) {
+    // release cached blocks and retry once
+    for (auto it = ctx->pool.begin(); it != ctx->pool.end();)
+      if (!it->used) { cudaFree(it->p); it = ctx->pool.erase(it); } else ++it;
+    e = cudaMalloc(&q, n);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(ctx, TBZ_E_NOMEM, "cudaMalloc", e); }
+  }
+  ctx->pool.push_back({q, n, true});
+  *p = q;
+  return TBZ_OK;
+}
+static void dev_release(tbz_ctx *ctx, void *p) {
+  if (!p) return;
+  for (auto &b : ctx->pool) if (b.p == p) { b.used = false; return; }
+}
+
+static int32_t ensure_stage(tbz_ctx *ctx, void **p, size_t *cap, size_t n) {
+  if (*cap >= n) return TBZ_OK;
+  if (*p) cudaFreeHost(*p);
+  *p = nullptr; *cap = 0;
+  size_t want = n + n / 4 + 4096;
+  cudaError_t e = cudaHostAlloc(p, want, cudaHostAllocDefault);
+  if (e != cudaSuccess) { cudaGetLastError(); return fail(ctx, TBZ_E_NOMEM, "cudaHostAlloc", e); }
+  *cap = want;
+  return TBZ_OK;
+}
+
+struct tbz_batch {
+  tbz_ctx *ctx = nullptr;
+  int format = 0;
+  uint32_t flags = 0;
+  uint64_t n = 0;
+  bool device_ptrs = false;
+  std::vector<tbz_member> host;        // caller's members (host mode)
+  std::vector<uint64_t> in_off, out_off;
+  uint64_t in_total = 0, out_total = 0;
+  bool in_direct = false;              // caller's inputs are one dense span: DMA straight from it
+  bool out_direct = false;             // caller's outputs are exactly adjacent: DMA straight into them
+  const uint8_t *in_span = nullptr; uint8_t *out_span = nullptr;
+  void *d_in = nullptr, *d_out = nullptr, *d_members = nullptr, *d_results = nullptr;
+  bool launched = false;
+};
+
+// =============================================================================================
+// library / context
+// =============================================================================================
+extern "C" int32_t tbz_abi_version(void) { return TBZ_ABI_VERSION; }
+
+extern "C" int32_t tbz_device_count(int32_t *n) {
+  if (!n) return TBZ_E_ARG;
+  int c = 0;
+  cudaError_t e = cudaGetDeviceCount(&c);
+  if (e != cudaSuccess) { cudaGetLastError(); *n = 0; return fail(nullptr, TBZ_E_NO_DEVICE, "cudaGetDeviceCount", e); }
+  *n = c;
+  return TBZ_OK;
+}
+
+extern "C" int32_t tbz_ctx_create(int32_t device, uint64_t flags, tbz_ctx **out) {
+  (void)flags;
+  if (!out) return TBZ_E_ARG;
+  *out = nullptr;
+  int c = 0;
+  cudaError_t e = cudaGetDeviceCount(&c);
+  if (e != cudaSuccess || c == 0) { cudaGetLastError(); return fail(nullptr, TBZ_E_NO_DEVICE, "no CUDA device (this engine has no CPU fallback)", e); }
+  if (device < 0 || device >= c) return fail(nullptr, TBZ_E_ARG, "device index out of range");
+  tbz_ctx *ctx = new tbz_ctx();
+  ctx->device = device;
+  CK(ctx, cudaSetDevice(device));
+  CK(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  CK(ctx, cudaEventCreate(&ctx->ev0)); CK(ctx, cudaEventCreate(&ctx->ev1));
+  CK(ctx, cudaEventCreate(&ctx->tev0)); CK(ctx, cudaEventCreate(&ctx->tev1));
+  CK(ctx, cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
+  *out = ctx;
+  return TBZ_OK;
+}
+
+extern "C" int32_t tbz_ctx_destroy(tbz_ctx *ctx) {
+  if (!ctx) return TBZ_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto &b : ctx->pool) cudaFree(b.p);
+  if (ctx->stage_in) cudaFreeHost(ctx->stage_in);
+  if (ctx->stage_out) cudaFreeHost(ctx->stage_out);
+  cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
+  cudaEventDestroy(ctx->tev0); cudaEventDestroy(ctx->tev1);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return TBZ_OK;
+}
+
+extern "C" const char *tbz_strerror(int32_t s) {
+  switch (s) {
+    case TBZ_OK: return "ok";
+    case TBZ_E_CUDA: return "CUDA runtime error";
+    case TBZ_E_NO_DEVICE: return "no CUDA device (no CPU fallback exists)";
+    case TBZ_E_ARG: return "bad argument";
+    case TBZ_E_NOMEM: return "out of memory";
+    case TBZ_E_BUFFER_SWITCH: return "can't switch buffers without filling old one yet.";
+    case TBZ_E_STATE: return "session is not usable in this state";
+    default: return "unknown status";
+  }
+}
+
+extern "C" const char *tbz_verdict_name(int32_t v) {
+  switch (v) {
+    case TBZ_FINISHED: return "finished";
+    case TBZ_INPUT_UNDERRUN: return "input-underrun";
+    case TBZ_OUTPUT_OVERFLOW: return "output-overflow";
+    case TBZ_ERR_BLOCK_TYPE: return "reserved block type";
+    case TBZ_ERR_STORED_LEN: return "stored block LEN/NLEN mismatch";
+    case TBZ_ERR_OVERSUBSCRIBED: return "too many entries in huffman table";
+    case TBZ_ERR_INCOMPLETE: return "incomplete huffman table";
+    case TBZ_ERR_REPEAT_NO_PREV: return "tried to repeat length without previous length";
+    case TBZ_ERR_REPEAT_OVERRUN: return "code length repeat runs past table";
+    case TBZ_ERR_INVALID_SYMBOL: return "invalid huffman code";
+    case TBZ_ERR_DISTANCE_TOO_FAR: return "distance reaches before start of output";
+    case TBZ_ERR_ZLIB_FCHECK: return "invalid zlib header checksum";
+    case TBZ_ERR_ZLIB_METHOD: return "invalid zlib compression type";
+    case TBZ_ERR_ZLIB_WINDOW: return "invalid window size in zlib header";
+    case TBZ_ERR_ZLIB_DICT: return "preset dictionary not supported yet";
+    case TBZ_ERR_GZIP_MAGIC: return "bad gzip magic";
+    case TBZ_ERR_GZIP_METHOD: return "unknown compression method";
+    case TBZ_ERR_GZIP_RESERVED: return "reserved flag bits set";
+    case TBZ_ERR_GZIP_HCRC: return "gzip header crc mismatch";
+    case TBZ_ERR_CHECKSUM: return "checksum mismatch";
+    case TBZ_ERR_TREE_TOO_LARGE: return "huffman table does not fit";
+    default: return "unknown verdict";
+  }
+}
+
+extern "C" const char *tbz_ctx_last_error(tbz_ctx *ctx) {
+  return ctx ? ctx->last_error.c_str() : g_last_error.c_str();
+}
+extern "C" int32_t tbz_ctx_synchronize(tbz_ctx *ctx) {
+  if (!ctx) return TBZ_E_ARG;
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  return TBZ_OK;
+}
+extern "C" int32_t tbz_ctx_stream(tbz_ctx *ctx, void **s) {
+  if (!ctx || !s) return TBZ_E_ARG;
+  *s = (void *)ctx->stream;
+  return TBZ_OK;
+}
+extern "C" int32_t tbz_ctx_timer_start(tbz_ctx *ctx) {
+  if (!ctx) return TBZ_E_ARG;
+  CK(ctx, cudaEventRecord(ctx->tev0, ctx->stream));
+  return TBZ_OK;
+}
+extern "C" int32_t tbz_ctx_timer_stop(tbz_ctx *ctx, float *ms) {
+  if (!ctx || !ms) return TBZ_E_ARG;
+  CK(ctx, cudaEventRecord(ctx->tev1, ctx->stream));
+  CK(ctx, cudaEventSynchronize(ctx->tev1));
+  CK(ctx, cudaEventElapsedTime(ms, ctx->tev0, ctx->tev1));
+  return TBZ_OK;
+}
+extern "C" int32_t tbz_ctx_launch_count(tbz_ctx *ctx, uint64_t *n) {
+  if (!ctx || !n) return TBZ_E_ARG;
+  *n = ctx->launches;
+  return TBZ_OK;
+}
+
+// =============================================================================================
+// memory
+// =============================================================================================
+extern "C" int32_t tbz_host_alloc(uint64_t n, void **p) {
+  if (!p) return TBZ_E_ARG;
+  cudaError_t e = cudaHostAlloc(p, n ? n : 1, cudaHostAllocPortable);
+  if (e != cudaSuccess) { cudaGetLastError(); *p = nullptr; return fail(nullptr, e == cudaErrorMemoryAllocation ? TBZ_E_NOMEM : TBZ_E_NO_DEVICE, "cudaHostAlloc", e); }
+  return TBZ_OK;
+}
+extern "C" int32_t tbz_host_free(void *p) {
+  if (p) cudaFreeHost(p);
+  return TBZ_OK;
+}
+extern "C" int32_t tbz_host_register(void *p, uint64_t n, uint32_t flags) {
+  (void)flags;
+  if (!p || !n) return TBZ_E_ARG;
+  cudaError_t e = cudaHostRegister(p, n, cudaHostRegisterPortable | cudaHostRegisterReadOnly);
+  if (e != cudaSuccess) { cudaGetLastError(); e = cudaHostRegister(p, n, cudaHostRegisterPortable); }
+  if (e != cudaSuccess) { cudaGetLastError(); return fail(nullptr, TBZ_E_CUDA, "cudaHostRegister", e); }
+  return TBZ_OK;
+}
+extern "C" int32_t tbz_host_unregister(void *p) {
+  if (!p) return TBZ_E_ARG;
+  cudaError_t e = cudaHostUnregister(p);
+  if (e != cudaSuccess) { cudaGetLastError(); return fail(nullptr, TBZ_E_CUDA, "cudaHostUnregister", e); }
+  return TBZ_OK;
+}
+extern "C" int32_t tbz_device_alloc(tbz_ctx *ctx, uint64_t n, void **p) {
+  if (!ctx || !p) return TBZ_E_ARG;
+  CK(ctx, cudaSetDevice(ctx->device));
+  cudaError_t e = cudaMalloc(p, n ? n : 1);
+  if (e != cudaSuccess) { cudaGetLastError(); return fail(ctx, TBZ_E_NOMEM, "cudaMalloc", e); }
+  return TBZ_OK;
+}
+extern "C" int32_t tbz_device_free(tbz_ctx *ctx, void *p) {
+  if (!ctx) return TBZ_E_ARG;
+  CK(ctx, cudaSetDevice(ctx->device));
+  if (p) CK(ctx, cudaFree(p));
+  return TBZ_OK;
+}
+extern "C" int32_t tbz_memcpy_h2d(tbz_ctx *ctx, void *dst, const void *src, uint64_t n) {
+  if (!ctx) return TBZ_E_ARG;
+  CK(ctx, cudaSetDevice(ctx->device));
+  CK(ctx, cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, ctx->stream));
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  return TBZ_OK;
+}
+extern "C" int32_t tbz_memcpy_d2h(tbz_ctx *ctx, void *dst, const void *src, uint64_t n) {
+  if (!ctx) return TBZ_E_ARG;
+  CK(ctx, cudaSetDevice(ctx->device));
+  CK(ctx, cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  return TBZ_OK;
+}
+extern "C" void tbz_free(void *p) { free(p); }
+
+// =============================================================================================
+// batches
+// =============================================================================================
+static void parallel_for(size_t n, size_t bytes, const std::function<void(size_t, size_t)> &f) {
+  unsigned hw = std::thread::hardware_concurrency();
+  size_t nt = bytes < (8u << 20) ? 1 : std::min<size_t>(hw ? hw : 1, 16);
+  if (nt <= 1 || n < 2 * nt) { f(0, n); return; }
+  std::vector<std::thread> th;
+  size_t per = (n + nt - 1) / nt;
+  for (size_t t = 0; t < nt; t++) {
+    size_t lo = t * per, hi = std::min(n, lo + per);
+    if (lo >= hi) break;
+    th.emplace_back([=, &f] { f(lo, hi); });
+  }
+  for (auto &t : th) t.join();
+}
+
+extern "C" int32_t tbz_batch_destroy(tbz_batch *b) {
+  if (!b) return TBZ_OK;
+  tbz_ctx *ctx = b->ctx;
+  cudaSetDevice(ctx->device);
+  if (b->launched) cudaStreamSynchronize(ctx->stream);
+  dev_release(ctx, b->d_in); dev_release(ctx, b->d_out);
+  dev_release(ctx, b->d_members); dev_release(ctx, b->d_results);
+  delete b;
+  return TBZ_OK;
+}
+
+extern "C" int32_t tbz_batch_prepare(tbz_ctx *ctx, int32_t format, const tbz_member *m, uint64_t n,
+                                     uint32_t flags, tbz_batch **out) {
+  if (!ctx || !out || (n && !m) || format < 0 || format > 2 || n > 0x7fffffffull) return fail(ctx, TBZ_E_ARG, "tbz_batch_prepare: bad argument");
+  *out = nullptr;
+  CK(ctx, cudaSetDevice(ctx->device));
+  tbz_batch *b = new tbz_batch();
+  b->ctx = ctx; b->format = format; b->flags = flags; b->n = n;
+  b->device_ptrs = (flags & TBZ_FLAG_DEVICE_PTRS) != 0;
+  int32_t rc;
+#define PCK(x) do { rc = (x); if (rc != TBZ_OK) { tbz_batch_destroy(b); return rc; } } while (0)
+  PCK(dev_alloc(ctx, std::max<uint64_t>(1, n) * sizeof(DMember), &b->d_members));
+  PCK(dev_alloc(ctx, std::max<uint64_t>(1, n) * sizeof(tbz_result), &b->d_results));
+  std::vector<DMember> dm(n);
+  if (b->device_ptrs) {
+    for (uint64_t i = 0; i < n; i++) dm[i] = DMember{m[i].in, m[i].in_len, m[i].out, m[i].out_cap};
+  } else {
+    b->host.assign(m, m + n);
+    b->in_off.resize(n); b->out_off.resize(n);
+    // dense, ordered inputs -> one DMA straight from the caller's span
+    bool in_dense = n > 0, out_adj = n > 0;
+    uint64_t in_sum = 0;
+    for (uint64_t i = 0; i < n; i++) {
+      in_sum += m[i].in_len;
+      if (i + 1 < n) {
+        if (m[i].in + m[i].in_len > m[i + 1].in) in_dense = false;
+        if (m[i].out + m[i].out_cap != m[i + 1].out) out_adj = false;
+      }
+    }
+    if (in_dense) {
+      uint64_t span = (uint64_t)((m[n - 1].in + m[n - 1].in_len) - m[0].in);
+      if (span > in_sum + 64 * n + 4096) in_dense = false;
+      else {
+        b->in_direct = true; b->in_span = m[0].in; b->in_total = span;
+        for (uint64_t i = 0; i < n; i++) b->in_off[i] = (uint64_t)(m[i].in - m[0].in);
+      }
+    }
+    if (!b->in_direct) {
+      uint64_t o = 0;
+      for (uint64_t i = 0; i < n; i++) { b->in_off[i] = o; o += (m[i].in_len + 15) & ~15ull; }
+      b->in_total = o;
+    }
+    if (out_adj) {
+      b->out_direct = true; b->out_span = m[0].out;
+      uint64_t o = 0;
+      for (uint64_t i = 0; i < n; i++) { b->out_off[i] = o; o += m[i].out_cap; }
+      b->out_total = o;
+    } else {
+      uint64_t o = 0;
+      for (uint64_t i = 0; i < n; i++) { b->out_off[i] = o; o += (m[i].out_cap + 15) & ~15ull; }
+      b->out_total = o;
+    }
+    PCK(dev_alloc(ctx, b->in_total + 16, &b->d_in));
+    PCK(dev_alloc(ctx, b->out_total + 16, &b->d_out));
+    for (uint64_t i = 0; i < n; i++)
+      dm[i] = DMember{(const uint8_t *)b->d_in + b->in_off[i], m[i].in_len,
+                      (uint8_t *)b->d_out + b->out_off[i], m[i].out_cap};
+  }
+  if (n) {
+    cudaError_t e = cudaMemcpyAsync(b->d_members, dm.data(), n * sizeof(DMember), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);   // dm is a local
+    if (e != cudaSuccess) { tbz_batch_destroy(b); return fail(ctx, TBZ_E_CUDA, "upload member table", e); }
+  }
+#undef PCK
+  *out = b;
+  return TBZ_OK;
+}
+
+static int32_t launch_kernels(tbz_batch *b) {
+  tbz_ctx *ctx = b->ctx;
+  if (!b->n) return TBZ_OK;
+  uint32_t n = (uint32_t)b->n;
+  k_inflate_seq<<<(n + SEQ_WARPS - 1) / SEQ_WARPS, SEQ_WARPS * 32, 0, ctx->stream>>>(
+      (const DMember *)b->d_members, (tbz_result *)b->d_results, n, b->format, nullptr, nullptr);
+  ctx->launches++;
+  CK(ctx, cudaGetLastError());
+  return TBZ_OK;
+}
+
+extern "C" int32_t tbz_batch_launch(tbz_batch *b) {
+  if (!b) return TBZ_E_ARG;
+  tbz_ctx *ctx = b->ctx;
+  CK(ctx, cudaSetDevice(ctx->device));
+  if (!b->device_ptrs && b->n) {
+    if (b->in_direct) {
+      CK(ctx, cudaMemcpyAsync(b->d_in, b->in_span, b->in_total, cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+      int32_t rc = ensure_stage(ctx, &ctx->stage_in, &ctx->stage_in_cap, b->in_total);
+      if (rc) return rc;
+      CK(ctx, cudaStreamSynchronize(ctx->stream));   // staging buffer may still be in flight
+      uint8_t *st = (uint8_t *)ctx->stage_in;
+      parallel_for(b->n, b->in_total, [&](size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; i++) memcpy(st + b->in_off[i], b->host[i].in, b->host[i].in_len);
+      });
+      CK(ctx, cudaMemcpyAsync(b->d_in, st, b->in_total, cudaMemcpyHostToDevice, ctx->stream));
+    }
+  }
+  CK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  int32_t rc = launch_kernels(b);
+  if (rc) return rc;
+  CK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  b->launched = true;
+  return TBZ_OK;
+}
+
+extern "C" int32_t tbz_batch_finish(tbz_batch *b, tbz_result *r) {
+  if (!b) return TBZ_E_ARG;
+  tbz_ctx *ctx = b->ctx;
+  CK(ctx, cudaSetDevice(ctx->device));
+  if (!b->launched) return fail(ctx, TBZ_E_STATE, "tbz_batch_finish before tbz_batch_launch");
+  if (!b->n) return TBZ_OK;
+  std::vector<tbz_result> tmp;
+  tbz_result *res = r;
+  if (!res) { tmp.resize(b->n); res = tmp.data(); }
+  CK(ctx, cudaMemcpyAsync(res, b->d_results, b->n * sizeof(tbz_result), cudaMemcpyDeviceToHost, ctx->stream));
+  if (!b->device_ptrs) {
+    if (b->out_direct) {
+      CK(ctx, cudaMemcpyAsync(b->out_span, b->d_out, b->out_total, cudaMemcpyDeviceToHost, ctx->stream));
+      CK(ctx, cudaStreamSynchronize(ctx->stream));
+    } else {
+      int32_t rc = ensure_stage(ctx, &ctx->stage_out, &ctx->stage_out_cap, b->out_total);
+      if (rc) return rc;
+      CK(ctx, cudaMemcpyAsync(ctx->stage_out, b->d_out, b->out_total, cudaMemcpyDeviceToHost, ctx->stream));
+      CK(ctx, cudaStreamSynchronize(ctx->stream));
+      const uint8_t *st = (const uint8_t *)ctx->stage_out;
+      parallel_for(b->n, b->out_total, [&](size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; i++)
+          memcpy(b->host[i].out, st + b->out_off[i], std::min<uint64_t>(res[i].out_len, b->host[i].out_cap));
+      });
+    }
+  } else {
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return TBZ_OK;
+}
+
+static int32_t batch_device_ms(tbz_batch *b, float *ms) {
+  tbz_ctx *ctx = b->ctx;
+  if (!ms) return TBZ_OK;
+  *ms = 0.f;
+  if (!b->n) return TBZ_OK;
+  CK(ctx, cudaEventSynchronize(ctx->ev1));
+  CK(ctx, cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+  return TBZ_OK;
+}
+
+extern "C" int32_t tbz_inflate_batch(tbz_ctx *ctx, int32_t format, const tbz_member *m, uint64_t n,
+                                     tbz_result *r, uint32_t flags, float *device_ms) {
+  tbz_batch *b = nullptr;
+  int32_t rc = tbz_batch_prepare(ctx, format, m, n, flags, &b);
+  if (rc) return rc;
+  rc = tbz_batch_launch(b);
+  if (!rc) rc = tbz_batch_finish(b, r);
+  if (!rc) rc = batch_device_ms(b, device_ms);
+  tbz_batch_destroy(b);
+  return rc;
+}
+
+extern "C" int32_t tbz_inflate_single(tbz_ctx *ctx, int32_t format, const uint8_t *in, uint64_t in_len,
+                                      uint8_t *out, uint64_t out_cap, tbz_result *r, uint32_t flags,
+                                      float *device_ms) {
+  tbz_member m{in, in_len, out, out_cap};
+  return tbz_inflate_batch(ctx, format, &m, 1, r, flags, device_ms);
+}
+
+// Decode `in` (host) fully into a device buffer that grows until the stream no longer overflows.
+static int32_t inflate_to_device(tbz_ctx *ctx, int32_t format, const uint8_t *in, uint64_t in_len,
+                                 void **d_out, uint64_t *d_cap, tbz_result *res) {
+  CK(ctx, cudaSetDevice(ctx->device));
+  void *d_in = nullptr;
+  int32_t rc = dev_alloc(ctx, in_len + 16, &d_in);
+  if (rc) return rc;
+  if (in_len) {
+    cudaError_t e = cudaMemcpyAsync(d_in, in, in_len, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { dev_release(ctx, d_in); return fail(ctx, TBZ_E_CUDA, "H2D", e); }
+  }
+  uint64_t cap = *d_cap;
+  if (!*d_out) {
+    cap = std::max<uint64_t>(65536, in_len * 4);
+    if (format == TBZ_GZIP && in_len >= 18) {           // ISIZE is only a sizing hint (gzip.lisp:95-106 ignores it)
+      uint32_t isz; memcpy(&isz, in + in_len - 4, 4);
+      if (isz >= cap / 8 && isz <= in_len * 1100 + 65536) cap = (uint64_t)isz + 64;
+    }
+  }
+  for (;;) {
+    if (!*d_out) {
+      rc = dev_alloc(ctx, cap, d_out);
+      if (rc) { dev_release(ctx, d_in); return rc; }
+      *d_cap = cap;
+    }
+    tbz_member m{(const uint8_t *)d_in, in_len, (uint8_t *)*d_out, *d_cap};
+    rc = tbz_inflate_batch(ctx, format, &m, 1, res, TBZ_FLAG_DEVICE_PTRS, nullptr);
+    if (rc) break;
+    if (res->verdict != TBZ_OUTPUT_OVERFLOW) break;
+    dev_release(ctx, *d_out); *d_out = nullptr;
+    cap = *d_cap * 4;
+  }
+  dev_release(ctx, d_in);
+  return rc;
+}
+
+extern "C" int32_t tbz_inflate_alloc(tbz_ctx *ctx, int32_t format, const uint8_t *in, uint64_t in_len,
+                                     uint8_t **out, tbz_result *r) {
+  if (!ctx || !out || !r || (in_len && !in)) return fail(ctx, TBZ_E_ARG, "tbz_inflate_alloc: bad argument");
+  *out = nullptr;
+  void *d_out = nullptr; uint64_t d_cap = 0;
+  int32_t rc = inflate_to_device(ctx, format, in, in_len, &d_out, &d_cap, r);
+  if (!rc) {
+    uint8_t *h = (uint8_t *)malloc(r->out_len ? r->out_len : 1);
+    if (!h) rc = fail(ctx, TBZ_E_NOMEM, "malloc");
+    else {
+      if (r->out_len) {
+        cudaError_t e = cudaMemcpyAsync(h, d_out, r->out_len, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { free(h); h = nullptr; rc = fail(ctx, TBZ_E_CUDA, "D2H", e); }
+      }
+      *out = h;
+    }
+  }
+  dev_release(ctx, d_out);
+  return rc;
+}
+
+// =============================================================================================
+// multi-GPU: host-side partition, one thread per device, no collective
+// =============================================================================================
+extern "C" int32_t tbz_partition(const uint64_t *in_len, uint64_t n, int32_t g, int32_t *owner) {
+  if (g <= 0 || (n && (!in_len || !owner))) return TBZ_E_ARG;
+  std::vector<uint64_t> idx(n);
+  for (uint64_t i = 0; i < n; i++) idx[i] = i;
+  std::stable_sort(idx.begin(), idx.end(), [&](uint64_t a, uint64_t b) { return in_len[a] > in_len[b]; });
+  std::vector<uint64_t> load(g, 0), cnt(g, 0);
+  for (uint64_t k = 0; k < n; k++) {
+    int best = 0;
+    for (int d = 1; d < g; d++)
+      if (load[d] < load[best] || (load[d] == load[best] && cnt[d] < cnt[best])) best = d;
+    owner[idx[k]] = best;
+    load[best] += in_len[idx[k]] + 1;
+    cnt[best]++;
+  }
+  return TBZ_OK;
+}
+
+extern "C" int32_t tbz_inflate_batch_multi(tbz_ctx *const *ctxs, int32_t g, int32_t format,
+                                           const tbz_member *m, uint64_t n, tbz_result *r,
+                                           uint32_t flags, float *device_ms_per_gpu) {
+  if (!ctxs || g <= 0 || (n && (!m || !r))) return TBZ_E_ARG;
+  if (flags & TBZ_FLAG_DEVICE_PTRS) return fail(ctxs[0], TBZ_E_ARG, "tbz_inflate_batch_multi takes host members");
+  std::vector<uint64_t> lens(n);
+  for (uint64_t i = 0; i < n; i++) lens[i] = m[i].in_len;
+  std::vector<int32_t> owner(n);
+  int32_t rc = tbz_partition(lens.data(), n, g, owner.data());
+  if (rc) return rc;
+  std::vector<std::vector<uint64_t>> part(g);
+  for (uint64_t i = 0; i < n; i++) part[owner[i]].push_back(i);
+  std::vector<int32_t> rcs(g, TBZ_OK);
+  std::vector<std::thread> th;
+  for (int d = 0; d < g; d++)
+    th.emplace_back([&, d] {
+      std::vector<tbz_member> mm(part[d].size());
+      std::vector<tbz_result> rr(part[d].size());
+      for (size_t k = 0; k < mm.size(); k++) mm[k] = m[part[d][k]];
+      float ms = 0.f;
+      rcs[d] = tbz_inflate_batch(ctxs[d], format, mm.data(), mm.size(), rr.data(), flags, &ms);
+      if (device_ms_per_gpu) device_ms_per_gpu[d] = ms;
+      if (rcs[d] == TBZ_OK)
+        for (size_t k = 0; k < mm.size(); k++) r[part[d][k]] = rr[k];
+    });
+  for (auto &t : th) t.join();
+  for (int d = 0; d < g; d++) if (rcs[d]) return rcs[d];
+  return TBZ_OK;
+}
+
+// =============================================================================================
+// sessions: decompress / replace-output-buffer over a device-resident decoded member
+// =============================================================================================
+struct tbz_session {
+  tbz_ctx *ctx;
+  int format;
+  std::vector<uint8_t> input;     // every octet handed over so far
+  bool decoded = false;           // d_out/total reflect `input`
+  void *d_out = nullptr; uint64_t d_cap = 0;
+  tbz_result total{};
+  uint64_t served = 0;            // decoded bytes already delivered
+  uint8_t *out = nullptr; uint64_t cap = 0, off = 0;
+  bool finished = false, underrun = false, overflow = false;
+  int32_t error = 0;
+};
+
+extern "C" int32_t tbz_session_create(tbz_ctx *ctx, int32_t format, tbz_session **s) {
+  if (!ctx || !s || format < 0 || format > 2) return TBZ_E_ARG;
+  tbz_session *x = new tbz_session();
+  x->ctx = ctx; x->format = format;
+  *s = x;
+  return TBZ_OK;
+}
+extern "C" int32_t tbz_session_destroy(tbz_session *s) {
+  if (!s) return TBZ_OK;
+  dev_release(s->ctx, s->d_out);
+  delete s;
+  return TBZ_OK;
+}
+extern "C" int32_t tbz_session_set_output(tbz_session *s, uint8_t *out, uint64_t cap) {
+  if (!s || (cap && !out)) return TBZ_E_ARG;
+  s->out = out; s->cap = cap; s->off = 0;
+  return TBZ_OK;
+}
+extern "C" int32_t tbz_session_replace_output(tbz_session *s, uint8_t *out, uint64_t cap) {
+  if (!s || (cap && !out)) return TBZ_E_ARG;
+  if (!(s->off == 0 || s->overflow)) return TBZ_E_BUFFER_SWITCH;     // api.lisp:13-18
+  s->out = out; s->cap = cap; s->off = 0; s->overflow = false;
+  return TBZ_OK;
+}
+extern "C" int32_t tbz_session_flags(tbz_session *s, int32_t *fin, int32_t *under, int32_t *over) {
+  if (!s) return TBZ_E_ARG;
+  if (fin) *fin = s->finished;
+  if (under) *under = s->underrun;
+  if (over) *over = s->overflow;
+  return TBZ_OK;
+}
+
+extern "C" int32_t tbz_session_decompress(tbz_session *s, const uint8_t *in, uint64_t n,
+                                          int64_t *ret, int32_t *verdict) {
+  if (!s || !ret || !verdict || (n && !in)) return TBZ_E_ARG;
+  tbz_ctx *ctx = s->ctx;
+  if (s->error) { *ret = -1; *verdict = s->error; return TBZ_E_STATE; }
+  if (s->finished) { *ret = -1; *verdict = TBZ_FINISHED; return TBZ_E_STATE; }   // ecase on :done (gzip.lisp:279-286)
+  s->underrun = false;                       // deflate.lisp:102-103
+  if (n) { s->input.insert(s->input.end(), in, in + n); s->decoded = false; }
+  if (!s->decoded) {
+    int32_t rc = inflate_to_device(ctx, s->format, s->input.data(), s->input.size(), &s->d_out, &s->d_cap, &s->total);
+    if (rc) return rc;
+    s->decoded = true;
+  }
+  uint64_t room = s->cap - s->off, left = s->total.out_len - s->served;
+  uint64_t take = std::min(room, left);
+  if (take) {
+    cudaError_t e = cudaMemcpyAsync(s->out + s->off, (const uint8_t *)s->d_out + s->served, take,
+                                    cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) return fail(ctx, TBZ_E_CUDA, "session D2H", e);
+    s->off += take; s->served += take;
+  }
+  if (left > room) {                          // every overflow site fires with the buffer exactly full
+    s->overflow = true;
+    *ret = (int64_t)s->off; *verdict = TBZ_OUTPUT_OVERFLOW;
+    return TBZ_OK;
+  }
+  s->overflow = false;
+  int32_t v = s->total.verdict;
+  *verdict = v;
+  if (v == TBZ_FINISHED) { s->finished = true; *ret = (int64_t)s->off; }
+  else if (v == TBZ_INPUT_UNDERRUN) {
+    s->underrun = true;
+    bool zero = (s->format == TBZ_GZIP && s->total.where != TBZ_AT_BODY) ||
+                (s->format == TBZ_ZLIB && s->total.where == TBZ_AT_HEADER);
+    *ret = zero ? 0 : (int64_t)s->off;        // gzip.lisp:86,99,117 / zlib.lisp:111
+  } else { s->error = v; *ret = -1; }
+  return TBZ_OK;
+}

@@ -1,0 +1,252 @@
+"""GPU parity: the CUDA path through the C ABI vs the CPU oracle, bit-exact (integer/byte work)."""
+import hashlib
+import random
+import zlib
+
+import pytest
+
+import datagen
+from tests import cases
+from tests.gpuutil import compare, run_batch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_config1_fixture(engine, ctx, oracle):
+    """3bz:decompress-vector on test.deflated (:format :deflate :start 8) — bit-exact output + size."""
+    raw, meta = cases.test_deflated()
+    out = bytearray(meta["size_field"])
+    buf, n = engine.decompress_vector(raw, format="deflate", start=8, output=out)
+    assert n == 22728 and hashlib.sha256(bytes(buf[:n])).hexdigest() == meta["sha256"]
+    buf, n = engine.decompress_vector(raw, format=":deflate", start=8)       # no :output (api.lisp:50-65)
+    assert n == 22728 and hashlib.sha256(bytes(buf)).hexdigest() == meta["sha256"]
+    with pytest.raises(engine.ThreeBzError, match="not enough space"):
+        engine.decompress_vector(raw, format="deflate", start=8, output=bytearray(22727))
+    with pytest.raises(engine.ThreeBzError, match="incomplete"):
+        engine.decompress_vector(raw, format="deflate", start=8, end=len(raw) - 1, output=bytearray(22728))
+
+
+def test_nayuki_vectors(ctx, oracle):
+    vs = cases.nayuki()
+    ins = [bytes.fromhex(v["input_hex"]) for v in vs]
+    got, _ = run_batch(ctx, "deflate", ins, 1024)
+    for v, d, g in zip(vs, ins, got):
+        w = oracle.decompress_vector(d, "deflate", out_cap=1024)
+        compare(g, w, v["line"])
+        if v["marker"] is None:
+            assert g["verdict"] == 0 and g["out"].hex() == v["expected_hex"]
+
+
+def test_edge_mix(ctx, oracle):
+    for fmt in cases.FMTS:
+        items = [(n, c, p) for n, f, c, p in cases.edge_streams() if f == fmt]
+        got, _ = run_batch(ctx, fmt, [c for _, c, _ in items], [len(p) for _, _, p in items])
+        for (name, comp, plain), g in zip(items, got):
+            w = oracle.decompress_vector(comp, fmt, out_cap=len(plain))
+            compare(g, w, (name, fmt))
+            assert g["verdict"] == 0 and g["out"] == plain, (name, fmt)
+
+
+def test_truncation_sweep(ctx, oracle):
+    """every prefix of a stream: same verdict, same bytes so far (deflate.lisp:114-120, :399-427)."""
+    raw, meta = cases.test_deflated()
+    payload = raw[8:]
+    ins = [payload[:k] for k in range(0, len(payload) + 1, 1)]
+    got, _ = run_batch(ctx, "deflate", ins, 22728)
+    for k, g in enumerate(got):
+        compare(g, oracle.decompress_vector(ins[k], "deflate", out_cap=22728), k)
+    for fmt in ("zlib", "gzip"):
+        plain = datagen.text(3000, 11) + bytes(500) + datagen.random_bytes(300, 3)
+        comp = datagen.compress(plain, fmt)
+        ins = [comp[:k] for k in range(len(comp) + 1)]
+        got, _ = run_batch(ctx, fmt, ins, len(plain))
+        for k, g in enumerate(got):
+            w = oracle.decompress_vector(ins[k], fmt, out_cap=len(plain))
+            compare(g, w, (fmt, k))
+            if w["verdict"] == 1:
+                st = oracle.State(fmt, output_size=len(plain))
+                ret = st.decompress(st.make_context(ins[k]))
+                want_where = 1 if ret == w["out_len"] and w["out_len"] else None
+                if want_where:
+                    assert g["where"] in (1, 2) or fmt == "zlib"
+
+
+def test_capacity_sweep(ctx, oracle):
+    """output-overflow fires exactly when the buffer is full (deflate.lisp:239-241,254-269,693-697)."""
+    for name, fmt, comp, plain in cases.edge_streams():
+        if name not in ("text64k", "zeros", "stored", "fixed", "period3") or fmt == "gzip":
+            continue
+        n = len(plain)
+        caps = sorted(set([0, 1, 2, 3, 100, 257, 258, 259, 4095, 4096, n // 2, n - 259, n - 2, n - 1, n, n + 1, n + 100]))
+        caps = [c for c in caps if c >= 0]
+        got, _ = run_batch(ctx, fmt, [comp] * len(caps), caps)
+        for c, g in zip(caps, got):
+            compare(g, oracle.decompress_vector(comp, fmt, out_cap=c), (name, fmt, c))
+
+
+def test_corruption_fuzz(ctx, oracle):
+    """random bit flips / byte stomps: verdict class and produced bytes equal the oracle's."""
+    rnd = random.Random(2024)
+    bases = []
+    for fmt in cases.FMTS:
+        bases.append((fmt, datagen.compress(datagen.text(6000, 21), fmt), 6000))
+        bases.append((fmt, datagen.compress(datagen.text(4000, 22), fmt, strategy=zlib.Z_FIXED), 4000))
+        bases.append((fmt, datagen.compress(datagen.random_bytes(3000, 23), fmt, level=0), 3000))
+    for fmt, comp, n in bases:
+        ins = []
+        for _ in range(400):
+            b = bytearray(comp)
+            for _ in range(rnd.choice((1, 1, 2, 5))):
+                k = rnd.randrange(len(b)) if rnd.random() < .7 else rnd.randrange(min(len(b), 80))
+                if rnd.random() < .5:
+                    b[k] ^= 1 << rnd.randrange(8)
+                else:
+                    b[k] = rnd.randrange(256)
+            ins.append(bytes(b))
+        cap = n + 5000
+        got, _ = run_batch(ctx, fmt, ins, cap)
+        for i, g in enumerate(got):
+            compare(g, oracle.decompress_vector(ins[i], fmt, out_cap=cap), (fmt, i))
+
+
+def test_odd_huffman_codes(ctx, oracle):
+    """hand-built dynamic headers: lone-symbol codes of every length, HLIT > 286, unused distance tree."""
+    def bits_to_bytes(bits):
+        out = bytearray((len(bits) + 7) // 8)
+        for i, c in enumerate(bits):
+            if c == "1":
+                out[i // 8] |= 1 << (i % 8)
+        return bytes(out)
+
+    ins = []
+    rnd = random.Random(7)
+    for _ in range(300):
+        # random (mostly invalid) dynamic headers followed by random payload bits
+        b = "1" + "01" + "".join(rnd.choice("01") for _ in range(rnd.randrange(14, 600)))
+        ins.append(bits_to_bytes(b))
+    got, _ = run_batch(ctx, "deflate", ins, 4096)
+    for i, g in enumerate(got):
+        compare(g, oracle.decompress_vector(ins[i], "deflate", out_cap=4096), i)
+
+
+def test_config2_subset(ctx, oracle):
+    """batch of independent 64 KiB zlib members (level 6, dynamic Huffman) — bit-exact, Adler verdicts."""
+    ms = datagen.members(96, 65536, 1000, "zlib")
+    got, _ = run_batch(ctx, "zlib", [c for _, c in ms], 65536)
+    for i, ((plain, comp), g) in enumerate(zip(ms, got)):
+        assert g["verdict"] == 0 and g["out"] == plain and g["checksum"] == zlib.adler32(plain), i
+        assert g["in_used"] == len(comp)
+    w = oracle.decompress_vector(ms[0][1], "zlib", out_cap=65536)
+    compare(got[0], w, 0)
+
+
+def test_config4_members(ctx, oracle):
+    """1 MiB gzip members, several dynamic blocks each."""
+    ms = datagen.members(6, 1 << 20, 5000, "gzip")
+    got, _ = run_batch(ctx, "gzip", [c for _, c in ms], 1 << 20)
+    for (plain, comp), g in zip(ms, got):
+        assert g["verdict"] == 0 and g["out"] == plain and g["checksum"] == zlib.crc32(plain)
+
+
+def test_gzip_header_fields(ctx, oracle):
+    plain = datagen.text(5000, 5)
+    variants = [cases.gzip_with_header_fields(plain),
+                cases.gzip_with_header_fields(plain, extra=None),
+                cases.gzip_with_header_fields(plain, name=None, comment=None, hcrc=False),
+                cases.gzip_with_header_fields(plain, extra=b"", name=b"", comment=b"")]
+    bad = bytearray(variants[0]); bad[12] ^= 0x40
+    variants.append(bytes(bad))
+    variants += [variants[0][:k] for k in range(0, 60)]
+    got, _ = run_batch(ctx, "gzip", variants, 5000)
+    for i, g in enumerate(got):
+        compare(g, oracle.decompress_vector(variants[i], "gzip", out_cap=5000), i)
+
+
+def _drain_both(engine, oracle, comp, fmt, sizes, start=0):
+    sizes = list(sizes)
+    it = iter(sizes)
+    ost = oracle.State(fmt, output_size=sizes[0])
+    octx = ost.make_context(comp, start=start)
+    first = bytearray(next(it))
+    est = {"deflate": engine.make_deflate_state, "zlib": engine.make_zlib_state,
+           "gzip": engine.make_gzip_state}[fmt](output_buffer=first)
+    ectx = engine.make_octet_vector_context(comp, start=start)
+    out = bytearray()
+    for _ in range(len(sizes)):
+        want = ost.decompress(octx)
+        got = engine.decompress(ectx, est)
+        assert got == want
+        assert (engine.finished(est), engine.input_underrun(est), engine.output_overflow(est)) == \
+               (ost.finished, ost.input_underrun, ost.output_overflow)
+        assert bytes(est.output_buffer[:got]) == ost.output(want)
+        if ost.finished or ost.output_overflow:
+            out += est.output_buffer[:got]
+            if ost.finished:
+                return bytes(out)
+            nxt = next(it)
+            ost.replace_output_buffer(nxt)
+            engine.replace_output_buffer(est, bytearray(nxt))
+        else:
+            return bytes(out)
+    raise AssertionError("ran out of buffers")
+
+
+def test_chunked_output_sessions(engine, ctx, oracle):
+    """config 5: drained through replace-output-buffer; per-call return values and flags equal."""
+    raw, meta = cases.test_deflated()
+    ref = zlib.decompress(raw[8:], -15)
+    assert _drain_both(engine, oracle, raw, "deflate", [3] * (len(ref) // 3 + 2), start=8) == ref
+    rnd = random.Random(77)
+    for _ in range(5):
+        sizes = [1 + rnd.randrange(12345) for _ in range(len(ref) + 2)]
+        assert _drain_both(engine, oracle, raw, "deflate", sizes, start=8) == ref
+    for name, fmt, comp, plain in cases.edge_streams():
+        if name not in ("stored", "zeros", "rle", "period3", "fixed", "empty", "one_byte", "text64k"):
+            continue
+        n = len(plain)
+        for sizes in ([32768] * (n // 32768 + 2), [max(1, n)] * 2,
+                      [1 + rnd.randrange(12345) for _ in range(n // 1 + 2)][: n + 2]):
+            assert _drain_both(engine, oracle, comp, fmt, sizes) == plain, (name, fmt)
+
+
+def test_chunked_input_sessions(engine, ctx, oracle):
+    """§8f.1: input in pieces; after each call finished or input-underrun (test-chunked-input.lisp:27-44)."""
+    raw, meta = cases.test_deflated()
+    payload = raw[8:]
+    ref = zlib.decompress(payload, -15)
+    rnd = random.Random(5)
+    for gen in (lambda: 997, lambda: 1 + rnd.randrange(1233)):
+        ost = oracle.State("deflate", output_size=len(ref))
+        est = engine.make_deflate_state(output_buffer=bytearray(len(ref)))
+        o = 0
+        while o < len(payload):
+            end = min(len(payload), o + gen())
+            want = ost.decompress(ost.make_context(payload[o:end]))
+            got = engine.decompress(engine.make_octet_vector_context(payload[o:end]), est)
+            assert got == want
+            assert (engine.finished(est), engine.input_underrun(est)) == (ost.finished, ost.input_underrun)
+            assert bytes(est.output_buffer[:got]) == ost.output(want)
+            o = end
+        assert engine.finished(est) and bytes(est.output_buffer[:got]) == ref
+
+
+def test_decompress_batch_api(engine, ctx):
+    ms = datagen.members(8, 20000, 300, "zlib")
+    ins = [c for _, c in ms]
+    ins[3] = ins[3][:-3]            # a bad member never poisons the batch
+    res = engine.decompress_batch(ins, "zlib", 20000)
+    for i, (buf, n, v) in enumerate(res):
+        assert bytes(buf[:n]) == ms[i][0]
+        assert v == (1 if i == 3 else 0)
+
+
+def test_octet_pointer_context(engine, ctx):
+    import ctypes as C
+    plain, comp = datagen.member(50000, 8, "gzip")
+    raw = C.create_string_buffer(comp, len(comp))
+    with engine.with_octet_pointer(C.addressof(raw), len(comp)) as op:
+        st = engine.make_gzip_state(output_buffer=bytearray(50000))
+        n = engine.decompress(engine.make_octet_pointer_context(op), st)
+        assert engine.finished(st) and bytes(st.output_buffer[:n]) == plain
+    with pytest.raises(engine.ThreeBzError):
+        engine.decompress(engine.make_octet_pointer_context(op), engine.make_gzip_state(output_buffer=bytearray(8)))
