@@ -226,6 +226,14 @@ struct o3bz_state {                /* deflate.lisp:4-62, zlib.lisp:3-12, gzip.li
 
 static int need(o3bz_state *s, o3bz_context *c, int n) {
   /* word64/word32 refills (io.lisp:17-58) restated bytewise: same bits, same order */
+  if (s->nbits < n && c->end - c->offset >= 8) {   /* word64, io.lisp:17-37 */
+    uint64_t w;
+    int take = (63 - s->nbits) >> 3;
+    memcpy(&w, c->p + c->offset, 8);
+    s->bits |= (w & ((1ull << (8 * take)) - 1)) << s->nbits;
+    s->nbits += 8 * take;
+    c->offset += (size_t)take;
+  }
   while (s->nbits < n && s->nbits <= 56 && c->offset < c->end) {
     s->bits |= (uint64_t)c->p[c->offset++] << s->nbits;
     s->nbits += 8;
@@ -679,12 +687,14 @@ int o3bz_decompress_vector_grow(const uint8_t *in, size_t start, size_t end, int
 void o3bz_free(void *p) { free(p); }
 
 int o3bz_batch(const uint8_t *const *in, const size_t *in_len, uint8_t *const *out,
-               const size_t *out_cap, size_t *out_len, int *verdict, int format,
+               const size_t *out_cap, size_t *out_len, int *verdict, uint64_t *match_bytes, int format,
                size_t lo, size_t hi) {
   int bad = 0;
   for (size_t i = lo; i < hi; i++) {
     size_t n = 0;
-    int v = o3bz_decompress_vector(in[i], 0, in_len[i], format, out[i], out_cap[i], &n, NULL, NULL);
+    o3bz_stats st;
+    int v = o3bz_decompress_vector(in[i], 0, in_len[i], format, out[i], out_cap[i], &n, NULL, &st);
+    if (match_bytes) match_bytes[i] = st.match_bytes;
     if (out_len) out_len[i] = n;
     if (verdict) verdict[i] = v;
     bad += v != O3_FINISHED;

@@ -102,8 +102,8 @@ uint32_t o3bz_crc32(const uint8_t *buf, size_t end, uint32_t crc);
 
 /* batch helper for CPU baselines: members i in [lo,hi) ; returns number of non-finished */
 int o3bz_batch(const uint8_t *const *in, const size_t *in_len, uint8_t *const *out,
-               const size_t *out_cap, size_t *out_len, int *verdict, int format,
-               size_t lo, size_t hi);
+               const size_t *out_cap, size_t *out_len, int *verdict, uint64_t *match_bytes,
+               int format, size_t lo, size_t hi);
 
 #ifdef __cplusplus
 }
