@@ -16,6 +16,7 @@
 #include "threebz_cuda.h"
 #include "tbz_device.cuh"
 #include "inflate_seq.cuh"
+#include "inflate_fast.cuh"
 
 // =============================================================================================
 // kernels
@@ -35,6 +36,27 @@ k_inflate_seq(const DMember *members, tbz_result *results, uint32_t n, int fmt,
   if (i >= n) return;
   if (todo) i = todo[i];
   tbzseq::inflate_member(members[i], fmt, results[i], sm[warp], crc_tab, lane);
+}
+
+// persistent CTAs: each pulls the next member from a global counter; members the fast path
+// cannot prove clean are queued for k_inflate_seq
+__global__ void __launch_bounds__(tbzfast::NT, 2)
+k_inflate_fast(const DMember *members, tbz_result *results, uint32_t n, int fmt,
+               uint32_t *tokens, uint32_t *counters, uint32_t *todo) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  tbzfast::Smem &sm = *reinterpret_cast<tbzfast::Smem *>(smem_raw);
+  const int tid = threadIdx.x;
+  crc_table_init(sm.crc_tab, tid, tbzfast::NT);
+  uint32_t *tokbuf = tokens + (size_t)blockIdx.x * tbzfast::NT * tbzfast::TOKCAP;
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) sm.member = atomicAdd(&counters[0], 1u);
+    __syncthreads();
+    const uint32_t i = sm.member;
+    if (i >= n) break;
+    const bool ok = tbzfast::inflate_member(members[i], fmt, results[i], sm, tokbuf, tid);
+    if (!ok && tid == 0) todo[atomicAdd(&counters[1], 1u)] = i;
+  }
 }
 
 // =============================================================================================
@@ -119,6 +141,8 @@ struct tbz_batch {
   bool out_direct = false;             // caller's outputs are exactly adjacent: DMA straight into them
   const uint8_t *in_span = nullptr; uint8_t *out_span = nullptr;
   void *d_in = nullptr, *d_out = nullptr, *d_members = nullptr, *d_results = nullptr;
+  void *d_tokens = nullptr, *d_counters = nullptr, *d_todo = nullptr;
+  int fast_grid = 0;
   bool launched = false;
 };
 
@@ -320,6 +344,7 @@ extern "C" int32_t tbz_batch_destroy(tbz_batch *b) {
   if (b->launched) cudaStreamSynchronize(ctx->stream);
   dev_release(ctx, b->d_in); dev_release(ctx, b->d_out);
   dev_release(ctx, b->d_members); dev_release(ctx, b->d_results);
+  dev_release(ctx, b->d_tokens); dev_release(ctx, b->d_counters); dev_release(ctx, b->d_todo);
   delete b;
   return TBZ_OK;
 }
@@ -336,6 +361,12 @@ extern "C" int32_t tbz_batch_prepare(tbz_ctx *ctx, int32_t format, const tbz_mem
 #define PCK(x) do { rc = (x); if (rc != TBZ_OK) { tbz_batch_destroy(b); return rc; } } while (0)
   PCK(dev_alloc(ctx, std::max<uint64_t>(1, n) * sizeof(DMember), &b->d_members));
   PCK(dev_alloc(ctx, std::max<uint64_t>(1, n) * sizeof(tbz_result), &b->d_results));
+  if (!(flags & TBZ_FLAG_NO_FASTPATH) && n) {
+    b->fast_grid = (int)std::min<uint64_t>(n, (uint64_t)ctx->sm_count * 2);
+    PCK(dev_alloc(ctx, (size_t)b->fast_grid * tbzfast::NT * tbzfast::TOKCAP * 4, &b->d_tokens));
+    PCK(dev_alloc(ctx, 256, &b->d_counters));
+    PCK(dev_alloc(ctx, n * 4, &b->d_todo));
+  }
   std::vector<DMember> dm(n);
   if (b->device_ptrs) {
     for (uint64_t i = 0; i < n; i++) dm[i] = DMember{m[i].in, m[i].in_len, m[i].out, m[i].out_cap};
@@ -395,6 +426,21 @@ static int32_t launch_kernels(tbz_batch *b) {
   tbz_ctx *ctx = b->ctx;
   if (!b->n) return TBZ_OK;
   uint32_t n = (uint32_t)b->n;
+  if (b->fast_grid) {
+    CK(ctx, cudaFuncSetAttribute(k_inflate_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tbzfast::Smem)));
+    CK(ctx, cudaMemsetAsync(b->d_counters, 0, 256, ctx->stream));
+    k_inflate_fast<<<b->fast_grid, tbzfast::NT, sizeof(tbzfast::Smem), ctx->stream>>>(
+        (const DMember *)b->d_members, (tbz_result *)b->d_results, n, b->format,
+        (uint32_t *)b->d_tokens, (uint32_t *)b->d_counters, (uint32_t *)b->d_todo);
+    ctx->launches++;
+    CK(ctx, cudaGetLastError());
+    k_inflate_seq<<<(n + SEQ_WARPS - 1) / SEQ_WARPS, SEQ_WARPS * 32, 0, ctx->stream>>>(
+        (const DMember *)b->d_members, (tbz_result *)b->d_results, n, b->format,
+        (const uint32_t *)b->d_todo, (const uint32_t *)b->d_counters + 1);
+    ctx->launches++;
+    CK(ctx, cudaGetLastError());
+    return TBZ_OK;
+  }
   k_inflate_seq<<<(n + SEQ_WARPS - 1) / SEQ_WARPS, SEQ_WARPS * 32, 0, ctx->stream>>>(
       (const DMember *)b->d_members, (tbz_result *)b->d_results, n, b->format, nullptr, nullptr);
   ctx->launches++;

@@ -136,8 +136,13 @@ def test_config2_subset(ctx, oracle):
     for i, ((plain, comp), g) in enumerate(zip(ms, got)):
         assert g["verdict"] == 0 and g["out"] == plain and g["checksum"] == zlib.adler32(plain), i
         assert g["in_used"] == len(comp)
+        assert g["path"] == 1, "clean members must be decoded by the fast lane-parallel kernel"
     w = oracle.decompress_vector(ms[0][1], "zlib", out_cap=65536)
     compare(got[0], w, 0)
+    # the same members through the sequential kernel only
+    got2, _ = run_batch(ctx, "zlib", [c for _, c in ms], 65536, flags=2)
+    for (plain, comp), g in zip(ms, got2):
+        assert g["verdict"] == 0 and g["out"] == plain and g["path"] == 0
 
 
 def test_config4_members(ctx, oracle):
@@ -146,6 +151,7 @@ def test_config4_members(ctx, oracle):
     got, _ = run_batch(ctx, "gzip", [c for _, c in ms], 1 << 20)
     for (plain, comp), g in zip(ms, got):
         assert g["verdict"] == 0 and g["out"] == plain and g["checksum"] == zlib.crc32(plain)
+        assert g["path"] == 1
 
 
 def test_gzip_header_fields(ctx, oracle):
