@@ -1,24 +1,20 @@
-// inflate_fast.cuh — the batched fast path: one CTA per member, every thread a decode lane.
+// inflate_decode.cuh — phase one of the batched fast path: Huffman decode into a token stream.
+// One CTA per member, every thread a decode lane.
 //
 // Inside one Huffman block the compressed bits are cut into NT equal sub-chunks.  Lane i starts
 // decoding at the first bit of sub-chunk i *speculatively* (only lane 0 is known to start on a
 // symbol boundary) and relies on the self-synchronisation of Huffman streams:
-//   phase 1a  every lane decodes its sub-chunk into a token stream (global scratch, coalesced
-//             rows) and marks its token-start bits in a bitmap (shared memory)
-//   phase 1b  every lane keeps decoding past its sub-chunk end until it lands on a bit the next
-//             lane(s) marked — from there on both decodes are identical (same tables, same bit,
-//             same state), so the rest of that lane's tokens are proven correct
-//   resolve   pointer-doubling over "who synchronised into whom" from lane 0 gives the set of
-//             proven lanes, their entry points, token ranges and output sizes (prefix sum)
-//   phase 2   every proven lane replays its tokens into a 64 KiB output ring in shared memory:
-//             literals are byte stores, matches are copied in <=16-byte pieces once their source
-//             range is final (per-lane progress words; overlapping matches copy through the
-//             period); the ring is flushed to global memory with coalesced 16-byte stores and
-//             the Adler-32 / CRC-32 is folded in from shared memory on the way out.
-// Anything this kernel cannot prove clean (stored blocks, malformed codes, truncated input, too
-// small an output buffer, checksum mismatch ...) is queued for the sequential kernel, which
-// reproduces the reference's exact verdict.  Replaces deflate.lisp:465-509,673-702 (decode),
-// :244-359 (copy-history), huffman-tree.lisp:99-218 (tables), checksums.lisp.
+//   1a  every lane decodes its sub-chunk into its own token list (a slab in global memory,
+//       16-byte stores) and marks its token-start bits in a bitmap (shared memory)
+//   1b  every lane keeps decoding past its sub-chunk end until it lands on a bit a later lane
+//       marked — from there on both decodes are identical (same tables, same bit, same state),
+//       so the rest of that lane's list is proven correct
+//   1c  pointer doubling over "who synchronised into whom" from lane 0 gives the proven lanes,
+//       their entry points (tokens before an entry point are dropped) and the round's output size
+// Phase two (inflate_resolve.cuh) turns the token stream into bytes.  Anything this kernel cannot
+// prove clean (stored blocks, malformed codes, truncated input, too small an output buffer ...)
+// is queued for the sequential kernel, which reproduces the reference's exact verdict.
+// Replaces deflate.lisp:465-509,673-702 (decode) and huffman-tree.lisp:99-218 (tables).
 #pragma once
 #include "tbz_device.cuh"
 
@@ -27,10 +23,28 @@ namespace tbzfast {
 constexpr int NT = 256;                 // threads per CTA = decode lanes
 constexpr int NWARP = NT / 32;
 constexpr int KLL = 10, KD = 9;         // root table bits: lit/len, distance
-constexpr uint32_t RING = 65536u, RMASK = RING - 1u;
 constexpr int TOKCAP = 160;             // tokens a lane may emit per round (sub-chunk + overrun)
-constexpr uint32_t S_MAX = 992, S_MIN = 256;   // sub-chunk size in bits (bitmap <= 32 KiB - 4)
-constexpr uint32_t PIECE = 16;          // bytes copied per readiness check
+constexpr uint32_t S_MAX = 992, S_MIN = 256;   // sub-chunk size in bits
+constexpr uint32_t BMWORDS = S_MAX * NT / 32;  // sync bitmap, one bit per compressed bit of the round
+
+// A slab holds the token lists of one round: header, then NT lists of TOKCAP tokens.
+struct SlabHdr {
+  uint32_t next;        // next slab of the member, or NO_SLAB
+  uint32_t out_bytes;   // output bytes of the round
+  uint32_t ntokens;     // proven tokens of the round
+  uint32_t pad;
+  uint32_t gn[NT];      // per lane: first proven token | (end << 16); 0 = lane not proven
+};
+constexpr uint32_t SLAB_WORDS = sizeof(SlabHdr) / 4 + NT * TOKCAP;
+constexpr uint32_t NO_SLAB = 0xffffffffu;
+
+// what phase one leaves per member for phase two
+struct P1Rec {
+  uint32_t status;      // 1 = token stream complete, 0 = member goes to the sequential kernel
+  uint32_t first_slab;
+  uint32_t out_len;     // total output bytes
+  uint32_t end_pos;     // bit position (relative to the 4-byte aligned input base) after the last block
+};
 
 constexpr uint32_t E_LONG = 0x00000300u, E_INVALID = 0x00010300u;   // table specials (code length 0)
 constexpr uint32_t TOK_MATCH = 0x80000000u, TOK_EOB = 0x40000000u;
@@ -40,32 +54,23 @@ enum { ST_IDLE = 0, ST_END, ST_SYNC, ST_EOB, ST_CAP, ST_BAD };
 struct Canon16 { uint16_t first[16], count[16], base[16]; uint16_t maxlen, nsyms; };
 
 struct Smem {
-  alignas(16) uint8_t ring[RING];        // output ring; its free half doubles as the sync bitmap
+  uint32_t bitmap[BMWORDS];              // token-start bits of the current round
   uint32_t lut_ll[1 << KLL];
   uint32_t lut_d[1 << KD];
   uint32_t lut_cl[128];
-  uint32_t crc_tab[256];
   Canon16 c_ll, c_d, c_cl;
   uint16_t sorted_ll[288], sorted_d[32], sorted_cl[32];
   uint8_t lens[352];                     // [0,19) code-length code, [32,352) lit/len + distance
   uint16_t run[2][16];                   // running offsets of the two table-building warps
-  uint32_t e_pos[NT];                    // where the lane's decode stopped
   uint32_t entry[NT];                    // proven entry point of the lane (bit position)
-  uint32_t outb[NT];                     // output bytes of the lane's proven range
-  uint32_t obase[NT + 1];                // absolute output offset of each lane's range
-  uint32_t prog[NT];                     // output position up to which the lane's bytes are final
   uint16_t nxt[2][NT + 1];               // successor lane (pointer doubling, double buffered)
-  uint16_t ntok[NT], gtok[NT];
-  uint8_t status[NT];
   uint8_t truth[NT + 1];
-  uint16_t blk_owner[RING / 64];
-  uint32_t wscan[NWARP];
-  unsigned long long wsum[NWARP][2];
+  uint32_t wscan[NWARP], wscan2[NWARP];
   // scalars
   uint32_t member;
   int fail;
-  uint32_t term_pos; int term_status; uint32_t term_lane;
-  uint32_t adler_s1, adler_s2, crc;
+  uint32_t term_pos; int term_status;
+  uint32_t slab;
 };
 
 struct In {
@@ -208,128 +213,39 @@ __device__ __forceinline__ uint32_t tok_outlen(uint32_t t) {
 }
 
 // ---- CTA-wide helpers --------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t cta_exclusive_scan(uint32_t v, Smem &sm, int tid, uint32_t &total) {
+__device__ __forceinline__ void cta_sum2(uint32_t a, uint32_t b, Smem &sm, int tid, uint32_t &ta, uint32_t &tb) {
   const int lane = tid & 31, warp = tid >> 5;
-  uint32_t x = v;
 #pragma unroll
-  for (int s = 1; s < 32; s <<= 1) {
-    uint32_t y = __shfl_up_sync(TBZ_FULL, x, s);
-    if (lane >= s) x += y;
-  }
-  if (lane == 31) sm.wscan[warp] = x;
+  for (int s = 16; s; s >>= 1) { a += __shfl_xor_sync(TBZ_FULL, a, s); b += __shfl_xor_sync(TBZ_FULL, b, s); }
+  if (lane == 0) { sm.wscan[warp] = a; sm.wscan2[warp] = b; }
   __syncthreads();
-  uint32_t off = 0, tot = 0;
+  ta = 0; tb = 0;
 #pragma unroll
-  for (int w = 0; w < NWARP; w++) { uint32_t t = sm.wscan[w]; if (w < warp) off += t; tot += t; }
-  total = tot;
+  for (int w = 0; w < NWARP; w++) { ta += sm.wscan[w]; tb += sm.wscan2[w]; }
   __syncthreads();
-  return off + x - v;
 }
 
-// Flush ring[a,b) (absolute output positions) to global memory, folding the bytes into the
-// running Adler-32 (zlib) on the way.  Vector path when the member's output pointer is 16-byte
-// aligned; bytewise otherwise.
-__device__ inline void flush_range(Smem &sm, uint8_t *out, uint32_t a, uint32_t b, int fmt, int tid) {
-  const uint32_t m = b - a;
-  if (m == 0) return;
-  unsigned long long sa = 0, sb = 0;   // sum d ; sum (m - j) d_j   (j relative to a)
-  if ((((uintptr_t)out) & 15) == 0) {
-    uint32_t head = (16 - (a & 15)) & 15;
-    if (head > m) head = m;
-    if ((uint32_t)tid < head) {
-      uint32_t d = sm.ring[(a + tid) & RMASK];
-      out[a + tid] = (uint8_t)d;
-      sa += d; sb += (unsigned long long)(m - tid) * d;
-    }
-    const uint32_t body0 = a + head, nunits = (b - body0) >> 4;
-    for (uint32_t u = tid; u < nunits; u += NT) {
-      const uint32_t p = body0 + (u << 4);
-      const uint4 v = *reinterpret_cast<const uint4 *>(&sm.ring[p & RMASK]);
-      *reinterpret_cast<uint4 *>(out + p) = v;
-      if (fmt == TBZ_ZLIB) {
-        uint32_t s = __dp4a(v.x, 0x01010101u, 0u); s = __dp4a(v.y, 0x01010101u, s);
-        s = __dp4a(v.z, 0x01010101u, s); s = __dp4a(v.w, 0x01010101u, s);
-        uint32_t wj = __dp4a(v.x, 0x03020100u, 0u); wj = __dp4a(v.y, 0x07060504u, wj);
-        wj = __dp4a(v.z, 0x0b0a0908u, wj); wj = __dp4a(v.w, 0x0f0e0d0cu, wj);
-        sa += s;
-        sb += (unsigned long long)(m - (p - a)) * s - wj;
-      }
-    }
-    const uint32_t tail0 = body0 + (nunits << 4);
-    if (tail0 + tid < b) {
-      uint32_t d = sm.ring[(tail0 + tid) & RMASK];
-      out[tail0 + tid] = (uint8_t)d;
-      sa += d; sb += (unsigned long long)(b - (tail0 + tid)) * d;
-    }
-  } else {
-    for (uint32_t p = a + tid; p < b; p += NT) {
-      uint32_t d = sm.ring[p & RMASK];
-      out[p] = (uint8_t)d;
-      sa += d; sb += (unsigned long long)(b - p) * d;
-    }
+// token list writer: four tokens per 16-byte store
+struct TokW {
+  uint32_t *list; uint32_t q0, q1, q2, q3;
+  __device__ __forceinline__ void push(uint32_t tok, uint32_t k) {
+    q0 = q1; q1 = q2; q2 = q3; q3 = tok;
+    if ((k & 3) == 3) *reinterpret_cast<uint4 *>(list + (k & ~3u)) = make_uint4(q0, q1, q2, q3);
   }
-  if (fmt == TBZ_ZLIB) {
-    const int lane = tid & 31, warp = tid >> 5;
-#pragma unroll
-    for (int s = 16; s; s >>= 1) {
-      sa += __shfl_xor_sync(TBZ_FULL, sa, s);
-      sb += __shfl_xor_sync(TBZ_FULL, sb, s);
-    }
-    if (lane == 0) { sm.wsum[warp][0] = sa; sm.wsum[warp][1] = sb; }
-    __syncthreads();
-    if (tid == 0) {
-      unsigned long long A = 0, B = 0;
-      for (int w = 0; w < NWARP; w++) { A += sm.wsum[w][0]; B += sm.wsum[w][1]; }
-      // append m bytes: s2' = s2 + m*s1 + sum (m-j) d_j ; s1' = s1 + sum d
-      unsigned long long s2 = (sm.adler_s2 + (unsigned long long)m % TBZ_ADLER_MOD * sm.adler_s1 + B % TBZ_ADLER_MOD) % TBZ_ADLER_MOD;
-      sm.adler_s1 = (uint32_t)((sm.adler_s1 + A) % TBZ_ADLER_MOD);
-      sm.adler_s2 = (uint32_t)s2;
-    }
-    __syncthreads();
+  __device__ __forceinline__ void finish(uint32_t k) {     // k tokens pushed so far
+    const uint32_t r = k & 3, b = k & ~3u;
+    if (r == 1) list[b] = q3;
+    else if (r == 2) { list[b] = q2; list[b + 1] = q3; }
+    else if (r == 3) { list[b] = q1; list[b + 1] = q2; list[b + 2] = q3; }
   }
-}
-
-// CRC-32 of ring[a,b): every thread takes one contiguous slice, slices are merged pairwise with
-// x^(8 len) shifts (the per-level shift is the square of the previous one).
-__device__ inline void crc_range(Smem &sm, uint32_t a, uint32_t b, int tid) {
-  const uint32_t m = b - a;
-  if (m == 0) return;
-  const uint32_t seg = (m + NT - 1) / NT;
-  uint32_t lo = a + seg * tid, hi = lo + seg;
-  if (lo > b) lo = b;
-  if (hi > b) hi = b;
-  uint32_t c = 0xffffffffu;
-  for (uint32_t p = lo; p < hi; p++) c = (c >> 8) ^ sm.crc_tab[(c ^ sm.ring[p & RMASK]) & 0xff];
-  c ^= 0xffffffffu;
-  if (lo == hi) c = 0;
-  // tree over NT slices; all full slices have length seg, trailing ones may be shorter or empty,
-  // so each node carries its own length and uses the generic combine only when needed
-  uint32_t len = hi - lo;
-  uint32_t shift = crc_x8n(seg);                 // x^(8 seg), squared per level
-  __shared__ uint32_t s_c[NT], s_l[NT];
-  for (int s = 1; s < NT; s <<= 1) {
-    s_c[tid] = c; s_l[tid] = len;
-    __syncthreads();
-    if ((tid & (2 * s - 1)) == 0 && tid + s < NT) {
-      uint32_t oc = s_c[tid + s], ol = s_l[tid + s];
-      if (ol) {
-        uint32_t f = (ol == seg * (uint32_t)s) ? shift : crc_x8n(ol);
-        c = crc_mulmod(f, c) ^ oc;
-        len += ol;
-      }
-    }
-    shift = crc_mulmod(shift, shift);
-    __syncthreads();
-  }
-  if (tid == 0) sm.crc = crc_combine(sm.crc, c, m);   // crc of the empty prefix is 0
-}
+};
 
 // ------------------------------------------------------------------------------------------------
-// One member.  Returns true when the member was completed here, false when it must be redone by
-// the sequential kernel.
+// One member.  Returns true when its token stream is complete, false when the member must be
+// redone by the sequential kernel.
 // ------------------------------------------------------------------------------------------------
-__device__ inline bool inflate_member(const DMember &mem, int fmt, tbz_result &res, Smem &sm,
-                                      uint32_t *__restrict__ tokbuf, int tid) {
+__device__ inline bool decode_member(const DMember &mem, int fmt, P1Rec &rec, Smem &sm,
+                                     uint32_t *__restrict__ slabs, uint32_t nslabs, uint32_t *slab_counter, int tid) {
   const int lane = tid & 31, warp = tid >> 5;
   In in;
   {
@@ -341,7 +257,6 @@ __device__ inline bool inflate_member(const DMember &mem, int fmt, tbz_result &r
     in.end = (mis + (uint32_t)mem.in_len) * 8;
     in.nwords = (in.end + 31) >> 5;
   }
-  if (mem.out_cap >= (1ull << 31)) return false;
   uint32_t pos = in.pos0;
   // ---- wrapper header (zlib.lisp:108-126, gzip.lisp:113-177; optional gzip fields -> sequential kernel)
   if (fmt == TBZ_ZLIB) {
@@ -355,8 +270,9 @@ __device__ inline bool inflate_member(const DMember &mem, int fmt, tbz_result &r
     if (byte_at(in, bp) != 0x1f || byte_at(in, bp + 1) != 0x8b || byte_at(in, bp + 2) != 8 || byte_at(in, bp + 3) != 0) return false;
     pos += 80;
   }
-  if (tid == 0) { sm.fail = 0; sm.adler_s1 = 1; sm.adler_s2 = 0; sm.crc = 0; }
-  uint32_t A = 0;              // output bytes produced and flushed so far
+  if (tid == 0) sm.fail = 0;
+  unsigned long long A = 0;    // output bytes so far
+  uint32_t first_slab = NO_SLAB, prev_slab = NO_SLAB;
   bool last = false;
   __syncthreads();
 
@@ -385,10 +301,7 @@ __device__ inline bool inflate_member(const DMember &mem, int fmt, tbz_result &r
         int err = warp_canon(sm.lens, 19, sm.c_cl, sm.sorted_cl, sm.run[0], lane);
         if (!err && sm.c_cl.nsyms == 0) err = TBZ_ERR_INVALID_SYMBOL;
         if (!err) {
-          for (int e = lane; e < 128; e += 32) {
-            uint32_t r = canon_lookup(sm.c_cl, sm.sorted_cl, (uint32_t)e, 1, 7);
-            sm.lut_cl[e] = r;               // (sym << 4) | L, 0 = no code
-          }
+          for (int e = lane; e < 128; e += 32) sm.lut_cl[e] = canon_lookup(sm.c_cl, sm.sorted_cl, (uint32_t)e, 1, 7);
           __syncwarp();
           if (lane == 0) {
             // the code lengths themselves: one lane, table driven (deflate.lisp:626-669)
@@ -443,6 +356,12 @@ __device__ inline bool inflate_member(const DMember &mem, int fmt, tbz_result &r
     // ================= rounds over the block's compressed bits =================
     bool block_done = false;
     while (!block_done) {
+      // ---- a slab for this round's token lists
+      if (tid == 0) {
+        uint32_t s = atomicAdd(slab_counter, 1u);
+        if (s >= nslabs) { s = NO_SLAB; sm.fail = 1; }
+        sm.slab = s;
+      }
       // ---- geometry of this round
       const uint32_t P0 = pos;
       const uint32_t winbase = P0 & ~31u;
@@ -450,13 +369,17 @@ __device__ inline bool inflate_member(const DMember &mem, int fmt, tbz_result &r
       if (S > S_MAX) S = S_MAX;
       if (S < S_MIN) S = S_MIN;
       const uint32_t winend = winbase + S * NT;
-      const uint32_t bm0 = (A + 3) >> 2;                  // bitmap lives in the ring half not holding history
-      uint32_t *ring32 = reinterpret_cast<uint32_t *>(sm.ring);
       const uint32_t bmwords = (S * NT) >> 5;
-      for (uint32_t w = tid; w < bmwords; w += NT) ring32[(bm0 + w) & (RING / 4 - 1)] = 0;
+      for (uint32_t w = tid; w < bmwords; w += NT) sm.bitmap[w] = 0;
       __syncthreads();
+      if (sm.fail) return false;
+      uint32_t *slab = slabs + (size_t)sm.slab * SLAB_WORDS;
+      SlabHdr *sh = reinterpret_cast<SlabHdr *>(slab);
+      TokW tw;
+      tw.list = slab + sizeof(SlabHdr) / 4 + tid * TOKCAP;
+      tw.q0 = tw.q1 = tw.q2 = tw.q3 = 0;
 
-      // ---- phase 1a: speculative decode of the lane's sub-chunk
+      // ---- 1a: speculative decode of the lane's sub-chunk
       const uint32_t cstart = winbase + S * tid, cend = cstart + S;
       uint32_t p = tid == 0 ? P0 : cstart;
       uint32_t k = 0, ob = 0;
@@ -469,40 +392,40 @@ __device__ inline bool inflate_member(const DMember &mem, int fmt, tbz_result &r
           if (p >= cend) { st = ST_END; break; }
           if (k >= TOKCAP) { st = ST_CAP; break; }
           const uint32_t rel = p - winbase, wi = rel >> 5;
-          if (wi != curw) { ring32[(bm0 + curw) & (RING / 4 - 1)] = acc; acc = 0; curw = wi; }
+          if (wi != curw) { sm.bitmap[curw] = acc; acc = 0; curw = wi; }
           acc |= 1u << (rel & 31);
           uint32_t tok, nb, ol;
           const int kind = decode_token(b, in, sm, tok, nb, ol);
           if (kind == 3 || p + nb > in.end) { st = ST_BAD; break; }
-          tokbuf[k * NT + tid] = tok;
+          tw.push(tok, k);
           k++; p += nb; ob += ol;
           if (kind == 2) { st = ST_EOB; break; }
         }
-        ring32[(bm0 + curw) & (RING / 4 - 1)] = acc;
+        sm.bitmap[curw] = acc;
       }
       __syncthreads();
-      // ---- phase 1b: run on until the decode lands on a marked bit of a later lane
+      // ---- 1b: run on until the decode lands on a marked bit of a later lane
       uint32_t nx = NT;
       if (st == ST_END) {
         for (;;) {
           if (p >= winend) break;                                 // round ends here, block continues
           const uint32_t rel = p - winbase;
-          if ((ring32[(bm0 + (rel >> 5)) & (RING / 4 - 1)] >> (rel & 31)) & 1u) { st = ST_SYNC; nx = rel / S; break; }
+          if ((sm.bitmap[rel >> 5] >> (rel & 31)) & 1u) { st = ST_SYNC; nx = rel / S; break; }
           if (k >= TOKCAP) { st = ST_CAP; break; }
           uint32_t tok, nb, ol;
           const int kind = decode_token(b, in, sm, tok, nb, ol);
           if (kind == 3 || p + nb > in.end) { st = ST_BAD; break; }
-          tokbuf[k * NT + tid] = tok;
+          tw.push(tok, k);
           k++; p += nb; ob += ol;
           if (kind == 2) { st = ST_EOB; break; }
         }
       }
-      sm.e_pos[tid] = p; sm.status[tid] = (uint8_t)st; sm.ntok[tid] = (uint16_t)k;
+      tw.finish(k);
       sm.nxt[0][tid] = (uint16_t)nx;
       sm.truth[tid] = tid == 0;
       if (tid == 0) { sm.nxt[0][NT] = NT; sm.truth[NT] = 0; }
       __syncthreads();
-      // ---- resolve: lanes reachable from lane 0 through "synchronised into" edges are proven
+      // ---- 1c: lanes reachable from lane 0 through "synchronised into" edges are proven
       {
         int cur = 0;
         for (int r = 0; r < 8; r++) {
@@ -517,140 +440,44 @@ __device__ inline bool inflate_member(const DMember &mem, int fmt, tbz_result &r
       const bool proven = sm.truth[tid];
       if (proven) {
         if (st == ST_SYNC) sm.entry[nx] = p;
-        else { sm.term_lane = tid; sm.term_status = st; sm.term_pos = p; }
+        else { sm.term_status = st; sm.term_pos = p; }
       }
       if (tid == 0) sm.entry[0] = P0;
       __syncthreads();
       if (sm.term_status == ST_BAD || sm.term_status == ST_IDLE) return false;
-      // ---- tokens decoded before the entry point are garbage: count and size them
+      // ---- tokens decoded before the entry point are dropped: count and size them
       uint32_t g = 0, gb = 0;
       if (proven && tid != 0) {
         const uint32_t r0 = cstart - winbase, r1 = sm.entry[tid] - winbase;   // r1 in [r0, r0 + S)
         for (uint32_t w = r0 >> 5; w <= (r1 >> 5); w++) {
-          uint32_t bits = ring32[(bm0 + w) & (RING / 4 - 1)];
+          uint32_t bits = sm.bitmap[w];
           if (w == (r1 >> 5)) bits &= (1u << (r1 & 31)) - 1u;
           g += __popc(bits);
         }
-        for (uint32_t i = 0; i < g; i++) gb += tok_outlen(tokbuf[i * NT + tid]);
+        for (uint32_t i = 0; i < g; i++) gb += tok_outlen(tw.list[i]);
       }
-      uint32_t total;
-      const uint32_t myout = proven ? ob - gb : 0;
-      const uint32_t off = cta_exclusive_scan(myout, sm, tid, total);
-      if ((unsigned long long)A + total > mem.out_cap) return false;       // overflow: sequential kernel
-      sm.obase[tid] = A + off;
-      if (tid == 0) sm.obase[NT] = A + total;
-      sm.prog[tid] = A + off;
-      sm.gtok[tid] = (uint16_t)g;
-      __syncthreads();
-
-      // ---- phase 2: replay tokens into the ring
-      const uint32_t R_end = A + total;
-      uint32_t opos = A + off;
-      const uint32_t oend = opos + myout;
-      uint32_t kk = g, rem = 0, dist = 0;
-      const uint32_t kend = k;
-      while (A < R_end) {
-        // the ring keeps [A - 32K, A) as history, so this step may write up to A + 64K - min(A, 32K)
-        uint32_t lim = A + RING - (A < 32768u ? A : 32768u);
-        if (lim > R_end) lim = R_end;
-        // block-owner map for readiness checks inside [A, lim): who owns the first byte of each
-        // 64-byte output block (for the block that straddles A: who owns byte A)
-        if (myout && opos < oend) {
-          for (uint32_t bl = (opos + 63) >> 6; (bl << 6) < oend && (bl << 6) < lim; bl++)
-            sm.blk_owner[bl & (RING / 64 - 1)] = (uint16_t)tid;
-          if (opos == A) sm.blk_owner[(A >> 6) & (RING / 64 - 1)] = (uint16_t)tid;
-        }
-        __syncthreads();
-        bool busy = proven && opos < oend && opos < lim;
-        while (__syncthreads_or(busy)) {
-          // a few tokens per barrier round to amortise the barrier
-          for (int it = 0; it < 8 && busy; it++) {
-            if (rem == 0) {
-              if (kk >= kend) { busy = false; break; }
-              const uint32_t t = tokbuf[kk * NT + tid];
-              kk++;
-              if (t & TOK_MATCH) {
-                rem = (t & 255u) + 3u; dist = ((t >> 8) & 0x7fffu) + 1u;
-                if (dist > opos) { sm.fail = 1; busy = false; break; }   // deflate.lisp:343-345
-              } else if (t & TOK_EOB) { busy = false; break; }
-              else {
-                sm.ring[opos & RMASK] = (uint8_t)t;
-                opos++;
-                __threadfence_block();
-                *(volatile uint32_t *)&sm.prog[tid] = opos;
-                if (opos >= lim) busy = false;
-                continue;
-              }
-            }
-            // a piece of the pending match
-            uint32_t n = rem < PIECE ? rem : PIECE;
-            if (n > lim - opos) n = lim - opos;
-            const uint32_t s0 = opos - dist;
-            uint32_t s1 = s0 + n;                    // source bytes [s0, s1) must be final ...
-            if (s1 > opos) s1 = opos;                // ... an overlapping copy reads only behind itself
-            bool ready = true;
-            const uint32_t mybase = sm.obase[tid];
-            const uint32_t f1 = s1 < mybase ? s1 : mybase;   // the part of the source other lanes write is [s0, f1)
-            if (s0 < mybase && f1 > A) {
-              // lane owning byte f1-1, then downwards over every lane that covers [s0, f1)
-              uint32_t o = sm.blk_owner[((f1 - 1) >> 6) & (RING / 64 - 1)];
-              while (sm.obase[o + 1] <= f1 - 1) o++;
-              for (;;) {
-                const uint32_t ob1 = sm.obase[o + 1];
-                const uint32_t need = ob1 < f1 ? ob1 : f1;
-                if (*(volatile uint32_t *)&sm.prog[o] < need) { ready = false; break; }
-                const uint32_t ob0 = sm.obase[o];
-                if (ob0 <= s0 || ob0 <= A) break;              // everything below A is final
-                o--;
-              }
-            }
-            if (!ready) break;
-            for (uint32_t i = 0; i < n; i++) sm.ring[(opos + i) & RMASK] = sm.ring[(s0 + i) & RMASK];
-            opos += n; rem -= n;
-            __threadfence_block();
-            *(volatile uint32_t *)&sm.prog[tid] = opos;
-            if (opos >= lim) busy = false;
-          }
-          if (sm.fail) busy = false;
-        }
-        if (sm.fail) return false;
-        // ---- flush [A, lim) and fold it into the checksum
-        if (fmt == TBZ_GZIP) crc_range(sm, A, lim, tid);
-        flush_range(sm, mem.out, A, lim, fmt, tid);
-        A = lim;
-        __syncthreads();
+      sh->gn[tid] = proven ? (g | (k << 16)) : 0u;
+      uint32_t total, ntok;
+      cta_sum2(proven ? ob - gb : 0u, proven ? k - g : 0u, sm, tid, total, ntok);
+      A += total;
+      if (A > mem.out_cap || A >= (1ull << 32)) return false;       // overflow: sequential kernel
+      if (tid == 0) {
+        sh->next = NO_SLAB; sh->out_bytes = total; sh->ntokens = ntok;
+        if (prev_slab != NO_SLAB) reinterpret_cast<SlabHdr *>(slabs + (size_t)prev_slab * SLAB_WORDS)->next = sm.slab;
       }
+      if (first_slab == NO_SLAB) first_slab = sm.slab;
+      prev_slab = sm.slab;
       // ---- how did the round end?
       pos = sm.term_pos;
       if (sm.term_status == ST_EOB) block_done = true;
       __syncthreads();
     }
   }
-  // ================= trailer (zlib.lisp:80-96, gzip.lisp:82-106) =================
-  pos = (pos + 7) & ~7u;
-  uint32_t ck = 0;
-  if (fmt == TBZ_ZLIB) {
-    if (in.end - pos < 32) return false;
-    const uint32_t bp = pos >> 3;
-    const uint32_t t = (byte_at(in, bp) << 24) | (byte_at(in, bp + 1) << 16) | (byte_at(in, bp + 2) << 8) | byte_at(in, bp + 3);
-    ck = sm.adler_s1 | (sm.adler_s2 << 16);
-    if (t != ck) return false;
-    pos += 32;
-  } else if (fmt == TBZ_GZIP) {
-    if (in.end - pos < 64) return false;
-    const uint32_t bp = pos >> 3;
-    const uint32_t t = byte_at(in, bp) | (byte_at(in, bp + 1) << 8) | (byte_at(in, bp + 2) << 16) | (byte_at(in, bp + 3) << 24);
-    ck = sm.crc;
-    if (t != ck) return false;
-    pos += 64;
-  }
   if (tid == 0) {
-    res.out_len = A;
-    res.in_used = (pos - in.pos0 + 7) >> 3;
-    res.checksum = ck;
-    res.verdict = TBZ_FINISHED;
-    res.where = TBZ_AT_BODY;
-    res.path = 1;
+    rec.first_slab = first_slab;
+    rec.out_len = (uint32_t)A;
+    rec.end_pos = pos;
+    rec.status = 1;
   }
   return true;
 }

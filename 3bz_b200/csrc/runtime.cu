@@ -16,7 +16,8 @@
 #include "threebz_cuda.h"
 #include "tbz_device.cuh"
 #include "inflate_seq.cuh"
-#include "inflate_fast.cuh"
+#include "inflate_decode.cuh"
+#include "inflate_resolve.cuh"
 
 // =============================================================================================
 // kernels
@@ -38,30 +39,52 @@ k_inflate_seq(const DMember *members, tbz_result *results, uint32_t n, int fmt,
   tbzseq::inflate_member(members[i], fmt, results[i], sm[warp], crc_tab, lane);
 }
 
-// persistent CTAs: each pulls the next member from a global counter; members the fast path
-// cannot prove clean are queued for k_inflate_seq
+// counters: [0] next member for phase one, [1] members queued for the sequential kernel,
+//           [2] slabs handed out, [3] next member for phase two
+// Phase one, persistent CTAs: each pulls the next member from a global counter and decodes it
+// into token slabs; members it cannot prove clean are queued for k_inflate_seq.
 __global__ void __launch_bounds__(tbzfast::NT, 2)
-k_inflate_fast(const DMember *members, tbz_result *results, uint32_t n, int fmt,
-               uint32_t *tokens, uint32_t *counters, uint32_t *todo) {
+k_inflate_decode(const DMember *members, uint32_t n, int fmt, tbzfast::P1Rec *recs,
+                 uint32_t *slabs, uint32_t nslabs, uint32_t *counters, uint32_t *todo) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   tbzfast::Smem &sm = *reinterpret_cast<tbzfast::Smem *>(smem_raw);
   const int tid = threadIdx.x;
-  crc_table_init(sm.crc_tab, tid, tbzfast::NT);
-  uint32_t *tokbuf = tokens + (size_t)blockIdx.x * tbzfast::NT * tbzfast::TOKCAP;
   for (;;) {
     __syncthreads();
     if (tid == 0) sm.member = atomicAdd(&counters[0], 1u);
     __syncthreads();
     const uint32_t i = sm.member;
     if (i >= n) break;
-    const bool ok = tbzfast::inflate_member(members[i], fmt, results[i], sm, tokbuf, tid);
-    if (!ok && tid == 0) todo[atomicAdd(&counters[1], 1u)] = i;
+    const bool ok = tbzfast::decode_member(members[i], fmt, recs[i], sm, slabs, nslabs, &counters[2], tid);
+    if (!ok && tid == 0) { recs[i].status = 0; todo[atomicAdd(&counters[1], 1u)] = i; }
+  }
+}
+
+// Phase two: one warp per member resolves the token stream into bytes and checks the trailer.
+#define RES_WARPS 4
+__global__ void __launch_bounds__(RES_WARPS * 32)
+k_inflate_resolve(const DMember *members, tbz_result *results, uint32_t n, int fmt,
+                  const tbzfast::P1Rec *recs, const uint32_t *slabs, uint32_t *counters, uint32_t *todo) {
+  __shared__ uint32_t crc_tab[256];
+  if (fmt == TBZ_GZIP) crc_table_init(crc_tab, threadIdx.x, blockDim.x);
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  for (;;) {
+    uint32_t i = 0;
+    if (lane == 0) i = atomicAdd(&counters[3], 1u);
+    i = __shfl_sync(TBZ_FULL, i, 0);
+    if (i >= n) break;
+    if (!recs[i].status) continue;
+    const bool ok = tbzres::resolve_member(members[i], fmt, recs[i], slabs, results[i], crc_tab, lane);
+    if (!ok && lane == 0) todo[atomicAdd(&counters[1], 1u)] = i;
   }
 }
 
 // =============================================================================================
 // host objects
 // =============================================================================================
+static const uint64_t kSlabPoolBytes = 6ull << 30;   // upper bound of the token slab pool per batch
+
 struct DevBlock { void *p; size_t size; bool used; };
 
 struct tbz_ctx {
@@ -141,8 +164,9 @@ struct tbz_batch {
   bool out_direct = false;             // caller's outputs are exactly adjacent: DMA straight into them
   const uint8_t *in_span = nullptr; uint8_t *out_span = nullptr;
   void *d_in = nullptr, *d_out = nullptr, *d_members = nullptr, *d_results = nullptr;
-  void *d_tokens = nullptr, *d_counters = nullptr, *d_todo = nullptr;
+  void *d_slabs = nullptr, *d_counters = nullptr, *d_todo = nullptr, *d_recs = nullptr;
   int fast_grid = 0;
+  uint32_t nslabs = 0;
   bool launched = false;
 };
 
@@ -344,7 +368,7 @@ extern "C" int32_t tbz_batch_destroy(tbz_batch *b) {
   if (b->launched) cudaStreamSynchronize(ctx->stream);
   dev_release(ctx, b->d_in); dev_release(ctx, b->d_out);
   dev_release(ctx, b->d_members); dev_release(ctx, b->d_results);
-  dev_release(ctx, b->d_tokens); dev_release(ctx, b->d_counters); dev_release(ctx, b->d_todo);
+  dev_release(ctx, b->d_slabs); dev_release(ctx, b->d_counters); dev_release(ctx, b->d_todo); dev_release(ctx, b->d_recs);
   delete b;
   return TBZ_OK;
 }
@@ -362,10 +386,18 @@ extern "C" int32_t tbz_batch_prepare(tbz_ctx *ctx, int32_t format, const tbz_mem
   PCK(dev_alloc(ctx, std::max<uint64_t>(1, n) * sizeof(DMember), &b->d_members));
   PCK(dev_alloc(ctx, std::max<uint64_t>(1, n) * sizeof(tbz_result), &b->d_results));
   if (!(flags & TBZ_FLAG_NO_FASTPATH) && n) {
-    b->fast_grid = (int)std::min<uint64_t>(n, (uint64_t)ctx->sm_count * 2);
-    PCK(dev_alloc(ctx, (size_t)b->fast_grid * tbzfast::NT * tbzfast::TOKCAP * 4, &b->d_tokens));
+    b->fast_grid = (int)std::min<uint64_t>(n, (uint64_t)ctx->sm_count * 3);
+    // token slabs: one per round; a round covers at most ~31 KiB of compressed input and never
+    // crosses a block boundary.  Members that find the pool empty go to the sequential kernel.
+    uint64_t want = 0;
+    for (uint64_t i = 0; i < n; i++) want += m[i].in_len / 12288 + 2;
+    const uint64_t slab_bytes = (uint64_t)tbzfast::SLAB_WORDS * 4;
+    const uint64_t cap = std::max<uint64_t>(64, kSlabPoolBytes / slab_bytes);
+    b->nslabs = (uint32_t)std::min<uint64_t>(want, cap);
+    PCK(dev_alloc(ctx, (size_t)b->nslabs * slab_bytes, &b->d_slabs));
     PCK(dev_alloc(ctx, 256, &b->d_counters));
     PCK(dev_alloc(ctx, n * 4, &b->d_todo));
+    PCK(dev_alloc(ctx, n * sizeof(tbzfast::P1Rec), &b->d_recs));
   }
   std::vector<DMember> dm(n);
   if (b->device_ptrs) {
@@ -427,11 +459,17 @@ static int32_t launch_kernels(tbz_batch *b) {
   if (!b->n) return TBZ_OK;
   uint32_t n = (uint32_t)b->n;
   if (b->fast_grid) {
-    CK(ctx, cudaFuncSetAttribute(k_inflate_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tbzfast::Smem)));
+    CK(ctx, cudaFuncSetAttribute(k_inflate_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tbzfast::Smem)));
     CK(ctx, cudaMemsetAsync(b->d_counters, 0, 256, ctx->stream));
-    k_inflate_fast<<<b->fast_grid, tbzfast::NT, sizeof(tbzfast::Smem), ctx->stream>>>(
+    k_inflate_decode<<<b->fast_grid, tbzfast::NT, sizeof(tbzfast::Smem), ctx->stream>>>(
+        (const DMember *)b->d_members, n, b->format, (tbzfast::P1Rec *)b->d_recs,
+        (uint32_t *)b->d_slabs, b->nslabs, (uint32_t *)b->d_counters, (uint32_t *)b->d_todo);
+    ctx->launches++;
+    CK(ctx, cudaGetLastError());
+    const int res_grid = (int)std::min<uint64_t>((n + RES_WARPS - 1) / RES_WARPS, (uint64_t)ctx->sm_count * 16);
+    k_inflate_resolve<<<res_grid, RES_WARPS * 32, 0, ctx->stream>>>(
         (const DMember *)b->d_members, (tbz_result *)b->d_results, n, b->format,
-        (uint32_t *)b->d_tokens, (uint32_t *)b->d_counters, (uint32_t *)b->d_todo);
+        (const tbzfast::P1Rec *)b->d_recs, (const uint32_t *)b->d_slabs, (uint32_t *)b->d_counters, (uint32_t *)b->d_todo);
     ctx->launches++;
     CK(ctx, cudaGetLastError());
     k_inflate_seq<<<(n + SEQ_WARPS - 1) / SEQ_WARPS, SEQ_WARPS * 32, 0, ctx->stream>>>(
