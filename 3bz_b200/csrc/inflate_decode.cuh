@@ -25,6 +25,7 @@ constexpr int NWARP = NT / 32;
 constexpr int KLL = 10, KD = 9;         // root table bits: lit/len, distance
 constexpr int TOKCAP = 160;             // tokens a lane may emit per round (sub-chunk + overrun)
 constexpr uint32_t S_MAX = 992, S_MIN = 256;   // sub-chunk size in bits
+constexpr uint32_t SYNC_SLACK = 640;           // bits a lane searches for its sync point before the barrier
 constexpr uint32_t BMWORDS = S_MAX * NT / 32;  // sync bitmap, one bit per compressed bit of the round
 
 // A slab holds the token lists of one round: header, then NT lists of TOKCAP tokens.
@@ -34,6 +35,7 @@ struct SlabHdr {
   uint32_t ntokens;     // proven tokens of the round
   uint32_t pad;
   uint32_t gn[NT];      // per lane: first proven token | (end << 16); 0 = lane not proven
+  uint32_t tb[NT];      // per lane: number of proven tokens in the lanes before it (flat token index base)
 };
 constexpr uint32_t SLAB_WORDS = sizeof(SlabHdr) / 4 + NT * TOKCAP;
 constexpr uint32_t NO_SLAB = 0xffffffffu;
@@ -308,8 +310,11 @@ __device__ inline bool decode_member(const DMember &mem, int fmt, P1Rec &rec, Sm
             uint32_t p = pos + 14 + 3 * ncl;
             int idx = 0, lastlen = 0xff;
             const int total = hlit + hdist;
+            Bits hb;
+            bits_init(hb, in, p);
             while (idx < total) {
-              uint32_t w = peek32(in, p);
+              bits_refill(hb, in);
+              uint32_t w = (uint32_t)hb.bb;
               uint32_t r = sm.lut_cl[w & 127];
               if (!r) { err = TBZ_ERR_INVALID_SYMBOL; break; }
               int L = r & 15, sym = r >> 4;
@@ -317,6 +322,7 @@ __device__ inline bool decode_member(const DMember &mem, int fmt, P1Rec &rec, Sm
               if (p + L + xb > in.end) { err = TBZ_INPUT_UNDERRUN; break; }
               uint32_t extra = (w >> L) & ((1u << xb) - 1);
               p += L + xb;
+              bits_skip(hb, L + xb);
               int rep, val;
               if (sym < 16) { rep = 1; val = sym; lastlen = sym; }
               else if (sym == 16) { if (lastlen >= 16) { err = TBZ_ERR_REPEAT_NO_PREV; break; } rep = 3 + extra; val = lastlen; }
@@ -382,18 +388,29 @@ __device__ inline bool decode_member(const DMember &mem, int fmt, P1Rec &rec, Sm
       // ---- 1a: speculative decode of the lane's sub-chunk
       const uint32_t cstart = winbase + S * tid, cend = cstart + S;
       uint32_t p = tid == 0 ? P0 : cstart;
-      uint32_t k = 0, ob = 0;
+      uint32_t k = 0, ob = 0, nx = NT;
       int st = ST_IDLE;
       Bits b;
       if (p < in.end) {
         bits_init(b, in, p);
         uint32_t curw = (p - winbase) >> 5, acc = 0;
         for (;;) {
-          if (p >= cend) { st = ST_END; break; }
+          const uint32_t rel = p - winbase;
+          if (p >= cend) {
+            // Past the own sub-chunk: look for a bit a later lane marked.  That lane is usually far
+            // ahead in its own sub-chunk by now; a mark that is not visible yet only delays the
+            // match (any later common token start is as good), and after SYNC_SLACK bits the lane
+            // parks until the barrier below has made every mark visible.
+            if (curw != NO_SLAB) { sm.bitmap[curw] = acc; curw = NO_SLAB; }     // own marks are complete
+            if (p >= winend || p >= cend + SYNC_SLACK) { st = ST_END; break; }
+            if ((*(volatile uint32_t *)&sm.bitmap[rel >> 5] >> (rel & 31)) & 1u) { st = ST_SYNC; nx = rel / S; break; }
+          }
           if (k >= TOKCAP) { st = ST_CAP; break; }
-          const uint32_t rel = p - winbase, wi = rel >> 5;
-          if (wi != curw) { sm.bitmap[curw] = acc; acc = 0; curw = wi; }
-          acc |= 1u << (rel & 31);
+          if (p < cend) {
+            const uint32_t wi = rel >> 5;
+            if (wi != curw) { sm.bitmap[curw] = acc; acc = 0; curw = wi; }
+            acc |= 1u << (rel & 31);
+          }
           uint32_t tok, nb, ol;
           const int kind = decode_token(b, in, sm, tok, nb, ol);
           if (kind == 3 || p + nb > in.end) { st = ST_BAD; break; }
@@ -401,11 +418,10 @@ __device__ inline bool decode_member(const DMember &mem, int fmt, P1Rec &rec, Sm
           k++; p += nb; ob += ol;
           if (kind == 2) { st = ST_EOB; break; }
         }
-        sm.bitmap[curw] = acc;
+        if (curw != NO_SLAB) sm.bitmap[curw] = acc;
       }
       __syncthreads();
-      // ---- 1b: run on until the decode lands on a marked bit of a later lane
-      uint32_t nx = NT;
+      // ---- 1b: lanes still looking for their synchronisation point go on with every mark visible
       if (st == ST_END) {
         for (;;) {
           if (p >= winend) break;                                 // round ends here, block continues
@@ -458,7 +474,26 @@ __device__ inline bool decode_member(const DMember &mem, int fmt, P1Rec &rec, Sm
       }
       sh->gn[tid] = proven ? (g | (k << 16)) : 0u;
       uint32_t total, ntok;
-      cta_sum2(proven ? ob - gb : 0u, proven ? k - g : 0u, sm, tid, total, ntok);
+      {
+        // exclusive scan of the proven token counts (flat token order for phase two) + output total
+        const uint32_t cnt = proven ? k - g : 0u;
+        uint32_t x = cnt, y = proven ? ob - gb : 0u;
+#pragma unroll
+        for (int sft = 1; sft < 32; sft <<= 1) {
+          const uint32_t u = __shfl_up_sync(TBZ_FULL, x, sft);
+          if (lane >= sft) x += u;
+        }
+#pragma unroll
+        for (int sft = 16; sft; sft >>= 1) y += __shfl_xor_sync(TBZ_FULL, y, sft);
+        if (lane == 31) { sm.wscan[warp] = x; sm.wscan2[warp] = y; }
+        __syncthreads();
+        uint32_t off = 0;
+        ntok = 0; total = 0;
+#pragma unroll
+        for (int w = 0; w < NWARP; w++) { const uint32_t c = sm.wscan[w]; if (w < warp) off += c; ntok += c; total += sm.wscan2[w]; }
+        sh->tb[tid] = off + x - cnt;
+        __syncthreads();
+      }
       A += total;
       if (A > mem.out_cap || A >= (1ull << 32)) return false;       // overflow: sequential kernel
       if (tid == 0) {

@@ -60,23 +60,24 @@ k_inflate_decode(const DMember *members, uint32_t n, int fmt, tbzfast::P1Rec *re
   }
 }
 
-// Phase two: one warp per member resolves the token stream into bytes and checks the trailer.
-#define RES_WARPS 4
-__global__ void __launch_bounds__(RES_WARPS * 32)
+// Phase two, persistent CTAs: one CTA per member resolves the token stream into bytes through a
+// shared-memory ring and checks the trailer.
+__global__ void __launch_bounds__(tbzfast::NT, 3)
 k_inflate_resolve(const DMember *members, tbz_result *results, uint32_t n, int fmt,
                   const tbzfast::P1Rec *recs, const uint32_t *slabs, uint32_t *counters, uint32_t *todo) {
-  __shared__ uint32_t crc_tab[256];
-  if (fmt == TBZ_GZIP) crc_table_init(crc_tab, threadIdx.x, blockDim.x);
-  __syncthreads();
-  const int lane = threadIdx.x & 31;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  tbzres::Smem &sm = *reinterpret_cast<tbzres::Smem *>(smem_raw);
+  const int tid = threadIdx.x;
+  if (fmt == TBZ_GZIP) crc_table_init(sm.crc_tab, tid, tbzfast::NT);
   for (;;) {
-    uint32_t i = 0;
-    if (lane == 0) i = atomicAdd(&counters[3], 1u);
-    i = __shfl_sync(TBZ_FULL, i, 0);
+    __syncthreads();
+    if (tid == 0) sm.member = atomicAdd(&counters[3], 1u);
+    __syncthreads();
+    const uint32_t i = sm.member;
     if (i >= n) break;
     if (!recs[i].status) continue;
-    const bool ok = tbzres::resolve_member(members[i], fmt, recs[i], slabs, results[i], crc_tab, lane);
-    if (!ok && lane == 0) todo[atomicAdd(&counters[1], 1u)] = i;
+    const bool ok = tbzres::resolve_member(members[i], fmt, recs[i], slabs, results[i], sm, tid);
+    if (!ok && tid == 0) todo[atomicAdd(&counters[1], 1u)] = i;
   }
 }
 
@@ -466,8 +467,9 @@ static int32_t launch_kernels(tbz_batch *b) {
         (uint32_t *)b->d_slabs, b->nslabs, (uint32_t *)b->d_counters, (uint32_t *)b->d_todo);
     ctx->launches++;
     CK(ctx, cudaGetLastError());
-    const int res_grid = (int)std::min<uint64_t>((n + RES_WARPS - 1) / RES_WARPS, (uint64_t)ctx->sm_count * 16);
-    k_inflate_resolve<<<res_grid, RES_WARPS * 32, 0, ctx->stream>>>(
+    CK(ctx, cudaFuncSetAttribute(k_inflate_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tbzres::Smem)));
+    const int res_grid = (int)std::min<uint64_t>(n, (uint64_t)ctx->sm_count * 3);
+    k_inflate_resolve<<<res_grid, tbzfast::NT, sizeof(tbzres::Smem), ctx->stream>>>(
         (const DMember *)b->d_members, (tbz_result *)b->d_results, n, b->format,
         (const tbzfast::P1Rec *)b->d_recs, (const uint32_t *)b->d_slabs, (uint32_t *)b->d_counters, (uint32_t *)b->d_todo);
     ctx->launches++;

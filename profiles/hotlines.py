@@ -54,7 +54,8 @@ def src(loc):
             L = src_cache[p]
             return L[loc[1] - 1].strip()[:90] if loc[1] <= len(L) else ""
     return ""
-for loc, a in sorted(agg.items(), key=lambda kv: -kv[1]["samp"])[:top]:
+key = (lambda kv: -kv[1]["inst"]) if os.environ.get("BY") == "inst" else (lambda kv: -kv[1]["samp"])
+for loc, a in sorted(agg.items(), key=key)[:top]:
     st = ",".join("%s:%d" % (k[6:], v) for k, v in sorted(a["st"].items(), key=lambda kv: -kv[1])[:3])
     print("%5.1f%% samp %5.1f%% inst thr/inst %4.1f %-22s %-40s | %s" % (100 * a["samp"] / max(1, ts), 100 * a["inst"] / max(1, ti),
           a["thr"] / max(1, a["inst"]), "%s:%d" % loc if loc else "?", st, src(loc)))
