@@ -1,16 +1,20 @@
 // inflate_decode.cuh — phase one of the batched fast path: Huffman decode into a token stream.
-// One CTA per member, every thread a decode lane.
+// One WARP per member, every lane a decode lane; a CTA holds WPC independent warps.
 //
-// Inside one Huffman block the compressed bits are cut into NT equal sub-chunks.  Lane i starts
-// decoding at the first bit of sub-chunk i *speculatively* (only lane 0 is known to start on a
-// symbol boundary) and relies on the self-synchronisation of Huffman streams:
-//   1a  every lane decodes its sub-chunk into its own token list (a slab in global memory,
-//       16-byte stores) and marks its token-start bits in a bitmap (shared memory)
-//   1b  every lane keeps decoding past its sub-chunk end until it lands on a bit a later lane
-//       marked — from there on both decodes are identical (same tables, same bit, same state),
-//       so the rest of that lane's list is proven correct
-//   1c  pointer doubling over "who synchronised into whom" from lane 0 gives the proven lanes,
-//       their entry points (tokens before an entry point are dropped) and the round's output size
+// Inside one Huffman block the compressed bits are cut into 32 equal sub-chunks of S bits.  Lane i
+// starts decoding at the first bit of sub-chunk i *speculatively* (only lane 0 is known to start
+// on a symbol boundary) and relies on the self-synchronisation of Huffman streams:
+//   1a  every lane decodes its sub-chunk into its own token list (global memory, 16-byte stores)
+//       and records a checkpoint (bit position, output bytes so far) every CKSTEP tokens in
+//       shared memory
+//   1b  every lane keeps decoding past its sub-chunk end until the start of one of its tokens
+//       coincides with a checkpoint of a later lane — from there on both decodes are identical
+//       (same tables, same bit), so the rest of that lane's list is proven correct and the
+//       tokens that lane decoded before the checkpoint are dropped
+//   1c  a walk over "who synchronised into whom" from lane 0 gives the proven lanes, their first
+//       proven token and the round's output size
+// Measured on the level-6 text of BASELINE config 2: a mis-aligned start re-synchronises after
+// 117 bits on average (p99 595), against S ~ 6000 bits per lane, so ~95 % of decode work is kept.
 // Phase two (inflate_resolve.cuh) turns the token stream into bytes.  Anything this kernel cannot
 // prove clean (stored blocks, malformed codes, truncated input, too small an output buffer ...)
 // is queued for the sequential kernel, which reproduces the reference's exact verdict.
@@ -20,24 +24,25 @@
 
 namespace tbzfast {
 
-constexpr int NT = 256;                 // threads per CTA = decode lanes
-constexpr int NWARP = NT / 32;
+constexpr int WPC = 4;                  // warps (members in flight) per CTA
+constexpr int NT = WPC * 32;
+constexpr int NL = 32;                  // decode lanes per member
 constexpr int KLL = 10, KD = 9;         // root table bits: lit/len, distance
-constexpr int TOKCAP = 160;             // tokens a lane may emit per round (sub-chunk + overrun)
-constexpr uint32_t S_MAX = 992, S_MIN = 256;   // sub-chunk size in bits
-constexpr uint32_t SYNC_SLACK = 640;           // bits a lane searches for its sync point before the barrier
-constexpr uint32_t BMWORDS = S_MAX * NT / 32;  // sync bitmap, one bit per compressed bit of the round
+constexpr int TOKCAP = 1024;            // tokens a lane may emit per round (sub-chunk + overrun)
+constexpr int CKSTEP = 32;              // a checkpoint every CKSTEP tokens
+constexpr int NCK = TOKCAP / CKSTEP;
+constexpr uint32_t S_MAX = 8000, S_MIN = 64;   // sub-chunk size in bits (13-bit field in a checkpoint)
+constexpr uint32_t CK_NONE = 0xffffffffu;
 
-// A slab holds the token lists of one round: header, then NT lists of TOKCAP tokens.
+// A slab holds the token lists of one round: header, then NL lists of TOKCAP tokens.
 struct SlabHdr {
   uint32_t next;        // next slab of the member, or NO_SLAB
   uint32_t out_bytes;   // output bytes of the round
-  uint32_t ntokens;     // proven tokens of the round
-  uint32_t pad;
-  uint32_t gn[NT];      // per lane: first proven token | (end << 16); 0 = lane not proven
-  uint32_t tb[NT];      // per lane: number of proven tokens in the lanes before it (flat token index base)
+  uint32_t pad[2];
+  uint32_t fc[NL];      // per lane: first proven token | (number of proven tokens << 16); 0 = nothing
 };
-constexpr uint32_t SLAB_WORDS = sizeof(SlabHdr) / 4 + NT * TOKCAP;
+constexpr uint32_t SLAB_HDR_WORDS = sizeof(SlabHdr) / 4;
+constexpr uint32_t SLAB_WORDS = SLAB_HDR_WORDS + NL * TOKCAP;
 constexpr uint32_t NO_SLAB = 0xffffffffu;
 
 // what phase one leaves per member for phase two
@@ -49,30 +54,23 @@ struct P1Rec {
 };
 
 constexpr uint32_t E_LONG = 0x00000300u, E_INVALID = 0x00010300u;   // table specials (code length 0)
-constexpr uint32_t TOK_MATCH = 0x80000000u, TOK_EOB = 0x40000000u;
+// token: literal = byte value; match = TOK_MATCH | (distance - 1) << 8 | (length - 3).  End of block
+// is not a token.
+constexpr uint32_t TOK_MATCH = 0x80000000u;
 
-enum { ST_IDLE = 0, ST_END, ST_SYNC, ST_EOB, ST_CAP, ST_BAD };
+enum { ST_IDLE = 0, ST_OVER, ST_END, ST_SYNC, ST_EOB, ST_CAP, ST_BAD };
 
 struct Canon16 { uint16_t first[16], count[16], base[16]; uint16_t maxlen, nsyms; };
 
-struct Smem {
-  uint32_t bitmap[BMWORDS];              // token-start bits of the current round
+struct WSmem {                           // one per warp
   uint32_t lut_ll[1 << KLL];
   uint32_t lut_d[1 << KD];
+  uint32_t ckpt[NCK][NL];                // [checkpoint][lane]: (bit offset in the sub-chunk) | (output bytes << 13)
   uint32_t lut_cl[128];
   Canon16 c_ll, c_d, c_cl;
   uint16_t sorted_ll[288], sorted_d[32], sorted_cl[32];
   uint8_t lens[352];                     // [0,19) code-length code, [32,352) lit/len + distance
-  uint16_t run[2][16];                   // running offsets of the two table-building warps
-  uint32_t entry[NT];                    // proven entry point of the lane (bit position)
-  uint16_t nxt[2][NT + 1];               // successor lane (pointer doubling, double buffered)
-  uint8_t truth[NT + 1];
-  uint32_t wscan[NWARP], wscan2[NWARP];
-  // scalars
-  uint32_t member;
-  int fail;
-  uint32_t term_pos; int term_status;
-  uint32_t slab;
+  uint16_t run[16];
 };
 
 struct In {
@@ -175,57 +173,47 @@ __device__ __forceinline__ void bits_refill(Bits &b, const In &in) {
 }
 __device__ __forceinline__ void bits_skip(Bits &b, uint32_t n) { b.bb >>= n; b.bc -= n; }
 
-// One token.  Returns 0 literal, 1 match, 2 end of block, 3 invalid code.
-__device__ __forceinline__ int decode_token(Bits &b, const In &in, const Smem &sm, uint32_t &tok, uint32_t &nbits, uint32_t &olen) {
-  bits_refill(b, in);
-  uint32_t e = sm.lut_ll[(uint32_t)b.bb & ((1u << KLL) - 1)];
+// One token, literal and match on one instruction path (the distance lookup is always issued and
+// masked for literals) so that the lanes of a warp do not diverge on the token kind.
+// Returns 0 literal, 1 match, 2 end of block, 3 invalid code.
+__device__ __forceinline__ int decode_token(Bits &b, const In &in, const WSmem &sm, uint32_t &tok, uint32_t &nbits, uint32_t &olen) {
+  bits_refill(b, in);                                        // >= 33 bits
+  uint32_t w = (uint32_t)b.bb;
+  uint32_t e = sm.lut_ll[w & ((1u << KLL) - 1)];
   if ((e & 15) == 0) {
     if (e != E_LONG) return 3;
-    uint32_t r = canon_lookup(sm.c_ll, sm.sorted_ll, (uint32_t)b.bb, KLL + 1, 15);
+    uint32_t r = canon_lookup(sm.c_ll, sm.sorted_ll, w, KLL + 1, 15);
     if (!r) return 3;
     e = ll_entry(r >> 4, r & 15);
     if ((e & 15) == 0) return 3;
   }
-  const uint32_t L = e & 15, kind = (e >> 8) & 3;
-  if (kind == 0) { tok = e >> 16; nbits = L; olen = 1; bits_skip(b, L); return 0; }
-  if (kind == 2) { tok = TOK_EOB; nbits = L; olen = 0; bits_skip(b, L); return 2; }
-  const uint32_t xb = (e >> 4) & 7;
-  const uint32_t len = (e >> 16) + ((uint32_t)(b.bb >> L) & ((1u << xb) - 1));
-  bits_skip(b, L + xb);
-  bits_refill(b, in);
-  uint32_t d = sm.lut_d[(uint32_t)b.bb & ((1u << KD) - 1)];
-  if ((d & 15) == 0) {
+  const uint32_t L = e & 15, kind = (e >> 8) & 3, xb = (e >> 4) & 7;
+  const uint32_t val = (e >> 16) + ((w >> L) & ((1u << xb) - 1));   // literal byte / match length
+  const uint32_t n1 = L + xb;
+  bits_skip(b, n1);
+  const bool ism = kind == 1;
+  if (ism && b.bc < 28) bits_refill(b, in);
+  const uint32_t w2 = (uint32_t)b.bb;
+  uint32_t d = sm.lut_d[w2 & ((1u << KD) - 1)];
+  if (ism && (d & 15) == 0) {
     if (d != E_LONG) return 3;
-    uint32_t r = canon_lookup(sm.c_d, sm.sorted_d, (uint32_t)b.bb, KD + 1, 15);
+    uint32_t r = canon_lookup(sm.c_d, sm.sorted_d, w2, KD + 1, 15);
     if (!r) return 3;
     d = d_entry(r >> 4, r & 15);
     if ((d & 15) == 0) return 3;
   }
+  if (!ism) d = 0;
   const uint32_t DL = d & 15, dxb = (d >> 4) & 15;
-  const uint32_t dist = (d >> 16) + ((uint32_t)(b.bb >> DL) & ((1u << dxb) - 1));
-  bits_skip(b, DL + dxb);
-  tok = TOK_MATCH | ((dist - 1) << 8) | (len - 3);
-  nbits = L + xb + DL + dxb;
-  olen = len;
-  return 1;
+  const uint32_t dist = (d >> 16) + ((w2 >> DL) & ((1u << dxb) - 1));
+  const uint32_t n2 = DL + dxb;
+  bits_skip(b, n2);
+  tok = ism ? (TOK_MATCH | ((dist - 1) << 8) | (val - 3)) : val;
+  nbits = n1 + n2;
+  olen = ism ? val : (kind == 0 ? 1u : 0u);
+  return (int)kind;
 }
 
-__device__ __forceinline__ uint32_t tok_outlen(uint32_t t) {
-  return (t & TOK_MATCH) ? (t & 255u) + 3u : ((t & TOK_EOB) ? 0u : 1u);
-}
-
-// ---- CTA-wide helpers --------------------------------------------------------------------------
-__device__ __forceinline__ void cta_sum2(uint32_t a, uint32_t b, Smem &sm, int tid, uint32_t &ta, uint32_t &tb) {
-  const int lane = tid & 31, warp = tid >> 5;
-#pragma unroll
-  for (int s = 16; s; s >>= 1) { a += __shfl_xor_sync(TBZ_FULL, a, s); b += __shfl_xor_sync(TBZ_FULL, b, s); }
-  if (lane == 0) { sm.wscan[warp] = a; sm.wscan2[warp] = b; }
-  __syncthreads();
-  ta = 0; tb = 0;
-#pragma unroll
-  for (int w = 0; w < NWARP; w++) { ta += sm.wscan[w]; tb += sm.wscan2[w]; }
-  __syncthreads();
-}
+__device__ __forceinline__ uint32_t tok_outlen(uint32_t t) { return (t & TOK_MATCH) ? (t & 255u) + 3u : 1u; }
 
 // token list writer: four tokens per 16-byte store
 struct TokW {
@@ -243,12 +231,11 @@ struct TokW {
 };
 
 // ------------------------------------------------------------------------------------------------
-// One member.  Returns true when its token stream is complete, false when the member must be
-// redone by the sequential kernel.
+// One member, one warp.  Returns true when its token stream is complete, false when the member
+// must be redone by the sequential kernel.  Every return value is warp-uniform.
 // ------------------------------------------------------------------------------------------------
-__device__ inline bool decode_member(const DMember &mem, int fmt, P1Rec &rec, Smem &sm,
-                                     uint32_t *__restrict__ slabs, uint32_t nslabs, uint32_t *slab_counter, int tid) {
-  const int lane = tid & 31, warp = tid >> 5;
+__device__ inline bool decode_member(const DMember &mem, int fmt, P1Rec &rec, WSmem &sm,
+                                     uint32_t *__restrict__ slabs, uint32_t nslabs, uint32_t *slab_counter, int lane) {
   In in;
   {
     uintptr_t a = (uintptr_t)mem.in;
@@ -272,243 +259,221 @@ __device__ inline bool decode_member(const DMember &mem, int fmt, P1Rec &rec, Sm
     if (byte_at(in, bp) != 0x1f || byte_at(in, bp + 1) != 0x8b || byte_at(in, bp + 2) != 8 || byte_at(in, bp + 3) != 0) return false;
     pos += 80;
   }
-  if (tid == 0) sm.fail = 0;
   unsigned long long A = 0;    // output bytes so far
   uint32_t first_slab = NO_SLAB, prev_slab = NO_SLAB;
+  uint32_t prev_block_bits = 0;   // size of the previous block of this member: predicts this one
   bool last = false;
-  __syncthreads();
 
   while (!last) {
     // ================= block header (deflate.lisp:518-528, :577-669) =================
     if (in.end - pos < 3) return false;
+    const uint32_t block_start = pos;
     const uint32_t hdr = peek32(in, pos) & 7;
     pos += 3;
     last = hdr & 1;
     const uint32_t btype = hdr >> 1;
     int hlit, hdist;
+    __syncwarp();
     if (btype == 1) {
       hlit = 288; hdist = 32;
-      for (int i = tid; i < 320; i += NT) sm.lens[32 + i] = i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : i < 288 ? 8 : 5;
+      for (int i = lane; i < 320; i += 32) sm.lens[32 + i] = i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : i < 288 ? 8 : 5;
     } else if (btype == 2) {
       if (in.end - pos < 14) return false;
       const uint32_t v = peek32(in, pos);
       hlit = (v & 31) + 257; hdist = ((v >> 5) & 31) + 1;
       const int ncl = ((v >> 10) & 15) + 4;
       if (in.end - pos < 14u + 3u * ncl) return false;
-      if (warp == 0) {
-        if (lane < 19) sm.lens[lane] = 0;
-        __syncwarp();
-        if (lane < ncl) sm.lens[c_clen_order[lane]] = peek32(in, pos + 14 + 3 * lane) & 7;
-        __syncwarp();
-        int err = warp_canon(sm.lens, 19, sm.c_cl, sm.sorted_cl, sm.run[0], lane);
-        if (!err && sm.c_cl.nsyms == 0) err = TBZ_ERR_INVALID_SYMBOL;
-        if (!err) {
-          for (int e = lane; e < 128; e += 32) sm.lut_cl[e] = canon_lookup(sm.c_cl, sm.sorted_cl, (uint32_t)e, 1, 7);
-          __syncwarp();
-          if (lane == 0) {
-            // the code lengths themselves: one lane, table driven (deflate.lisp:626-669)
-            uint32_t p = pos + 14 + 3 * ncl;
-            int idx = 0, lastlen = 0xff;
-            const int total = hlit + hdist;
-            Bits hb;
-            bits_init(hb, in, p);
-            while (idx < total) {
-              bits_refill(hb, in);
-              uint32_t w = (uint32_t)hb.bb;
-              uint32_t r = sm.lut_cl[w & 127];
-              if (!r) { err = TBZ_ERR_INVALID_SYMBOL; break; }
-              int L = r & 15, sym = r >> 4;
-              int xb = sym < 16 ? 0 : sym == 16 ? 2 : sym == 17 ? 3 : 7;
-              if (p + L + xb > in.end) { err = TBZ_INPUT_UNDERRUN; break; }
-              uint32_t extra = (w >> L) & ((1u << xb) - 1);
-              p += L + xb;
-              bits_skip(hb, L + xb);
-              int rep, val;
-              if (sym < 16) { rep = 1; val = sym; lastlen = sym; }
-              else if (sym == 16) { if (lastlen >= 16) { err = TBZ_ERR_REPEAT_NO_PREV; break; } rep = 3 + extra; val = lastlen; }
-              else { rep = (sym == 17 ? 3 : 11) + extra; val = 0; lastlen = 0; }
-              if (idx + rep > total) { err = TBZ_ERR_REPEAT_OVERRUN; break; }
-              for (int k = 0; k < rep; k++) sm.lens[32 + idx + k] = (uint8_t)val;
-              idx += rep;
-            }
-            sm.term_pos = p;
-          }
-        }
-        err = __shfl_sync(TBZ_FULL, err, 0) | err;
-        if (err && lane == 0) sm.fail = 1;
+      if (lane < 19) sm.lens[lane] = 0;
+      __syncwarp();
+      if (lane < ncl) sm.lens[c_clen_order[lane]] = peek32(in, pos + 14 + 3 * lane) & 7;
+      __syncwarp();
+      int err = warp_canon(sm.lens, 19, sm.c_cl, sm.sorted_cl, sm.run, lane);
+      if (!err && sm.c_cl.nsyms == 0) err = TBZ_ERR_INVALID_SYMBOL;
+      if (err) return false;
+      // entry: [3:0] code length, [7:4] extra bits, [12:8] symbol; 0 = no code
+      for (int e = lane; e < 128; e += 32) {
+        const uint32_t r = canon_lookup(sm.c_cl, sm.sorted_cl, (uint32_t)e, 1, 7);
+        const uint32_t sym = r >> 4;
+        const uint32_t xb = sym < 16 ? 0 : sym == 16 ? 2 : sym == 17 ? 3 : 7;
+        sm.lut_cl[e] = r ? ((r & 15) | (xb << 4) | (sym << 8)) : 0;
       }
-      __syncthreads();
-      if (sm.fail) return false;
-      pos = sm.term_pos;
+      __syncwarp();
+      uint32_t p = pos + 14 + 3 * ncl;
+      if (lane == 0) {
+        // the code lengths themselves: one lane, table driven (deflate.lisp:626-669)
+        int idx = 0, lastlen = 0xff;
+        const int total = hlit + hdist;
+        Bits hb;
+        bits_init(hb, in, p);
+        while (idx < total) {
+          bits_refill(hb, in);
+          const uint32_t w = (uint32_t)hb.bb;
+          const uint32_t r = sm.lut_cl[w & 127];
+          if (!r) { err = 1; break; }
+          const uint32_t L = r & 15, xb = (r >> 4) & 15, sym = r >> 8;
+          if (p + L + xb > in.end) { err = 1; break; }
+          p += L + xb;
+          if (sym < 16) {
+            sm.lens[32 + idx] = (uint8_t)sym; idx++; lastlen = (int)sym;
+            bits_skip(hb, L);
+            continue;
+          }
+          const uint32_t extra = (w >> L) & ((1u << xb) - 1);
+          bits_skip(hb, L + xb);
+          int rep, val;
+          if (sym == 16) { if (lastlen >= 16) { err = 1; break; } rep = 3 + extra; val = lastlen; }
+          else { rep = (sym == 17 ? 3 : 11) + extra; val = 0; lastlen = 0; }
+          if (idx + rep > total) { err = 1; break; }
+          for (int k = 0; k < rep; k++) sm.lens[32 + idx + k] = (uint8_t)val;
+          idx += rep;
+        }
+      }
+      err = __shfl_sync(TBZ_FULL, err, 0);
+      if (err) return false;
+      pos = __shfl_sync(TBZ_FULL, p, 0);
     } else {
       return false;                        // stored / reserved block type: sequential kernel
     }
-    __syncthreads();
+    __syncwarp();
     // ================= tables (huffman-tree.lisp:99-218) =================
-    if (warp == 0) { if (warp_canon(sm.lens + 32, hlit, sm.c_ll, sm.sorted_ll, sm.run[0], lane) && lane == 0) sm.fail = 1; }
-    else if (warp == 1) { if (warp_canon(sm.lens + 32 + hlit, hdist, sm.c_d, sm.sorted_d, sm.run[1], lane) && lane == 0) sm.fail = 1; }
-    __syncthreads();
-    if (sm.fail || sm.c_ll.nsyms == 0) return false;
-    for (int e = tid; e < (1 << KLL); e += NT) {
+    if (warp_canon(sm.lens + 32, hlit, sm.c_ll, sm.sorted_ll, sm.run, lane)) return false;
+    if (warp_canon(sm.lens + 32 + hlit, hdist, sm.c_d, sm.sorted_d, sm.run, lane)) return false;
+    if (sm.c_ll.nsyms == 0) return false;
+    for (int e = lane; e < (1 << KLL); e += 32) {
       uint32_t r = canon_lookup(sm.c_ll, sm.sorted_ll, (uint32_t)e, 1, KLL);
       sm.lut_ll[e] = r ? ll_entry(r >> 4, r & 15) : (sm.c_ll.maxlen > KLL ? E_LONG : E_INVALID);
     }
-    for (int e = tid; e < (1 << KD); e += NT) {
+    for (int e = lane; e < (1 << KD); e += 32) {
       uint32_t r = canon_lookup(sm.c_d, sm.sorted_d, (uint32_t)e, 1, KD);
       sm.lut_d[e] = r ? d_entry(r >> 4, r & 15) : (sm.c_d.maxlen > KD ? E_LONG : E_INVALID);
     }
-    __syncthreads();
+    __syncwarp();
 
     // ================= rounds over the block's compressed bits =================
+    // The end of the block is unknown: assume it is about as long as the previous one (libz cuts
+    // blocks by symbol count), else that it runs to the end of the input.
+    uint32_t expect = in.end - pos;
+    if (prev_block_bits && prev_block_bits + prev_block_bits / 16 < expect) expect = prev_block_bits + prev_block_bits / 16;
     bool block_done = false;
+    uint32_t shrink = 0;
     while (!block_done) {
       // ---- a slab for this round's token lists
-      if (tid == 0) {
-        uint32_t s = atomicAdd(slab_counter, 1u);
-        if (s >= nslabs) { s = NO_SLAB; sm.fail = 1; }
-        sm.slab = s;
-      }
+      uint32_t slab_id = 0;
+      if (lane == 0) slab_id = atomicAdd(slab_counter, 1u);
+      slab_id = __shfl_sync(TBZ_FULL, slab_id, 0);
+      if (slab_id >= nslabs) return false;
       // ---- geometry of this round
       const uint32_t P0 = pos;
-      const uint32_t winbase = P0 & ~31u;
-      uint32_t S = ((in.end - winbase + NT - 1) / NT + 31) & ~31u;
+      uint32_t left = in.end - P0;
+      if (expect > pos - block_start && expect - (pos - block_start) < left) left = expect - (pos - block_start);
+      const uint32_t nrounds = (left + NL * S_MAX - 1) / (NL * S_MAX);
+      uint32_t S = ((left + nrounds - 1) / nrounds + NL - 1) / NL;
+      S >>= shrink;
       if (S > S_MAX) S = S_MAX;
       if (S < S_MIN) S = S_MIN;
-      const uint32_t winend = winbase + S * NT;
-      const uint32_t bmwords = (S * NT) >> 5;
-      for (uint32_t w = tid; w < bmwords; w += NT) sm.bitmap[w] = 0;
-      __syncthreads();
-      if (sm.fail) return false;
-      uint32_t *slab = slabs + (size_t)sm.slab * SLAB_WORDS;
+      const uint32_t winend = P0 + S * NL;
+      for (int c = 0; c < NCK; c++) sm.ckpt[c][lane] = CK_NONE;
+      uint32_t *slab = slabs + (size_t)slab_id * SLAB_WORDS;
       SlabHdr *sh = reinterpret_cast<SlabHdr *>(slab);
       TokW tw;
-      tw.list = slab + sizeof(SlabHdr) / 4 + tid * TOKCAP;
+      tw.list = slab + SLAB_HDR_WORDS + lane * TOKCAP;
       tw.q0 = tw.q1 = tw.q2 = tw.q3 = 0;
+      __syncwarp();
 
       // ---- 1a: speculative decode of the lane's sub-chunk
-      const uint32_t cstart = winbase + S * tid, cend = cstart + S;
-      uint32_t p = tid == 0 ? P0 : cstart;
-      uint32_t k = 0, ob = 0, nx = NT;
+      const uint32_t cstart = P0 + S * lane, cend = cstart + S;
+      uint32_t p = cstart;
+      uint32_t k = 0, ob = 0;
       int st = ST_IDLE;
       Bits b;
       if (p < in.end) {
         bits_init(b, in, p);
-        uint32_t curw = (p - winbase) >> 5, acc = 0;
         for (;;) {
-          const uint32_t rel = p - winbase;
-          if (p >= cend) {
-            // Past the own sub-chunk: look for a bit a later lane marked.  That lane is usually far
-            // ahead in its own sub-chunk by now; a mark that is not visible yet only delays the
-            // match (any later common token start is as good), and after SYNC_SLACK bits the lane
-            // parks until the barrier below has made every mark visible.
-            if (curw != NO_SLAB) { sm.bitmap[curw] = acc; curw = NO_SLAB; }     // own marks are complete
-            if (p >= winend || p >= cend + SYNC_SLACK) { st = ST_END; break; }
-            if ((*(volatile uint32_t *)&sm.bitmap[rel >> 5] >> (rel & 31)) & 1u) { st = ST_SYNC; nx = rel / S; break; }
-          }
+          if (p >= cend) { st = ST_OVER; break; }
           if (k >= TOKCAP) { st = ST_CAP; break; }
-          if (p < cend) {
-            const uint32_t wi = rel >> 5;
-            if (wi != curw) { sm.bitmap[curw] = acc; acc = 0; curw = wi; }
-            acc |= 1u << (rel & 31);
-          }
+          if ((k & (CKSTEP - 1)) == 0) sm.ckpt[k / CKSTEP][lane] = (p - cstart) | (ob << 13);
           uint32_t tok, nb, ol;
           const int kind = decode_token(b, in, sm, tok, nb, ol);
           if (kind == 3 || p + nb > in.end) { st = ST_BAD; break; }
-          tw.push(tok, k);
-          k++; p += nb; ob += ol;
+          p += nb;
           if (kind == 2) { st = ST_EOB; break; }
+          tw.push(tok, k);
+          k++; ob += ol;
         }
-        if (curw != NO_SLAB) sm.bitmap[curw] = acc;
       }
-      __syncthreads();
-      // ---- 1b: lanes still looking for their synchronisation point go on with every mark visible
-      if (st == ST_END) {
+      __syncwarp();
+      // ---- 1b: past the own sub-chunk: decode on until a token start coincides with a checkpoint
+      // of the lane whose sub-chunk the position lies in
+      uint32_t nx = 0, g_sync = 0, ob_sync = 0;
+      if (st == ST_OVER) {
+        uint32_t j = lane, jend = cend, c = 0;       // lane being searched, end of its sub-chunk, next checkpoint
         for (;;) {
-          if (p >= winend) break;                                 // round ends here, block continues
-          const uint32_t rel = p - winbase;
-          if ((sm.bitmap[rel >> 5] >> (rel & 31)) & 1u) { st = ST_SYNC; nx = rel / S; break; }
-          if (k >= TOKCAP) { st = ST_CAP; break; }
-          uint32_t tok, nb, ol;
-          const int kind = decode_token(b, in, sm, tok, nb, ol);
-          if (kind == 3 || p + nb > in.end) { st = ST_BAD; break; }
-          tw.push(tok, k);
-          k++; p += nb; ob += ol;
-          if (kind == 2) { st = ST_EOB; break; }
+          if (p >= winend) { st = ST_END; break; }
+          while (p >= jend) { j++; jend += S; c = 0; }
+          const uint32_t rel = p - (jend - S);
+          uint32_t ck = CK_NONE;
+          while (c < NCK && ((ck = sm.ckpt[c][j]) & 0x1fffu) < rel) c++;
+          if (c < NCK && ck != CK_NONE && (ck & 0x1fffu) == rel) { st = ST_SYNC; nx = j; g_sync = c * CKSTEP; ob_sync = ck >> 13; break; }
+          uint32_t tgt = jend;
+          if (c < NCK && ck != CK_NONE) tgt = (jend - S) + (ck & 0x1fffu);
+          // decode up to the next place a synchronisation can happen
+          while (p < tgt) {
+            if (k >= TOKCAP) { st = ST_CAP; break; }
+            uint32_t tok, nb, ol;
+            const int kind = decode_token(b, in, sm, tok, nb, ol);
+            if (kind == 3 || p + nb > in.end) { st = ST_BAD; break; }
+            p += nb;
+            if (kind == 2) { st = ST_EOB; break; }
+            tw.push(tok, k);
+            k++; ob += ol;
+          }
+          if (st != ST_OVER) break;
         }
       }
       tw.finish(k);
-      sm.nxt[0][tid] = (uint16_t)nx;
-      sm.truth[tid] = tid == 0;
-      if (tid == 0) { sm.nxt[0][NT] = NT; sm.truth[NT] = 0; }
-      __syncthreads();
+      __syncwarp();
       // ---- 1c: lanes reachable from lane 0 through "synchronised into" edges are proven
+      uint32_t my_g = 0, my_gob = 0;
+      bool proven = false;
+      int term_st;
+      uint32_t term_pos;
       {
         int cur = 0;
-        for (int r = 0; r < 8; r++) {
-          const uint16_t n1 = sm.nxt[cur][tid];
-          if (sm.truth[tid]) sm.truth[n1] = 1;
-          sm.nxt[cur ^ 1][tid] = sm.nxt[cur][n1];
-          if (tid == 0) sm.nxt[cur ^ 1][NT] = NT;
-          cur ^= 1;
-          __syncthreads();
+        for (;;) {
+          if (lane == cur) proven = true;
+          const int st_c = __shfl_sync(TBZ_FULL, st, cur);
+          if (st_c != ST_SYNC) { term_st = st_c; term_pos = __shfl_sync(TBZ_FULL, p, cur); break; }
+          const uint32_t nx_c = __shfl_sync(TBZ_FULL, nx, cur);
+          const uint32_t g_c = __shfl_sync(TBZ_FULL, g_sync, cur), gob_c = __shfl_sync(TBZ_FULL, ob_sync, cur);
+          if ((uint32_t)lane == nx_c) { my_g = g_c; my_gob = gob_c; }
+          cur = (int)nx_c;
         }
       }
-      const bool proven = sm.truth[tid];
-      if (proven) {
-        if (st == ST_SYNC) sm.entry[nx] = p;
-        else { sm.term_status = st; sm.term_pos = p; }
-      }
-      if (tid == 0) sm.entry[0] = P0;
-      __syncthreads();
-      if (sm.term_status == ST_BAD || sm.term_status == ST_IDLE) return false;
-      // ---- tokens decoded before the entry point are dropped: count and size them
-      uint32_t g = 0, gb = 0;
-      if (proven && tid != 0) {
-        const uint32_t r0 = cstart - winbase, r1 = sm.entry[tid] - winbase;   // r1 in [r0, r0 + S)
-        for (uint32_t w = r0 >> 5; w <= (r1 >> 5); w++) {
-          uint32_t bits = sm.bitmap[w];
-          if (w == (r1 >> 5)) bits &= (1u << (r1 & 31)) - 1u;
-          g += __popc(bits);
-        }
-        for (uint32_t i = 0; i < g; i++) gb += tok_outlen(tw.list[i]);
-      }
-      sh->gn[tid] = proven ? (g | (k << 16)) : 0u;
-      uint32_t total, ntok;
-      {
-        // exclusive scan of the proven token counts (flat token order for phase two) + output total
-        const uint32_t cnt = proven ? k - g : 0u;
-        uint32_t x = cnt, y = proven ? ob - gb : 0u;
+      if (term_st == ST_BAD || term_st == ST_IDLE || term_st == ST_OVER) return false;
+      // a lane that ran into its token cap ends the round early: use shorter sub-chunks from here on
+      if (term_st == ST_CAP && shrink < 6) shrink++;
+      const uint32_t cnt = proven ? k - my_g : 0u;
+      uint32_t total = proven ? ob - my_gob : 0u;
 #pragma unroll
-        for (int sft = 1; sft < 32; sft <<= 1) {
-          const uint32_t u = __shfl_up_sync(TBZ_FULL, x, sft);
-          if (lane >= sft) x += u;
-        }
-#pragma unroll
-        for (int sft = 16; sft; sft >>= 1) y += __shfl_xor_sync(TBZ_FULL, y, sft);
-        if (lane == 31) { sm.wscan[warp] = x; sm.wscan2[warp] = y; }
-        __syncthreads();
-        uint32_t off = 0;
-        ntok = 0; total = 0;
-#pragma unroll
-        for (int w = 0; w < NWARP; w++) { const uint32_t c = sm.wscan[w]; if (w < warp) off += c; ntok += c; total += sm.wscan2[w]; }
-        sh->tb[tid] = off + x - cnt;
-        __syncthreads();
-      }
+      for (int sft = 16; sft; sft >>= 1) total += __shfl_xor_sync(TBZ_FULL, total, sft);
       A += total;
       if (A > mem.out_cap || A >= (1ull << 32)) return false;       // overflow: sequential kernel
-      if (tid == 0) {
-        sh->next = NO_SLAB; sh->out_bytes = total; sh->ntokens = ntok;
-        if (prev_slab != NO_SLAB) reinterpret_cast<SlabHdr *>(slabs + (size_t)prev_slab * SLAB_WORDS)->next = sm.slab;
+      sh->fc[lane] = cnt ? (my_g | (cnt << 16)) : 0u;
+      if (lane == 0) {
+        sh->next = NO_SLAB; sh->out_bytes = total;
+        if (prev_slab != NO_SLAB) reinterpret_cast<SlabHdr *>(slabs + (size_t)prev_slab * SLAB_WORDS)->next = slab_id;
       }
-      if (first_slab == NO_SLAB) first_slab = sm.slab;
-      prev_slab = sm.slab;
+      if (first_slab == NO_SLAB) first_slab = slab_id;
+      prev_slab = slab_id;
       // ---- how did the round end?
-      pos = sm.term_pos;
-      if (sm.term_status == ST_EOB) block_done = true;
-      __syncthreads();
+      if (term_pos <= pos && term_st != ST_EOB) return false;     // no progress (cannot happen; guards the loop)
+      pos = term_pos;
+      if (term_st == ST_EOB) block_done = true;
+      __syncwarp();
     }
+    prev_block_bits = pos - block_start;
   }
-  if (tid == 0) {
+  if (lane == 0) {
     rec.first_slab = first_slab;
     rec.out_len = (uint32_t)A;
     rec.end_pos = pos;

@@ -1,19 +1,21 @@
 // inflate_resolve.cuh — phase two of the batched fast path: LZ77 resolution of a token stream
 // (deflate.lisp:244-359 `copy-history`, restated for a whole CTA).
 //
-// One CTA per member.  The member's output is produced in windows of up to WB bytes that live in
-// a 64 KiB ring in shared memory (the last 32 KiB of it are the deflate history):
-//   1. the next <= WT tokens are fetched in flat order (two per thread) from the member's slabs
-//   2. a CTA prefix sum over their lengths gives every token its offset in the window; the token
-//      that straddles the window end is split and its tail carried into the next window
-//   3. token indices are scattered to their start offsets and a prefix-max turns that into a
-//      byte -> token map
-//   4. every output byte is resolved *by address arithmetic only*: follow byte -> token ->
-//      (byte - distance) while the source still lies inside the window (overlapping matches go
-//      through their period); the chase ends at a literal token or at a byte below the window,
-//      which is final and sits in the ring.  No byte written in this window is read in this window,
-//      so all 256 threads work on 8 bytes each without any ordering between them
-//   5. the window is flushed to global memory with 16-byte stores; Adler-32 is folded in with
+// One CTA per member.  The member's output is produced in windows that live in a 64 KiB ring in
+// shared memory (the last 32 KiB of it are the deflate history).  A window is one proven token
+// list of phase one (or a piece of it, when it would exceed WB bytes):
+//   1. the list's tokens are loaded (up to TPT consecutive tokens per thread) and a CTA prefix
+//      sum over their lengths gives every token its byte offset in the window; the token that
+//      straddles the window end is split and its tail carried into the next window
+//   2. every token sets one bit in a "token starts here" bitmap over the window's bytes; a prefix
+//      popcount over the bitmap words turns byte -> token lookup into a rank query (two loads)
+//   3. the window is resolved in sub-passes of 4*NT bytes, one aligned 32-bit word of output per
+//      thread and sub-pass.  A word that lies inside one match whose source is final (below the
+//      sub-pass) is one unaligned 4-byte ring read; other words go byte by byte: follow
+//      byte -> token -> (byte - distance) while the source still lies inside the sub-pass
+//      (overlapping matches go through their period); the chase ends at a literal or at a final
+//      byte in the ring.  No byte written in a sub-pass is read in it, so threads need no ordering
+//   4. the window is flushed to global memory with 16-byte stores; Adler-32 is folded in with
 //      dp4a as s1 = 1 + sum d, s2 = N + N sum d - sum i d_i (order independent per thread)
 // CRC-32 (gzip) is a thread-parallel pass per window with x^(8 len) combines.  The trailer is then
 // checked as zlib.lisp:80-96 / gzip.lisp:82-106 do; any disagreement sends the member to the
@@ -24,27 +26,30 @@
 
 namespace tbzres {
 
+using tbzfast::NL;
 using tbzfast::NO_SLAB;
-using tbzfast::NT;
-using tbzfast::NWARP;
 using tbzfast::P1Rec;
+using tbzfast::SLAB_HDR_WORDS;
 using tbzfast::SLAB_WORDS;
 using tbzfast::SlabHdr;
 using tbzfast::TOKCAP;
-using tbzfast::TOK_EOB;
 using tbzfast::TOK_MATCH;
 
+constexpr int NT = 256;
+constexpr int NWARP = NT / 32;
 constexpr uint32_t RING = 65536u, RMASK = RING - 1u;
-constexpr uint32_t WB = 2048;            // window bytes (8 per thread)
-constexpr uint32_t WT = 2 * NT;          // window tokens (2 per thread)
+constexpr uint32_t WB = 4096;            // window bytes (including the <= 3 bytes of alignment lead-in)
+constexpr int TPT = 4;                   // tokens per thread and window
+constexpr uint32_t WT = TPT * NT;        // window tokens
+constexpr uint32_t SUB = 4 * NT;         // bytes per sub-pass
 
 struct Smem {
   alignas(16) uint8_t ring[RING];
   uint32_t toks[WT + 1];                 // [0] = tail of the match carried over from the previous window
   uint16_t tstart[WT + 2];
-  alignas(16) uint16_t bytemap[WB];      // byte -> token index + 1; doubles as scratch of the crc tree
-  uint16_t tb[NT];
-  uint16_t g0[NT];
+  uint32_t bitmap[WB / 32];              // token-start bits over the window's bytes
+  uint16_t wrank[WB / 32];               // token starts in the bitmap words before this one
+  uint32_t hdr[SLAB_HDR_WORDS];
   uint32_t crc_tab[256];
   uint32_t wscan[NWARP], wscan2[NWARP];
   unsigned long long wsum[NWARP][2];
@@ -54,9 +59,7 @@ struct Smem {
   uint32_t crc;
 };
 
-__device__ __forceinline__ uint32_t tok_len(uint32_t t) {
-  return (t & TOK_MATCH) ? (t & 255u) + 3u : ((t & TOK_EOB) ? 0u : 1u);
-}
+__device__ __forceinline__ uint32_t tok_len(uint32_t t) { return (t & TOK_MATCH) ? (t & 255u) + 3u : 1u; }
 
 // CRC-32 of ring[a, a+m): every thread takes one contiguous slice; slices are merged pairwise with
 // x^(8 len) shifts (the per-level shift is the square of the previous one).  All threads must call.
@@ -71,7 +74,7 @@ __device__ inline void crc_window(Smem &sm, uint32_t a, uint32_t m, int tid) {
   if (lo == hi) c = 0;
   uint32_t len = hi - lo;
   uint32_t shift = crc_x8n(seg);
-  uint32_t *s_c = reinterpret_cast<uint32_t *>(sm.bytemap), *s_l = s_c + NT;   // the map is dead by now
+  uint32_t *s_c = sm.toks, *s_l = sm.toks + NT;                  // the token array is dead by now
   for (int s = 1; s < NT; s <<= 1) {
     s_c[tid] = c; s_l[tid] = len;
     __syncthreads();
@@ -89,221 +92,236 @@ __device__ inline void crc_window(Smem &sm, uint32_t a, uint32_t m, int tid) {
   if (tid == 0) sm.crc = crc_combine(sm.crc, c, m);
 }
 
+// per-member state that lives in registers (uniform unless noted)
+struct RState {
+  uint32_t pos;                           // output bytes produced so far (window base)
+  uint32_t flushed;                       // output bytes already stored to global memory
+  unsigned long long acc_a, acc_w;        // per thread: Adler sum d, sum i*d over the bytes it flushed
+  uint32_t carry_len, carry_dist;         // tail of a match that straddled the previous window end
+};
+
+// byte r (relative to the window's aligned base) -> index of the token that covers it
+__device__ __forceinline__ uint32_t token_of(const Smem &sm, uint32_t r, uint32_t adj) {
+  const uint32_t w = r >> 5;
+  return sm.wrank[w] + __popc(sm.bitmap[w] & (0xffffffffu >> (31u - (r & 31u)))) - adj;
+}
+
+// One window: tokens list[0, n) (n <= WT); consumes as many as fit, returns the number consumed.
+// A pending carry is flushed first.  All threads must call; the result is uniform.
+__device__ inline uint32_t resolve_window(const DMember &mem, int fmt, const uint32_t *__restrict__ list, uint32_t n,
+                                          RState &rs, Smem &sm, int tid) {
+  const int lane = tid & 31, warp = tid >> 5;
+  uint8_t *out = mem.out;
+  const uint32_t pos = rs.pos;
+  const uint32_t mis = pos & 3u, P4 = pos - mis;      // the window's coordinates start at the aligned base
+  const uint32_t carry_len = rs.carry_len, carry_dist = rs.carry_dist;
+  // ---- 1. tokens and their offsets
+  const uint32_t tpt = (n + NT - 1) / NT;             // consecutive tokens per thread (<= TPT)
+  uint32_t tk[TPT], ln[TPT];
+  uint32_t mine = 0;
+#pragma unroll
+  for (int q = 0; q < TPT; q++) {
+    const uint32_t idx = tid * tpt + q;
+    const bool have = (uint32_t)q < tpt && idx < n;
+    tk[q] = have ? __ldg(list + idx) : 0u;
+    ln[q] = have ? tok_len(tk[q]) : 0u;
+    mine += ln[q];
+  }
+  uint32_t x = mine;
+#pragma unroll
+  for (int sft = 1; sft < 32; sft <<= 1) {
+    const uint32_t u = __shfl_up_sync(TBZ_FULL, x, sft);
+    if (lane >= sft) x += u;
+  }
+  if (lane == 31) sm.wscan[warp] = x;
+  if (tid < (int)(WB / 32)) sm.bitmap[tid] = 0;
+  if (tid == 0) sm.carry_len = 0;        // rewritten below by the thread that owns a straddling match
+  __syncthreads();
+  uint32_t off = mis + carry_len, total = mis + carry_len;
+#pragma unroll
+  for (int w = 0; w < NWARP; w++) { const uint32_t c = sm.wscan[w]; if (w < warp) off += c; total += c; }
+  const uint32_t wend = total < WB ? total : WB;      // window = [mis, wend) in aligned coordinates
+  uint32_t st = off + x - mine;
+  uint32_t used = 0;
+  bool bad = false;
+#pragma unroll
+  for (int q = 0; q < TPT; q++) {
+    const uint32_t idx = tid * tpt + q;
+    const bool have = (uint32_t)q < tpt && idx < n;
+    if (have && st < WB) {
+      used++;
+      sm.toks[1 + idx] = tk[q];
+      sm.tstart[1 + idx] = (uint16_t)st;
+      atomicOr(&sm.bitmap[st >> 5], 1u << (st & 31u));
+      if (tk[q] & TOK_MATCH) {
+        const uint32_t d = ((tk[q] >> 8) & 0x7fffu) + 1u;
+        if (d > P4 + st) bad = true;                              // deflate.lisp:343-345
+        if (st + ln[q] > WB) { sm.carry_len = st + ln[q] - WB; sm.carry_dist = d; }   // the straddler
+      }
+    }
+    st += ln[q];
+  }
+  if (bad) sm.fail = 1;
+  if (tid == 0) {
+    sm.toks[0] = TOK_MATCH | ((carry_dist - 1) << 8) | ((carry_len >= 3 ? carry_len : 3) - 3);
+    sm.tstart[0] = (uint16_t)mis;
+    if (carry_len) atomicOr(&sm.bitmap[0], 1u << mis);
+  }
+  uint32_t nused = n;
+  if (total > WB) {                                   // rare: count the tokens that start inside the window
+#pragma unroll
+    for (int sft = 16; sft; sft >>= 1) used += __shfl_xor_sync(TBZ_FULL, used, sft);
+    if (lane == 0) sm.wscan2[warp] = used;
+  }
+  __syncthreads();
+  if (total > WB) {
+    nused = 0;
+#pragma unroll
+    for (int w = 0; w < NWARP; w++) nused += sm.wscan2[w];
+  }
+  // ---- 2. rank directory over the bitmap words
+  if (warp == 0) {
+    uint32_t c[WB / 1024], s = 0;
+#pragma unroll
+    for (int i = 0; i < (int)(WB / 1024); i++) { c[i] = __popc(sm.bitmap[lane * (WB / 1024) + i]); s += c[i]; }
+    uint32_t y = s;
+#pragma unroll
+    for (int sft = 1; sft < 32; sft <<= 1) {
+      const uint32_t u = __shfl_up_sync(TBZ_FULL, y, sft);
+      if (lane >= sft) y += u;
+    }
+    uint32_t run = y - s;
+#pragma unroll
+    for (int i = 0; i < (int)(WB / 1024); i++) { sm.wrank[lane * (WB / 1024) + i] = (uint16_t)run; run += c[i]; }
+  }
+  __syncthreads();
+  if (sm.fail) return 0xffffffffu;
+  const uint32_t adj = carry_len ? 1u : 0u;           // rank 1 is the carry pseudo-token (index 0) if there is one
+  // ---- 3. resolve, one aligned word per thread and sub-pass
+#pragma unroll 1
+  for (uint32_t sb = 0; sb < wend; sb += SUB) {
+    const uint32_t r0 = sb + 4u * tid;
+    const uint32_t lo = sb > mis ? sb : mis;          // bytes below lo are final (earlier sub-pass or earlier window)
+    if (r0 < wend && r0 + 4u > mis) {
+      uint32_t word = 0;
+      bool done = false;
+      const bool full = r0 >= mis && r0 + 4u <= wend;
+      if (full) {
+        const uint32_t bw = sm.bitmap[r0 >> 5];
+        if (((bw >> (r0 & 31u)) & 0xeu) == 0u) {                 // no token starts at bytes 1..3: one token covers the word
+          const uint32_t ti = token_of(sm, r0, adj);
+          const uint32_t t = sm.toks[ti];
+          if (t & TOK_MATCH) {
+            const uint32_t d = ((t >> 8) & 0x7fffu) + 1u, o = r0 - sm.tstart[ti];
+            if (o + 3u < d && r0 + 3u < lo + d) {                 // no period wrap, source entirely below the sub-pass
+              const uint32_t sa = P4 + r0 - d;
+              const uint32_t w0 = *reinterpret_cast<const uint32_t *>(&sm.ring[sa & RMASK & ~3u]);
+              const uint32_t w1 = *reinterpret_cast<const uint32_t *>(&sm.ring[(sa + 4u) & RMASK & ~3u]);
+              word = __funnelshift_r(w0, w1, 8u * (sa & 3u));
+              done = true;
+            }
+          }
+        }
+      }
+      if (!done) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          uint32_t r = r0 + j;
+          uint32_t byte = 0;
+          if (r >= mis && r < wend) {
+            for (int hop = 0;; hop++) {
+              if (hop > 4096) { sm.fail = 1; break; }            // cannot happen: every hop moves to a lower byte
+              const uint32_t ti = token_of(sm, r, adj);
+              const uint32_t t = sm.toks[ti];
+              if (!(t & TOK_MATCH)) { byte = t & 255u; break; }
+              const uint32_t d = ((t >> 8) & 0x7fffu) + 1u, o = r - sm.tstart[ti];
+              uint32_t back = d;
+              if (o >= d) back = o - o % d + d;                   // overlapping match: read through the period
+              if (back + lo > r) { byte = sm.ring[(P4 + r - back) & RMASK]; break; }
+              r -= back;
+            }
+          }
+          word |= byte << (8 * j);
+        }
+      }
+      if (full) *reinterpret_cast<uint32_t *>(&sm.ring[(P4 + r0) & RMASK]) = word;
+      else {
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+          if (r0 + j >= mis && r0 + j < wend) sm.ring[(P4 + r0 + j) & RMASK] = (uint8_t)(word >> (8 * j));
+      }
+    }
+    __syncthreads();
+  }
+  const uint32_t wsize = wend - mis;
+  // ---- 4. flush complete 16-byte units, fold them into the checksum
+  if (fmt == TBZ_GZIP) crc_window(sm, pos, wsize, tid);
+  if ((((uintptr_t)out) & 15) == 0) {
+    const uint32_t upto = (pos + wsize) & ~15u;
+    for (uint32_t p = rs.flushed + 16 * tid; p < upto; p += 16 * NT) {
+      const uint4 v = *reinterpret_cast<const uint4 *>(&sm.ring[p & RMASK]);
+      *reinterpret_cast<uint4 *>(out + p) = v;
+      if (fmt == TBZ_ZLIB) {
+        uint32_t sd = __dp4a(v.x, 0x01010101u, 0u); sd = __dp4a(v.y, 0x01010101u, sd);
+        sd = __dp4a(v.z, 0x01010101u, sd); sd = __dp4a(v.w, 0x01010101u, sd);
+        uint32_t wj = __dp4a(v.x, 0x03020100u, 0u); wj = __dp4a(v.y, 0x07060504u, wj);
+        wj = __dp4a(v.z, 0x0b0a0908u, wj); wj = __dp4a(v.w, 0x0f0e0d0cu, wj);
+        rs.acc_a += sd;
+        rs.acc_w += (unsigned long long)p * sd + wj;
+      }
+    }
+    rs.flushed = upto;
+  } else {
+    for (uint32_t p = pos + tid; p < pos + wsize; p += NT) {
+      const uint32_t d = sm.ring[p & RMASK];
+      out[p] = (uint8_t)d;
+      rs.acc_a += d; rs.acc_w += (unsigned long long)p * d;
+    }
+    rs.flushed = pos + wsize;
+  }
+  if (rs.acc_w >> 62) rs.acc_w %= TBZ_ADLER_MOD;
+  rs.pos = pos + wsize;
+  rs.carry_len = sm.carry_len; rs.carry_dist = sm.carry_dist;
+  __syncthreads();
+  return nused;
+}
+
 __device__ inline bool resolve_member(const DMember &mem, int fmt, const P1Rec &rec, const uint32_t *__restrict__ slabs,
                                       tbz_result &res, Smem &sm, int tid) {
   const int lane = tid & 31, warp = tid >> 5;
   uint8_t *out = mem.out;
-  const bool out_aligned = (((uintptr_t)out) & 15) == 0;
-  uint32_t pos = 0;                       // output bytes produced so far (window base)
-  uint32_t flushed = 0;                   // output bytes already stored to global memory
-  unsigned long long acc_a = 0, acc_w = 0;   // Adler: sum d, sum i*d over this thread's flushed bytes
-  if (tid == 0) { sm.fail = 0; sm.carry_len = 0; sm.carry_dist = 1; sm.crc = 0; }
-  uint32_t carry_len = 0, carry_dist = 1;   // tail of a match that straddled the previous window end (uniform)
+  RState rs;
+  rs.pos = 0; rs.flushed = 0; rs.acc_a = 0; rs.acc_w = 0; rs.carry_len = 0; rs.carry_dist = 1;
+  if (tid == 0) { sm.fail = 0; sm.crc = 0; }
   __syncthreads();
   for (uint32_t s = rec.first_slab; s != NO_SLAB;) {
     const uint32_t *slab = slabs + (size_t)s * SLAB_WORDS;
-    const SlabHdr *sh = reinterpret_cast<const SlabHdr *>(slab);
-    const uint32_t *lists = slab + sizeof(SlabHdr) / 4;
-    s = sh->next;
-    const uint32_t ntok = sh->ntokens;
-    sm.tb[tid] = (uint16_t)sh->tb[tid];
-    sm.g0[tid] = (uint16_t)(sh->gn[tid] & 0xffffu);
+    if (tid < (int)SLAB_HDR_WORDS) sm.hdr[tid] = slab[tid];
     __syncthreads();
-    uint32_t f = 0;                       // next flat token of this slab
-    // the tail carried over from the previous slab is flushed with this slab's first window; a
-    // slab without tokens still needs one pass if a tail is pending
-    while (f < ntok || carry_len) {
-      if (tid == 0) sm.carry_len = 0;      // rewritten below by the thread that owns a straddling match
-      // ---- 1. fetch two tokens per thread, flat order.  One binary search per warp for the list
-      // that holds the warp's first token, then every thread walks forward from there.
-      uint32_t tk[2], ln[2];
-      {
-        const uint32_t fw = f + 64 * warp;          // first flat token of this warp
-        uint32_t j0 = 0;                            // last lane with tb[j0] <= fw
-        if (fw < ntok) {
-#pragma unroll
-          for (int stp = NT / 2; stp; stp >>= 1)
-            if (sm.tb[j0 + stp] <= fw) j0 += stp;
-        }
-#pragma unroll
-        for (int q = 0; q < 2; q++) {
-          const uint32_t fi = f + 2 * tid + q;
-          tk[q] = TOK_EOB;
-          if (fi < ntok) {
-            uint32_t j = j0;
-            while (j + 1 < NT && sm.tb[j + 1] <= fi) j++;
-            tk[q] = lists[j * TOKCAP + sm.g0[j] + (fi - sm.tb[j])];
-          }
-          ln[q] = tok_len(tk[q]);
-        }
+    s = sm.hdr[0];
+    for (int j = 0; j < NL; j++) {
+      const uint32_t fc = sm.hdr[4 + j];
+      const uint32_t cnt = fc >> 16;
+      if (!cnt) continue;
+      const uint32_t *list = slab + SLAB_HDR_WORDS + j * TOKCAP + (fc & 0xffffu);
+      uint32_t f = 0;
+      while (f < cnt) {
+        const uint32_t n = cnt - f < WT ? cnt - f : WT;
+        const uint32_t used = resolve_window(mem, fmt, list + f, n, rs, sm, tid);
+        if (used == 0xffffffffu || used == 0) return false;
+        f += used;
       }
-      // ---- 2. offsets inside the window
-      uint32_t x = ln[0] + ln[1];
-      const uint32_t mine = x;
-#pragma unroll
-      for (int sft = 1; sft < 32; sft <<= 1) {
-        const uint32_t u = __shfl_up_sync(TBZ_FULL, x, sft);
-        if (lane >= sft) x += u;
-      }
-      if (lane == 31) sm.wscan[warp] = x;
-      __syncthreads();
-      uint32_t off = carry_len, total = carry_len;
-#pragma unroll
-      for (int w = 0; w < NWARP; w++) { const uint32_t c = sm.wscan[w]; if (w < warp) off += c; total += c; }
-      uint32_t st[2];
-      st[0] = off + x - mine;
-      st[1] = st[0] + ln[0];
-      const uint32_t wsize = total < WB ? total : WB;
-      // tokens that start inside the window are consumed by it
-      uint32_t used = 0;
-      bool bad = false;
-#pragma unroll
-      for (int q = 0; q < 2; q++) {
-        const uint32_t fi = f + 2 * tid + q;
-        const bool inc = fi < ntok && st[q] < WB;
-        used += inc;
-        const uint32_t idx = 1 + 2 * tid + q;
-        sm.toks[idx] = tk[q];
-        sm.tstart[idx] = (uint16_t)(st[q] < WB ? st[q] : WB);
-        if (inc && (tk[q] & TOK_MATCH)) {
-          const uint32_t d = ((tk[q] >> 8) & 0x7fffu) + 1u;
-          if (d > pos + st[q]) bad = true;                       // deflate.lisp:343-345
-          if (st[q] + ln[q] > WB) { sm.carry_len = st[q] + ln[q] - WB; sm.carry_dist = d; }   // the straddler
-        }
-      }
-      if (bad) sm.fail = 1;
-      if (tid == 0) {
-        sm.toks[0] = TOK_MATCH | ((carry_dist - 1) << 8) | ((carry_len >= 3 ? carry_len : 3) - 3);
-        sm.tstart[0] = 0;
-      }
-      // ---- 3. byte -> token map: scatter the token starts, prefix-max
-      *reinterpret_cast<uint4 *>(&sm.bytemap[8 * tid]) = make_uint4(0, 0, 0, 0);
-#pragma unroll
-      for (int sft = 16; sft; sft >>= 1) used += __shfl_xor_sync(TBZ_FULL, used, sft);
-      if (lane == 0) sm.wscan2[warp] = used;
-      __syncthreads();
-      uint32_t nused = 0;
-#pragma unroll
-      for (int w = 0; w < NWARP; w++) nused += sm.wscan2[w];
-#pragma unroll
-      for (int q = 0; q < 2; q++)
-        if (ln[q] && st[q] < WB && f + 2 * tid + q < ntok) sm.bytemap[st[q]] = (uint16_t)(2 + 2 * tid + q);   // token index + 1
-      if (tid == 0 && carry_len) sm.bytemap[0] = 1;
-      __syncthreads();
-      if (sm.fail) return false;
-      uint32_t mp[8];
-      {
-        const uint4 v = *reinterpret_cast<const uint4 *>(&sm.bytemap[8 * tid]);
-        mp[0] = v.x & 0xffffu; mp[1] = v.x >> 16; mp[2] = v.y & 0xffffu; mp[3] = v.y >> 16;
-        mp[4] = v.z & 0xffffu; mp[5] = v.z >> 16; mp[6] = v.w & 0xffffu; mp[7] = v.w >> 16;
-      }
-#pragma unroll
-      for (int i = 1; i < 8; i++) mp[i] = mp[i] > mp[i - 1] ? mp[i] : mp[i - 1];
-      uint32_t run = mp[7];
-#pragma unroll
-      for (int sft = 1; sft < 32; sft <<= 1) {
-        const uint32_t u = __shfl_up_sync(TBZ_FULL, run, sft);
-        if (lane >= sft && u > run) run = u;
-      }
-      if (lane == 31) sm.wscan[warp] = run;
-      uint32_t before = __shfl_up_sync(TBZ_FULL, run, 1);
-      if (lane == 0) before = 0;
-      __syncthreads();
-#pragma unroll
-      for (int w = 0; w < NWARP; w++) { const uint32_t c = sm.wscan[w]; if (w < warp && c > before) before = c; }
-#pragma unroll
-      for (int i = 0; i < 8; i++) if (before > mp[i]) mp[i] = before;
-      *reinterpret_cast<uint4 *>(&sm.bytemap[8 * tid]) =
-          make_uint4(mp[0] | (mp[1] << 16), mp[2] | (mp[3] << 16), mp[4] | (mp[5] << 16), mp[6] | (mp[7] << 16));
-      __syncthreads();
-      // ---- 4. resolve the window in four 512-byte sub-passes, two bytes per thread each.  A byte
-      // whose source lies below the sub-pass start reads it from the ring (earlier sub-passes have
-      // stored there already), so only sources inside the same 512 bytes are chased further.
-#pragma unroll 1
-      for (uint32_t sub = 0; sub < WB; sub += 512) {
-        if (sub < wsize) {
-          uint32_t rr[2], byte[2];
-          bool open[2];
-#pragma unroll
-          for (int i = 0; i < 2; i++) {
-            rr[i] = sub + 2 * tid + i;
-            byte[i] = 0;
-            open[i] = rr[i] < wsize;
-          }
-#pragma unroll
-          for (int hop = 0; hop < 2; hop++) {
-#pragma unroll
-            for (int i = 0; i < 2; i++) {
-              if (open[i]) {
-                const uint32_t m = sm.bytemap[rr[i]];
-                const uint32_t t = sm.toks[m - 1];
-                if (!(t & TOK_MATCH)) { byte[i] = t & 255u; open[i] = false; }
-                else {
-                  const uint32_t d = ((t >> 8) & 0x7fffu) + 1u, o = rr[i] - sm.tstart[m - 1];
-                  uint32_t back = d;
-                  if (o >= d) back = o - o % d + d;             // overlapping match: read through the period
-                  if (back + sub > rr[i]) { byte[i] = sm.ring[(pos + rr[i] - back) & RMASK]; open[i] = false; }
-                  else rr[i] -= back;
-                }
-              }
-            }
-          }
-#pragma unroll
-          for (int i = 0; i < 2; i++) {
-            while (open[i]) {                                   // rare: three or more hops
-              const uint32_t m = sm.bytemap[rr[i]];
-              const uint32_t t = sm.toks[m - 1];
-              if (!(t & TOK_MATCH)) { byte[i] = t & 255u; break; }
-              const uint32_t d = ((t >> 8) & 0x7fffu) + 1u, o = rr[i] - sm.tstart[m - 1];
-              uint32_t back = d;
-              if (o >= d) back = o - o % d + d;
-              if (back + sub > rr[i]) { byte[i] = sm.ring[(pos + rr[i] - back) & RMASK]; break; }
-              rr[i] -= back;
-            }
-          }
-          const uint32_t r0 = sub + 2 * tid;
-          if (r0 < wsize) sm.ring[(pos + r0) & RMASK] = (uint8_t)byte[0];
-          if (r0 + 1 < wsize) sm.ring[(pos + r0 + 1) & RMASK] = (uint8_t)byte[1];
-        }
-        __syncthreads();
-      }
-      // ---- 5. flush complete 16-byte units, fold them into the checksum
-      if (fmt == TBZ_GZIP) crc_window(sm, pos, wsize, tid);
-      if (out_aligned) {
-        const uint32_t upto = (pos + wsize) & ~15u;
-        const uint32_t p = flushed + 16 * tid;
-        if (p < upto) {
-          const uint4 v = *reinterpret_cast<const uint4 *>(&sm.ring[p & RMASK]);
-          *reinterpret_cast<uint4 *>(out + p) = v;
-          if (fmt == TBZ_ZLIB) {
-            uint32_t sd = __dp4a(v.x, 0x01010101u, 0u); sd = __dp4a(v.y, 0x01010101u, sd);
-            sd = __dp4a(v.z, 0x01010101u, sd); sd = __dp4a(v.w, 0x01010101u, sd);
-            uint32_t wj = __dp4a(v.x, 0x03020100u, 0u); wj = __dp4a(v.y, 0x07060504u, wj);
-            wj = __dp4a(v.z, 0x0b0a0908u, wj); wj = __dp4a(v.w, 0x0f0e0d0cu, wj);
-            acc_a += sd;
-            acc_w += (unsigned long long)p * sd + wj;
-          }
-        }
-        flushed = upto;                                        // at most WB + 15 bytes = 129 units per window
-      } else {
-        for (uint32_t p = pos + tid; p < pos + wsize; p += NT) {
-          const uint32_t d = sm.ring[p & RMASK];
-          out[p] = (uint8_t)d;
-          acc_a += d; acc_w += (unsigned long long)p * d;
-        }
-        flushed = pos + wsize;
-      }
-      if (acc_w >> 62) acc_w %= TBZ_ADLER_MOD;
-      pos += wsize;
-      f += nused;
-      carry_len = sm.carry_len; carry_dist = sm.carry_dist;
-      __syncthreads();
     }
     __syncthreads();
   }
-  if (pos != rec.out_len) return false;
-  if (flushed + tid < pos) {               // the last partial 16-byte unit
-    const uint32_t p = flushed + tid;
+  while (rs.carry_len) {                   // tail of a match that straddled the last window
+    if (resolve_window(mem, fmt, nullptr, 0, rs, sm, tid) == 0xffffffffu) return false;
+  }
+  const uint32_t pos = rs.pos;
+  if (pos != rec.out_len || sm.fail) return false;
+  unsigned long long acc_a = rs.acc_a, acc_w = rs.acc_w;
+  if (rs.flushed + tid < pos) {            // the last partial 16-byte unit
+    const uint32_t p = rs.flushed + tid;
     const uint32_t d = sm.ring[p & RMASK];
     out[p] = (uint8_t)d;
     acc_a += d; acc_w += (unsigned long long)p * d;

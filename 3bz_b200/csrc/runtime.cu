@@ -41,34 +41,35 @@ k_inflate_seq(const DMember *members, tbz_result *results, uint32_t n, int fmt,
 
 // counters: [0] next member for phase one, [1] members queued for the sequential kernel,
 //           [2] slabs handed out, [3] next member for phase two
-// Phase one, persistent CTAs: each pulls the next member from a global counter and decodes it
-// into token slabs; members it cannot prove clean are queued for k_inflate_seq.
-__global__ void __launch_bounds__(tbzfast::NT, 2)
+// Phase one, persistent CTAs of WPC independent warps: each warp pulls the next member from a
+// global counter and decodes it into token slabs; members it cannot prove clean are queued for
+// k_inflate_seq.
+__global__ void __launch_bounds__(tbzfast::NT)
 k_inflate_decode(const DMember *members, uint32_t n, int fmt, tbzfast::P1Rec *recs,
                  uint32_t *slabs, uint32_t nslabs, uint32_t *counters, uint32_t *todo) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  tbzfast::Smem &sm = *reinterpret_cast<tbzfast::Smem *>(smem_raw);
-  const int tid = threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  tbzfast::WSmem &sm = reinterpret_cast<tbzfast::WSmem *>(smem_raw)[warp];
   for (;;) {
-    __syncthreads();
-    if (tid == 0) sm.member = atomicAdd(&counters[0], 1u);
-    __syncthreads();
-    const uint32_t i = sm.member;
+    uint32_t i = 0;
+    if (lane == 0) i = atomicAdd(&counters[0], 1u);
+    i = __shfl_sync(TBZ_FULL, i, 0);
     if (i >= n) break;
-    const bool ok = tbzfast::decode_member(members[i], fmt, recs[i], sm, slabs, nslabs, &counters[2], tid);
-    if (!ok && tid == 0) { recs[i].status = 0; todo[atomicAdd(&counters[1], 1u)] = i; }
+    const bool ok = tbzfast::decode_member(members[i], fmt, recs[i], sm, slabs, nslabs, &counters[2], lane);
+    __syncwarp();
+    if (!ok && lane == 0) { recs[i].status = 0; todo[atomicAdd(&counters[1], 1u)] = i; }
   }
 }
 
 // Phase two, persistent CTAs: one CTA per member resolves the token stream into bytes through a
 // shared-memory ring and checks the trailer.
-__global__ void __launch_bounds__(tbzfast::NT, 3)
+__global__ void __launch_bounds__(tbzres::NT, 3)
 k_inflate_resolve(const DMember *members, tbz_result *results, uint32_t n, int fmt,
                   const tbzfast::P1Rec *recs, const uint32_t *slabs, uint32_t *counters, uint32_t *todo) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   tbzres::Smem &sm = *reinterpret_cast<tbzres::Smem *>(smem_raw);
   const int tid = threadIdx.x;
-  if (fmt == TBZ_GZIP) crc_table_init(sm.crc_tab, tid, tbzfast::NT);
+  if (fmt == TBZ_GZIP) crc_table_init(sm.crc_tab, tid, tbzres::NT);
   for (;;) {
     __syncthreads();
     if (tid == 0) sm.member = atomicAdd(&counters[3], 1u);
@@ -387,7 +388,7 @@ extern "C" int32_t tbz_batch_prepare(tbz_ctx *ctx, int32_t format, const tbz_mem
   PCK(dev_alloc(ctx, std::max<uint64_t>(1, n) * sizeof(DMember), &b->d_members));
   PCK(dev_alloc(ctx, std::max<uint64_t>(1, n) * sizeof(tbz_result), &b->d_results));
   if (!(flags & TBZ_FLAG_NO_FASTPATH) && n) {
-    b->fast_grid = (int)std::min<uint64_t>(n, (uint64_t)ctx->sm_count * 3);
+    b->fast_grid = (int)std::min<uint64_t>((n + tbzfast::WPC - 1) / tbzfast::WPC, (uint64_t)ctx->sm_count * 4);
     // token slabs: one per round; a round covers at most ~31 KiB of compressed input and never
     // crosses a block boundary.  Members that find the pool empty go to the sequential kernel.
     uint64_t want = 0;
@@ -460,16 +461,17 @@ static int32_t launch_kernels(tbz_batch *b) {
   if (!b->n) return TBZ_OK;
   uint32_t n = (uint32_t)b->n;
   if (b->fast_grid) {
-    CK(ctx, cudaFuncSetAttribute(k_inflate_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tbzfast::Smem)));
+    const size_t dec_smem = sizeof(tbzfast::WSmem) * tbzfast::WPC;
+    CK(ctx, cudaFuncSetAttribute(k_inflate_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dec_smem));
     CK(ctx, cudaMemsetAsync(b->d_counters, 0, 256, ctx->stream));
-    k_inflate_decode<<<b->fast_grid, tbzfast::NT, sizeof(tbzfast::Smem), ctx->stream>>>(
+    k_inflate_decode<<<b->fast_grid, tbzfast::NT, dec_smem, ctx->stream>>>(
         (const DMember *)b->d_members, n, b->format, (tbzfast::P1Rec *)b->d_recs,
         (uint32_t *)b->d_slabs, b->nslabs, (uint32_t *)b->d_counters, (uint32_t *)b->d_todo);
     ctx->launches++;
     CK(ctx, cudaGetLastError());
     CK(ctx, cudaFuncSetAttribute(k_inflate_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tbzres::Smem)));
     const int res_grid = (int)std::min<uint64_t>(n, (uint64_t)ctx->sm_count * 3);
-    k_inflate_resolve<<<res_grid, tbzfast::NT, sizeof(tbzres::Smem), ctx->stream>>>(
+    k_inflate_resolve<<<res_grid, tbzres::NT, sizeof(tbzres::Smem), ctx->stream>>>(
         (const DMember *)b->d_members, (tbz_result *)b->d_results, n, b->format,
         (const tbzfast::P1Rec *)b->d_recs, (const uint32_t *)b->d_slabs, (uint32_t *)b->d_counters, (uint32_t *)b->d_todo);
     ctx->launches++;
