@@ -169,6 +169,7 @@ __device__ __forceinline__ void bits_refill(Bits &b, const In &in) {
     b.bc += 32;
     b.nw = ldw(in, b.wn);
     b.wn++;
+    if ((b.wn & 31u) == 0u && b.wn + 32u < in.nwords) asm volatile("prefetch.global.L1 [%0];" ::"l"(in.w + b.wn + 32));
   }
 }
 __device__ __forceinline__ void bits_skip(Bits &b, uint32_t n) { b.bb >>= n; b.bc -= n; }
@@ -177,6 +178,7 @@ __device__ __forceinline__ void bits_skip(Bits &b, uint32_t n) { b.bb >>= n; b.b
 // masked for literals) so that the lanes of a warp do not diverge on the token kind.
 // Returns 0 literal, 1 match, 2 end of block, 3 invalid code.
 __device__ __forceinline__ int decode_token(Bits &b, const In &in, const WSmem &sm, uint32_t &tok, uint32_t &nbits, uint32_t &olen) {
+  nbits = 0;
   bits_refill(b, in);                                        // >= 33 bits
   uint32_t w = (uint32_t)b.bb;
   uint32_t e = sm.lut_ll[w & ((1u << KLL) - 1)];
@@ -380,56 +382,71 @@ __device__ inline bool decode_member(const DMember &mem, int fmt, P1Rec &rec, WS
       tw.q0 = tw.q1 = tw.q2 = tw.q3 = 0;
       __syncwarp();
 
-      // ---- 1a: speculative decode of the lane's sub-chunk
+      // ---- 1a: speculative decode of the lane's sub-chunk.  The loop is kept warp-converged (one
+      // vote per iteration, the body predicated on `act`): lanes that leave a loop through a break
+      // are not guaranteed to re-converge, and a split warp issues the whole body once per fragment.
       const uint32_t cstart = P0 + S * lane, cend = cstart + S;
       uint32_t p = cstart;
       uint32_t k = 0, ob = 0;
       int st = ST_IDLE;
       Bits b;
-      if (p < in.end) {
-        bits_init(b, in, p);
-        for (;;) {
-          if (p >= cend) { st = ST_OVER; break; }
-          if (k >= TOKCAP) { st = ST_CAP; break; }
-          if ((k & (CKSTEP - 1)) == 0) sm.ckpt[k / CKSTEP][lane] = (p - cstart) | (ob << 13);
-          uint32_t tok, nb, ol;
-          const int kind = decode_token(b, in, sm, tok, nb, ol);
-          if (kind == 3 || p + nb > in.end) { st = ST_BAD; break; }
-          p += nb;
-          if (kind == 2) { st = ST_EOB; break; }
-          tw.push(tok, k);
-          k++; ob += ol;
+      bool act = p < in.end;
+      if (act) bits_init(b, in, p);
+      while (__any_sync(TBZ_FULL, act)) {
+        if (act) {
+          if (p >= cend) { st = ST_OVER; act = false; }
+          else {
+            if ((k & (CKSTEP - 1)) == 0) {
+              if (k >= TOKCAP) { st = ST_CAP; act = false; }
+              else sm.ckpt[k / CKSTEP][lane] = (p - cstart) | (ob << 13);
+            }
+            if (act) {
+              uint32_t tok, nb, ol;
+              const int kind = decode_token(b, in, sm, tok, nb, ol);
+              p += nb;
+              if (kind >= 2) { st = kind == 2 ? ST_EOB : ST_BAD; act = false; }
+              else { tw.push(tok, k); k++; ob += ol; }
+            }
+          }
         }
       }
       __syncwarp();
       // ---- 1b: past the own sub-chunk: decode on until a token start coincides with a checkpoint
-      // of the lane whose sub-chunk the position lies in
+      // of the lane whose sub-chunk the position lies in.  Same converged loop; an iteration either
+      // decodes one token or looks up the next place a synchronisation can happen (`tgt`).
       uint32_t nx = 0, g_sync = 0, ob_sync = 0;
-      if (st == ST_OVER) {
-        uint32_t j = lane, jend = cend, c = 0;       // lane being searched, end of its sub-chunk, next checkpoint
-        for (;;) {
-          if (p >= winend) { st = ST_END; break; }
-          while (p >= jend) { j++; jend += S; c = 0; }
-          const uint32_t rel = p - (jend - S);
-          uint32_t ck = CK_NONE;
-          while (c < NCK && ((ck = sm.ckpt[c][j]) & 0x1fffu) < rel) c++;
-          if (c < NCK && ck != CK_NONE && (ck & 0x1fffu) == rel) { st = ST_SYNC; nx = j; g_sync = c * CKSTEP; ob_sync = ck >> 13; break; }
-          uint32_t tgt = jend;
-          if (c < NCK && ck != CK_NONE) tgt = (jend - S) + (ck & 0x1fffu);
-          // decode up to the next place a synchronisation can happen
-          while (p < tgt) {
-            if (k >= TOKCAP) { st = ST_CAP; break; }
-            uint32_t tok, nb, ol;
-            const int kind = decode_token(b, in, sm, tok, nb, ol);
-            if (kind == 3 || p + nb > in.end) { st = ST_BAD; break; }
-            p += nb;
-            if (kind == 2) { st = ST_EOB; break; }
-            tw.push(tok, k);
-            k++; ob += ol;
+      {
+        uint32_t j = lane, jend = cend, c = 0, tgt = 0;
+        act = st == ST_OVER;
+        while (__any_sync(TBZ_FULL, act)) {
+          if (act) {
+            if (p >= tgt) {
+              if (p >= winend) { st = ST_END; act = false; }
+              else {
+                while (p >= jend) { j++; jend += S; c = 0; }
+                const uint32_t rel = p - (jend - S);
+                uint32_t ck = CK_NONE;
+                while (c < NCK && ((ck = sm.ckpt[c][j]) & 0x1fffu) < rel) c++;
+                if (c < NCK && ck != CK_NONE && (ck & 0x1fffu) == rel) {
+                  st = ST_SYNC; act = false; nx = j; g_sync = c * CKSTEP; ob_sync = ck >> 13;
+                } else {
+                  tgt = jend;
+                  if (c < NCK && ck != CK_NONE) tgt = (jend - S) + (ck & 0x1fffu);
+                }
+              }
+            } else if (k >= TOKCAP) { st = ST_CAP; act = false; }
+            else {
+              uint32_t tok, nb, ol;
+              const int kind = decode_token(b, in, sm, tok, nb, ol);
+              p += nb;
+              if (kind >= 2) { st = kind == 2 ? ST_EOB : ST_BAD; act = false; }
+              else { tw.push(tok, k); k++; ob += ol; }
+            }
           }
-          if (st != ST_OVER) break;
         }
       }
+      // a lane that decoded past the end of the input has nothing proven to offer (zeros are read there)
+      if (st != ST_IDLE && p > in.end) st = ST_BAD;
       tw.finish(k);
       __syncwarp();
       // ---- 1c: lanes reachable from lane 0 through "synchronised into" edges are proven

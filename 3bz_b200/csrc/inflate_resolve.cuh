@@ -1,22 +1,22 @@
 // inflate_resolve.cuh — phase two of the batched fast path: LZ77 resolution of a token stream
 // (deflate.lisp:244-359 `copy-history`, restated for a whole CTA).
 //
-// One CTA per member.  The member's output is produced in windows that live in a 64 KiB ring in
-// shared memory (the last 32 KiB of it are the deflate history).  A window is one proven token
-// list of phase one (or a piece of it, when it would exceed WB bytes):
-//   1. the list's tokens are loaded (up to TPT consecutive tokens per thread) and a CTA prefix
-//      sum over their lengths gives every token its byte offset in the window; the token that
-//      straddles the window end is split and its tail carried into the next window
-//   2. every token sets one bit in a "token starts here" bitmap over the window's bytes; a prefix
-//      popcount over the bitmap words turns byte -> token lookup into a rank query (two loads)
-//   3. the window is resolved in sub-passes of 4*NT bytes, one aligned 32-bit word of output per
-//      thread and sub-pass.  A word that lies inside one match whose source is final (below the
-//      sub-pass) is one unaligned 4-byte ring read; other words go byte by byte: follow
-//      byte -> token -> (byte - distance) while the source still lies inside the sub-pass
-//      (overlapping matches go through their period); the chase ends at a literal or at a final
-//      byte in the ring.  No byte written in a sub-pass is read in it, so threads need no ordering
-//   4. the window is flushed to global memory with 16-byte stores; Adler-32 is folded in with
-//      dp4a as s1 = 1 + sum d, s2 = N + N sum d - sum i d_i (order independent per thread)
+// One CTA per member.  Shared memory holds the 32 KiB deflate history as a ring (hist) and the
+// window being produced (win).  A window is one proven token list of phase one (or a piece of it,
+// when it would exceed WT tokens or WB bytes):
+//   1. token-parallel: the tokens are loaded, a CTA prefix sum over their lengths gives every
+//      token its byte offset, and every token sets one bit in a "token starts here" bitmap over
+//      the window's bytes; a prefix popcount over the bitmap words makes byte -> token a rank query
+//   2. byte-parallel, the same straight-line code for every byte: one aligned output word per
+//      thread and step; byte -> token -> literal value, or source = byte - distance (overlapping
+//      matches go through their period).  A source below the window is final history and is read
+//      at once.  A source inside the window leaves the byte pending: its source pointer is
+//      stored in val[] and the byte is queued
+//   3. pending bytes are resolved by pointer jumping over val[], dense and balanced because they
+//      sit in a queue: a byte whose source is final copies it; otherwise it adopts the source's
+//      pointer (equal bytes) and is queued again.  Chains halve every level
+//   4. the window is appended to the history ring and flushed to global memory with 16-byte
+//      stores; Adler-32 is folded in with dp4a as s1 = 1 + sum d, s2 = N + N sum d - sum i d_i
 // CRC-32 (gzip) is a thread-parallel pass per window with x^(8 len) combines.  The trailer is then
 // checked as zlib.lisp:80-96 / gzip.lisp:82-106 do; any disagreement sends the member to the
 // sequential kernel, which owns the verdict rules.
@@ -37,18 +37,22 @@ using tbzfast::TOK_MATCH;
 
 constexpr int NT = 256;
 constexpr int NWARP = NT / 32;
-constexpr uint32_t RING = 65536u, RMASK = RING - 1u;
-constexpr uint32_t WB = 4096;            // window bytes (including the <= 3 bytes of alignment lead-in)
-constexpr int TPT = 4;                   // tokens per thread and window
+constexpr uint32_t HIST = 32768u, HMASK = HIST - 1u;
+constexpr uint32_t WB = 2048;            // window bytes (including the <= 3 bytes of alignment lead-in)
+constexpr int TPT = 2;                   // tokens per thread and window
 constexpr uint32_t WT = TPT * NT;        // window tokens
-constexpr uint32_t SUB = 4 * NT;         // bytes per sub-pass
+constexpr uint32_t V_FINAL = 0xffffu;
 
 struct Smem {
-  alignas(16) uint8_t ring[RING];
+  alignas(16) uint8_t hist[HIST];        // ring over absolute output offsets: the last 32 KiB
+  alignas(16) uint8_t win[WB];           // the window, in coordinates relative to its 4-byte aligned base
+  alignas(8) uint16_t val[WB];           // per window byte: V_FINAL or the window offset of an equal byte
+  uint16_t queue[2][WB];                 // pending bytes of this / the next level
   uint32_t toks[WT + 1];                 // [0] = tail of the match carried over from the previous window
   uint16_t tstart[WT + 2];
   uint32_t bitmap[WB / 32];              // token-start bits over the window's bytes
   uint16_t wrank[WB / 32];               // token starts in the bitmap words before this one
+  uint32_t qcnt[3];
   uint32_t hdr[SLAB_HDR_WORDS];
   uint32_t crc_tab[256];
   uint32_t wscan[NWARP], wscan2[NWARP];
@@ -61,7 +65,7 @@ struct Smem {
 
 __device__ __forceinline__ uint32_t tok_len(uint32_t t) { return (t & TOK_MATCH) ? (t & 255u) + 3u : 1u; }
 
-// CRC-32 of ring[a, a+m): every thread takes one contiguous slice; slices are merged pairwise with
+// CRC-32 of hist[a, a+m): every thread takes one contiguous slice; slices are merged pairwise with
 // x^(8 len) shifts (the per-level shift is the square of the previous one).  All threads must call.
 __device__ inline void crc_window(Smem &sm, uint32_t a, uint32_t m, int tid) {
   const uint32_t seg = (m + NT - 1) / NT;
@@ -69,7 +73,7 @@ __device__ inline void crc_window(Smem &sm, uint32_t a, uint32_t m, int tid) {
   if (lo > m) lo = m;
   if (hi > m) hi = m;
   uint32_t c = 0xffffffffu;
-  for (uint32_t p = lo; p < hi; p++) c = (c >> 8) ^ sm.crc_tab[(c ^ sm.ring[(a + p) & RMASK]) & 0xff];
+  for (uint32_t p = lo; p < hi; p++) c = (c >> 8) ^ sm.crc_tab[(c ^ sm.hist[(a + p) & HMASK]) & 0xff];
   c ^= 0xffffffffu;
   if (lo == hi) c = 0;
   uint32_t len = hi - lo;
@@ -100,14 +104,9 @@ struct RState {
   uint32_t carry_len, carry_dist;         // tail of a match that straddled the previous window end
 };
 
-// byte r (relative to the window's aligned base) -> index of the token that covers it
-__device__ __forceinline__ uint32_t token_of(const Smem &sm, uint32_t r, uint32_t adj) {
-  const uint32_t w = r >> 5;
-  return sm.wrank[w] + __popc(sm.bitmap[w] & (0xffffffffu >> (31u - (r & 31u)))) - adj;
-}
-
-// One window: tokens list[0, n) (n <= WT); consumes as many as fit, returns the number consumed.
-// A pending carry is flushed first.  All threads must call; the result is uniform.
+// One window: tokens list[0, n) (n <= WT); consumes as many as fit, returns the number consumed
+// (0xffffffff = the member must go to the sequential kernel).  A pending carry is flushed first.
+// All threads must call; the result is uniform.
 __device__ inline uint32_t resolve_window(const DMember &mem, int fmt, const uint32_t *__restrict__ list, uint32_t n,
                                           RState &rs, Smem &sm, int tid) {
   const int lane = tid & 31, warp = tid >> 5;
@@ -135,7 +134,7 @@ __device__ inline uint32_t resolve_window(const DMember &mem, int fmt, const uin
   }
   if (lane == 31) sm.wscan[warp] = x;
   if (tid < (int)(WB / 32)) sm.bitmap[tid] = 0;
-  if (tid == 0) sm.carry_len = 0;        // rewritten below by the thread that owns a straddling match
+  if (tid == 0) { sm.carry_len = 0; sm.qcnt[0] = 0; sm.qcnt[1] = 0; sm.qcnt[2] = 0; }
   __syncthreads();
   uint32_t off = mis + carry_len, total = mis + carry_len;
 #pragma unroll
@@ -163,7 +162,7 @@ __device__ inline uint32_t resolve_window(const DMember &mem, int fmt, const uin
   }
   if (bad) sm.fail = 1;
   if (tid == 0) {
-    sm.toks[0] = TOK_MATCH | ((carry_dist - 1) << 8) | ((carry_len >= 3 ? carry_len : 3) - 3);
+    sm.toks[0] = TOK_MATCH | ((carry_dist - 1) << 8);
     sm.tstart[0] = (uint16_t)mis;
     if (carry_len) atomicOr(&sm.bitmap[0], 1u << mis);
   }
@@ -179,7 +178,7 @@ __device__ inline uint32_t resolve_window(const DMember &mem, int fmt, const uin
 #pragma unroll
     for (int w = 0; w < NWARP; w++) nused += sm.wscan2[w];
   }
-  // ---- 2. rank directory over the bitmap words
+  // rank directory over the bitmap words
   if (warp == 0) {
     uint32_t c[WB / 1024], s = 0;
 #pragma unroll
@@ -197,69 +196,91 @@ __device__ inline uint32_t resolve_window(const DMember &mem, int fmt, const uin
   __syncthreads();
   if (sm.fail) return 0xffffffffu;
   const uint32_t adj = carry_len ? 1u : 0u;           // rank 1 is the carry pseudo-token (index 0) if there is one
-  // ---- 3. resolve, one aligned word per thread and sub-pass
-#pragma unroll 1
-  for (uint32_t sb = 0; sb < wend; sb += SUB) {
-    const uint32_t r0 = sb + 4u * tid;
-    const uint32_t lo = sb > mis ? sb : mis;          // bytes below lo are final (earlier sub-pass or earlier window)
-    if (r0 < wend && r0 + 4u > mis) {
-      uint32_t word = 0;
-      bool done = false;
-      const bool full = r0 >= mis && r0 + 4u <= wend;
-      if (full) {
-        const uint32_t bw = sm.bitmap[r0 >> 5];
-        if (((bw >> (r0 & 31u)) & 0xeu) == 0u) {                 // no token starts at bytes 1..3: one token covers the word
-          const uint32_t ti = token_of(sm, r0, adj);
-          const uint32_t t = sm.toks[ti];
-          if (t & TOK_MATCH) {
-            const uint32_t d = ((t >> 8) & 0x7fffu) + 1u, o = r0 - sm.tstart[ti];
-            if (o + 3u < d && r0 + 3u < lo + d) {                 // no period wrap, source entirely below the sub-pass
-              const uint32_t sa = P4 + r0 - d;
-              const uint32_t w0 = *reinterpret_cast<const uint32_t *>(&sm.ring[sa & RMASK & ~3u]);
-              const uint32_t w1 = *reinterpret_cast<const uint32_t *>(&sm.ring[(sa + 4u) & RMASK & ~3u]);
-              word = __funnelshift_r(w0, w1, 8u * (sa & 3u));
-              done = true;
-            }
-          }
+  // ---- 2. every byte: literal, final history, or pending
+  for (uint32_t rb = 0; rb < wend; rb += 4u * NT) {   // uniform trip count: the warp votes inside
+    const uint32_t r0 = rb + 4u * tid;
+    const uint32_t bw = sm.bitmap[(r0 >> 5) & (WB / 32 - 1)];
+    uint32_t ti = sm.wrank[(r0 >> 5) & (WB / 32 - 1)] + __popc(bw & (0xffffffffu >> (31u - (r0 & 31u)))) - adj;
+    const uint32_t nib = bw >> (r0 & 31u);
+    uint32_t word = 0, v01 = 0, v23 = 0, npend = 0, pmask = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const uint32_t r = r0 + j;
+      if (j) ti += (nib >> j) & 1u;
+      uint32_t byte = 0, v = V_FINAL;
+      if (r >= mis && r < wend) {
+        const uint32_t t = sm.toks[ti];
+        if (t & TOK_MATCH) {
+          const uint32_t d = ((t >> 8) & 0x7fffu) + 1u, o = r - sm.tstart[ti];
+          uint32_t back = d;
+          if (o >= d) back = o - o % d + d;                       // overlapping match: read through the period
+          if (back + mis > r) byte = sm.hist[(P4 + r - back) & HMASK];   // the source is below the window: final
+          else { v = r - back; npend++; pmask |= 1u << j; }
+        } else {
+          byte = t & 255u;
         }
       }
-      if (!done) {
+      word |= byte << (8 * j);
+      if (j < 2) v01 |= v << (16 * j); else v23 |= v << (16 * (j - 2));
+    }
+    if (r0 < wend) {
+      *reinterpret_cast<uint32_t *>(&sm.win[r0]) = word;
+      *reinterpret_cast<uint2 *>(&sm.val[r0]) = make_uint2(v01, v23);
+    }
+    // queue the pending bytes: one shared-memory atomic per warp
+    uint32_t incl = npend;
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-          uint32_t r = r0 + j;
-          uint32_t byte = 0;
-          if (r >= mis && r < wend) {
-            for (int hop = 0;; hop++) {
-              if (hop > 4096) { sm.fail = 1; break; }            // cannot happen: every hop moves to a lower byte
-              const uint32_t ti = token_of(sm, r, adj);
-              const uint32_t t = sm.toks[ti];
-              if (!(t & TOK_MATCH)) { byte = t & 255u; break; }
-              const uint32_t d = ((t >> 8) & 0x7fffu) + 1u, o = r - sm.tstart[ti];
-              uint32_t back = d;
-              if (o >= d) back = o - o % d + d;                   // overlapping match: read through the period
-              if (back + lo > r) { byte = sm.ring[(P4 + r - back) & RMASK]; break; }
-              r -= back;
-            }
-          }
-          word |= byte << (8 * j);
-        }
-      }
-      if (full) *reinterpret_cast<uint32_t *>(&sm.ring[(P4 + r0) & RMASK]) = word;
-      else {
+    for (int sft = 1; sft < 32; sft <<= 1) {
+      const uint32_t u = __shfl_up_sync(TBZ_FULL, incl, sft);
+      if (lane >= sft) incl += u;
+    }
+    uint32_t base = 0;
+    if (lane == 31 && incl) base = atomicAdd(&sm.qcnt[0], incl);
+    base = __shfl_sync(TBZ_FULL, base, 31);
+    uint32_t qi = base + incl - npend;
 #pragma unroll
-        for (int j = 0; j < 4; j++)
-          if (r0 + j >= mis && r0 + j < wend) sm.ring[(P4 + r0 + j) & RMASK] = (uint8_t)(word >> (8 * j));
+    for (int j = 0; j < 4; j++)
+      if (pmask & (1u << j)) sm.queue[0][qi++] = (uint16_t)(r0 + j);
+  }
+  // ---- 3. pointer jumping over the pending bytes
+  for (uint32_t lvl = 0;; lvl++) {
+    __syncthreads();
+    const uint32_t qn = sm.qcnt[lvl % 3];
+    if (!qn) break;
+    if (tid == 0) sm.qcnt[(lvl + 2) % 3] = 0;
+    const uint16_t *qin = sm.queue[lvl & 1];
+    uint16_t *qout = sm.queue[(lvl + 1) & 1];
+    for (uint32_t i = tid; i < qn; i += NT) {
+      const uint32_t r = qin[i];
+      const uint32_t s = sm.val[r];
+      const uint32_t vs = *reinterpret_cast<volatile uint16_t *>(&sm.val[s]);
+      if (vs == V_FINAL) {
+        sm.win[r] = *reinterpret_cast<volatile uint8_t *>(&sm.win[s]);
+        __threadfence_block();
+        *reinterpret_cast<volatile uint16_t *>(&sm.val[r]) = (uint16_t)V_FINAL;
+      } else {
+        sm.val[r] = (uint16_t)vs;                      // equal bytes: adopt the source's pointer
+        qout[atomicAdd(&sm.qcnt[(lvl + 1) % 3], 1u)] = (uint16_t)r;
       }
     }
-    __syncthreads();
   }
+  // ---- 4. append the window to the history ring
+  for (uint32_t r0 = 4u * tid; r0 < wend; r0 += 4u * NT) {
+    if (r0 >= mis && r0 + 4u <= wend) *reinterpret_cast<uint32_t *>(&sm.hist[(P4 + r0) & HMASK]) = *reinterpret_cast<const uint32_t *>(&sm.win[r0]);
+    else {
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+        if (r0 + j >= mis && r0 + j < wend) sm.hist[(P4 + r0 + j) & HMASK] = sm.win[r0 + j];
+    }
+  }
+  __syncthreads();
   const uint32_t wsize = wend - mis;
-  // ---- 4. flush complete 16-byte units, fold them into the checksum
+  // ---- 5. flush complete 16-byte units, fold them into the checksum
   if (fmt == TBZ_GZIP) crc_window(sm, pos, wsize, tid);
   if ((((uintptr_t)out) & 15) == 0) {
     const uint32_t upto = (pos + wsize) & ~15u;
     for (uint32_t p = rs.flushed + 16 * tid; p < upto; p += 16 * NT) {
-      const uint4 v = *reinterpret_cast<const uint4 *>(&sm.ring[p & RMASK]);
+      const uint4 v = *reinterpret_cast<const uint4 *>(&sm.hist[p & HMASK]);
       *reinterpret_cast<uint4 *>(out + p) = v;
       if (fmt == TBZ_ZLIB) {
         uint32_t sd = __dp4a(v.x, 0x01010101u, 0u); sd = __dp4a(v.y, 0x01010101u, sd);
@@ -273,7 +294,7 @@ __device__ inline uint32_t resolve_window(const DMember &mem, int fmt, const uin
     rs.flushed = upto;
   } else {
     for (uint32_t p = pos + tid; p < pos + wsize; p += NT) {
-      const uint32_t d = sm.ring[p & RMASK];
+      const uint32_t d = sm.hist[p & HMASK];
       out[p] = (uint8_t)d;
       rs.acc_a += d; rs.acc_w += (unsigned long long)p * d;
     }
@@ -322,7 +343,7 @@ __device__ inline bool resolve_member(const DMember &mem, int fmt, const P1Rec &
   unsigned long long acc_a = rs.acc_a, acc_w = rs.acc_w;
   if (rs.flushed + tid < pos) {            // the last partial 16-byte unit
     const uint32_t p = rs.flushed + tid;
-    const uint32_t d = sm.ring[p & RMASK];
+    const uint32_t d = sm.hist[p & HMASK];
     out[p] = (uint8_t)d;
     acc_a += d; acc_w += (unsigned long long)p * d;
   }

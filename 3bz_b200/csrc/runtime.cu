@@ -63,7 +63,7 @@ k_inflate_decode(const DMember *members, uint32_t n, int fmt, tbzfast::P1Rec *re
 
 // Phase two, persistent CTAs: one CTA per member resolves the token stream into bytes through a
 // shared-memory ring and checks the trailer.
-__global__ void __launch_bounds__(tbzres::NT, 3)
+__global__ void __launch_bounds__(tbzres::NT, 4)
 k_inflate_resolve(const DMember *members, tbz_result *results, uint32_t n, int fmt,
                   const tbzfast::P1Rec *recs, const uint32_t *slabs, uint32_t *counters, uint32_t *todo) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -470,7 +470,7 @@ static int32_t launch_kernels(tbz_batch *b) {
     ctx->launches++;
     CK(ctx, cudaGetLastError());
     CK(ctx, cudaFuncSetAttribute(k_inflate_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tbzres::Smem)));
-    const int res_grid = (int)std::min<uint64_t>(n, (uint64_t)ctx->sm_count * 3);
+    const int res_grid = (int)std::min<uint64_t>(n, (uint64_t)ctx->sm_count * 4);
     k_inflate_resolve<<<res_grid, tbzres::NT, sizeof(tbzres::Smem), ctx->stream>>>(
         (const DMember *)b->d_members, (tbz_result *)b->d_results, n, b->format,
         (const tbzfast::P1Rec *)b->d_recs, (const uint32_t *)b->d_slabs, (uint32_t *)b->d_counters, (uint32_t *)b->d_todo);
