@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO = os.path.join(HERE, "libthreebz_cuda.so")
+SO = os.environ.get("TBZ_LIB") or os.path.join(HERE, "libthreebz_cuda.so")   # TBZ_LIB: tuning builds (tools/)
 
 DEFLATE, ZLIB, GZIP = 0, 1, 2
 FORMATS = {"deflate": DEFLATE, "zlib": ZLIB, "gzip": GZIP, ":deflate": DEFLATE, ":zlib": ZLIB, ":gzip": GZIP}

@@ -26,10 +26,11 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False, extra=()):
-    if not force and not _stale():
+def build(force=False, verbose=False, extra=(), out=None):
+    """out: alternative output path (tuning variants built with -D overrides; see tools/)."""
+    if out is None and not force and not _stale():
         return SO
-    cmd = [NVCC] + FLAGS + list(extra) + ["-o", SO] + sources()
+    cmd = [NVCC] + FLAGS + list(extra) + ["-o", out or SO] + sources()
     if verbose:
         print(" ".join(cmd), file=sys.stderr)
     subprocess.check_call(cmd)

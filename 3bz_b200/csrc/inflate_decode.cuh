@@ -24,14 +24,23 @@
 
 namespace tbzfast {
 
+#ifndef TBZ_DEC_TOKCAP
+#define TBZ_DEC_TOKCAP 768
+#endif
+#ifndef TBZ_DEC_CKSTEP
+#define TBZ_DEC_CKSTEP 32
+#endif
+#ifndef TBZ_DEC_SMAX
+#define TBZ_DEC_SMAX 4000
+#endif
 constexpr int WPC = 4;                  // warps (members in flight) per CTA
 constexpr int NT = WPC * 32;
 constexpr int NL = 32;                  // decode lanes per member
 constexpr int KLL = 10, KD = 9;         // root table bits: lit/len, distance
-constexpr int TOKCAP = 1024;            // tokens a lane may emit per round (sub-chunk + overrun)
-constexpr int CKSTEP = 32;              // a checkpoint every CKSTEP tokens
+constexpr int TOKCAP = TBZ_DEC_TOKCAP;            // tokens a lane may emit per round (sub-chunk + overrun)
+constexpr int CKSTEP = TBZ_DEC_CKSTEP;              // a checkpoint every CKSTEP tokens
 constexpr int NCK = TOKCAP / CKSTEP;
-constexpr uint32_t S_MAX = 8000, S_MIN = 64;   // sub-chunk size in bits (13-bit field in a checkpoint)
+constexpr uint32_t S_MAX = TBZ_DEC_SMAX, S_MIN = 64;   // sub-chunk size in bits (13-bit field in a checkpoint)
 constexpr uint32_t CK_NONE = 0xffffffffu;
 
 // A slab holds the token lists of one round: header, then NL lists of TOKCAP tokens.
@@ -54,24 +63,32 @@ struct P1Rec {
 };
 
 constexpr uint32_t E_LONG = 0x00000300u, E_INVALID = 0x00010300u;   // table specials (code length 0)
-// token: literal = byte value; match = TOK_MATCH | (distance - 1) << 8 | (length - 3).  End of block
-// is not a token.
-constexpr uint32_t TOK_MATCH = 0x80000000u;
+// token: one literal = byte value; two literals = TOK_LIT2 | second << 8 | first;
+// match = TOK_MATCH | (distance - 1) << 8 | (length - 3).  End of block is not a token.
+constexpr uint32_t TOK_MATCH = 0x80000000u, TOK_LIT2 = 0x40000000u;
 
 enum { ST_IDLE = 0, ST_OVER, ST_END, ST_SYNC, ST_EOB, ST_CAP, ST_BAD };
 
 struct Canon16 { uint16_t first[16], count[16], base[16]; uint16_t maxlen, nsyms; };
 
-struct WSmem {                           // one per warp
-  uint32_t lut_ll[1 << KLL];
-  uint32_t lut_d[1 << KD];
-  uint32_t ckpt[NCK][NL];                // [checkpoint][lane]: (bit offset in the sub-chunk) | (output bytes << 13)
+struct HdrScratch {                      // only alive while a block header is parsed
   uint32_t lut_cl[128];
-  Canon16 c_ll, c_d, c_cl;
-  uint16_t sorted_ll[288], sorted_d[32], sorted_cl[32];
+  Canon16 c_cl;
+  uint16_t sorted_cl[32];
   uint8_t lens[352];                     // [0,19) code-length code, [32,352) lit/len + distance
   uint16_t run[16];
 };
+struct WSmem {                           // one per warp
+  uint32_t lut_ll[1 << KLL];
+  uint32_t lut_d[1 << KD];
+  union {
+    uint32_t ckpt[NCK][NL];              // [checkpoint][lane]: (bit offset in the sub-chunk) | (output bytes << 13)
+    HdrScratch h;
+  };
+  Canon16 c_ll, c_d;
+  uint16_t sorted_ll[288], sorted_d[32];
+};
+static_assert(sizeof(HdrScratch) <= sizeof(uint32_t) * NCK * NL, "header scratch must fit under the checkpoints");
 
 struct In {
   const uint32_t *w; uint32_t nwords; uint32_t pos0, end;
@@ -174,9 +191,11 @@ __device__ __forceinline__ void bits_refill(Bits &b, const In &in) {
 }
 __device__ __forceinline__ void bits_skip(Bits &b, uint32_t n) { b.bb >>= n; b.bc -= n; }
 
-// One token, literal and match on one instruction path (the distance lookup is always issued and
-// masked for literals) so that the lanes of a warp do not diverge on the token kind.
-// Returns 0 literal, 1 match, 2 end of block, 3 invalid code.
+// One token.  Two table lookups on one instruction path for every lane: the first decodes a
+// lit/len symbol; the second decodes the distance after a length, or — after a literal — a second
+// literal, which is consumed only if it is one (two literals travel in one token).  The lanes of a
+// warp do not diverge on the token kind.
+// Returns 0 literal(s), 1 match, 2 end of block, 3 invalid code.
 __device__ __forceinline__ int decode_token(Bits &b, const In &in, const WSmem &sm, uint32_t &tok, uint32_t &nbits, uint32_t &olen) {
   nbits = 0;
   bits_refill(b, in);                                        // >= 33 bits
@@ -194,9 +213,9 @@ __device__ __forceinline__ int decode_token(Bits &b, const In &in, const WSmem &
   const uint32_t n1 = L + xb;
   bits_skip(b, n1);
   const bool ism = kind == 1;
-  if (ism && b.bc < 28) bits_refill(b, in);
+  if (ism && b.bc < 28) bits_refill(b, in);                  // a literal leaves >= 18 bits: enough for any code
   const uint32_t w2 = (uint32_t)b.bb;
-  uint32_t d = sm.lut_d[w2 & ((1u << KD) - 1)];
+  uint32_t d = ism ? sm.lut_d[w2 & ((1u << KD) - 1)] : sm.lut_ll[w2 & ((1u << KLL) - 1)];
   if (ism && (d & 15) == 0) {
     if (d != E_LONG) return 3;
     uint32_t r = canon_lookup(sm.c_d, sm.sorted_d, w2, KD + 1, 15);
@@ -204,18 +223,20 @@ __device__ __forceinline__ int decode_token(Bits &b, const In &in, const WSmem &
     d = d_entry(r >> 4, r & 15);
     if ((d & 15) == 0) return 3;
   }
-  if (!ism) d = 0;
-  const uint32_t DL = d & 15, dxb = (d >> 4) & 15;
-  const uint32_t dist = (d >> 16) + ((w2 >> DL) & ((1u << dxb) - 1));
+  // after a literal: keep the second symbol only if it is a literal with a short code
+  const bool two = kind == 0 && (d & 0x30f) != 0 && (d & 0x300) == 0;
+  if (!ism && !two) d = 0;
+  const uint32_t DL = d & 15, dxb = (d >> 4) & 15;          // a literal entry has no extra bits
+  const uint32_t dv = (d >> 16) + ((w2 >> DL) & ((1u << dxb) - 1));   // distance / second literal
   const uint32_t n2 = DL + dxb;
   bits_skip(b, n2);
-  tok = ism ? (TOK_MATCH | ((dist - 1) << 8) | (val - 3)) : val;
+  tok = ism ? (TOK_MATCH | ((dv - 1) << 8) | (val - 3)) : two ? (TOK_LIT2 | (dv << 8) | val) : val;
   nbits = n1 + n2;
-  olen = ism ? val : (kind == 0 ? 1u : 0u);
+  olen = ism ? val : (kind == 0 ? 1u + (two ? 1u : 0u) : 0u);
   return (int)kind;
 }
 
-__device__ __forceinline__ uint32_t tok_outlen(uint32_t t) { return (t & TOK_MATCH) ? (t & 255u) + 3u : 1u; }
+__device__ __forceinline__ uint32_t tok_outlen(uint32_t t) { return (t & TOK_MATCH) ? (t & 255u) + 3u : 1u + ((t >> 30) & 1u); }
 
 // token list writer: four tokens per 16-byte store
 struct TokW {
@@ -269,7 +290,6 @@ __device__ inline bool decode_member(const DMember &mem, int fmt, P1Rec &rec, WS
   while (!last) {
     // ================= block header (deflate.lisp:518-528, :577-669) =================
     if (in.end - pos < 3) return false;
-    const uint32_t block_start = pos;
     const uint32_t hdr = peek32(in, pos) & 7;
     pos += 3;
     last = hdr & 1;
@@ -278,26 +298,26 @@ __device__ inline bool decode_member(const DMember &mem, int fmt, P1Rec &rec, WS
     __syncwarp();
     if (btype == 1) {
       hlit = 288; hdist = 32;
-      for (int i = lane; i < 320; i += 32) sm.lens[32 + i] = i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : i < 288 ? 8 : 5;
+      for (int i = lane; i < 320; i += 32) sm.h.lens[32 + i] = i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : i < 288 ? 8 : 5;
     } else if (btype == 2) {
       if (in.end - pos < 14) return false;
       const uint32_t v = peek32(in, pos);
       hlit = (v & 31) + 257; hdist = ((v >> 5) & 31) + 1;
       const int ncl = ((v >> 10) & 15) + 4;
       if (in.end - pos < 14u + 3u * ncl) return false;
-      if (lane < 19) sm.lens[lane] = 0;
+      if (lane < 19) sm.h.lens[lane] = 0;
       __syncwarp();
-      if (lane < ncl) sm.lens[c_clen_order[lane]] = peek32(in, pos + 14 + 3 * lane) & 7;
+      if (lane < ncl) sm.h.lens[c_clen_order[lane]] = peek32(in, pos + 14 + 3 * lane) & 7;
       __syncwarp();
-      int err = warp_canon(sm.lens, 19, sm.c_cl, sm.sorted_cl, sm.run, lane);
-      if (!err && sm.c_cl.nsyms == 0) err = TBZ_ERR_INVALID_SYMBOL;
+      int err = warp_canon(sm.h.lens, 19, sm.h.c_cl, sm.h.sorted_cl, sm.h.run, lane);
+      if (!err && sm.h.c_cl.nsyms == 0) err = TBZ_ERR_INVALID_SYMBOL;
       if (err) return false;
       // entry: [3:0] code length, [7:4] extra bits, [12:8] symbol; 0 = no code
       for (int e = lane; e < 128; e += 32) {
-        const uint32_t r = canon_lookup(sm.c_cl, sm.sorted_cl, (uint32_t)e, 1, 7);
+        const uint32_t r = canon_lookup(sm.h.c_cl, sm.h.sorted_cl, (uint32_t)e, 1, 7);
         const uint32_t sym = r >> 4;
         const uint32_t xb = sym < 16 ? 0 : sym == 16 ? 2 : sym == 17 ? 3 : 7;
-        sm.lut_cl[e] = r ? ((r & 15) | (xb << 4) | (sym << 8)) : 0;
+        sm.h.lut_cl[e] = r ? ((r & 15) | (xb << 4) | (sym << 8)) : 0;
       }
       __syncwarp();
       uint32_t p = pos + 14 + 3 * ncl;
@@ -310,13 +330,13 @@ __device__ inline bool decode_member(const DMember &mem, int fmt, P1Rec &rec, WS
         while (idx < total) {
           bits_refill(hb, in);
           const uint32_t w = (uint32_t)hb.bb;
-          const uint32_t r = sm.lut_cl[w & 127];
+          const uint32_t r = sm.h.lut_cl[w & 127];
           if (!r) { err = 1; break; }
           const uint32_t L = r & 15, xb = (r >> 4) & 15, sym = r >> 8;
           if (p + L + xb > in.end) { err = 1; break; }
           p += L + xb;
           if (sym < 16) {
-            sm.lens[32 + idx] = (uint8_t)sym; idx++; lastlen = (int)sym;
+            sm.h.lens[32 + idx] = (uint8_t)sym; idx++; lastlen = (int)sym;
             bits_skip(hb, L);
             continue;
           }
@@ -326,7 +346,7 @@ __device__ inline bool decode_member(const DMember &mem, int fmt, P1Rec &rec, WS
           if (sym == 16) { if (lastlen >= 16) { err = 1; break; } rep = 3 + extra; val = lastlen; }
           else { rep = (sym == 17 ? 3 : 11) + extra; val = 0; lastlen = 0; }
           if (idx + rep > total) { err = 1; break; }
-          for (int k = 0; k < rep; k++) sm.lens[32 + idx + k] = (uint8_t)val;
+          for (int k = 0; k < rep; k++) sm.h.lens[32 + idx + k] = (uint8_t)val;
           idx += rep;
         }
       }
@@ -338,8 +358,8 @@ __device__ inline bool decode_member(const DMember &mem, int fmt, P1Rec &rec, WS
     }
     __syncwarp();
     // ================= tables (huffman-tree.lisp:99-218) =================
-    if (warp_canon(sm.lens + 32, hlit, sm.c_ll, sm.sorted_ll, sm.run, lane)) return false;
-    if (warp_canon(sm.lens + 32 + hlit, hdist, sm.c_d, sm.sorted_d, sm.run, lane)) return false;
+    if (warp_canon(sm.h.lens + 32, hlit, sm.c_ll, sm.sorted_ll, sm.h.run, lane)) return false;
+    if (warp_canon(sm.h.lens + 32 + hlit, hdist, sm.c_d, sm.sorted_d, sm.h.run, lane)) return false;
     if (sm.c_ll.nsyms == 0) return false;
     for (int e = lane; e < (1 << KLL); e += 32) {
       uint32_t r = canon_lookup(sm.c_ll, sm.sorted_ll, (uint32_t)e, 1, KLL);
@@ -354,6 +374,7 @@ __device__ inline bool decode_member(const DMember &mem, int fmt, P1Rec &rec, WS
     // ================= rounds over the block's compressed bits =================
     // The end of the block is unknown: assume it is about as long as the previous one (libz cuts
     // blocks by symbol count), else that it runs to the end of the input.
+    const uint32_t data_start = pos;
     uint32_t expect = in.end - pos;
     if (prev_block_bits && prev_block_bits + prev_block_bits / 16 < expect) expect = prev_block_bits + prev_block_bits / 16;
     bool block_done = false;
@@ -367,7 +388,7 @@ __device__ inline bool decode_member(const DMember &mem, int fmt, P1Rec &rec, WS
       // ---- geometry of this round
       const uint32_t P0 = pos;
       uint32_t left = in.end - P0;
-      if (expect > pos - block_start && expect - (pos - block_start) < left) left = expect - (pos - block_start);
+      if (expect > pos - data_start && expect - (pos - data_start) < left) left = expect - (pos - data_start);
       const uint32_t nrounds = (left + NL * S_MAX - 1) / (NL * S_MAX);
       uint32_t S = ((left + nrounds - 1) / nrounds + NL - 1) / NL;
       S >>= shrink;
@@ -488,7 +509,7 @@ __device__ inline bool decode_member(const DMember &mem, int fmt, P1Rec &rec, WS
       if (term_st == ST_EOB) block_done = true;
       __syncwarp();
     }
-    prev_block_bits = pos - block_start;
+    prev_block_bits = pos - data_start;
   }
   if (lane == 0) {
     rec.first_slab = first_slab;

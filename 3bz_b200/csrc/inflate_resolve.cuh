@@ -38,8 +38,11 @@ using tbzfast::TOK_MATCH;
 constexpr int NT = 256;
 constexpr int NWARP = NT / 32;
 constexpr uint32_t HIST = 32768u, HMASK = HIST - 1u;
-constexpr uint32_t WB = 2048;            // window bytes (including the <= 3 bytes of alignment lead-in)
-constexpr int TPT = 2;                   // tokens per thread and window
+#ifndef TBZ_RES_TPT
+#define TBZ_RES_TPT 4
+#endif
+constexpr int TPT = TBZ_RES_TPT;         // tokens per thread and window
+constexpr uint32_t WB = 1024u * TPT;     // window bytes (including the <= 3 bytes of alignment lead-in)
 constexpr uint32_t WT = TPT * NT;        // window tokens
 constexpr uint32_t V_FINAL = 0xffffu;
 
@@ -54,16 +57,18 @@ struct Smem {
   uint16_t wrank[WB / 32];               // token starts in the bitmap words before this one
   uint32_t qcnt[3];
   uint32_t hdr[SLAB_HDR_WORDS];
+  uint32_t segstart[NL + 1];             // flat index of the first token of every list of the current slab
+  uint32_t segptr[NL];                   // word offset of that token in the slab
   uint32_t crc_tab[256];
   uint32_t wscan[NWARP], wscan2[NWARP];
   unsigned long long wsum[NWARP][2];
   uint32_t member;
   int fail;
-  uint32_t carry_len, carry_dist;
+  uint32_t carry_len, carry_tok;
   uint32_t crc;
 };
 
-__device__ __forceinline__ uint32_t tok_len(uint32_t t) { return (t & TOK_MATCH) ? (t & 255u) + 3u : 1u; }
+__device__ __forceinline__ uint32_t tok_len(uint32_t t) { return (t & TOK_MATCH) ? (t & 255u) + 3u : 1u + ((t >> 30) & 1u); }
 
 // CRC-32 of hist[a, a+m): every thread takes one contiguous slice; slices are merged pairwise with
 // x^(8 len) shifts (the per-level shift is the square of the previous one).  All threads must call.
@@ -101,30 +106,45 @@ struct RState {
   uint32_t pos;                           // output bytes produced so far (window base)
   uint32_t flushed;                       // output bytes already stored to global memory
   unsigned long long acc_a, acc_w;        // per thread: Adler sum d, sum i*d over the bytes it flushed
-  uint32_t carry_len, carry_dist;         // tail of a match that straddled the previous window end
+  uint32_t carry_len, carry_tok;          // tail of the token that straddled the previous window end (as a token)
 };
 
-// One window: tokens list[0, n) (n <= WT); consumes as many as fit, returns the number consumed
-// (0xffffffff = the member must go to the sequential kernel).  A pending carry is flushed first.
-// All threads must call; the result is uniform.
-__device__ inline uint32_t resolve_window(const DMember &mem, int fmt, const uint32_t *__restrict__ list, uint32_t n,
+// One window: the slab's tokens [f, f + n) in flat order (n <= WT); consumes as many as fit,
+// returns the number consumed (0xffffffff = the member must go to the sequential kernel).  A
+// pending carry is flushed first.  All threads must call; the result is uniform.
+__device__ inline uint32_t resolve_window(const DMember &mem, int fmt, const uint32_t *__restrict__ slab, uint32_t f, uint32_t n,
                                           RState &rs, Smem &sm, int tid) {
   const int lane = tid & 31, warp = tid >> 5;
   uint8_t *out = mem.out;
   const uint32_t pos = rs.pos;
   const uint32_t mis = pos & 3u, P4 = pos - mis;      // the window's coordinates start at the aligned base
-  const uint32_t carry_len = rs.carry_len, carry_dist = rs.carry_dist;
+  const uint32_t carry_len = rs.carry_len, carry_tok = rs.carry_tok;
   // ---- 1. tokens and their offsets
   const uint32_t tpt = (n + NT - 1) / NT;             // consecutive tokens per thread (<= TPT)
   uint32_t tk[TPT], ln[TPT];
   uint32_t mine = 0;
+  {
+    // the list that holds the thread's first token: last j with segstart[j] <= g
+    const uint32_t g0 = f + tid * tpt;
+    uint32_t j = 0;
+    if (tid * tpt < n) {
 #pragma unroll
-  for (int q = 0; q < TPT; q++) {
-    const uint32_t idx = tid * tpt + q;
-    const bool have = (uint32_t)q < tpt && idx < n;
-    tk[q] = have ? __ldg(list + idx) : 0u;
-    ln[q] = have ? tok_len(tk[q]) : 0u;
-    mine += ln[q];
+      for (int stp = NL / 2; stp; stp >>= 1)
+        if (sm.segstart[j + stp] <= g0) j += stp;
+    }
+#pragma unroll
+    for (int q = 0; q < TPT; q++) {
+      const uint32_t idx = tid * tpt + q;
+      const bool have = (uint32_t)q < tpt && idx < n;
+      tk[q] = 0u;
+      if (have) {
+        const uint32_t g = f + idx;
+        while (g >= sm.segstart[j + 1]) j++;
+        tk[q] = __ldg(slab + sm.segptr[j] + (g - sm.segstart[j]));
+      }
+      ln[q] = have ? tok_len(tk[q]) : 0u;
+      mine += ln[q];
+    }
   }
   uint32_t x = mine;
 #pragma unroll
@@ -155,14 +175,15 @@ __device__ inline uint32_t resolve_window(const DMember &mem, int fmt, const uin
       if (tk[q] & TOK_MATCH) {
         const uint32_t d = ((tk[q] >> 8) & 0x7fffu) + 1u;
         if (d > P4 + st) bad = true;                              // deflate.lisp:343-345
-        if (st + ln[q] > WB) { sm.carry_len = st + ln[q] - WB; sm.carry_dist = d; }   // the straddler
-      }
+        if (st + ln[q] > WB) { sm.carry_len = st + ln[q] - WB; sm.carry_tok = tk[q] & 0xffffff00u; }   // the straddler
+      } else if (st + ln[q] > WB) { sm.carry_len = 1; sm.carry_tok = (tk[q] >> 8) & 255u; }          // second of two literals
+
     }
     st += ln[q];
   }
   if (bad) sm.fail = 1;
   if (tid == 0) {
-    sm.toks[0] = TOK_MATCH | ((carry_dist - 1) << 8);
+    sm.toks[0] = carry_tok;
     sm.tstart[0] = (uint16_t)mis;
     if (carry_len) atomicOr(&sm.bitmap[0], 1u << mis);
   }
@@ -210,14 +231,15 @@ __device__ inline uint32_t resolve_window(const DMember &mem, int fmt, const uin
       uint32_t byte = 0, v = V_FINAL;
       if (r >= mis && r < wend) {
         const uint32_t t = sm.toks[ti];
+        const uint32_t o = r - sm.tstart[ti];
         if (t & TOK_MATCH) {
-          const uint32_t d = ((t >> 8) & 0x7fffu) + 1u, o = r - sm.tstart[ti];
+          const uint32_t d = ((t >> 8) & 0x7fffu) + 1u;
           uint32_t back = d;
           if (o >= d) back = o - o % d + d;                       // overlapping match: read through the period
           if (back + mis > r) byte = sm.hist[(P4 + r - back) & HMASK];   // the source is below the window: final
           else { v = r - back; npend++; pmask |= 1u << j; }
         } else {
-          byte = t & 255u;
+          byte = (t >> (8u * o)) & 255u;                          // one or two literals in a token
         }
       }
       word |= byte << (8 * j);
@@ -300,9 +322,9 @@ __device__ inline uint32_t resolve_window(const DMember &mem, int fmt, const uin
     }
     rs.flushed = pos + wsize;
   }
-  if (rs.acc_w >> 62) rs.acc_w %= TBZ_ADLER_MOD;
+  if (__builtin_expect((rs.acc_w >> 62) != 0, 0)) rs.acc_w %= TBZ_ADLER_MOD;
   rs.pos = pos + wsize;
-  rs.carry_len = sm.carry_len; rs.carry_dist = sm.carry_dist;
+  rs.carry_len = sm.carry_len; rs.carry_tok = sm.carry_tok;
   __syncthreads();
   return nused;
 }
@@ -312,7 +334,7 @@ __device__ inline bool resolve_member(const DMember &mem, int fmt, const P1Rec &
   const int lane = tid & 31, warp = tid >> 5;
   uint8_t *out = mem.out;
   RState rs;
-  rs.pos = 0; rs.flushed = 0; rs.acc_a = 0; rs.acc_w = 0; rs.carry_len = 0; rs.carry_dist = 1;
+  rs.pos = 0; rs.flushed = 0; rs.acc_a = 0; rs.acc_w = 0; rs.carry_len = 0; rs.carry_tok = 0;
   if (tid == 0) { sm.fail = 0; sm.crc = 0; }
   __syncthreads();
   for (uint32_t s = rec.first_slab; s != NO_SLAB;) {
@@ -320,23 +342,32 @@ __device__ inline bool resolve_member(const DMember &mem, int fmt, const P1Rec &
     if (tid < (int)SLAB_HDR_WORDS) sm.hdr[tid] = slab[tid];
     __syncthreads();
     s = sm.hdr[0];
-    for (int j = 0; j < NL; j++) {
-      const uint32_t fc = sm.hdr[4 + j];
+    if (tid < 32) {                        // flat token order of the slab: exclusive scan of the list sizes
+      const uint32_t fc = sm.hdr[4 + tid];
       const uint32_t cnt = fc >> 16;
-      if (!cnt) continue;
-      const uint32_t *list = slab + SLAB_HDR_WORDS + j * TOKCAP + (fc & 0xffffu);
-      uint32_t f = 0;
-      while (f < cnt) {
-        const uint32_t n = cnt - f < WT ? cnt - f : WT;
-        const uint32_t used = resolve_window(mem, fmt, list + f, n, rs, sm, tid);
-        if (used == 0xffffffffu || used == 0) return false;
-        f += used;
+      uint32_t y = cnt;
+#pragma unroll
+      for (int sft = 1; sft < 32; sft <<= 1) {
+        const uint32_t u = __shfl_up_sync(TBZ_FULL, y, sft);
+        if (tid >= sft) y += u;
       }
+      sm.segstart[tid] = y - cnt;
+      sm.segptr[tid] = SLAB_HDR_WORDS + tid * TOKCAP + (fc & 0xffffu);
+      if (tid == 31) sm.segstart[32] = y;
+    }
+    __syncthreads();
+    const uint32_t total = sm.segstart[32];
+    uint32_t f = 0;
+    while (f < total) {
+      const uint32_t n = total - f < WT ? total - f : WT;
+      const uint32_t used = resolve_window(mem, fmt, slab, f, n, rs, sm, tid);
+      if (used == 0xffffffffu || used == 0) return false;
+      f += used;
     }
     __syncthreads();
   }
   while (rs.carry_len) {                   // tail of a match that straddled the last window
-    if (resolve_window(mem, fmt, nullptr, 0, rs, sm, tid) == 0xffffffffu) return false;
+    if (resolve_window(mem, fmt, nullptr, 0, 0, rs, sm, tid) == 0xffffffffu) return false;
   }
   const uint32_t pos = rs.pos;
   if (pos != rec.out_len || sm.fail) return false;

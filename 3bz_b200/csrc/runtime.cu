@@ -63,7 +63,7 @@ k_inflate_decode(const DMember *members, uint32_t n, int fmt, tbzfast::P1Rec *re
 
 // Phase two, persistent CTAs: one CTA per member resolves the token stream into bytes through a
 // shared-memory ring and checks the trailer.
-__global__ void __launch_bounds__(tbzres::NT, 4)
+__global__ void __launch_bounds__(tbzres::NT, TBZ_RES_TPT > 2 ? 3 : 4)
 k_inflate_resolve(const DMember *members, tbz_result *results, uint32_t n, int fmt,
                   const tbzfast::P1Rec *recs, const uint32_t *slabs, uint32_t *counters, uint32_t *todo) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -93,6 +93,8 @@ struct tbz_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, tev0 = nullptr, tev1 = nullptr;
+  cudaEvent_t kev[4] = {nullptr, nullptr, nullptr, nullptr};   // TBZ_KTIME=1: events between the kernels of a launch
+  bool ktime = false;
   std::vector<DevBlock> pool;
   void *stage_in = nullptr;  size_t stage_in_cap = 0;    // pinned staging
   void *stage_out = nullptr; size_t stage_out_cap = 0;
@@ -167,7 +169,7 @@ struct tbz_batch {
   const uint8_t *in_span = nullptr; uint8_t *out_span = nullptr;
   void *d_in = nullptr, *d_out = nullptr, *d_members = nullptr, *d_results = nullptr;
   void *d_slabs = nullptr, *d_counters = nullptr, *d_todo = nullptr, *d_recs = nullptr;
-  int fast_grid = 0;
+  int fast_grid = 0, res_grid = 0;
   uint32_t nslabs = 0;
   bool launched = false;
 };
@@ -201,6 +203,8 @@ extern "C" int32_t tbz_ctx_create(int32_t device, uint64_t flags, tbz_ctx **out)
   CK(ctx, cudaEventCreate(&ctx->ev0)); CK(ctx, cudaEventCreate(&ctx->ev1));
   CK(ctx, cudaEventCreate(&ctx->tev0)); CK(ctx, cudaEventCreate(&ctx->tev1));
   CK(ctx, cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
+  if (const char *kt = getenv("TBZ_KTIME")) ctx->ktime = kt[0] == '1';
+  if (ctx->ktime) for (auto &e : ctx->kev) CK(ctx, cudaEventCreate(&e));
   *out = ctx;
   return TBZ_OK;
 }
@@ -388,11 +392,20 @@ extern "C" int32_t tbz_batch_prepare(tbz_ctx *ctx, int32_t format, const tbz_mem
   PCK(dev_alloc(ctx, std::max<uint64_t>(1, n) * sizeof(DMember), &b->d_members));
   PCK(dev_alloc(ctx, std::max<uint64_t>(1, n) * sizeof(tbz_result), &b->d_results));
   if (!(flags & TBZ_FLAG_NO_FASTPATH) && n) {
-    b->fast_grid = (int)std::min<uint64_t>((n + tbzfast::WPC - 1) / tbzfast::WPC, (uint64_t)ctx->sm_count * 4);
+    int occ = 0;
+    cudaFuncSetAttribute(k_inflate_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(tbzfast::WSmem) * tbzfast::WPC));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_inflate_decode, tbzfast::NT, sizeof(tbzfast::WSmem) * tbzfast::WPC);
+    b->fast_grid = (int)std::min<uint64_t>((n + tbzfast::WPC - 1) / tbzfast::WPC, (uint64_t)ctx->sm_count * std::max(1, occ));
+    cudaFuncSetAttribute(k_inflate_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tbzres::Smem));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_inflate_resolve, tbzres::NT, sizeof(tbzres::Smem));
+    b->res_grid = (int)std::min<uint64_t>(n, (uint64_t)ctx->sm_count * std::max(1, occ));
     // token slabs: one per round; a round covers at most ~31 KiB of compressed input and never
     // crosses a block boundary.  Members that find the pool empty go to the sequential kernel.
     uint64_t want = 0;
-    for (uint64_t i = 0; i < n; i++) want += m[i].in_len / 12288 + 2;
+    // a round covers up to NL * S_MAX bits; blocks end rounds early and a lane that fills its token
+    // list shortens them, hence the factor 2 and the slack
+    const uint64_t round_bytes = (uint64_t)tbzfast::NL * tbzfast::S_MAX / 8;
+    for (uint64_t i = 0; i < n; i++) want += 2 * (m[i].in_len / round_bytes) + 4;
     const uint64_t slab_bytes = (uint64_t)tbzfast::SLAB_WORDS * 4;
     const uint64_t cap = std::max<uint64_t>(64, kSlabPoolBytes / slab_bytes);
     b->nslabs = (uint32_t)std::min<uint64_t>(want, cap);
@@ -464,23 +477,36 @@ static int32_t launch_kernels(tbz_batch *b) {
     const size_t dec_smem = sizeof(tbzfast::WSmem) * tbzfast::WPC;
     CK(ctx, cudaFuncSetAttribute(k_inflate_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dec_smem));
     CK(ctx, cudaMemsetAsync(b->d_counters, 0, 256, ctx->stream));
+    if (ctx->ktime) CK(ctx, cudaEventRecord(ctx->kev[0], ctx->stream));
     k_inflate_decode<<<b->fast_grid, tbzfast::NT, dec_smem, ctx->stream>>>(
         (const DMember *)b->d_members, n, b->format, (tbzfast::P1Rec *)b->d_recs,
         (uint32_t *)b->d_slabs, b->nslabs, (uint32_t *)b->d_counters, (uint32_t *)b->d_todo);
     ctx->launches++;
     CK(ctx, cudaGetLastError());
+    if (ctx->ktime) CK(ctx, cudaEventRecord(ctx->kev[1], ctx->stream));
     CK(ctx, cudaFuncSetAttribute(k_inflate_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tbzres::Smem)));
-    const int res_grid = (int)std::min<uint64_t>(n, (uint64_t)ctx->sm_count * 4);
-    k_inflate_resolve<<<res_grid, tbzres::NT, sizeof(tbzres::Smem), ctx->stream>>>(
+    k_inflate_resolve<<<b->res_grid, tbzres::NT, sizeof(tbzres::Smem), ctx->stream>>>(
         (const DMember *)b->d_members, (tbz_result *)b->d_results, n, b->format,
         (const tbzfast::P1Rec *)b->d_recs, (const uint32_t *)b->d_slabs, (uint32_t *)b->d_counters, (uint32_t *)b->d_todo);
     ctx->launches++;
     CK(ctx, cudaGetLastError());
+    if (ctx->ktime) CK(ctx, cudaEventRecord(ctx->kev[2], ctx->stream));
     k_inflate_seq<<<(n + SEQ_WARPS - 1) / SEQ_WARPS, SEQ_WARPS * 32, 0, ctx->stream>>>(
         (const DMember *)b->d_members, (tbz_result *)b->d_results, n, b->format,
         (const uint32_t *)b->d_todo, (const uint32_t *)b->d_counters + 1);
     ctx->launches++;
     CK(ctx, cudaGetLastError());
+    if (ctx->ktime) {
+      CK(ctx, cudaEventRecord(ctx->kev[3], ctx->stream));
+      CK(ctx, cudaEventSynchronize(ctx->kev[3]));
+      float a = 0, c = 0, d = 0;
+      cudaEventElapsedTime(&a, ctx->kev[0], ctx->kev[1]);
+      cudaEventElapsedTime(&c, ctx->kev[1], ctx->kev[2]);
+      cudaEventElapsedTime(&d, ctx->kev[2], ctx->kev[3]);
+      uint32_t cnt[4] = {0, 0, 0, 0};
+      cudaMemcpy(cnt, b->d_counters, sizeof cnt, cudaMemcpyDeviceToHost);
+      fprintf(stderr, "[tbz] decode %.3f ms, resolve %.3f ms, seq %.3f ms (%u members), %u slabs\n", a, c, d, cnt[1], cnt[2]);
+    }
     return TBZ_OK;
   }
   k_inflate_seq<<<(n + SEQ_WARPS - 1) / SEQ_WARPS, SEQ_WARPS * 32, 0, ctx->stream>>>(
