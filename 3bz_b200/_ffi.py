@@ -27,7 +27,7 @@ SYMBOLS = [
     "tbz_batch_prepare", "tbz_batch_launch", "tbz_batch_finish", "tbz_batch_destroy",
     "tbz_inflate_batch_multi", "tbz_partition",
     "tbz_session_create", "tbz_session_destroy", "tbz_session_set_output",
-    "tbz_session_replace_output", "tbz_session_decompress", "tbz_session_flags",
+    "tbz_session_rebind_output", "tbz_session_replace_output", "tbz_session_decompress", "tbz_session_flags",
 ]
 
 
@@ -94,6 +94,7 @@ def lib():
         "tbz_session_create": (i32, [vp, i32, P(vp)]),
         "tbz_session_destroy": (i32, [vp]),
         "tbz_session_set_output": (i32, [vp, vp, u64]),
+        "tbz_session_rebind_output": (i32, [vp, vp]),
         "tbz_session_replace_output": (i32, [vp, vp, u64]),
         "tbz_session_decompress": (i32, [vp, vp, u64, P(C.c_int64), P(i32)]),
         "tbz_session_flags": (i32, [vp, P(i32), P(i32), P(i32)]),

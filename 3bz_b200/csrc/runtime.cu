@@ -745,6 +745,11 @@ extern "C" int32_t tbz_session_set_output(tbz_session *s, uint8_t *out, uint64_t
   s->out = out; s->cap = cap; s->off = 0;
   return TBZ_OK;
 }
+extern "C" int32_t tbz_session_rebind_output(tbz_session *s, uint8_t *out) {
+  if (!s || (s->cap && !out)) return TBZ_E_ARG;
+  s->out = out;
+  return TBZ_OK;
+}
 extern "C" int32_t tbz_session_replace_output(tbz_session *s, uint8_t *out, uint64_t cap) {
   if (!s || (cap && !out)) return TBZ_E_ARG;
   if (!(s->off == 0 || s->overflow)) return TBZ_E_BUFFER_SWITCH;     // api.lisp:13-18

@@ -154,6 +154,9 @@ int32_t tbz_session_create(tbz_ctx *ctx, int32_t format, tbz_session **s);
 int32_t tbz_session_destroy(tbz_session *s);
 /* (make-*-state :output-buffer out)  or  (setf ds-output-buffer) + (setf ds-output-offset 0) */
 int32_t tbz_session_set_output(tbz_session *s, uint8_t *out, uint64_t cap);
+/* same buffer, new address: a managed host (SBCL) pins its vectors only for the duration of one
+ * foreign call, so the shim passes the current address before every decompress */
+int32_t tbz_session_rebind_output(tbz_session *s, uint8_t *out);
 /* replace-output-buffer: TBZ_E_BUFFER_SWITCH unless the old buffer is untouched or overflowed */
 int32_t tbz_session_replace_output(tbz_session *s, uint8_t *out, uint64_t cap);
 /* decompress: hands the session the unread octets [in, in+n) of the caller's context (the shim

@@ -1,0 +1,127 @@
+;;; api.lisp — decompress-vector, decompress, replace-output-buffer and the status readers with the
+;;; signatures of the reference (api.lisp:3-72), plus DECOMPRESS-BATCH.
+(in-package #:3bz)
+
+;;; states: (make-deflate-state :output-buffer b) etc. keep their keyword constructor
+;;; (deflate.lisp:4, zlib.lisp:3, gzip.lisp:3).  A state owns one tbz_session: the device keeps the
+;;; decoded member, DECOMPRESS hands out slices of it.
+(defclass deflate-state ()
+  ((session :accessor %session :initform nil)
+   (format :reader %format :initform :deflate :allocation :class)
+   (output-buffer :accessor ds-output-buffer :initarg :output-buffer :initform nil)
+   (output-offset :accessor ds-output-offset :initform 0)
+   (bound :accessor %bound :initform nil)))
+(defclass zlib-state (deflate-state) ((format :initform :zlib :allocation :class)))
+(defclass gzip-state (deflate-state) ((format :initform :gzip :allocation :class)))
+
+(defun %make-state (class output-buffer)
+  (let ((s (make-instance class :output-buffer output-buffer)))
+    (cffi:with-foreign-object (p :pointer)
+      (check (tbz-session-create (ctx) (format-code (%format s)) p))
+      (setf (%session s) (cffi:mem-ref p :pointer)))
+    #+sbcl (let ((h (%session s))) (sb-ext:finalize s (lambda () (tbz-session-destroy h))))
+    s))
+(defun make-deflate-state (&key output-buffer) (%make-state 'deflate-state output-buffer))
+(defun make-zlib-state (&key output-buffer) (%make-state 'zlib-state output-buffer))
+(defun make-gzip-state (&key output-buffer) (%make-state 'gzip-state output-buffer))
+
+(defun %flags (state)
+  (cffi:with-foreign-objects ((f :int32) (u :int32) (o :int32))
+    (check (tbz-session-flags (%session state) f u o))
+    (values (plusp (cffi:mem-ref f :int32)) (plusp (cffi:mem-ref u :int32)) (plusp (cffi:mem-ref o :int32)))))
+(defun finished (state) (nth-value 0 (%flags state)))
+(defun input-underrun (state) (nth-value 1 (%flags state)))
+(defun output-overflow (state) (nth-value 2 (%flags state)))
+
+(defun decompress (context state)
+  "api.lisp:3-10.  Returns the current offset into the output buffer; sets exactly the three flags."
+  (let ((out (or (ds-output-buffer state) (setf (ds-output-buffer state) (make-array 0 :element-type 'octet)))))
+    (cffi:with-pointer-to-vector-data (po out)
+      ;; SBCL pins OUT only for this call: (re)bind its current address every time
+      (if (and (zerop (ds-output-offset state)) (not (%bound state)))
+          (progn (check (tbz-session-set-output (%session state) po (length out)))
+                 (setf (%bound state) t))
+          (check (tbz-session-rebind-output (%session state) po)))
+      (call-with-unread-octets
+       context
+       (lambda (pin n)
+         (cffi:with-foreign-objects ((ret :int64) (verdict :int32))
+           (let ((rc (tbz-session-decompress (%session state) pin n ret verdict)))
+             ;; the session now owns every unread octet: the context is consumed to its end
+             (setf (cb-offset (boxes context)) (cb-end (boxes context)))
+             (when (= rc +tbz-e-state+) (error "decompress called on a finished or failed state"))
+             (check rc)
+             (let ((v (cffi:mem-ref verdict :int32)))
+               (when (>= v 16) (error "~a" (tbz-verdict-name v))))    ; where the reference signals
+             (setf (ds-output-offset state) (cffi:mem-ref ret :int64)))))))))
+
+(defun replace-output-buffer (state buffer)
+  "api.lisp:12-21."
+  (cffi:with-pointer-to-vector-data (p buffer)
+    (let ((rc (tbz-session-replace-output (%session state) p (length buffer))))
+      (when (= rc +tbz-e-buffer-switch+)
+        (error "can't switch buffers without filling old one yet."))
+      (check rc)))
+  (setf (ds-output-buffer state) buffer
+        (ds-output-offset state) 0
+        (%bound state) t))
+
+(defun %verdict-error (verdict format)
+  (cond ((= verdict +tbz-input-underrun+) (error "incomplete ~a stream" format))
+        ((= verdict +tbz-output-overflow+) (error "not enough space to decompress ~a stream" format))
+        (t (error "~a" (tbz-verdict-name verdict)))))
+
+(defun decompress-vector (compressed &key (format :zlib) (start 0) (end (length compressed)) output)
+  "api.lisp:23-65: returns (values buffer count)."
+  (cffi:with-foreign-object (r '(:struct tbz-result))
+    (cffi:with-pointer-to-vector-data (pin compressed)
+      (if output
+          (cffi:with-pointer-to-vector-data (pout output)
+            (check (tbz-inflate-single (ctx) (format-code format) (cffi:inc-pointer pin start) (- end start)
+                                       pout (length output) r 0 (cffi:null-pointer)))
+            (let ((v (cffi:foreign-slot-value r '(:struct tbz-result) 'verdict)))
+              (unless (= v +tbz-finished+) (%verdict-error v format)))
+            (values output (cffi:foreign-slot-value r '(:struct tbz-result) 'out-len)))
+          ;; no :output — the reference grows 32 KiB buffers by doubling and concatenates
+          ;; (api.lisp:50-65); the engine sizes the result on the device and returns it whole
+          (cffi:with-foreign-object (pp :pointer)
+            (check (tbz-inflate-alloc (ctx) (format-code format) (cffi:inc-pointer pin start) (- end start) pp r))
+            (let* ((p (cffi:mem-ref pp :pointer))
+                   (v (cffi:foreign-slot-value r '(:struct tbz-result) 'verdict))
+                   (n (cffi:foreign-slot-value r '(:struct tbz-result) 'out-len)))
+              (unwind-protect
+                   (progn
+                     (unless (= v +tbz-finished+) (%verdict-error v format))
+                     (let ((b (make-array n :element-type 'octet)))
+                       (cffi:with-pointer-to-vector-data (pb b)
+                         (cffi:foreign-funcall "memcpy" :pointer pb :pointer p :size n :pointer))
+                       (values b n)))
+                (tbz-free p))))))))
+
+(defun decompress-batch (members &key (format :zlib) capacities)
+  "NEW: many independent members in one engine call.  MEMBERS: sequence of octet-vectors;
+CAPACITIES: per-member output size (one integer or a sequence).  Returns a list of
+\(buffer count verdict) — verdict :finished / :input-underrun / :output-overflow or the engine's
+name for the place where the reference would have signalled.  A bad member never poisons the batch."
+  (let* ((n (length members))
+         (caps (if (integerp capacities) (make-list n :initial-element capacities) (coerce capacities 'list)))
+         (outs (mapcar (lambda (c) (make-array c :element-type 'octet)) caps)))
+    (cffi:with-foreign-objects ((m '(:struct tbz-member) (max 1 n)) (r '(:struct tbz-result) (max 1 n)))
+      (labels ((pin (i ins os)
+                 (if ins
+                     (cffi:with-pointer-to-vector-data (pi (car ins))
+                       (cffi:with-pointer-to-vector-data (po (car os))
+                         (let ((e (cffi:mem-aptr m '(:struct tbz-member) i)))
+                           (setf (cffi:foreign-slot-value e '(:struct tbz-member) 'in) pi
+                                 (cffi:foreign-slot-value e '(:struct tbz-member) 'in-len) (length (car ins))
+                                 (cffi:foreign-slot-value e '(:struct tbz-member) 'out) po
+                                 (cffi:foreign-slot-value e '(:struct tbz-member) 'out-cap) (length (car os))))
+                         (pin (1+ i) (cdr ins) (cdr os))))
+                     (check (tbz-inflate-batch (ctx) (format-code format) m n r 0 (cffi:null-pointer))))))
+        (pin 0 (coerce members 'list) outs))
+      (loop for i below n for o in outs
+            for e = (cffi:mem-aptr r '(:struct tbz-result) i)
+            for v = (cffi:foreign-slot-value e '(:struct tbz-result) 'verdict)
+            collect (list o (cffi:foreign-slot-value e '(:struct tbz-result) 'out-len)
+                          (case v (0 :finished) (1 :input-underrun) (2 :output-overflow)
+                            (t (tbz-verdict-name v))))))))
