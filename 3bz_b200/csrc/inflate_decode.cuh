@@ -254,34 +254,13 @@ struct TokW {
 };
 
 // ------------------------------------------------------------------------------------------------
-// One member, one warp.  Returns true when its token stream is complete, false when the member
-// must be redone by the sequential kernel.  Every return value is warp-uniform.
+// Blocks from bit `pos` (a block start) on, one warp.  Stops after the final block, or — for a
+// chunk of a split member — after the first block that ends at or beyond `stop_bit`.  Returns
+// true when the token stream is complete (rec filled in), false when the caller must fall back.
+// Every return value is warp-uniform.
 // ------------------------------------------------------------------------------------------------
-__device__ inline bool decode_member(const DMember &mem, int fmt, P1Rec &rec, WSmem &sm,
-                                     uint32_t *__restrict__ slabs, uint32_t nslabs, uint32_t *slab_counter, int lane) {
-  In in;
-  {
-    uintptr_t a = (uintptr_t)mem.in;
-    uint32_t mis = (uint32_t)(a & 3);
-    in.w = (const uint32_t *)(a - mis);
-    in.pos0 = mis * 8;
-    if (mem.in_len >= (1ull << 28)) return false;
-    in.end = (mis + (uint32_t)mem.in_len) * 8;
-    in.nwords = (in.end + 31) >> 5;
-  }
-  uint32_t pos = in.pos0;
-  // ---- wrapper header (zlib.lisp:108-126, gzip.lisp:113-177; optional gzip fields -> sequential kernel)
-  if (fmt == TBZ_ZLIB) {
-    if (in.end - pos < 16) return false;
-    uint32_t cmf = byte_at(in, pos >> 3), flg = byte_at(in, (pos >> 3) + 1);
-    if ((cmf * 256 + flg) % 31 || (cmf & 15) != 8 || (cmf >> 4) > 7 || (flg & 32)) return false;
-    pos += 16;
-  } else if (fmt == TBZ_GZIP) {
-    if (in.end - pos < 80) return false;
-    uint32_t bp = pos >> 3;
-    if (byte_at(in, bp) != 0x1f || byte_at(in, bp + 1) != 0x8b || byte_at(in, bp + 2) != 8 || byte_at(in, bp + 3) != 0) return false;
-    pos += 80;
-  }
+__device__ inline bool decode_blocks(const In &in, uint32_t pos, uint32_t stop_bit, unsigned long long out_cap, P1Rec &rec,
+                                     WSmem &sm, uint32_t *__restrict__ slabs, uint32_t nslabs, uint32_t *slab_counter, int lane) {
   unsigned long long A = 0;    // output bytes so far
   uint32_t first_slab = NO_SLAB, prev_slab = NO_SLAB;
   uint32_t prev_block_bits = 0;   // size of the previous block of this member: predicts this one
@@ -495,7 +474,7 @@ __device__ inline bool decode_member(const DMember &mem, int fmt, P1Rec &rec, WS
 #pragma unroll
       for (int sft = 16; sft; sft >>= 1) total += __shfl_xor_sync(TBZ_FULL, total, sft);
       A += total;
-      if (A > mem.out_cap || A >= (1ull << 32)) return false;       // overflow: sequential kernel
+      if (A > out_cap || A >= (1ull << 32)) return false;            // overflow: sequential kernel
       sh->fc[lane] = cnt ? (my_g | (cnt << 16)) : 0u;
       if (lane == 0) {
         sh->next = NO_SLAB; sh->out_bytes = total;
@@ -510,14 +489,138 @@ __device__ inline bool decode_member(const DMember &mem, int fmt, P1Rec &rec, WS
       __syncwarp();
     }
     prev_block_bits = pos - data_start;
+    if (pos >= stop_bit) break;
   }
   if (lane == 0) {
     rec.first_slab = first_slab;
     rec.out_len = (uint32_t)A;
     rec.end_pos = pos;
-    rec.status = 1;
+    rec.status = last ? 1u : 2u;           // 2: stopped at a block boundary before the final block
   }
   return true;
+}
+
+// One member, one warp: wrapper header, then every block.
+__device__ inline bool decode_member(const DMember &mem, int fmt, P1Rec &rec, WSmem &sm,
+                                     uint32_t *__restrict__ slabs, uint32_t nslabs, uint32_t *slab_counter, int lane) {
+  In in;
+  {
+    uintptr_t a = (uintptr_t)mem.in;
+    uint32_t mis = (uint32_t)(a & 3);
+    in.w = (const uint32_t *)(a - mis);
+    in.pos0 = mis * 8;
+    if (mem.in_len >= (1ull << 28)) return false;
+    in.end = (mis + (uint32_t)mem.in_len) * 8;
+    in.nwords = (in.end + 31) >> 5;
+  }
+  uint32_t pos = in.pos0;
+  // ---- wrapper header (zlib.lisp:108-126, gzip.lisp:113-177; optional gzip fields -> sequential kernel)
+  if (fmt == TBZ_ZLIB) {
+    if (in.end - pos < 16) return false;
+    uint32_t cmf = byte_at(in, pos >> 3), flg = byte_at(in, (pos >> 3) + 1);
+    if ((cmf * 256 + flg) % 31 || (cmf & 15) != 8 || (cmf >> 4) > 7 || (flg & 32)) return false;
+    pos += 16;
+  } else if (fmt == TBZ_GZIP) {
+    if (in.end - pos < 80) return false;
+    uint32_t bp = pos >> 3;
+    if (byte_at(in, bp) != 0x1f || byte_at(in, bp + 1) != 0x8b || byte_at(in, bp + 2) != 8 || byte_at(in, bp + 3) != 0) return false;
+    pos += 80;
+  }
+  return decode_blocks(in, pos, 0xffffffffu, mem.out_cap, rec, sm, slabs, nslabs, slab_counter, lane);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Split decode of one large member (pugz-style): where does the first dynamic block at or after
+// bit `from` start?  32 candidate bit positions per step, one per lane: block type, HLIT / HDIST
+// range and completeness of the code-length code are tested by every lane for its own candidate;
+// the few survivors are validated by the whole warp (code lengths decode without error, lit/len
+// and distance codes complete, end-of-block coded).  Returns the bit position or 0xffffffff.  A
+// false positive is caught later: the previous chunk's decoder must land exactly on this bit.
+// ------------------------------------------------------------------------------------------------
+__device__ inline uint32_t find_block_start(const In &in, uint32_t from, uint32_t to, WSmem &sm, int lane) {
+  for (uint32_t base = from; base < to; base += 32) {
+    const uint32_t p = base + lane;
+    bool cand = p < to && p + 17 + 12 <= in.end;
+    uint32_t h = 0;
+    if (cand) {
+      h = peek32(in, p);
+      cand = ((h >> 1) & 3) == 2 && ((h >> 3) & 31) <= 29 && ((h >> 8) & 31) <= 29;
+    }
+    if (cand) {                                        // Kraft sum of the code-length code
+      const uint32_t ncl = ((h >> 13) & 15) + 4;
+      uint32_t sum = 0, q = p + 17;
+      for (uint32_t i = 0; i < ncl; i += 10) {
+        const uint32_t w = peek32(in, q + 3 * i);
+        for (uint32_t k = 0; k < 10 && i + k < ncl; k++) {
+          const uint32_t l = (w >> (3 * k)) & 7;
+          if (l) sum += 128u >> l;
+        }
+      }
+      cand = sum == 128u && p + 17 + 3 * ncl <= in.end;
+    }
+    uint32_t m = __ballot_sync(TBZ_FULL, cand);
+    while (m) {                                        // full validation, one survivor at a time
+      const int src = __ffs(m) - 1;
+      m &= m - 1;
+      const uint32_t q = base + src;
+      const uint32_t v = peek32(in, q + 3);
+      const int hlit = (v & 31) + 257, hdist = ((v >> 5) & 31) + 1, ncl = ((v >> 10) & 15) + 4;
+      __syncwarp();
+      if (lane < 19) sm.h.lens[lane] = 0;
+      __syncwarp();
+      if (lane < ncl) sm.h.lens[c_clen_order[lane]] = peek32(in, q + 17 + 3 * lane) & 7;
+      __syncwarp();
+      if (warp_canon(sm.h.lens, 19, sm.h.c_cl, sm.h.sorted_cl, sm.h.run, lane)) continue;
+      for (int e = lane; e < 128; e += 32) {
+        const uint32_t r = canon_lookup(sm.h.c_cl, sm.h.sorted_cl, (uint32_t)e, 1, 7);
+        const uint32_t sym = r >> 4;
+        const uint32_t xb = sym < 16 ? 0 : sym == 16 ? 2 : sym == 17 ? 3 : 7;
+        sm.h.lut_cl[e] = r ? ((r & 15) | (xb << 4) | (sym << 8)) : 0;
+      }
+      __syncwarp();
+      int err = 0;
+      if (lane == 0) {
+        uint32_t pp = q + 17 + 3 * ncl;
+        int idx = 0, lastlen = 0xff;
+        const int total = hlit + hdist;
+        while (idx < total) {
+          const uint32_t w = peek32(in, pp);
+          const uint32_t r = sm.h.lut_cl[w & 127];
+          if (!r) { err = 1; break; }
+          const uint32_t L = r & 15, xb = (r >> 4) & 15, sym = r >> 8;
+          if (pp + L + xb > in.end) { err = 1; break; }
+          pp += L + xb;
+          const uint32_t extra = (w >> L) & ((1u << xb) - 1);
+          int rep, val;
+          if (sym < 16) { rep = 1; val = (int)sym; lastlen = (int)sym; }
+          else if (sym == 16) { if (lastlen >= 16) { err = 1; break; } rep = 3 + extra; val = lastlen; }
+          else { rep = (sym == 17 ? 3 : 11) + extra; val = 0; lastlen = 0; }
+          if (idx + rep > total) { err = 1; break; }
+          for (int k = 0; k < rep; k++) sm.h.lens[32 + idx + k] = (uint8_t)val;
+          idx += rep;
+        }
+        if (!err && sm.h.lens[32 + 256] == 0) err = 1;      // a block must be able to end
+      }
+      err = __shfl_sync(TBZ_FULL, err, 0);
+      if (err) continue;
+      __syncwarp();
+      // both codes complete (a lone distance code is what libz writes for literal-only blocks)
+      if (warp_canon(sm.h.lens + 32, hlit, sm.c_ll, sm.sorted_ll, sm.h.run, lane)) continue;
+      {
+        uint32_t k = 0;
+        for (int L = 1; L <= 15; L++) k += (uint32_t)sm.c_ll.count[L] << (15 - L);
+        if (k != 32768u) continue;
+      }
+      if (warp_canon(sm.h.lens + 32 + hlit, hdist, sm.c_d, sm.sorted_d, sm.h.run, lane)) continue;
+      {
+        uint32_t k = 0;
+        for (int L = 1; L <= 15; L++) k += (uint32_t)sm.c_d.count[L] << (15 - L);
+        if (k != 32768u && sm.c_d.nsyms > 1) continue;
+      }
+      return q;
+    }
+  }
+  return 0xffffffffu;
 }
 
 }  // namespace tbzfast

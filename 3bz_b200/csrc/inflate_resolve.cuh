@@ -46,9 +46,18 @@ constexpr uint32_t WB = 1024u * TPT;     // window bytes (including the <= 3 byt
 constexpr uint32_t WT = TPT * NT;        // window tokens
 constexpr uint32_t V_FINAL = 0xffffu;
 
-struct Smem {
-  alignas(16) uint8_t hist[HIST];        // ring over absolute output offsets: the last 32 KiB
-  alignas(16) uint8_t win[WB];           // the window, in coordinates relative to its 4-byte aligned base
+// T = uint8_t: bytes.  T = uint16_t: symbols of the split decode of one large member — a byte, or
+// SYM_MARK | i for "the byte i positions into the 32 KiB that precede this chunk" (unknown until the
+// previous chunk is final).  Everything below moves T around without looking inside.
+constexpr uint32_t SYM_MARK = 0x8000u;
+template <typename T> struct Vec4;
+template <> struct Vec4<uint8_t> { typedef uint32_t type; };
+template <> struct Vec4<uint16_t> { typedef uint2 type; };
+
+template <typename T>
+struct SmemT {
+  alignas(16) T hist[HIST];              // ring over absolute output offsets: the last 32 KiB
+  alignas(16) T win[WB];                 // the window, in coordinates relative to its 4-byte aligned base
   alignas(8) uint16_t val[WB];           // per window byte: V_FINAL or the window offset of an equal byte
   uint16_t queue[2][WB];                 // pending bytes of this / the next level
   uint32_t toks[WT + 1];                 // [0] = tail of the match carried over from the previous window
@@ -67,6 +76,7 @@ struct Smem {
   uint32_t carry_len, carry_tok;
   uint32_t crc;
 };
+typedef SmemT<uint8_t> Smem;
 
 __device__ __forceinline__ uint32_t tok_len(uint32_t t) { return (t & TOK_MATCH) ? (t & 255u) + 3u : 1u + ((t >> 30) & 1u); }
 
@@ -112,10 +122,12 @@ struct RState {
 // One window: the slab's tokens [f, f + n) in flat order (n <= WT); consumes as many as fit,
 // returns the number consumed (0xffffffff = the member must go to the sequential kernel).  A
 // pending carry is flushed first.  All threads must call; the result is uniform.
-__device__ inline uint32_t resolve_window(const DMember &mem, int fmt, const uint32_t *__restrict__ slab, uint32_t f, uint32_t n,
-                                          RState &rs, Smem &sm, int tid) {
+template <typename T>
+__device__ inline uint32_t resolve_window(T *__restrict__ out, int fmt, const uint32_t *__restrict__ slab, uint32_t f, uint32_t n,
+                                          RState &rs, SmemT<T> &sm, int tid) {
+  typedef typename Vec4<T>::type V4;
+  constexpr uint32_t UNIT = 16 / sizeof(T);           // elements per 16-byte flush unit
   const int lane = tid & 31, warp = tid >> 5;
-  uint8_t *out = mem.out;
   const uint32_t pos = rs.pos;
   const uint32_t mis = pos & 3u, P4 = pos - mis;      // the window's coordinates start at the aligned base
   const uint32_t carry_len = rs.carry_len, carry_tok = rs.carry_tok;
@@ -223,12 +235,14 @@ __device__ inline uint32_t resolve_window(const DMember &mem, int fmt, const uin
     const uint32_t bw = sm.bitmap[(r0 >> 5) & (WB / 32 - 1)];
     uint32_t ti = sm.wrank[(r0 >> 5) & (WB / 32 - 1)] + __popc(bw & (0xffffffffu >> (31u - (r0 & 31u)))) - adj;
     const uint32_t nib = bw >> (r0 & 31u);
-    uint32_t word = 0, v01 = 0, v23 = 0, npend = 0, pmask = 0;
+    uint32_t v01 = 0, v23 = 0, npend = 0, pmask = 0;
+    T el[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       const uint32_t r = r0 + j;
       if (j) ti += (nib >> j) & 1u;
-      uint32_t byte = 0, v = V_FINAL;
+      T byte = 0;
+      uint32_t v = V_FINAL;
       if (r >= mis && r < wend) {
         const uint32_t t = sm.toks[ti];
         const uint32_t o = r - sm.tstart[ti];
@@ -239,14 +253,15 @@ __device__ inline uint32_t resolve_window(const DMember &mem, int fmt, const uin
           if (back + mis > r) byte = sm.hist[(P4 + r - back) & HMASK];   // the source is below the window: final
           else { v = r - back; npend++; pmask |= 1u << j; }
         } else {
-          byte = (t >> (8u * o)) & 255u;                          // one or two literals in a token
+          byte = (T)((t >> (8u * o)) & 255u);                     // one or two literals in a token
         }
       }
-      word |= byte << (8 * j);
+      el[j] = byte;
       if (j < 2) v01 |= v << (16 * j); else v23 |= v << (16 * (j - 2));
     }
     if (r0 < wend) {
-      *reinterpret_cast<uint32_t *>(&sm.win[r0]) = word;
+      if (sizeof(T) == 1) *reinterpret_cast<uint32_t *>(&sm.win[r0]) = (uint32_t)el[0] | ((uint32_t)el[1] << 8) | ((uint32_t)el[2] << 16) | ((uint32_t)el[3] << 24);
+      else *reinterpret_cast<uint2 *>(&sm.win[r0]) = make_uint2((uint32_t)el[0] | ((uint32_t)el[1] << 16), (uint32_t)el[2] | ((uint32_t)el[3] << 16));
       *reinterpret_cast<uint2 *>(&sm.val[r0]) = make_uint2(v01, v23);
     }
     // queue the pending bytes: one shared-memory atomic per warp
@@ -277,7 +292,7 @@ __device__ inline uint32_t resolve_window(const DMember &mem, int fmt, const uin
       const uint32_t s = sm.val[r];
       const uint32_t vs = *reinterpret_cast<volatile uint16_t *>(&sm.val[s]);
       if (vs == V_FINAL) {
-        sm.win[r] = *reinterpret_cast<volatile uint8_t *>(&sm.win[s]);
+        sm.win[r] = *reinterpret_cast<volatile T *>(&sm.win[s]);
         __threadfence_block();
         *reinterpret_cast<volatile uint16_t *>(&sm.val[r]) = (uint16_t)V_FINAL;
       } else {
@@ -288,7 +303,7 @@ __device__ inline uint32_t resolve_window(const DMember &mem, int fmt, const uin
   }
   // ---- 4. append the window to the history ring
   for (uint32_t r0 = 4u * tid; r0 < wend; r0 += 4u * NT) {
-    if (r0 >= mis && r0 + 4u <= wend) *reinterpret_cast<uint32_t *>(&sm.hist[(P4 + r0) & HMASK]) = *reinterpret_cast<const uint32_t *>(&sm.win[r0]);
+    if (r0 >= mis && r0 + 4u <= wend) *reinterpret_cast<V4 *>(&sm.hist[(P4 + r0) & HMASK]) = *reinterpret_cast<const V4 *>(&sm.win[r0]);
     else {
 #pragma unroll
       for (int j = 0; j < 4; j++)
@@ -298,13 +313,19 @@ __device__ inline uint32_t resolve_window(const DMember &mem, int fmt, const uin
   __syncthreads();
   const uint32_t wsize = wend - mis;
   // ---- 5. flush complete 16-byte units, fold them into the checksum
-  if (fmt == TBZ_GZIP) crc_window(sm, pos, wsize, tid);
+  if (sizeof(T) == 1 && fmt == TBZ_GZIP) crc_window(reinterpret_cast<Smem &>(sm), pos, wsize, tid);
   if ((((uintptr_t)out) & 15) == 0) {
-    const uint32_t upto = (pos + wsize) & ~15u;
-    for (uint32_t p = rs.flushed + 16 * tid; p < upto; p += 16 * NT) {
+    if (rs.flushed & (UNIT - 1u)) {                    // a chunk of a split member starts inside a unit: element-wise head
+      uint32_t upto = (rs.flushed + UNIT - 1u) & ~(UNIT - 1u);
+      if (upto > pos + wsize) upto = pos + wsize;
+      if (rs.flushed + tid < upto) out[rs.flushed + tid] = sm.hist[(rs.flushed + tid) & HMASK];
+      rs.flushed = upto;
+    }
+    const uint32_t upto = (pos + wsize) & ~(UNIT - 1u);
+    for (uint32_t p = rs.flushed + UNIT * tid; p < upto; p += UNIT * NT) {
       const uint4 v = *reinterpret_cast<const uint4 *>(&sm.hist[p & HMASK]);
       *reinterpret_cast<uint4 *>(out + p) = v;
-      if (fmt == TBZ_ZLIB) {
+      if (sizeof(T) == 1 && fmt == TBZ_ZLIB) {
         uint32_t sd = __dp4a(v.x, 0x01010101u, 0u); sd = __dp4a(v.y, 0x01010101u, sd);
         sd = __dp4a(v.z, 0x01010101u, sd); sd = __dp4a(v.w, 0x01010101u, sd);
         uint32_t wj = __dp4a(v.x, 0x03020100u, 0u); wj = __dp4a(v.y, 0x07060504u, wj);
@@ -313,11 +334,11 @@ __device__ inline uint32_t resolve_window(const DMember &mem, int fmt, const uin
         rs.acc_w += (unsigned long long)p * sd + wj;
       }
     }
-    rs.flushed = upto;
+    if (upto > rs.flushed) rs.flushed = upto;
   } else {
     for (uint32_t p = pos + tid; p < pos + wsize; p += NT) {
       const uint32_t d = sm.hist[p & HMASK];
-      out[p] = (uint8_t)d;
+      out[p] = (T)d;
       rs.acc_a += d; rs.acc_w += (unsigned long long)p * d;
     }
     rs.flushed = pos + wsize;
@@ -329,12 +350,11 @@ __device__ inline uint32_t resolve_window(const DMember &mem, int fmt, const uin
   return nused;
 }
 
-__device__ inline bool resolve_member(const DMember &mem, int fmt, const P1Rec &rec, const uint32_t *__restrict__ slabs,
-                                      tbz_result &res, Smem &sm, int tid) {
-  const int lane = tid & 31, warp = tid >> 5;
-  uint8_t *out = mem.out;
-  RState rs;
-  rs.pos = 0; rs.flushed = 0; rs.acc_a = 0; rs.acc_w = 0; rs.carry_len = 0; rs.carry_tok = 0;
+// Every window of one token stream (a member, or one chunk of a split member).  rs.pos / rs.flushed
+// hold the absolute output offset the stream starts at.  Returns false when the caller must fall back.
+template <typename T>
+__device__ inline bool resolve_stream(T *__restrict__ out, int fmt, const P1Rec &rec, const uint32_t *__restrict__ slabs,
+                                      RState &rs, SmemT<T> &sm, int tid) {
   if (tid == 0) { sm.fail = 0; sm.crc = 0; }
   __syncthreads();
   for (uint32_t s = rec.first_slab; s != NO_SLAB;) {
@@ -360,24 +380,34 @@ __device__ inline bool resolve_member(const DMember &mem, int fmt, const P1Rec &
     uint32_t f = 0;
     while (f < total) {
       const uint32_t n = total - f < WT ? total - f : WT;
-      const uint32_t used = resolve_window(mem, fmt, slab, f, n, rs, sm, tid);
+      const uint32_t used = resolve_window<T>(out, fmt, slab, f, n, rs, sm, tid);
       if (used == 0xffffffffu || used == 0) return false;
       f += used;
     }
     __syncthreads();
   }
-  while (rs.carry_len) {                   // tail of a match that straddled the last window
-    if (resolve_window(mem, fmt, nullptr, 0, 0, rs, sm, tid) == 0xffffffffu) return false;
+  while (rs.carry_len) {                   // tail of a token that straddled the last window
+    if (resolve_window<T>(out, fmt, nullptr, 0, 0, rs, sm, tid) == 0xffffffffu) return false;
   }
-  const uint32_t pos = rs.pos;
-  if (pos != rec.out_len || sm.fail) return false;
-  unsigned long long acc_a = rs.acc_a, acc_w = rs.acc_w;
-  if (rs.flushed + tid < pos) {            // the last partial 16-byte unit
+  if (sm.fail) return false;
+  if (rs.flushed + tid < rs.pos) {         // the last partial 16-byte unit
     const uint32_t p = rs.flushed + tid;
     const uint32_t d = sm.hist[p & HMASK];
-    out[p] = (uint8_t)d;
-    acc_a += d; acc_w += (unsigned long long)p * d;
+    out[p] = (T)d;
+    rs.acc_a += d; rs.acc_w += (unsigned long long)p * d;
   }
+  return true;
+}
+
+__device__ inline bool resolve_member(const DMember &mem, int fmt, const P1Rec &rec, const uint32_t *__restrict__ slabs,
+                                      tbz_result &res, Smem &sm, int tid) {
+  const int lane = tid & 31, warp = tid >> 5;
+  RState rs;
+  rs.pos = 0; rs.flushed = 0; rs.acc_a = 0; rs.acc_w = 0; rs.carry_len = 0; rs.carry_tok = 0;
+  if (!resolve_stream<uint8_t>(mem.out, fmt, rec, slabs, rs, sm, tid)) return false;
+  const uint32_t pos = rs.pos;
+  if (pos != rec.out_len) return false;
+  unsigned long long acc_a = rs.acc_a, acc_w = rs.acc_w;
   // ---- checksum of the whole member
   uint32_t ck = 0;
   if (fmt == TBZ_ZLIB) {

@@ -1,0 +1,262 @@
+// inflate_split.cuh — speculative split decode of ONE large member across the whole GPU
+// (pugz / rapidgzip style; the reference has no equivalent: it decodes a stream strictly in order,
+// deflate.lisp:92-730).
+//
+//   K0 k_split_find      the compressed body is cut at fixed offsets; a warp per chunk searches for the
+//                        first dynamic-block start inside its chunk (find_block_start)
+//   K1 k_split_decode    a warp per chunk decodes blocks from its start until the first block that
+//                        ends at or beyond the next chunk's start: token slabs, output size and the
+//                        bit it landed on.  The host validates the chain (every chunk must land exactly
+//                        on its successor's start; a false positive is dropped and its predecessor
+//                        re-decoded) and prefix-sums the output sizes
+//   K2 k_split_resolve   a CTA per chunk resolves its tokens with 16-bit symbols: bytes, or markers
+//                        "byte i of the 32 KiB before this chunk" for what it cannot know yet
+//   K3 k_split_tails     one CTA walks the chunks in order and makes the last 32 KiB of every chunk
+//                        final (the only sequential step: 32 KiB per chunk)
+//   K4 k_split_translate every other symbol becomes a byte, all chunks in parallel
+//   K5 k_split_checksum  CRC-32 / Adler-32 partials per 4 KiB segment; the host combines them
+#pragma once
+#include "tbz_device.cuh"
+#include "inflate_decode.cuh"
+#include "inflate_resolve.cuh"
+
+namespace tbzsplit {
+
+constexpr uint64_t NONE64 = ~0ull;
+constexpr uint32_t CSEG = 4096;          // checksum segment bytes
+
+struct Chunk {                           // host fills start/stop, the kernels fill the rest
+  uint64_t start_bit;                    // absolute bit (from the member's 4-byte aligned base) of a block start
+  uint64_t stop_bit;                     // decode until a block ends at or beyond this bit (NONE64: to the final block)
+  uint64_t out_off;                      // absolute output offset of the chunk
+  uint64_t land_bit;                     // K1: absolute bit after the chunk's last block
+  tbzfast::P1Rec rec;                    // K1
+  uint32_t ok;                           // K2
+  uint32_t pad;
+};
+
+__device__ __forceinline__ tbzfast::In chunk_input(const uint32_t *words, uint64_t end_bit, uint64_t from_bit, uint32_t &rel) {
+  tbzfast::In in;
+  const uint64_t bw = from_bit >> 5;
+  in.w = words + bw;
+  rel = (uint32_t)(from_bit - (bw << 5));
+  in.pos0 = rel;
+  uint64_t e = end_bit - (bw << 5);
+  if (e > 0xf0000000ull) e = 0xf0000000ull;
+  in.end = (uint32_t)e;
+  in.nwords = (in.end + 31) >> 5;
+  return in;
+}
+
+// found[c] = first dynamic-block start in [c * chunk_bits, (c + 1) * chunk_bits) + body_bit, c >= 1
+__global__ void __launch_bounds__(tbzfast::NT)
+k_split_find(const uint32_t *words, uint64_t end_bit, uint64_t body_bit, uint64_t chunk_bits, uint32_t nchunks, uint64_t *found) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  tbzfast::WSmem &sm = reinterpret_cast<tbzfast::WSmem *>(smem_raw)[warp];
+  const uint32_t c = blockIdx.x * tbzfast::WPC + warp + 1;
+  if (c >= nchunks) return;
+  const uint64_t from = body_bit + chunk_bits * c;
+  uint64_t to = from + chunk_bits;
+  if (to > end_bit) to = end_bit;
+  uint64_t res = NONE64;
+  if (from < to) {
+    uint32_t rel;
+    const tbzfast::In in = chunk_input(words, end_bit, from, rel);
+    const uint32_t r = tbzfast::find_block_start(in, rel, rel + (uint32_t)(to - from), sm, lane);
+    if (r != 0xffffffffu) res = from + (r - rel);
+  }
+  if (lane == 0) found[c] = res;
+}
+
+// todo[i]: index of a chunk to decode
+__global__ void __launch_bounds__(tbzfast::NT)
+k_split_decode(const uint32_t *words, uint64_t end_bit, Chunk *chunks, const uint32_t *todo, uint32_t ntodo,
+               uint32_t *slabs, uint32_t nslabs, uint32_t *counters) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  tbzfast::WSmem &sm = reinterpret_cast<tbzfast::WSmem *>(smem_raw)[warp];
+  for (;;) {
+    uint32_t i = 0;
+    if (lane == 0) i = atomicAdd(&counters[0], 1u);
+    i = __shfl_sync(TBZ_FULL, i, 0);
+    if (i >= ntodo) break;
+    Chunk &ch = chunks[todo[i]];
+    uint32_t rel;
+    const tbzfast::In in = chunk_input(words, end_bit, ch.start_bit, rel);
+    const uint64_t base = ch.start_bit - rel;
+    uint32_t stop = 0xffffffffu;
+    if (ch.stop_bit != NONE64) {
+      const uint64_t s = ch.stop_bit - base;
+      stop = s > 0xf0000000ull ? 0xf0000000u : (uint32_t)s;
+    }
+    const bool ok = tbzfast::decode_blocks(in, rel, stop, 0xffffffffull, ch.rec, sm, slabs, nslabs, &counters[2], lane);
+    __syncwarp();
+    if (lane == 0) {
+      if (!ok) ch.rec.status = 0;
+      ch.land_bit = ok ? base + ch.rec.end_pos : NONE64;
+    }
+  }
+}
+
+typedef tbzres::SmemT<uint16_t> SymSmem;
+
+__global__ void __launch_bounds__(tbzres::NT)
+k_split_resolve(Chunk *chunks, uint32_t nchunks, const uint32_t *slabs, uint16_t *sym, uint32_t *counters) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SymSmem &sm = *reinterpret_cast<SymSmem *>(smem_raw);
+  const int tid = threadIdx.x;
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) sm.member = atomicAdd(&counters[3], 1u);
+    __syncthreads();
+    const uint32_t k = sm.member;
+    if (k >= nchunks) break;
+    Chunk &ch = chunks[k];
+    const uint32_t off = (uint32_t)ch.out_off;
+    // what precedes the chunk is unknown: position a of the last 32 KiB is the marker for itself
+    for (uint32_t i = tid; i < tbzres::HIST; i += tbzres::NT)
+      sm.hist[(off - tbzres::HIST + i) & tbzres::HMASK] = (uint16_t)(tbzres::SYM_MARK | i);
+    tbzres::RState rs;
+    rs.pos = off; rs.flushed = off; rs.acc_a = 0; rs.acc_w = 0; rs.carry_len = 0; rs.carry_tok = 0;
+    __syncthreads();
+    const bool ok = tbzres::resolve_stream<uint16_t>(sym, TBZ_DEFLATE, ch.rec, slabs, rs, sm, tid);
+    if (tid == 0) ch.ok = ok && rs.pos == off + ch.rec.out_len;
+  }
+}
+
+// the last 32 KiB of every chunk, in order: the only sequential step.  One CTA of 1024 threads, 32
+// symbols per thread.  The 32 KiB that precede the current chunk live in a shared-memory ring over
+// absolute offsets (a marker costs a shared-memory load), and the tail symbols of chunk k+1 are
+// fetched from HBM into registers while chunk k is resolved out of a shared-memory staging buffer,
+// so no iteration waits for a memory round trip.
+struct TailSmem { uint16_t stage[2][32768]; uint8_t ring[32768]; };
+
+__device__ __forceinline__ void tail_range(const Chunk *chunks, uint32_t nchunks, uint32_t k, uint64_t &start, uint64_t &lo, uint64_t &end) {
+  start = 0; lo = 0; end = 0;
+  if (k >= nchunks) return;
+  start = chunks[k].out_off;
+  end = start + chunks[k].rec.out_len;
+  lo = end > 32768 ? end - 32768 : 0;
+  if (lo < start) lo = start;
+}
+
+__global__ void __launch_bounds__(1024)
+k_split_tails(const Chunk *__restrict__ chunks, uint32_t nchunks, const uint16_t *__restrict__ sym, uint8_t *__restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  TailSmem &sm = *reinterpret_cast<TailSmem *>(smem_raw);
+  const uint32_t tid = threadIdx.x;
+  uint64_t start, lo, end;
+  tail_range(chunks, nchunks, 0, start, lo, end);
+  for (int j = 0; j < 32; j++) {
+    const uint64_t a = lo + tid + 1024u * j;
+    sm.stage[0][tid + 1024u * j] = a < end ? sym[a] : (uint16_t)0;
+  }
+  __syncthreads();
+  for (uint32_t k = 0; k < nchunks; k++) {
+    uint64_t nstart, nlo, nend;
+    tail_range(chunks, nchunks, k + 1, nstart, nlo, nend);
+    uint16_t nx[32];                                   // next chunk's tail symbols: in flight during this chunk
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+      const uint64_t a = nlo + tid + 1024u * j;
+      nx[j] = a < nend ? sym[a] : (uint16_t)0;
+    }
+    const uint16_t *cur = sm.stage[k & 1];
+    uint32_t pk[8];
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+      uint32_t s = cur[tid + 1024u * j];
+      if (s & tbzres::SYM_MARK) s = sm.ring[(start - 32768 + (s & 0x7fffu)) & 32767u];
+      if ((j & 3) == 0) pk[j >> 2] = s; else pk[j >> 2] |= s << (8 * (j & 3));
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+      const uint64_t a = lo + tid + 1024u * j;
+      const uint8_t bv = (uint8_t)(pk[j >> 2] >> (8 * (j & 3)));
+      if (a < end) { sm.ring[a & 32767u] = bv; out[a] = bv; }
+    }
+    uint16_t *nxt = sm.stage[(k + 1) & 1];
+#pragma unroll
+    for (int j = 0; j < 32; j++) nxt[tid + 1024u * j] = nx[j];
+    __syncthreads();
+    start = nstart; lo = nlo; end = nend;
+  }
+}
+
+// every symbol becomes a byte, eight per thread and step (16-byte loads, 8-byte stores).  The tails are
+// final already and come out the same again.  offs[k] = output offset of chunk k, offs[nchunks] = total.
+__global__ void __launch_bounds__(256)
+k_split_translate(const uint64_t *__restrict__ offs, uint32_t nchunks, const uint16_t *__restrict__ sym, uint8_t *out, uint64_t total) {
+  const uint64_t nunits = (total + 7) / 8;
+  for (uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; u < nunits; u += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t a0 = u * 8;
+    uint32_t k = 0;                                    // last chunk with offs[k] <= a0
+    for (uint32_t stp = 1u << 15; stp; stp >>= 1)
+      if (k + stp < nchunks && offs[k + stp] <= a0) k += stp;
+    uint64_t start = offs[k], next = offs[k + 1];
+    if (a0 + 8 <= total && a0 + 8 <= next) {
+      const uint4 v = *reinterpret_cast<const uint4 *>(sym + a0);
+      uint32_t s[8] = {v.x & 0xffffu, v.x >> 16, v.y & 0xffffu, v.y >> 16, v.z & 0xffffu, v.z >> 16, v.w & 0xffffu, v.w >> 16};
+#pragma unroll
+      for (int j = 0; j < 8; j++)
+        if (s[j] & tbzres::SYM_MARK) s[j] = *reinterpret_cast<const volatile uint8_t *>(out + (start - 32768 + (s[j] & 0x7fffu)));
+      *reinterpret_cast<uint2 *>(out + a0) = make_uint2(s[0] | (s[1] << 8) | (s[2] << 16) | (s[3] << 24), s[4] | (s[5] << 8) | (s[6] << 16) | (s[7] << 24));
+    } else {
+      for (uint64_t a = a0; a < a0 + 8 && a < total; a++) {
+        while (a >= next) { k++; start = next; next = offs[k + 1]; }
+        const uint32_t sv = sym[a];
+        out[a] = (sv & tbzres::SYM_MARK) ? *reinterpret_cast<const volatile uint8_t *>(out + (start - 32768 + (sv & 0x7fffu))) : (uint8_t)sv;
+      }
+    }
+  }
+}
+
+// parts[2 * seg] = CRC-32 of the segment (gzip) or sum of its bytes (zlib); parts[2 * seg + 1] = unused / sum (n - i) d_i
+// One thread per 4 KiB segment, 16-byte loads.
+__global__ void __launch_bounds__(256)
+k_split_checksum(const uint8_t *__restrict__ out, uint64_t n, int fmt, uint32_t *parts) {
+  __shared__ uint32_t tab[256];
+  crc_table_init(tab, threadIdx.x, blockDim.x);
+  __syncthreads();
+  const uint64_t seg = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t lo = seg * CSEG;
+  if (lo >= n) return;
+  const uint64_t hi = lo + CSEG < n ? lo + CSEG : n;
+  const bool vec = (((uintptr_t)(out + lo)) & 15) == 0;
+  uint64_t i = lo;
+  if (fmt == TBZ_GZIP) {
+    uint32_t c = 0xffffffffu;
+    if (vec)
+      for (; i + 16 <= hi; i += 16) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(out + i);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+#pragma unroll
+          for (int b = 0; b < 4; b++) c = (c >> 8) ^ tab[(c ^ (w[q] >> (8 * b))) & 0xff];
+      }
+    for (; i < hi; i++) c = (c >> 8) ^ tab[(c ^ out[i]) & 0xff];
+    parts[2 * seg] = c ^ 0xffffffffu;
+    parts[2 * seg + 1] = 0;
+  } else {
+    uint32_t a = 0, w = 0;
+    const uint32_t m = (uint32_t)(hi - lo);
+    if (vec)
+      for (; i + 16 <= hi; i += 16) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(out + i);
+        uint32_t sd = __dp4a(v.x, 0x01010101u, 0u); sd = __dp4a(v.y, 0x01010101u, sd);
+        sd = __dp4a(v.z, 0x01010101u, sd); sd = __dp4a(v.w, 0x01010101u, sd);
+        uint32_t wj = __dp4a(v.x, 0x03020100u, 0u); wj = __dp4a(v.y, 0x07060504u, wj);
+        wj = __dp4a(v.z, 0x0b0a0908u, wj); wj = __dp4a(v.w, 0x0f0e0d0cu, wj);
+        a += sd;
+        w += (m - (uint32_t)(i - lo)) * sd - wj;       // sum (m - j) d_j over the unit
+      }
+    for (; i < hi; i++) { const uint32_t d = out[i]; a += d; w += (m - (uint32_t)(i - lo)) * d; }
+    parts[2 * seg] = a;
+    parts[2 * seg + 1] = w;
+  }
+}
+
+}  // namespace tbzsplit

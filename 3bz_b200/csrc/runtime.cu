@@ -6,6 +6,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <chrono>
 #include <atomic>
 #include <functional>
 #include <mutex>
@@ -18,6 +19,7 @@
 #include "inflate_seq.cuh"
 #include "inflate_decode.cuh"
 #include "inflate_resolve.cuh"
+#include "inflate_split.cuh"
 
 // =============================================================================================
 // kernels
@@ -86,6 +88,8 @@ k_inflate_resolve(const DMember *members, tbz_result *results, uint32_t n, int f
 // host objects
 // =============================================================================================
 static const uint64_t kSlabPoolBytes = 6ull << 30;   // upper bound of the token slab pool per batch
+static const uint64_t kSplitMinBytes = 4ull << 20;   // members at least this large are split across the GPU
+static const uint64_t kSplitChunkBytes = 128ull << 10;
 
 struct DevBlock { void *p; size_t size; bool used; };
 
@@ -172,6 +176,7 @@ struct tbz_batch {
   int fast_grid = 0, res_grid = 0;
   uint32_t nslabs = 0;
   bool launched = false;
+  std::vector<std::pair<uint64_t, DMember>> big;   // members decoded by the split path (index, device view)
 };
 
 // =============================================================================================
@@ -459,6 +464,12 @@ extern "C" int32_t tbz_batch_prepare(tbz_ctx *ctx, int32_t format, const tbz_mem
       dm[i] = DMember{(const uint8_t *)b->d_in + b->in_off[i], m[i].in_len,
                       (uint8_t *)b->d_out + b->out_off[i], m[i].out_cap};
   }
+  if (!(flags & (TBZ_FLAG_NO_SPLIT | TBZ_FLAG_NO_FASTPATH)))
+    for (uint64_t i = 0; i < n; i++)
+      if (dm[i].in_len >= kSplitMinBytes) {           // the batched kernels see an empty member; split_inflate fills the result
+        b->big.push_back({i, dm[i]});
+        dm[i].in_len = 0; dm[i].out_cap = 0;
+      }
   if (n) {
     cudaError_t e = cudaMemcpyAsync(b->d_members, dm.data(), n * sizeof(DMember), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);   // dm is a local
@@ -466,6 +477,251 @@ extern "C" int32_t tbz_batch_prepare(tbz_ctx *ctx, int32_t format, const tbz_mem
   }
 #undef PCK
   *out = b;
+  return TBZ_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// one large member, split across the whole GPU (inflate_split.cuh).  Synchronous.  Returns TBZ_OK
+// with *handled = false when the member has to take the ordinary path (odd header, broken chain,
+// truncated or corrupt stream, too small an output buffer): the sequential kernel then owns the verdict.
+// ---------------------------------------------------------------------------------------------
+static uint32_t crc_mulmod_h(uint32_t a, uint32_t b) {
+  uint32_t p = 0;
+  for (int i = 0; i < 32 && a; i++) {
+    if (a & 0x80000000u) p ^= b;
+    a <<= 1;
+    b = (b >> 1) ^ ((b & 1) ? 0xedb88320u : 0);
+  }
+  return p;
+}
+static uint32_t crc_x8n_h(uint64_t n) {            // x^(8n) mod P
+  uint32_t p = 0x80000000u, sq = 0x00800000u;     // x^0, x^8
+  while (n) {
+    if (n & 1) p = crc_mulmod_h(sq, p);
+    sq = crc_mulmod_h(sq, sq);
+    n >>= 1;
+  }
+  return p;
+}
+
+static int32_t split_inflate(tbz_ctx *ctx, int fmt, const DMember &m, tbz_result *d_result, bool *handled) {
+  using tbzsplit::Chunk;
+  *handled = false;
+  cudaStream_t st = ctx->stream;
+  auto t_prev = std::chrono::steady_clock::now();
+  auto stage = [&](const char *name) {                // TBZ_KTIME=1: wall time per stage (each ends in a stream sync)
+    if (!ctx->ktime) return;
+    cudaStreamSynchronize(st);
+    auto t = std::chrono::steady_clock::now();
+    fprintf(stderr, "[tbz split] %-10s %8.3f ms\n", name, std::chrono::duration<double, std::milli>(t - t_prev).count());
+    t_prev = t;
+  };
+  // ---- wrapper header, on the host (zlib.lisp:108-126, gzip.lisp:113-177 without optional fields)
+  uint8_t head[16] = {0};
+  CK(ctx, cudaMemcpyAsync(head, m.in, 16, cudaMemcpyDeviceToHost, st));
+  CK(ctx, cudaStreamSynchronize(st));
+  uint64_t hdr_bytes = 0;
+  if (fmt == TBZ_ZLIB) {
+    if ((head[0] * 256 + head[1]) % 31 || (head[0] & 15) != 8 || (head[0] >> 4) > 7 || (head[1] & 32)) return TBZ_OK;
+    hdr_bytes = 2;
+  } else if (fmt == TBZ_GZIP) {
+    if (head[0] != 0x1f || head[1] != 0x8b || head[2] != 8 || head[3] != 0) return TBZ_OK;
+    hdr_bytes = 10;
+  }
+  const uint64_t trailer = fmt == TBZ_ZLIB ? 4 : fmt == TBZ_GZIP ? 8 : 0;
+  if (m.in_len < hdr_bytes + trailer + 64 || m.in_len >= (1ull << 40) || m.out_cap >= (1ull << 32)) return TBZ_OK;
+  const uint64_t mis = (uintptr_t)m.in & 3;
+  const uint32_t *words = (const uint32_t *)(m.in - mis);
+  const uint64_t end_bit = (mis + m.in_len) * 8;
+  const uint64_t body_bit = (mis + hdr_bytes) * 8;
+  const uint64_t chunk_bits = kSplitChunkBytes * 8;
+  const uint32_t nchunks = (uint32_t)((end_bit - body_bit + chunk_bits - 1) / chunk_bits);
+  if (nchunks < 4) return TBZ_OK;
+
+  void *d_found = nullptr, *d_chunks = nullptr, *d_todo = nullptr, *d_cnt = nullptr, *d_slabs = nullptr, *d_sym = nullptr, *d_parts = nullptr;
+  int32_t rc = TBZ_OK;
+  auto cleanup = [&]() {
+    dev_release(ctx, d_found); dev_release(ctx, d_chunks); dev_release(ctx, d_todo); dev_release(ctx, d_cnt);
+    dev_release(ctx, d_slabs); dev_release(ctx, d_sym); dev_release(ctx, d_parts);
+  };
+#define SCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); return fail(ctx, TBZ_E_CUDA, #call, e_); } } while (0)
+#define SRC(x) do { rc = (x); if (rc) { cleanup(); return rc; } } while (0)
+  SRC(dev_alloc(ctx, (size_t)(nchunks + 2) * 8, &d_found));
+  SRC(dev_alloc(ctx, (size_t)nchunks * sizeof(Chunk), &d_chunks));
+  SRC(dev_alloc(ctx, (size_t)nchunks * 4, &d_todo));
+  SRC(dev_alloc(ctx, 256, &d_cnt));
+  const size_t dec_smem = sizeof(tbzfast::WSmem) * tbzfast::WPC;
+  // ---- K0: block starts
+  SCK(cudaFuncSetAttribute(tbzsplit::k_split_find, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dec_smem));
+  SCK(cudaMemsetAsync(d_found, 0xff, (size_t)nchunks * 8, st));
+  tbzsplit::k_split_find<<<(nchunks + tbzfast::WPC - 1) / tbzfast::WPC, tbzfast::NT, dec_smem, st>>>(
+      words, end_bit, body_bit, chunk_bits, nchunks, (uint64_t *)d_found);
+  ctx->launches++;
+  std::vector<uint64_t> found(nchunks);
+  SCK(cudaMemcpyAsync(found.data(), d_found, (size_t)nchunks * 8, cudaMemcpyDeviceToHost, st));
+  SCK(cudaStreamSynchronize(st));
+  found[0] = body_bit;
+  stage("find");
+  // ---- K1: decode the chunks, validate the chain, repair it where a start was a false positive
+  const uint64_t round_bytes = (uint64_t)tbzfast::NL * tbzfast::S_MAX / 8;
+  const uint64_t slab_bytes = (uint64_t)tbzfast::SLAB_WORDS * 4;
+  uint64_t want = 3 * (m.in_len / round_bytes) + 8ull * nchunks + 64;
+  if (want * slab_bytes > (32ull << 30)) want = (32ull << 30) / slab_bytes;
+  const uint32_t nslabs = (uint32_t)want;
+  SRC(dev_alloc(ctx, (size_t)nslabs * slab_bytes, &d_slabs));
+  SCK(cudaFuncSetAttribute(tbzsplit::k_split_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dec_smem));
+  std::vector<uint32_t> valid;                       // chunk indices that start a decode, ascending
+  for (uint32_t c = 0; c < nchunks; c++) if (found[c] != tbzsplit::NONE64) valid.push_back(c);
+  std::vector<Chunk> ch(nchunks);
+  std::vector<uint32_t> todo = valid;
+  SCK(cudaMemsetAsync(d_cnt, 0, 256, st));
+  bool chain_ok = false;
+  for (int pass = 0; pass < 6 && !chain_ok; pass++) {
+    for (size_t v = 0; v < valid.size(); v++) {
+      Chunk &c = ch[valid[v]];
+      c.start_bit = found[valid[v]];
+      c.stop_bit = v + 1 < valid.size() ? found[valid[v + 1]] : tbzsplit::NONE64;
+    }
+    if (todo.size() > 8) SCK(cudaMemcpyAsync(d_chunks, ch.data(), (size_t)nchunks * sizeof(Chunk), cudaMemcpyHostToDevice, st));
+    else for (uint32_t t : todo) SCK(cudaMemcpyAsync((Chunk *)d_chunks + t, &ch[t], sizeof(Chunk), cudaMemcpyHostToDevice, st));
+    SCK(cudaMemcpyAsync(d_todo, todo.data(), todo.size() * 4, cudaMemcpyHostToDevice, st));
+    SCK(cudaMemsetAsync(d_cnt, 0, 4, st));             // work counter only: slabs keep accumulating
+    int occ = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tbzsplit::k_split_decode, tbzfast::NT, dec_smem);
+    const int grid = (int)std::min<uint64_t>((todo.size() + tbzfast::WPC - 1) / tbzfast::WPC, (uint64_t)ctx->sm_count * std::max(1, occ));
+    tbzsplit::k_split_decode<<<grid, tbzfast::NT, dec_smem, st>>>(words, end_bit, (Chunk *)d_chunks, (const uint32_t *)d_todo,
+                                                                  (uint32_t)todo.size(), (uint32_t *)d_slabs, nslabs, (uint32_t *)d_cnt);
+    ctx->launches++;
+    if (todo.size() > 8) SCK(cudaMemcpyAsync(ch.data(), d_chunks, (size_t)nchunks * sizeof(Chunk), cudaMemcpyDeviceToHost, st));
+    else for (uint32_t t : todo) SCK(cudaMemcpyAsync(&ch[t], (Chunk *)d_chunks + t, sizeof(Chunk), cudaMemcpyDeviceToHost, st));
+    SCK(cudaStreamSynchronize(st));
+    // walk the chain from chunk 0; the first broken link decides what is decoded again
+    todo.clear();
+    chain_ok = true;
+    for (size_t v = 0; v < valid.size(); v++) {
+      const Chunk &c = ch[valid[v]];
+      const bool is_last = v + 1 == valid.size();
+      if (c.rec.status == 0) {                          // this chunk did not decode: its start was not a block start
+        if (v == 0) { cleanup(); return TBZ_OK; }
+        todo.push_back(valid[v - 1]);
+        valid.erase(valid.begin() + v);
+        chain_ok = false;
+        break;
+      }
+      if (is_last) { if (c.rec.status != 1) { cleanup(); return TBZ_OK; } break; }
+      if (c.rec.status == 1) { valid.resize(v + 1); break; }   // final block reached: later "starts" are not this member's deflate data
+      if (c.land_bit != c.stop_bit) {                       // missed the successor: it was not a block start
+        valid.erase(valid.begin() + v + 1);
+        todo.push_back(valid[v]);
+        chain_ok = false;
+        break;
+      }
+    }
+  }
+  if (!chain_ok) { cleanup(); return TBZ_OK; }
+  stage("decode");
+  // ---- output offsets
+  std::vector<Chunk> vch(valid.size());
+  uint64_t total = 0;
+  for (size_t v = 0; v < valid.size(); v++) { vch[v] = ch[valid[v]]; vch[v].out_off = total; vch[v].ok = 0; total += vch[v].rec.out_len; }
+  if (total > m.out_cap || total >= (1ull << 32)) { cleanup(); return TBZ_OK; }
+  const uint64_t end_pos_bit = vch.back().land_bit;
+  const uint64_t trailer_byte = (end_pos_bit + 7) / 8;                 // relative to the aligned base
+  if (trailer_byte + trailer > mis + m.in_len) { cleanup(); return TBZ_OK; }   // truncated trailer: sequential kernel
+  const uint32_t nv = (uint32_t)vch.size();
+  SCK(cudaMemcpyAsync(d_chunks, vch.data(), (size_t)nv * sizeof(Chunk), cudaMemcpyHostToDevice, st));
+  // ---- K2: symbols
+  SRC(dev_alloc(ctx, (size_t)total * 2 + 64, &d_sym));
+  SCK(cudaFuncSetAttribute(tbzsplit::k_split_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tbzsplit::SymSmem)));
+  {
+    int occ = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tbzsplit::k_split_resolve, tbzres::NT, sizeof(tbzsplit::SymSmem));
+    const int grid = (int)std::min<uint64_t>(nv, (uint64_t)ctx->sm_count * std::max(1, occ));
+    SCK(cudaMemsetAsync(d_cnt, 0, 256, st));
+    tbzsplit::k_split_resolve<<<grid, tbzres::NT, sizeof(tbzsplit::SymSmem), st>>>((Chunk *)d_chunks, nv, (const uint32_t *)d_slabs,
+                                                                                   (uint16_t *)d_sym, (uint32_t *)d_cnt);
+    ctx->launches++;
+  }
+  SCK(cudaMemcpyAsync(vch.data(), d_chunks, (size_t)nv * sizeof(Chunk), cudaMemcpyDeviceToHost, st));
+  SCK(cudaStreamSynchronize(st));
+  for (const Chunk &c : vch) if (!c.ok) { cleanup(); return TBZ_OK; }
+  stage("resolve");
+  // ---- K3, K4: bytes
+  SCK(cudaFuncSetAttribute(tbzsplit::k_split_tails, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tbzsplit::TailSmem)));
+  tbzsplit::k_split_tails<<<1, 1024, sizeof(tbzsplit::TailSmem), st>>>((const Chunk *)d_chunks, nv, (const uint16_t *)d_sym, m.out);
+  stage("tails");
+  {
+    std::vector<uint64_t> offs(nv + 1);
+    for (uint32_t v = 0; v < nv; v++) offs[v] = vch[v].out_off;
+    offs[nv] = total;
+    SCK(cudaMemcpyAsync(d_found, offs.data(), (size_t)(nv + 1) * 8, cudaMemcpyHostToDevice, st));   // nv + 1 <= nchunks + 1 words: fits
+    SCK(cudaStreamSynchronize(st));
+    tbzsplit::k_split_translate<<<ctx->sm_count * 16, 256, 0, st>>>((const uint64_t *)d_found, nv, (const uint16_t *)d_sym, m.out, total);
+  }
+  ctx->launches += 2;
+  stage("translate");
+  // ---- K5: checksum, trailer (zlib.lisp:80-96, gzip.lisp:82-106)
+  uint32_t ck = 0;
+  uint8_t tr[8] = {0};
+  if (trailer) {
+    const uint64_t nseg = (total + tbzsplit::CSEG - 1) / tbzsplit::CSEG;
+    SRC(dev_alloc(ctx, (size_t)std::max<uint64_t>(1, nseg) * 8, &d_parts));
+    if (nseg) {
+      tbzsplit::k_split_checksum<<<(uint32_t)((nseg + 255) / 256), 256, 0, st>>>(m.out, total, fmt, (uint32_t *)d_parts);
+      ctx->launches++;
+    }
+    std::vector<uint32_t> parts(2 * std::max<uint64_t>(1, nseg));
+    SCK(cudaMemcpyAsync(parts.data(), d_parts, (size_t)nseg * 8, cudaMemcpyDeviceToHost, st));
+    SCK(cudaMemcpyAsync(tr, (const uint8_t *)words + trailer_byte, trailer, cudaMemcpyDeviceToHost, st));
+    SCK(cudaStreamSynchronize(st));
+    if (fmt == TBZ_GZIP) {
+      // crc(A || B) = crc(A) * x^(8 |B|) + crc(B); multiplying by the constant of a full segment is linear: four byte tables
+      const uint32_t xs = crc_x8n_h(tbzsplit::CSEG);
+      std::vector<uint32_t> mt(4 * 256);
+      for (int bsel = 0; bsel < 4; bsel++)
+        for (uint32_t v = 0; v < 256; v++) mt[bsel * 256 + v] = crc_mulmod_h(v << (8 * bsel), xs);
+      uint32_t c = 0;
+      for (uint64_t s2 = 0; s2 < nseg; s2++) {
+        const uint64_t len = std::min<uint64_t>(tbzsplit::CSEG, total - s2 * tbzsplit::CSEG);
+        if (len == tbzsplit::CSEG) c = mt[c & 255] ^ mt[256 + ((c >> 8) & 255)] ^ mt[512 + ((c >> 16) & 255)] ^ mt[768 + (c >> 24)];
+        else c = crc_mulmod_h(crc_x8n_h(len), c);
+        c ^= parts[2 * s2];
+      }
+      ck = c;
+    } else {
+      uint64_t s1 = 1, s2v = 0;
+      for (uint64_t s = 0; s < nseg; s++) {
+        const uint64_t len = std::min<uint64_t>(tbzsplit::CSEG, total - s * tbzsplit::CSEG);
+        s2v = (s2v + len * s1 + parts[2 * s + 1]) % TBZ_ADLER_MOD;
+        s1 = (s1 + parts[2 * s]) % TBZ_ADLER_MOD;
+      }
+      ck = (uint32_t)(s1 | (s2v << 16));
+    }
+  } else {
+    SCK(cudaStreamSynchronize(st));
+  }
+  tbz_result r{};
+  r.out_len = total;
+  r.checksum = ck;
+  r.where = TBZ_AT_BODY;
+  r.path = 2;
+  r.verdict = TBZ_FINISHED;
+  r.in_used = trailer_byte + trailer - mis;
+  if (fmt == TBZ_ZLIB) {
+    const uint32_t t = ((uint32_t)tr[0] << 24) | ((uint32_t)tr[1] << 16) | ((uint32_t)tr[2] << 8) | tr[3];
+    if (t != ck) r.verdict = TBZ_ERR_CHECKSUM;
+  } else if (fmt == TBZ_GZIP) {
+    const uint32_t t = tr[0] | ((uint32_t)tr[1] << 8) | ((uint32_t)tr[2] << 16) | ((uint32_t)tr[3] << 24);
+    if (t != ck) { r.verdict = TBZ_ERR_CHECKSUM; r.in_used -= 4; }
+  }
+  SCK(cudaMemcpyAsync(d_result, &r, sizeof r, cudaMemcpyHostToDevice, st));
+  SCK(cudaStreamSynchronize(st));
+  stage("checksum");
+  if (ctx->ktime) fprintf(stderr, "[tbz split] %u chunks of %u, %llu bytes out\n", nv, nchunks, (unsigned long long)total);
+  cleanup();
+#undef SCK
+#undef SRC
+  *handled = true;
   return TBZ_OK;
 }
 
@@ -537,6 +793,28 @@ extern "C" int32_t tbz_batch_launch(tbz_batch *b) {
   CK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
   int32_t rc = launch_kernels(b);
   if (rc) return rc;
+  for (auto &bm : b->big) {                            // large members: split across the GPU, else the sequential kernel
+    bool handled = false;
+    rc = split_inflate(ctx, b->format, bm.second, (tbz_result *)b->d_results + bm.first, &handled);
+    if (rc) return rc;
+    if (!handled) {
+      CK(ctx, cudaMemcpyAsync((DMember *)b->d_members + bm.first, &bm.second, sizeof(DMember), cudaMemcpyHostToDevice, ctx->stream));
+      const uint32_t one = (uint32_t)bm.first;
+      void *d_one = nullptr;
+      rc = dev_alloc(ctx, 256, &d_one);
+      if (rc) return rc;
+      const uint32_t hdr[2] = {one, 1u};
+      CK(ctx, cudaMemcpyAsync(d_one, hdr, sizeof hdr, cudaMemcpyHostToDevice, ctx->stream));
+      k_inflate_seq<<<1, SEQ_WARPS * 32, 0, ctx->stream>>>((const DMember *)b->d_members, (tbz_result *)b->d_results, 1, b->format,
+                                                           (const uint32_t *)d_one, (const uint32_t *)d_one + 1);
+      ctx->launches++;
+      CK(ctx, cudaStreamSynchronize(ctx->stream));
+      DMember z = bm.second; z.in_len = 0; z.out_cap = 0;
+      CK(ctx, cudaMemcpyAsync((DMember *)b->d_members + bm.first, &z, sizeof(DMember), cudaMemcpyHostToDevice, ctx->stream));
+      CK(ctx, cudaStreamSynchronize(ctx->stream));
+      dev_release(ctx, d_one);
+    }
+  }
   CK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
   b->launched = true;
   return TBZ_OK;

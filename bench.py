@@ -31,6 +31,8 @@ WORKLOADS = {
     # name: (members per GPU, member size, format, first seed)
     "zlib64k": (4096, 65536, "zlib", 1000),     # BASELINE.json configs[1]
     "gzip1m": (2048, 1 << 20, "gzip", 5000),    # configs[3] shape: 1 MiB gzip members (2 GiB per GPU)
+    "gzip1g": (1, 1 << 30, "gzip", 3),          # configs[2]: one 1 GiB gzip member, speculative split decode
+    "gzip256m": (1, 1 << 28, "gzip", 3),        # the same shape, smaller (quick runs)
 }
 
 
@@ -127,7 +129,7 @@ def recorded_traffic(workload):
     return None
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, out=sys.stdout):
     """The reference's own CPU implementation of the path: 3bz on SBCL is not runnable in this
     image (no Lisp implementation), so this arm times the oracle port — the
     behaviour-faithful C restatement of 3bz — on all host threads, a bounded sample per step."""
@@ -154,10 +156,21 @@ def run_reference(args, rank, world):
                              "sample": "%d of %d members per step" % (sample, n)},
             "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=out, flush=True)
 
 
 def main():
+    # NCCL and friends print to fd 1; the contract is ONE JSON line on stdout: keep the real stdout
+    # aside and point fd 1 at stderr for everything else
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    try:
+        _main(real_stdout)
+    finally:
+        real_stdout.flush()
+
+
+def _main(real_stdout):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -173,7 +186,7 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank, local_rank, world = dist_env()
     if args.impl == "reference":
-        return run_reference(args, rank, world)
+        return run_reference(args, rank, world, real_stdout)
 
     import torch
     import threebz_b200 as t
@@ -311,7 +324,7 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     if line:
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=real_stdout, flush=True)
 
 
 if __name__ == "__main__":

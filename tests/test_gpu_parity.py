@@ -256,3 +256,32 @@ def test_octet_pointer_context(engine, ctx):
         assert engine.finished(st) and bytes(st.output_buffer[:n]) == plain
     with pytest.raises(engine.ThreeBzError):
         engine.decompress(engine.make_octet_pointer_context(op), engine.make_gzip_state(output_buffer=bytearray(8)))
+
+
+def test_split_single_member(engine, ctx, oracle):
+    """config 3 shape (scaled down): ONE large member is cut at fixed offsets, block starts are found
+    speculatively, chunks are decoded in parallel and unresolved window references patched afterwards."""
+    plain = datagen.text(24 << 20, 3)
+    for fmt in ("gzip", "zlib", "deflate"):
+        comp = datagen.compress(plain, fmt)
+        got, _ = run_batch(ctx, fmt, [comp], len(plain))
+        g = got[0]
+        assert g["path"] == 2, "large members must take the split path"
+        assert g["verdict"] == 0 and g["out_len"] == len(plain)
+        assert hashlib.sha256(g["out"]).digest() == hashlib.sha256(plain).digest()
+        ck = {"gzip": zlib.crc32(plain), "zlib": zlib.adler32(plain), "deflate": 0}[fmt]
+        assert g["checksum"] == ck and g["in_used"] == len(comp)
+        # the same stream with the split disabled: identical result record
+        got2, _ = run_batch(ctx, fmt, [comp], len(plain), flags=4)
+        assert got2[0]["path"] != 2 and got2[0]["out"] == g["out"] and got2[0]["checksum"] == g["checksum"]
+    # damage in the middle, a wrong trailer, a truncated stream, too small a buffer: verdict and bytes as the oracle's
+    comp = datagen.compress(plain[: 6 << 20], "gzip")
+    n = 6 << 20
+    bad_mid = bytearray(comp); bad_mid[len(comp) // 2] ^= 0x55
+    bad_crc = bytearray(comp); bad_crc[-6] ^= 1
+    variants = [bytes(bad_mid), bytes(bad_crc), comp[: len(comp) - 5], comp[: len(comp) // 3]]
+    got, _ = run_batch(ctx, "gzip", variants, n)
+    for v, g in zip(variants, got):
+        compare(g, oracle.decompress_vector(v, "gzip", out_cap=n), "split variant")
+    got, _ = run_batch(ctx, "gzip", [comp], n - 1000)
+    compare(got[0], oracle.decompress_vector(comp, "gzip", out_cap=n - 1000), "split overflow")
