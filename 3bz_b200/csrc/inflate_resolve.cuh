@@ -60,8 +60,8 @@ struct SmemT {
   alignas(16) T win[WB];                 // the window, in coordinates relative to its 4-byte aligned base
   alignas(8) uint16_t val[WB];           // per window byte: V_FINAL or the window offset of an equal byte
   uint16_t queue[2][WB];                 // pending bytes of this / the next level
-  uint32_t toks[WT + 1];                 // [0] = tail of the match carried over from the previous window
-  uint16_t tstart[WT + 2];
+  alignas(8) uint2 tent[WT + 1];         // per token: x = token, y = byte offset in the window | (distance - 1) << 16;
+                                         // [0] = tail of the token carried over from the previous window
   uint32_t bitmap[WB / 32];              // token-start bits over the window's bytes
   uint16_t wrank[WB / 32];               // token starts in the bitmap words before this one
   uint32_t qcnt[3];
@@ -93,7 +93,7 @@ __device__ inline void crc_window(Smem &sm, uint32_t a, uint32_t m, int tid) {
   if (lo == hi) c = 0;
   uint32_t len = hi - lo;
   uint32_t shift = crc_x8n(seg);
-  uint32_t *s_c = sm.toks, *s_l = sm.toks + NT;                  // the token array is dead by now
+  uint32_t *s_c = reinterpret_cast<uint32_t *>(sm.tent), *s_l = s_c + NT;   // the token array is dead by now
   for (int s = 1; s < NT; s <<= 1) {
     s_c[tid] = c; s_l[tid] = len;
     __syncthreads();
@@ -144,18 +144,29 @@ __device__ inline uint32_t resolve_window(T *__restrict__ out, int fmt, const ui
       for (int stp = NL / 2; stp; stp >>= 1)
         if (sm.segstart[j + stp] <= g0) j += stp;
     }
+    const uint32_t last = tid * tpt + tpt;             // one past the thread's last token
+    if (last <= n && f + last <= sm.segstart[j + 1]) {  // common: all of them in one list
+      const uint32_t *src = slab + sm.segptr[j] + (g0 - sm.segstart[j]);
 #pragma unroll
-    for (int q = 0; q < TPT; q++) {
-      const uint32_t idx = tid * tpt + q;
-      const bool have = (uint32_t)q < tpt && idx < n;
-      tk[q] = 0u;
-      if (have) {
-        const uint32_t g = f + idx;
-        while (g >= sm.segstart[j + 1]) j++;
-        tk[q] = __ldg(slab + sm.segptr[j] + (g - sm.segstart[j]));
+      for (int q = 0; q < TPT; q++) {
+        tk[q] = (uint32_t)q < tpt ? __ldg(src + q) : 0u;
+        ln[q] = (uint32_t)q < tpt ? tok_len(tk[q]) : 0u;
+        mine += ln[q];
       }
-      ln[q] = have ? tok_len(tk[q]) : 0u;
-      mine += ln[q];
+    } else {
+#pragma unroll
+      for (int q = 0; q < TPT; q++) {
+        const uint32_t idx = tid * tpt + q;
+        const bool have = (uint32_t)q < tpt && idx < n;
+        tk[q] = 0u;
+        if (have) {
+          const uint32_t g = f + idx;
+          while (g >= sm.segstart[j + 1]) j++;
+          tk[q] = __ldg(slab + sm.segptr[j] + (g - sm.segstart[j]));
+        }
+        ln[q] = have ? tok_len(tk[q]) : 0u;
+        mine += ln[q];
+      }
     }
   }
   uint32_t x = mine;
@@ -181,8 +192,7 @@ __device__ inline uint32_t resolve_window(T *__restrict__ out, int fmt, const ui
     const bool have = (uint32_t)q < tpt && idx < n;
     if (have && st < WB) {
       used++;
-      sm.toks[1 + idx] = tk[q];
-      sm.tstart[1 + idx] = (uint16_t)st;
+      sm.tent[1 + idx] = make_uint2(tk[q], st | (((tk[q] >> 8) & 0x7fffu) << 16));
       atomicOr(&sm.bitmap[st >> 5], 1u << (st & 31u));
       if (tk[q] & TOK_MATCH) {
         const uint32_t d = ((tk[q] >> 8) & 0x7fffu) + 1u;
@@ -195,8 +205,7 @@ __device__ inline uint32_t resolve_window(T *__restrict__ out, int fmt, const ui
   }
   if (bad) sm.fail = 1;
   if (tid == 0) {
-    sm.toks[0] = carry_tok;
-    sm.tstart[0] = (uint16_t)mis;
+    sm.tent[0] = make_uint2(carry_tok, mis | (((carry_tok >> 8) & 0x7fffu) << 16));
     if (carry_len) atomicOr(&sm.bitmap[0], 1u << mis);
   }
   uint32_t nused = n;
@@ -241,21 +250,22 @@ __device__ inline uint32_t resolve_window(T *__restrict__ out, int fmt, const ui
     for (int j = 0; j < 4; j++) {
       const uint32_t r = r0 + j;
       if (j) ti += (nib >> j) & 1u;
-      T byte = 0;
-      uint32_t v = V_FINAL;
-      if (r >= mis && r < wend) {
-        const uint32_t t = sm.toks[ti];
-        const uint32_t o = r - sm.tstart[ti];
-        if (t & TOK_MATCH) {
-          const uint32_t d = ((t >> 8) & 0x7fffu) + 1u;
-          uint32_t back = d;
-          if (o >= d) back = o - o % d + d;                       // overlapping match: read through the period
-          if (back + mis > r) byte = sm.hist[(P4 + r - back) & HMASK];   // the source is below the window: final
-          else { v = r - back; npend++; pmask |= 1u << j; }
-        } else {
-          byte = (T)((t >> (8u * o)) & 255u);                     // one or two literals in a token
-        }
-      }
+      // the same instructions for every byte: the history read is issued unconditionally (the ring
+      // index is always valid) and selected afterwards; only the period of an overlapping match branches
+      const uint2 e = sm.tent[ti < WT ? ti : WT];         // (a byte outside the window may have no token: any entry will do)
+      const bool valid = r >= mis && r < wend;
+      const bool ism = (e.x & TOK_MATCH) != 0;
+      const uint32_t o = r - (e.y & 0xffffu), d = (e.y >> 16) + 1u;
+      uint32_t back = d;
+      if (__builtin_expect(valid && ism && o >= d, 0)) back = o - o % d + d;   // overlapping match: read through the period
+      const T hv = sm.hist[(P4 + r - back) & HMASK];
+      const bool fin = back + mis > r;                    // the source is below the window: final
+      const T lit = (T)((e.x >> (8u * (o & 1u))) & 255u); // one or two literals in a token
+      const T byte = ism ? hv : lit;
+      const bool pend = valid && ism && !fin;
+      const uint32_t v = pend ? r - back : V_FINAL;
+      npend += pend ? 1u : 0u;
+      pmask |= (pend ? 1u : 0u) << j;
       el[j] = byte;
       if (j < 2) v01 |= v << (16 * j); else v23 |= v << (16 * (j - 2));
     }

@@ -95,13 +95,15 @@ struct DevBlock { void *p; size_t size; bool used; };
 
 struct tbz_ctx {
   int device = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;          // the stream new work is enqueued on (main_stream, or a pipeline stream)
+  cudaStream_t main_stream = nullptr, pstream[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, tev0 = nullptr, tev1 = nullptr;
   cudaEvent_t kev[4] = {nullptr, nullptr, nullptr, nullptr};   // TBZ_KTIME=1: events between the kernels of a launch
   bool ktime = false;
   std::vector<DevBlock> pool;
   void *stage_in = nullptr;  size_t stage_in_cap = 0;    // pinned staging
   void *stage_out = nullptr; size_t stage_out_cap = 0;
+  void *stage_res = nullptr; size_t stage_res_cap = 0;   // pinned landing zone for result records (the caller's array may be pageable)
   std::string last_error;
   uint64_t launches = 0;
   int sm_count = 0;
@@ -176,6 +178,10 @@ struct tbz_batch {
   int fast_grid = 0, res_grid = 0;
   uint32_t nslabs = 0;
   bool launched = false;
+  cudaStream_t stream = nullptr;       // the stream this batch lives on
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  tbz_result *eager_res = nullptr;     // pipelined sub-batch: results and outputs are copied back right behind the kernels
+  std::vector<DMember> dm;             // device view of the members (kept alive for the asynchronous upload)
   std::vector<std::pair<uint64_t, DMember>> big;   // members decoded by the split path (index, device view)
 };
 
@@ -205,6 +211,8 @@ extern "C" int32_t tbz_ctx_create(int32_t device, uint64_t flags, tbz_ctx **out)
   ctx->device = device;
   CK(ctx, cudaSetDevice(device));
   CK(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  ctx->main_stream = ctx->stream;
+  for (auto &ps : ctx->pstream) CK(ctx, cudaStreamCreateWithFlags(&ps, cudaStreamNonBlocking));
   CK(ctx, cudaEventCreate(&ctx->ev0)); CK(ctx, cudaEventCreate(&ctx->ev1));
   CK(ctx, cudaEventCreate(&ctx->tev0)); CK(ctx, cudaEventCreate(&ctx->tev1));
   CK(ctx, cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
@@ -221,9 +229,11 @@ extern "C" int32_t tbz_ctx_destroy(tbz_ctx *ctx) {
   for (auto &b : ctx->pool) cudaFree(b.p);
   if (ctx->stage_in) cudaFreeHost(ctx->stage_in);
   if (ctx->stage_out) cudaFreeHost(ctx->stage_out);
+  if (ctx->stage_res) cudaFreeHost(ctx->stage_res);
   cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
   cudaEventDestroy(ctx->tev0); cudaEventDestroy(ctx->tev1);
-  cudaStreamDestroy(ctx->stream);
+  cudaStreamDestroy(ctx->main_stream);
+  for (auto &ps : ctx->pstream) cudaStreamDestroy(ps);
   delete ctx;
   return TBZ_OK;
 }
@@ -376,7 +386,9 @@ extern "C" int32_t tbz_batch_destroy(tbz_batch *b) {
   if (!b) return TBZ_OK;
   tbz_ctx *ctx = b->ctx;
   cudaSetDevice(ctx->device);
-  if (b->launched) cudaStreamSynchronize(ctx->stream);
+  if (b->launched || b->n) cudaStreamSynchronize(b->stream);
+  if (b->ev0) cudaEventDestroy(b->ev0);
+  if (b->ev1) cudaEventDestroy(b->ev1);
   dev_release(ctx, b->d_in); dev_release(ctx, b->d_out);
   dev_release(ctx, b->d_members); dev_release(ctx, b->d_results);
   dev_release(ctx, b->d_slabs); dev_release(ctx, b->d_counters); dev_release(ctx, b->d_todo); dev_release(ctx, b->d_recs);
@@ -391,6 +403,8 @@ extern "C" int32_t tbz_batch_prepare(tbz_ctx *ctx, int32_t format, const tbz_mem
   CK(ctx, cudaSetDevice(ctx->device));
   tbz_batch *b = new tbz_batch();
   b->ctx = ctx; b->format = format; b->flags = flags; b->n = n;
+  b->stream = ctx->stream;
+  CK(ctx, cudaEventCreate(&b->ev0)); CK(ctx, cudaEventCreate(&b->ev1));
   b->device_ptrs = (flags & TBZ_FLAG_DEVICE_PTRS) != 0;
   int32_t rc;
 #define PCK(x) do { rc = (x); if (rc != TBZ_OK) { tbz_batch_destroy(b); return rc; } } while (0)
@@ -419,7 +433,8 @@ extern "C" int32_t tbz_batch_prepare(tbz_ctx *ctx, int32_t format, const tbz_mem
     PCK(dev_alloc(ctx, n * 4, &b->d_todo));
     PCK(dev_alloc(ctx, n * sizeof(tbzfast::P1Rec), &b->d_recs));
   }
-  std::vector<DMember> dm(n);
+  std::vector<DMember> &dm = b->dm;
+  dm.resize(n);
   if (b->device_ptrs) {
     for (uint64_t i = 0; i < n; i++) dm[i] = DMember{m[i].in, m[i].in_len, m[i].out, m[i].out_cap};
   } else {
@@ -471,8 +486,7 @@ extern "C" int32_t tbz_batch_prepare(tbz_ctx *ctx, int32_t format, const tbz_mem
         dm[i].in_len = 0; dm[i].out_cap = 0;
       }
   if (n) {
-    cudaError_t e = cudaMemcpyAsync(b->d_members, dm.data(), n * sizeof(DMember), cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);   // dm is a local
+    cudaError_t e = cudaMemcpyAsync(b->d_members, dm.data(), n * sizeof(DMember), cudaMemcpyHostToDevice, b->stream);
     if (e != cudaSuccess) { tbz_batch_destroy(b); return fail(ctx, TBZ_E_CUDA, "upload member table", e); }
   }
 #undef PCK
@@ -776,6 +790,11 @@ extern "C" int32_t tbz_batch_launch(tbz_batch *b) {
   if (!b) return TBZ_E_ARG;
   tbz_ctx *ctx = b->ctx;
   CK(ctx, cudaSetDevice(ctx->device));
+  struct StreamScope {                                 // everything below enqueues on the batch's stream
+    tbz_ctx *c; cudaStream_t saved;
+    StreamScope(tbz_ctx *c_, cudaStream_t s) : c(c_), saved(c_->stream) { c->stream = s; }
+    ~StreamScope() { c->stream = saved; }
+  } scope(ctx, b->stream);
   if (!b->device_ptrs && b->n) {
     if (b->in_direct) {
       CK(ctx, cudaMemcpyAsync(b->d_in, b->in_span, b->in_total, cudaMemcpyHostToDevice, ctx->stream));
@@ -790,7 +809,7 @@ extern "C" int32_t tbz_batch_launch(tbz_batch *b) {
       CK(ctx, cudaMemcpyAsync(b->d_in, st, b->in_total, cudaMemcpyHostToDevice, ctx->stream));
     }
   }
-  CK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  CK(ctx, cudaEventRecord(b->ev0, ctx->stream));
   int32_t rc = launch_kernels(b);
   if (rc) return rc;
   for (auto &bm : b->big) {                            // large members: split across the GPU, else the sequential kernel
@@ -815,7 +834,11 @@ extern "C" int32_t tbz_batch_launch(tbz_batch *b) {
       dev_release(ctx, d_one);
     }
   }
-  CK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  CK(ctx, cudaEventRecord(b->ev1, ctx->stream));
+  if (b->eager_res && b->n) {
+    CK(ctx, cudaMemcpyAsync(b->eager_res, b->d_results, b->n * sizeof(tbz_result), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaMemcpyAsync(b->out_span, b->d_out, b->out_total, cudaMemcpyDeviceToHost, ctx->stream));
+  }
   b->launched = true;
   return TBZ_OK;
 }
@@ -826,19 +849,21 @@ extern "C" int32_t tbz_batch_finish(tbz_batch *b, tbz_result *r) {
   CK(ctx, cudaSetDevice(ctx->device));
   if (!b->launched) return fail(ctx, TBZ_E_STATE, "tbz_batch_finish before tbz_batch_launch");
   if (!b->n) return TBZ_OK;
+  cudaStream_t st = b->stream;
+  if (b->eager_res) { CK(ctx, cudaStreamSynchronize(st)); return TBZ_OK; }
   std::vector<tbz_result> tmp;
   tbz_result *res = r;
   if (!res) { tmp.resize(b->n); res = tmp.data(); }
-  CK(ctx, cudaMemcpyAsync(res, b->d_results, b->n * sizeof(tbz_result), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(ctx, cudaMemcpyAsync(res, b->d_results, b->n * sizeof(tbz_result), cudaMemcpyDeviceToHost, st));
   if (!b->device_ptrs) {
     if (b->out_direct) {
-      CK(ctx, cudaMemcpyAsync(b->out_span, b->d_out, b->out_total, cudaMemcpyDeviceToHost, ctx->stream));
-      CK(ctx, cudaStreamSynchronize(ctx->stream));
+      CK(ctx, cudaMemcpyAsync(b->out_span, b->d_out, b->out_total, cudaMemcpyDeviceToHost, st));
+      CK(ctx, cudaStreamSynchronize(st));
     } else {
       int32_t rc = ensure_stage(ctx, &ctx->stage_out, &ctx->stage_out_cap, b->out_total);
       if (rc) return rc;
-      CK(ctx, cudaMemcpyAsync(ctx->stage_out, b->d_out, b->out_total, cudaMemcpyDeviceToHost, ctx->stream));
-      CK(ctx, cudaStreamSynchronize(ctx->stream));
+      CK(ctx, cudaMemcpyAsync(ctx->stage_out, b->d_out, b->out_total, cudaMemcpyDeviceToHost, st));
+      CK(ctx, cudaStreamSynchronize(st));
       const uint8_t *st = (const uint8_t *)ctx->stage_out;
       parallel_for(b->n, b->out_total, [&](size_t lo, size_t hi) {
         for (size_t i = lo; i < hi; i++)
@@ -846,7 +871,7 @@ extern "C" int32_t tbz_batch_finish(tbz_batch *b, tbz_result *r) {
       });
     }
   } else {
-    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    CK(ctx, cudaStreamSynchronize(st));
   }
   return TBZ_OK;
 }
@@ -856,13 +881,68 @@ static int32_t batch_device_ms(tbz_batch *b, float *ms) {
   if (!ms) return TBZ_OK;
   *ms = 0.f;
   if (!b->n) return TBZ_OK;
-  CK(ctx, cudaEventSynchronize(ctx->ev1));
-  CK(ctx, cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+  CK(ctx, cudaEventSynchronize(b->ev1));
+  CK(ctx, cudaEventElapsedTime(ms, b->ev0, b->ev1));
+  return TBZ_OK;
+}
+
+// Host buffers, many members: the batch is cut into contiguous sub-batches that travel down three
+// streams, so the H2D copy of one, the kernels of another and the D2H copy of a third overlap (the
+// copy engines and the SMs are separate units).  Needs dense inputs and adjacent outputs (the DMA
+// then runs straight on the caller's memory); anything else takes the one-piece path.
+static int32_t inflate_batch_pipelined(tbz_ctx *ctx, int32_t format, const tbz_member *m, uint64_t n,
+                                       tbz_result *r, uint32_t flags, float *device_ms, bool *done) {
+  *done = false;
+  uint64_t bytes = 0;
+  for (uint64_t i = 0; i < n; i++) {
+    if (m[i].in_len >= kSplitMinBytes) return TBZ_OK;
+    bytes += m[i].in_len + m[i].out_cap;
+  }
+  if (bytes < (32ull << 20)) return TBZ_OK;
+  const uint64_t parts = std::min<uint64_t>(16, std::max<uint64_t>(2, n / 256));
+  std::vector<tbz_batch *> sub(parts, nullptr);
+  {
+    int32_t src = ensure_stage(ctx, &ctx->stage_res, &ctx->stage_res_cap, n * sizeof(tbz_result));
+    if (src) return src;
+  }
+  tbz_result *pinned = (tbz_result *)ctx->stage_res;
+  cudaStream_t saved = ctx->stream;
+  int32_t rc = TBZ_OK;
+  bool ok = true;
+  for (uint64_t p = 0; p < parts && !rc; p++) {
+    const uint64_t lo = n * p / parts, hi = n * (p + 1) / parts;
+    ctx->stream = ctx->pstream[p % 3];
+    rc = tbz_batch_prepare(ctx, format, m + lo, hi - lo, flags, &sub[p]);
+    if (!rc && !(sub[p]->in_direct && sub[p]->out_direct)) { ok = false; break; }
+    if (!rc) { sub[p]->eager_res = pinned + lo; rc = tbz_batch_launch(sub[p]); }
+  }
+  ctx->stream = saved;
+  float total_ms = 0.f;
+  for (uint64_t p = 0; p < parts; p++) {
+    if (!sub[p]) continue;
+    if (!rc && ok && sub[p]->launched) {
+      rc = tbz_batch_finish(sub[p], nullptr);
+      float ms = 0.f;
+      if (!rc) rc = batch_device_ms(sub[p], &ms);
+      total_ms += ms;
+    }
+    tbz_batch_destroy(sub[p]);
+  }
+  if (rc) return rc;
+  if (!ok) return TBZ_OK;                              // (sub-batches already launched rewrote nothing the one-piece path will not rewrite)
+  memcpy(r, pinned, n * sizeof(tbz_result));
+  if (device_ms) *device_ms = total_ms;
+  *done = true;
   return TBZ_OK;
 }
 
 extern "C" int32_t tbz_inflate_batch(tbz_ctx *ctx, int32_t format, const tbz_member *m, uint64_t n,
                                      tbz_result *r, uint32_t flags, float *device_ms) {
+  if (ctx && m && r && n >= 512 && !(flags & TBZ_FLAG_DEVICE_PTRS)) {
+    bool done = false;
+    int32_t prc = inflate_batch_pipelined(ctx, format, m, n, r, flags, device_ms, &done);
+    if (prc || done) return prc;
+  }
   tbz_batch *b = nullptr;
   int32_t rc = tbz_batch_prepare(ctx, format, m, n, flags, &b);
   if (rc) return rc;
