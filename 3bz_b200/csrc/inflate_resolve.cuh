@@ -69,6 +69,8 @@ struct SmemT {
   uint32_t segstart[NL + 1];             // flat index of the first token of every list of the current slab
   uint32_t segptr[NL];                   // word offset of that token in the slab
   uint32_t crc_tab[256];
+  uint32_t x16[WB / 16 + 4];             // x^(8 * 16 k) mod P: shifts a CRC over k 16-byte units
+  uint32_t crcw[NWARP];
   uint32_t wscan[NWARP], wscan2[NWARP];
   unsigned long long wsum[NWARP][2];
   uint32_t member;
@@ -323,8 +325,9 @@ __device__ inline uint32_t resolve_window(T *__restrict__ out, int fmt, const ui
   __syncthreads();
   const uint32_t wsize = wend - mis;
   // ---- 5. flush complete 16-byte units, fold them into the checksum
-  if (sizeof(T) == 1 && fmt == TBZ_GZIP) crc_window(reinterpret_cast<Smem &>(sm), pos, wsize, tid);
-  if ((((uintptr_t)out) & 15) == 0) {
+  const bool aligned_out = (((uintptr_t)out) & 15) == 0;
+  if (sizeof(T) == 1 && fmt == TBZ_GZIP && !aligned_out) crc_window(reinterpret_cast<Smem &>(sm), pos, wsize, tid);
+  if (aligned_out) {
     if (rs.flushed & (UNIT - 1u)) {                    // a chunk of a split member starts inside a unit: element-wise head
       uint32_t upto = (rs.flushed + UNIT - 1u) & ~(UNIT - 1u);
       if (upto > pos + wsize) upto = pos + wsize;
@@ -332,9 +335,21 @@ __device__ inline uint32_t resolve_window(T *__restrict__ out, int fmt, const ui
       rs.flushed = upto;
     }
     const uint32_t upto = (pos + wsize) & ~(UNIT - 1u);
+    uint32_t myc = 0;                                  // gzip: CRCs of this thread's units, shifted to the end of the flushed range
     for (uint32_t p = rs.flushed + UNIT * tid; p < upto; p += UNIT * NT) {
       const uint4 v = *reinterpret_cast<const uint4 *>(&sm.hist[p & HMASK]);
       *reinterpret_cast<uint4 *>(out + p) = v;
+      if (sizeof(T) == 1 && fmt == TBZ_GZIP) {
+        // crc(A || B) = crc(A) * x^(8 |B|) + crc(B) for finalized CRCs: one table CRC per unit, one
+        // multiplication by the power for the bytes that follow it, XOR over all units
+        const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+        uint32_t c = 0xffffffffu;
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+#pragma unroll
+          for (int b8 = 0; b8 < 4; b8++) c = (c >> 8) ^ sm.crc_tab[(c ^ (w4[q] >> (8 * b8))) & 0xff];
+        myc ^= crc_mulmod(sm.x16[(upto - p - 16u) >> 4], c ^ 0xffffffffu);
+      }
       if (sizeof(T) == 1 && fmt == TBZ_ZLIB) {
         uint32_t sd = __dp4a(v.x, 0x01010101u, 0u); sd = __dp4a(v.y, 0x01010101u, sd);
         sd = __dp4a(v.z, 0x01010101u, sd); sd = __dp4a(v.w, 0x01010101u, sd);
@@ -342,6 +357,18 @@ __device__ inline uint32_t resolve_window(T *__restrict__ out, int fmt, const ui
         wj = __dp4a(v.z, 0x0b0a0908u, wj); wj = __dp4a(v.w, 0x0f0e0d0cu, wj);
         rs.acc_a += sd;
         rs.acc_w += (unsigned long long)p * sd + wj;
+      }
+    }
+    if (sizeof(T) == 1 && fmt == TBZ_GZIP) {
+#pragma unroll
+      for (int sft = 16; sft; sft >>= 1) myc ^= __shfl_xor_sync(TBZ_FULL, myc, sft);
+      if (lane == 0) sm.crcw[warp] = myc;
+      __syncthreads();
+      if (tid == 0 && upto > rs.flushed) {
+        uint32_t wc = 0;
+#pragma unroll
+        for (int w = 0; w < NWARP; w++) wc ^= sm.crcw[w];
+        sm.crc = crc_mulmod(sm.x16[(upto - rs.flushed) >> 4], sm.crc) ^ wc;
       }
     }
     if (upto > rs.flushed) rs.flushed = upto;
@@ -433,7 +460,14 @@ __device__ inline bool resolve_member(const DMember &mem, int fmt, const P1Rec &
     const uint32_t s2 = (uint32_t)((N + N * S + (unsigned long long)TBZ_ADLER_MOD * 4096 - w % TBZ_ADLER_MOD) % TBZ_ADLER_MOD);
     ck = s1 | (s2 << 16);
   } else if (fmt == TBZ_GZIP) {
-    ck = sm.crc;
+    __syncthreads();
+    uint32_t c = sm.crc;
+    if (rs.flushed < pos) {                  // the last partial unit (uniform: every thread computes the same value)
+      uint32_t t = 0xffffffffu;
+      for (uint32_t p = rs.flushed; p < pos; p++) t = (t >> 8) ^ sm.crc_tab[(t ^ sm.hist[p & HMASK]) & 0xff];
+      c = crc_combine(c, t ^ 0xffffffffu, pos - rs.flushed);
+    }
+    ck = c;
   }
   // ---- trailer (zlib.lisp:80-96, gzip.lisp:82-106): any disagreement goes to the sequential kernel
   uintptr_t a0 = (uintptr_t)mem.in;

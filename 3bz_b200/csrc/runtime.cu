@@ -71,7 +71,10 @@ k_inflate_resolve(const DMember *members, tbz_result *results, uint32_t n, int f
   extern __shared__ __align__(16) unsigned char smem_raw[];
   tbzres::Smem &sm = *reinterpret_cast<tbzres::Smem *>(smem_raw);
   const int tid = threadIdx.x;
-  if (fmt == TBZ_GZIP) crc_table_init(sm.crc_tab, tid, tbzres::NT);
+  if (fmt == TBZ_GZIP) {
+    crc_table_init(sm.crc_tab, tid, tbzres::NT);
+    for (uint32_t k = tid; k < tbzres::WB / 16 + 4; k += tbzres::NT) sm.x16[k] = crc_x8n(16ull * k);
+  }
   for (;;) {
     __syncthreads();
     if (tid == 0) sm.member = atomicAdd(&counters[3], 1u);
