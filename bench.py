@@ -282,7 +282,7 @@ def _main(real_stdout):
     # ---- max over ranks
     if world > 1:
         tt = torch.tensor([dev_ms, e2e_step], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)        # t.shard.reduce_max is the same reduction on CPU tensors (gloo test)
         dev_ms, e2e_step = float(tt[0]), float(tt[1])
 
     line = None
