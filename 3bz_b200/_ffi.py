@@ -20,7 +20,8 @@ E_CUDA, E_NO_DEVICE, E_ARG, E_NOMEM, E_BUFFER_SWITCH, E_STATE = -1, -2, -3, -4, 
 SYMBOLS = [
     "tbz_abi_version", "tbz_device_count", "tbz_ctx_create", "tbz_ctx_destroy", "tbz_strerror",
     "tbz_verdict_name", "tbz_ctx_last_error", "tbz_ctx_synchronize", "tbz_ctx_stream",
-    "tbz_ctx_timer_start", "tbz_ctx_timer_stop", "tbz_ctx_launch_count",
+    "tbz_ctx_timer_start", "tbz_ctx_timer_stop", "tbz_ctx_kernel_timing", "tbz_ctx_last_kernel_ms",
+    "tbz_ctx_launch_count",
     "tbz_host_alloc", "tbz_host_free", "tbz_host_register", "tbz_host_unregister",
     "tbz_device_alloc", "tbz_device_free", "tbz_memcpy_h2d", "tbz_memcpy_d2h",
     "tbz_inflate_batch", "tbz_inflate_single", "tbz_inflate_alloc", "tbz_free",
@@ -72,6 +73,8 @@ def lib():
         "tbz_ctx_stream": (i32, [vp, P(vp)]),
         "tbz_ctx_timer_start": (i32, [vp]),
         "tbz_ctx_timer_stop": (i32, [vp, P(C.c_float)]),
+        "tbz_ctx_kernel_timing": (i32, [vp, i32]),
+        "tbz_ctx_last_kernel_ms": (i32, [vp, P(C.c_float)]),
         "tbz_ctx_launch_count": (i32, [vp, P(u64)]),
         "tbz_host_alloc": (i32, [u64, P(vp)]),
         "tbz_host_free": (i32, [vp]),

@@ -102,7 +102,8 @@ struct tbz_ctx {
   cudaStream_t main_stream = nullptr, pstream[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, tev0 = nullptr, tev1 = nullptr;
   cudaEvent_t kev[4] = {nullptr, nullptr, nullptr, nullptr};   // TBZ_KTIME=1: events between the kernels of a launch
-  bool ktime = false;
+  bool ktime = false, ktime_quiet = false;
+  float last_kms[3] = {0.f, 0.f, 0.f};
   std::vector<DevBlock> pool;
   void *stage_in = nullptr;  size_t stage_in_cap = 0;    // pinned staging
   void *stage_out = nullptr; size_t stage_out_cap = 0;
@@ -304,6 +305,19 @@ extern "C" int32_t tbz_ctx_timer_stop(tbz_ctx *ctx, float *ms) {
   CK(ctx, cudaEventRecord(ctx->tev1, ctx->stream));
   CK(ctx, cudaEventSynchronize(ctx->tev1));
   CK(ctx, cudaEventElapsedTime(ms, ctx->tev0, ctx->tev1));
+  return TBZ_OK;
+}
+extern "C" int32_t tbz_ctx_kernel_timing(tbz_ctx *ctx, int32_t enable) {
+  if (!ctx) return TBZ_E_ARG;
+  CK(ctx, cudaSetDevice(ctx->device));
+  if (enable && !ctx->kev[0]) for (auto &e : ctx->kev) CK(ctx, cudaEventCreate(&e));
+  if (enable) { if (!ctx->ktime) ctx->ktime_quiet = true; ctx->ktime = true; }
+  else if (ctx->ktime_quiet) { ctx->ktime = false; ctx->ktime_quiet = false; }
+  return TBZ_OK;
+}
+extern "C" int32_t tbz_ctx_last_kernel_ms(tbz_ctx *ctx, float *ms3) {
+  if (!ctx || !ms3) return TBZ_E_ARG;
+  for (int i = 0; i < 3; i++) ms3[i] = ctx->last_kms[i];
   return TBZ_OK;
 }
 extern "C" int32_t tbz_ctx_launch_count(tbz_ctx *ctx, uint64_t *n) {
@@ -527,7 +541,7 @@ static int32_t split_inflate(tbz_ctx *ctx, int fmt, const DMember &m, tbz_result
   cudaStream_t st = ctx->stream;
   auto t_prev = std::chrono::steady_clock::now();
   auto stage = [&](const char *name) {                // TBZ_KTIME=1: wall time per stage (each ends in a stream sync)
-    if (!ctx->ktime) return;
+    if (!ctx->ktime || ctx->ktime_quiet) return;
     cudaStreamSynchronize(st);
     auto t = std::chrono::steady_clock::now();
     fprintf(stderr, "[tbz split] %-10s %8.3f ms\n", name, std::chrono::duration<double, std::milli>(t - t_prev).count());
@@ -734,7 +748,7 @@ static int32_t split_inflate(tbz_ctx *ctx, int fmt, const DMember &m, tbz_result
   SCK(cudaMemcpyAsync(d_result, &r, sizeof r, cudaMemcpyHostToDevice, st));
   SCK(cudaStreamSynchronize(st));
   stage("checksum");
-  if (ctx->ktime) fprintf(stderr, "[tbz split] %u chunks of %u, %llu bytes out\n", nv, nchunks, (unsigned long long)total);
+  if (ctx->ktime && !ctx->ktime_quiet) fprintf(stderr, "[tbz split] %u chunks of %u, %llu bytes out\n", nv, nchunks, (unsigned long long)total);
   cleanup();
 #undef SCK
 #undef SRC
@@ -778,7 +792,8 @@ static int32_t launch_kernels(tbz_batch *b) {
       cudaEventElapsedTime(&d, ctx->kev[2], ctx->kev[3]);
       uint32_t cnt[4] = {0, 0, 0, 0};
       cudaMemcpy(cnt, b->d_counters, sizeof cnt, cudaMemcpyDeviceToHost);
-      fprintf(stderr, "[tbz] decode %.3f ms, resolve %.3f ms, seq %.3f ms (%u members), %u slabs\n", a, c, d, cnt[1], cnt[2]);
+      ctx->last_kms[0] = a; ctx->last_kms[1] = c; ctx->last_kms[2] = d;
+      if (!ctx->ktime_quiet) fprintf(stderr, "[tbz] decode %.3f ms, resolve %.3f ms, seq %.3f ms (%u members), %u slabs\n", a, c, d, cnt[1], cnt[2]);
     }
     return TBZ_OK;
   }

@@ -264,6 +264,19 @@ def _main(real_stdout):
     for i in (0, n // 2, n - 1):
         assert res[i].checksum == ck(ms[i][0]), "checksum mismatch on member %d" % i
 
+    # ---- per-kernel times of the same launch (CUDA events between the kernels), three extra launches
+    kms = [[], [], []]
+    _ffi.check(L.tbz_ctx_kernel_timing(ctx.h, 1), ctx.h)
+    for _ in range(3):
+        _ffi.check(L.tbz_batch_launch(batch), ctx.h)
+        k3 = (C.c_float * 3)()
+        _ffi.check(L.tbz_ctx_last_kernel_ms(ctx.h, k3), ctx.h)
+        for j in range(3):
+            kms[j].append(k3[j])
+    _ffi.check(L.tbz_ctx_kernel_timing(ctx.h, 0), ctx.h)
+    kernel_ms = {"k_inflate_decode": statistics.median(kms[0]), "k_inflate_resolve": statistics.median(kms[1]),
+                 "k_inflate_seq": statistics.median(kms[2])}
+
     # ---- end to end through the public C-ABI call with HOST buffers
     e2e_t = []
     for k in range(args.e2e_steps + 1):
@@ -313,7 +326,10 @@ def _main(real_stdout):
                              "frac": achieved / peak, "traffic": recorded_traffic(args.workload),
                              "peak_source": how, "frac_of_8000": achieved / 8000.0,
                              "algorithmic_bytes_per_launch": C_total + U_total + B_total,
-                             "kernel_ms": ms_per_step},
+                             "kernel_ms": ms_per_step,
+                             "kernels_ms": kernel_ms,
+                             "note": "achieved = (C + U + B) of one launch of the hot path (decode + resolve kernels) / its "
+                                     "CUDA-event time; traffic = ncu dram bytes of the dominant kernel (k_inflate_resolve)"},
                 "cpu_baseline": {"value": sample * size / cpu_t / 1e9, "unit": "GB/s", "cores": cores, "kind": "port",
                                  "sample": "%d of %d members, one pass, %d threads" % (sample, n, cores)}}
     L.tbz_batch_destroy(batch)

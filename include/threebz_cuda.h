@@ -107,6 +107,10 @@ int32_t tbz_ctx_stream(tbz_ctx *ctx, void **cuda_stream);
 /* CUDA-event stopwatch on that stream: start, enqueue work, stop -> elapsed device ms */
 int32_t tbz_ctx_timer_start(tbz_ctx *ctx);
 int32_t tbz_ctx_timer_stop(tbz_ctx *ctx, float *ms);
+/* per-kernel CUDA-event times of the batched path: enable, launch, read the last launch's
+ * {decode, resolve, sequential} milliseconds (measurement only; adds one event sync per launch) */
+int32_t tbz_ctx_kernel_timing(tbz_ctx *ctx, int32_t enable);
+int32_t tbz_ctx_last_kernel_ms(tbz_ctx *ctx, float *ms3);
 /* number of engine kernels launched by this ctx so far */
 int32_t tbz_ctx_launch_count(tbz_ctx *ctx, uint64_t *n);
 
