@@ -1,0 +1,543 @@
+// inflate_copy.cuh — phase two of the batched fast path for byte members: LZ77 resolution of a
+// token stream (deflate.lisp:244-359 `copy-history`), one thread per token.
+//
+// One CTA per member.  The last 32 KiB of output and the window being produced live in ONE linear
+// shared-memory buffer (positions never wrap; when the buffer is full its last 32 KiB slide down).
+// A window is the next <= WT tokens (<= WCAP bytes); tokens are never split.  Per window:
+//   1. the tokens are loaded (TPT consecutive tokens per thread), a CTA prefix sum over their
+//      lengths gives every token its byte offset; a small table maps every 16-byte chunk of the
+//      window to the token that covers its first byte
+//   2. every thread writes its literals and sorts its matches into two dense job queues (warp scan,
+//      one shared-memory atomic per warp): READY = the source lies entirely below the window (final
+//      history), PENDING = the source reaches into the window
+//   3. the ready queue is copied by all threads, one job per thread and step, so the lanes of a
+//      warp all run the same straight-line copy: byte moves for the <= 3 bytes up to the first
+//      aligned destination word and after the last one, in between one aligned word load per 4
+//      source bytes and a funnel shift.  No atomics, no per-byte token search
+//   4. the pending queue (about a fifth of the tokens on text, in token order) is worked off in
+//      rounds: a job looks up the tokens that produce its source (chunk table + walk) and tests
+//      their done flags; when all are set it copies, fences and sets its own flag, so chains can
+//      also resolve inside one round.  Rounds end at a CTA barrier and stop when nothing is pending
+//   5. the window is flushed to global memory with 16-byte stores; Adler-32 is folded in with dp4a
+//      (order-independent form), CRC-32 per 16-byte unit with x^(8n) combines
+// The trailer is checked as zlib.lisp:80-96 / gzip.lisp:82-106 do; any disagreement sends the member
+// to the sequential kernel, which owns the verdict rules.
+#pragma once
+#include "tbz_device.cuh"
+#include "inflate_decode.cuh"
+
+namespace tbzcp {
+
+using tbzfast::NL;
+using tbzfast::NO_SLAB;
+using tbzfast::P1Rec;
+using tbzfast::SLAB_HDR_WORDS;
+using tbzfast::SLAB_WORDS;
+using tbzfast::SlabHdr;
+using tbzfast::TOKCAP;
+using tbzfast::TOK_MATCH;
+
+constexpr int NT = 256;
+constexpr int NWARP = NT / 32;
+#ifndef TBZ_CP_TPT
+#define TBZ_CP_TPT 4
+#endif
+constexpr int TPT = TBZ_CP_TPT;                 // tokens per thread and window
+constexpr uint32_t WT = (uint32_t)NT * TPT;     // window tokens
+constexpr uint32_t HIST = 32768u;
+constexpr uint32_t WCAP = 8192u;                // window bytes
+constexpr uint32_t LB = HIST + 16384u;          // linear buffer: history + room for two full windows
+constexpr uint32_t WB = WCAP;                   // (name shared with the other phase-two variants: sizes the x16 table)
+constexpr uint32_t FRONT = 16u;                 // slack on both sides: word reads next to a source stay inside
+
+struct Smem {
+  alignas(16) uint8_t raw[FRONT + LB + 16];    // buf = raw + FRONT
+  uint16_t tokoff[WT < 1024u ? 1026u : WT + 2u]; // window offset of every token; [tokens used] = window size (>= 2 KiB: CRC scratch)
+  uint16_t ctok[WCAP / 16 + 2];                // per 16-byte chunk of the window: the token that covers its first byte
+  uint32_t jobs[WT];                           // ready matches: token | (distance - 1) << 10
+  uint16_t pjobs[WT];                          // pending matches (token index), in token order
+  alignas(8) uint16_t tsrc[WT + 2];            // per token: 0 = its bytes are in the buffer once the ready queue is done
+                                               // (literal, or match from final history); else 0x8000 | (distance - 1)
+  uint32_t nready, npend;
+  uint32_t hdr[SLAB_HDR_WORDS];
+  uint32_t segstart[NL + 1];                   // flat index of the first token of every list of the current slab
+  uint32_t segptr[NL];                         // word offset of that token in the slab
+  uint32_t crc_tab[256];
+  uint32_t x16[WCAP / 16 + 4];                 // x^(8 * 16 k) mod P: shifts a CRC over k 16-byte units
+  uint32_t crcw[NWARP];
+  uint32_t wscan[NWARP], wscan2[NWARP];
+  unsigned long long wsum[NWARP][2];
+  uint32_t member;
+  int fail;
+  uint32_t wsize;
+  uint32_t crc;
+};
+
+__device__ __forceinline__ uint32_t tok_len(uint32_t t) { return (t & TOK_MATCH) ? (t & 255u) + 3u : 1u + ((t >> 30) & 1u); }
+
+// One match: n bytes from d bytes back, dst a buffer offset.  Straight-line for n <= 19 when the
+// source does not overlap the destination closely (d >= n, or d >= 8: the one-word lookahead of the
+// funnel stays behind the bytes this thread has already stored); bytewise otherwise.
+__device__ __forceinline__ void copy_match(uint8_t *buf, uint32_t dst, uint32_t d, uint32_t n) {
+  if (__builtin_expect(d >= n || d >= 8u, 1)) {
+    const uint32_t src = dst - d, dend = dst + n;
+    uint32_t hb = (0u - dst) & 3u;                       // bytes up to the first aligned destination word
+    if (hb > n) hb = n;
+#pragma unroll
+    for (uint32_t b = 0; b < 3; b++)
+      if (b < hb) buf[dst + b] = buf[src + b];
+    uint32_t p = dst + hb;                               // aligned (or the end)
+    const uint32_t sa = src + hb;
+    const uint32_t sh = (sa & 3u) * 8u;
+    const uint32_t *sw = reinterpret_cast<const uint32_t *>(buf + (sa & ~3u));
+    uint32_t lo = sw[0];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      if (p + 4u <= dend) {
+        const uint32_t hi = sw[i + 1];
+        *reinterpret_cast<uint32_t *>(buf + p) = __funnelshift_r(lo, hi, sh);
+        lo = hi;
+        p += 4u;
+      }
+    }
+    if (__builtin_expect(p + 4u <= dend, 0)) {           // long matches
+      sw += 4;
+      do {
+        const uint32_t hi = sw[1];
+        *reinterpret_cast<uint32_t *>(buf + p) = __funnelshift_r(lo, hi, sh);
+        lo = hi; sw++;
+        p += 4u;
+      } while (p + 4u <= dend);
+    }
+#pragma unroll
+    for (uint32_t b = 0; b < 3; b++)
+      if (p + b < dend) buf[p + b] = buf[p + b - d];
+  } else {                                               // close overlap: the thread's own stores are its sources
+    for (uint32_t k = 0; k < n; k++) buf[dst + k] = buf[dst + k - d];
+  }
+}
+
+// CRC-32 of buf[a, a+m): every thread takes one contiguous slice; slices are merged pairwise with
+// x^(8 len) shifts.  Only used when the output pointer is not 16-byte aligned.  All threads must call.
+__device__ inline void crc_window(Smem &sm, const uint8_t *buf, uint32_t a, uint32_t m, int tid) {
+  const uint32_t seg = (m + NT - 1) / NT;
+  uint32_t lo = seg * tid, hi = lo + seg;
+  if (lo > m) lo = m;
+  if (hi > m) hi = m;
+  uint32_t c = 0xffffffffu;
+  for (uint32_t p = lo; p < hi; p++) c = (c >> 8) ^ sm.crc_tab[(c ^ buf[a + p]) & 0xff];
+  c ^= 0xffffffffu;
+  if (lo == hi) c = 0;
+  uint32_t len = hi - lo;
+  uint32_t shift = crc_x8n(seg);
+  uint32_t *s_c = reinterpret_cast<uint32_t *>(sm.tokoff), *s_l = s_c + NT;   // 2 KiB: the token offsets are dead by now
+  static_assert(sizeof(Smem::tokoff) >= 2 * NT * sizeof(uint32_t), "crc scratch");
+  for (int s = 1; s < NT; s <<= 1) {
+    s_c[tid] = c; s_l[tid] = len;
+    __syncthreads();
+    if ((tid & (2 * s - 1)) == 0 && tid + s < NT) {
+      const uint32_t oc = s_c[tid + s], ol = s_l[tid + s];
+      if (ol) {
+        const uint32_t f = (ol == seg * (uint32_t)s) ? shift : crc_x8n(ol);
+        c = crc_mulmod(f, c) ^ oc;
+        len += ol;
+      }
+    }
+    shift = crc_mulmod(shift, shift);
+    __syncthreads();
+  }
+  if (tid == 0) sm.crc = crc_combine(sm.crc, c, m);
+}
+
+// per-member state that lives in registers (uniform unless noted)
+struct RState {
+  uint32_t pos;                           // output bytes produced so far (window base)
+  uint32_t bbase;                         // absolute output offset of buf[0] (a multiple of 16)
+  uint32_t flushed;                       // output bytes already stored to global memory
+  unsigned long long acc_a, acc_w;        // per thread: Adler sum d, sum i*d over the bytes it flushed
+};
+
+// One window: the slab's tokens [f, f + n) in flat order (n <= WT); consumes as many whole tokens
+// as fit, returns the number consumed (0xffffffff = the member must go to the sequential kernel).
+// All threads must call; the result is uniform.
+__device__ inline uint32_t resolve_window(uint8_t *__restrict__ out, int fmt, const uint32_t *__restrict__ slab, uint32_t f, uint32_t n,
+                                          RState &rs, Smem &sm, int tid) {
+  const int lane = tid & 31, warp = tid >> 5;
+  uint8_t *const buf = sm.raw + FRONT;
+  // ---- 0. room for a full window: slide the last 32 KiB down
+  if (rs.pos - rs.bbase + WCAP > LB) {
+    const uint32_t nb = (rs.pos - HIST) & ~15u;
+    const uint32_t shift = nb - rs.bbase;               // a multiple of 16, > 0
+    const uint32_t units = (rs.pos - nb + 15u) >> 4;    // 16-byte units to keep
+    for (uint32_t u0 = 0; u0 < units; u0 += 4u * NT) {  // reads of a batch precede its writes; later batches read above them
+      uint4 v[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const uint32_t u = u0 + (uint32_t)k * NT + tid;
+        if (u < units) v[k] = *reinterpret_cast<const uint4 *>(buf + shift + 16u * u);
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const uint32_t u = u0 + (uint32_t)k * NT + tid;
+        if (u < units) *reinterpret_cast<uint4 *>(buf + 16u * u) = v[k];
+      }
+    }
+    rs.bbase = nb;
+    __syncthreads();
+  }
+  const uint32_t pos = rs.pos;
+  const uint32_t wb = pos - rs.bbase;                   // buffer offset of the window's first byte
+  // ---- 1. tokens and their offsets
+  uint32_t tk[TPT], ln[TPT];
+  uint32_t mine = 0;
+  {
+    // the list that holds the thread's first token: last j with segstart[j] <= g
+    const uint32_t g0 = f + tid * TPT;
+    uint32_t j = 0;
+    if ((uint32_t)tid * TPT < n) {
+#pragma unroll
+      for (int stp = NL / 2; stp; stp >>= 1)
+        if (sm.segstart[j + stp] <= g0) j += stp;
+    }
+    const uint32_t last = tid * TPT + TPT;               // one past the thread's last token
+    if (last <= n && f + last <= sm.segstart[j + 1]) {   // common: all of them in one list
+      const uint32_t *src = slab + sm.segptr[j] + (g0 - sm.segstart[j]);
+#pragma unroll
+      for (int q = 0; q < TPT; q++) {
+        tk[q] = __ldg(src + q);
+        ln[q] = tok_len(tk[q]);
+        mine += ln[q];
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < TPT; q++) {
+        const uint32_t idx = tid * TPT + q;
+        const bool have = idx < n;
+        tk[q] = 0u;
+        if (have) {
+          const uint32_t g = f + idx;
+          while (g >= sm.segstart[j + 1]) j++;
+          tk[q] = __ldg(slab + sm.segptr[j] + (g - sm.segstart[j]));
+        }
+        ln[q] = have ? tok_len(tk[q]) : 0u;
+        mine += ln[q];
+      }
+    }
+  }
+  uint32_t x = mine;
+#pragma unroll
+  for (int sft = 1; sft < 32; sft <<= 1) {
+    const uint32_t u = __shfl_up_sync(TBZ_FULL, x, sft);
+    if (lane >= sft) x += u;
+  }
+  if (lane == 31) sm.wscan[warp] = x;
+  if (tid == 0) { sm.nready = 0; sm.npend = 0; }
+  __syncthreads();
+  uint32_t off = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < NWARP; w++) { const uint32_t c = sm.wscan[w]; if (w < warp) off += c; total += c; }
+  uint32_t st[TPT];
+  uint32_t used = 0;                                    // bit q: the token is part of this window
+  bool bad = false;
+  {
+    uint32_t s = off + x - mine;
+#pragma unroll
+    for (int q = 0; q < TPT; q++) {
+      const uint32_t idx = tid * TPT + q;
+      st[q] = s;
+      if (idx < n && s <= WCAP) {
+        sm.tokoff[idx] = (uint16_t)s;                   // (the first token that does not fit: its offset is the window size)
+        if (s + ln[q] <= WCAP) {
+          used |= 1u << q;
+          {                                             // the chunk boundaries this token covers: at most one unless it is long
+            const uint32_t bl = (s + ln[q] - 1u) & ~15u;
+            if (bl >= s) {
+              sm.ctok[bl >> 4] = (uint16_t)idx;
+              if (__builtin_expect(bl >= s + 16u, 0)) {
+#pragma unroll 1
+                for (uint32_t b = bl - 16u; b >= s && b < bl; b -= 16u) sm.ctok[b >> 4] = (uint16_t)idx;
+              }
+            }
+          }
+          if ((tk[q] & TOK_MATCH) && ((tk[q] >> 8) & 0x7fffu) + 1u > pos + s) bad = true;   // deflate.lisp:343-345
+        } else sm.wsize = s;
+      }
+      s += ln[q];
+    }
+  }
+  if (bad) sm.fail = 1;
+  if (tid == 0 && total <= WCAP) { sm.tokoff[n] = (uint16_t)total; sm.wsize = total; }
+  uint32_t nused = n;
+  if (total > WCAP) {                                   // count the tokens that fit
+    uint32_t c = __popc(used);
+#pragma unroll
+    for (int sft = 16; sft; sft >>= 1) c += __shfl_xor_sync(TBZ_FULL, c, sft);
+    if (lane == 0) sm.wscan2[warp] = c;
+  }
+  __syncthreads();
+  if (total > WCAP) {
+    nused = 0;
+#pragma unroll
+    for (int w = 0; w < NWARP; w++) nused += sm.wscan2[w];
+  }
+  if (sm.fail) return 0xffffffffu;
+  const uint32_t wsize = sm.wsize;
+  // ---- 2. literals; matches into the ready / pending queues
+  uint32_t rmask = 0, pmask = 0;
+  uint32_t ts[TPT];
+#pragma unroll
+  for (int q = 0; q < TPT; q++) {
+    ts[q] = 0;
+    if (used & (1u << q)) {
+      const uint32_t t = tk[q], dst = wb + st[q];
+      if (!(t & TOK_MATCH)) {
+        buf[dst] = (uint8_t)t;
+        if (t & tbzfast::TOK_LIT2) buf[dst + 1] = (uint8_t)(t >> 8);
+      } else {
+        const uint32_t d = ((t >> 8) & 0x7fffu) + 1u;
+        const uint32_t reach = d < ln[q] ? d : ln[q];    // source bytes that are not the token's own output
+        if (d >= st[q] + reach) rmask |= 1u << q;        // entirely below the window
+        else { pmask |= 1u << q; ts[q] = 0x8000u | (d - 1u); }
+      }
+    }
+  }
+  if (TPT == 4) *reinterpret_cast<uint2 *>(&sm.tsrc[tid * 4]) = make_uint2(ts[0] | (ts[1] << 16), ts[2] | (ts[3] << 16));
+  else {
+#pragma unroll
+    for (int q = 0; q < TPT; q++) sm.tsrc[tid * TPT + q] = (uint16_t)ts[q];
+  }
+  {
+    const uint32_t c = __popc(rmask) | (__popc(pmask) << 16);
+    uint32_t incl = c;
+#pragma unroll
+    for (int sft = 1; sft < 32; sft <<= 1) {
+      const uint32_t u = __shfl_up_sync(TBZ_FULL, incl, sft);
+      if (lane >= sft) incl += u;
+    }
+    uint32_t br = 0, bp = 0;
+    if (lane == 31) {
+      if (incl & 0xffffu) br = atomicAdd(&sm.nready, incl & 0xffffu);
+      if (incl >> 16) bp = atomicAdd(&sm.npend, incl >> 16);
+    }
+    br = __shfl_sync(TBZ_FULL, br, 31); bp = __shfl_sync(TBZ_FULL, bp, 31);
+    uint32_t ri = br + ((incl - c) & 0xffffu), pi = bp + ((incl - c) >> 16);
+#pragma unroll
+    for (int q = 0; q < TPT; q++) {
+      if (rmask & (1u << q)) sm.jobs[ri++] = (tid * TPT + q) | (((tk[q] >> 8) & 0x7fffu) << 10);
+      if (pmask & (1u << q)) sm.pjobs[pi++] = (uint16_t)(tid * TPT + q);
+    }
+  }
+  __syncthreads();
+  // ---- 3. the ready queue: one job per thread and step
+  {
+    const uint32_t nr = sm.nready;
+    for (uint32_t j = tid; j < nr; j += NT) {
+      const uint32_t job = sm.jobs[j], idx = job & 1023u;
+      const uint32_t o = sm.tokoff[idx];
+      copy_match(buf, wb + o, (job >> 10) + 1u, sm.tokoff[idx + 1] - o);
+    }
+  }
+  __syncthreads();
+  // ---- 4. the pending queue: no waiting.  A source piece that lies in a pending token T is an
+  // equal run of bytes dist(T) further back (through the period, if T overlaps itself); it is
+  // redirected until it reaches bytes that exist: final history, a literal, or a ready match.
+  {
+    const uint32_t np = sm.npend;
+    for (uint32_t j = tid; j < np; j += NT) {
+      const uint32_t idx = sm.pjobs[j];
+      const uint32_t s0 = sm.tokoff[idx], n_ = sm.tokoff[idx + 1] - s0, d = (sm.tsrc[idx] & 0x7fffu) + 1u;
+      uint32_t left = d < n_ ? d : n_;                    // bytes with a source outside the token
+      int cur = (int)s0 - (int)d;                         // window offset of the next source byte (negative: history)
+      uint32_t o = wb + s0;                               // buffer offset of the next output byte
+      while (left) {
+        int src = cur;
+        uint32_t m = left;
+        while (src >= 0) {
+          uint32_t k = sm.ctok[(uint32_t)src >> 4];       // the token that holds the byte
+          while (sm.tokoff[k + 1] <= (uint32_t)src) k++;
+          const uint32_t sT = sm.tokoff[k], eT = sm.tokoff[k + 1];
+          if (eT - (uint32_t)src < m) m = eT - (uint32_t)src;
+          const uint32_t tsv = sm.tsrc[k];
+          if (!tsv) break;                                // its bytes exist
+          const uint32_t dT = (tsv & 0x7fffu) + 1u;
+          if (dT < eT - sT) {                             // T overlaps itself: go through its period
+            const uint32_t o2 = ((uint32_t)src - sT) % dT;
+            if (dT - o2 < m) m = dT - o2;
+            src = (int)sT - (int)dT + (int)o2;
+          } else src -= (int)dT;
+        }
+        if (src < 0 && (uint32_t)(-src) < m) m = (uint32_t)(-src);   // the rest of the piece starts inside the window
+        const uint32_t sb = (uint32_t)((int)wb + src);
+        for (uint32_t b = 0; b < m; b++) buf[o + b] = buf[sb + b];
+        o += m; cur += (int)m; left -= m;
+      }
+      for (uint32_t b = d; b < n_; b++) buf[wb + s0 + b] = buf[wb + s0 + b - d];   // the token's own period
+    }
+  }
+  __syncthreads();
+  // ---- 4. flush complete 16-byte units, fold them into the checksum
+  const bool aligned_out = (((uintptr_t)out) & 15) == 0;
+  if (fmt == TBZ_GZIP && !aligned_out) crc_window(sm, buf, wb, wsize, tid);
+  if (aligned_out) {
+    const uint32_t upto = (pos + wsize) & ~15u;
+    const uint8_t *b0 = buf - rs.bbase;                  // b0 + absolute offset
+    uint32_t myc = 0;                                    // gzip: CRCs of this thread's units, shifted to the end of the flushed range
+    for (uint32_t p = rs.flushed + 16u * tid; p < upto; p += 16u * NT) {
+      const uint4 v = *reinterpret_cast<const uint4 *>(b0 + p);
+      *reinterpret_cast<uint4 *>(out + p) = v;
+      if (fmt == TBZ_GZIP) {
+        // crc(A || B) = crc(A) * x^(8 |B|) + crc(B) for finalized CRCs: one table CRC per unit, one
+        // multiplication by the power for the bytes that follow it, XOR over all units
+        const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+        uint32_t c = 0xffffffffu;
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+#pragma unroll
+          for (int b8 = 0; b8 < 4; b8++) c = (c >> 8) ^ sm.crc_tab[(c ^ (w4[q] >> (8 * b8))) & 0xff];
+        myc ^= crc_mulmod(sm.x16[(upto - p - 16u) >> 4], c ^ 0xffffffffu);
+      }
+      if (fmt == TBZ_ZLIB) {
+        uint32_t sd = __dp4a(v.x, 0x01010101u, 0u); sd = __dp4a(v.y, 0x01010101u, sd);
+        sd = __dp4a(v.z, 0x01010101u, sd); sd = __dp4a(v.w, 0x01010101u, sd);
+        uint32_t wj = __dp4a(v.x, 0x03020100u, 0u); wj = __dp4a(v.y, 0x07060504u, wj);
+        wj = __dp4a(v.z, 0x0b0a0908u, wj); wj = __dp4a(v.w, 0x0f0e0d0cu, wj);
+        rs.acc_a += sd;
+        rs.acc_w += (unsigned long long)p * sd + wj;
+      }
+    }
+    if (fmt == TBZ_GZIP) {
+#pragma unroll
+      for (int sft = 16; sft; sft >>= 1) myc ^= __shfl_xor_sync(TBZ_FULL, myc, sft);
+      if (lane == 0) sm.crcw[warp] = myc;
+      __syncthreads();
+      if (tid == 0 && upto > rs.flushed) {
+        uint32_t wc = 0;
+#pragma unroll
+        for (int w = 0; w < NWARP; w++) wc ^= sm.crcw[w];
+        sm.crc = crc_mulmod(sm.x16[(upto - rs.flushed) >> 4], sm.crc) ^ wc;
+      }
+    }
+    if (upto > rs.flushed) rs.flushed = upto;
+  } else {
+    for (uint32_t p = pos + tid; p < pos + wsize; p += NT) {
+      const uint32_t d = buf[p - rs.bbase];
+      out[p] = (uint8_t)d;
+      rs.acc_a += d; rs.acc_w += (unsigned long long)p * d;
+    }
+    rs.flushed = pos + wsize;
+  }
+  if (__builtin_expect((rs.acc_w >> 62) != 0, 0)) rs.acc_w %= TBZ_ADLER_MOD;
+  rs.pos = pos + wsize;
+  __syncthreads();
+  return nused;
+}
+
+// Every window of one member's token stream.  Returns false when the caller must fall back.
+__device__ inline bool resolve_stream(uint8_t *__restrict__ out, int fmt, const P1Rec &rec, const uint32_t *__restrict__ slabs,
+                                      RState &rs, Smem &sm, int tid) {
+  if (tid == 0) { sm.fail = 0; sm.crc = 0; }
+  __syncthreads();
+  for (uint32_t s = rec.first_slab; s != NO_SLAB;) {
+    const uint32_t *slab = slabs + (size_t)s * SLAB_WORDS;
+    if (tid < (int)SLAB_HDR_WORDS) sm.hdr[tid] = slab[tid];
+    __syncthreads();
+    s = sm.hdr[0];
+    if (tid < 32) {                        // flat token order of the slab: exclusive scan of the list sizes
+      const uint32_t fc = sm.hdr[4 + tid];
+      const uint32_t cnt = fc >> 16;
+      uint32_t y = cnt;
+#pragma unroll
+      for (int sft = 1; sft < 32; sft <<= 1) {
+        const uint32_t u = __shfl_up_sync(TBZ_FULL, y, sft);
+        if (tid >= sft) y += u;
+      }
+      sm.segstart[tid] = y - cnt;
+      sm.segptr[tid] = SLAB_HDR_WORDS + tid * TOKCAP + (fc & 0xffffu);
+      if (tid == 31) sm.segstart[32] = y;
+    }
+    __syncthreads();
+    const uint32_t total = sm.segstart[32];
+    uint32_t f = 0;
+    while (f < total) {
+      const uint32_t n = total - f < WT ? total - f : WT;
+      const uint32_t used = resolve_window(out, fmt, slab, f, n, rs, sm, tid);
+      if (used == 0xffffffffu || used == 0) return false;
+      f += used;
+    }
+    __syncthreads();
+  }
+  if (sm.fail) return false;
+  if (rs.flushed + tid < rs.pos) {         // the last partial 16-byte unit
+    const uint32_t p = rs.flushed + tid;
+    const uint32_t d = sm.raw[FRONT + p - rs.bbase];
+    out[p] = (uint8_t)d;
+    rs.acc_a += d; rs.acc_w += (unsigned long long)p * d;
+  }
+  return true;
+}
+
+__device__ inline bool resolve_member(const DMember &mem, int fmt, const P1Rec &rec, const uint32_t *__restrict__ slabs,
+                                      tbz_result &res, Smem &sm, int tid) {
+  const int lane = tid & 31, warp = tid >> 5;
+  RState rs;
+  rs.pos = 0; rs.bbase = 0; rs.flushed = 0; rs.acc_a = 0; rs.acc_w = 0;
+  if (!resolve_stream(mem.out, fmt, rec, slabs, rs, sm, tid)) return false;
+  const uint32_t pos = rs.pos;
+  if (pos != rec.out_len) return false;
+  unsigned long long acc_a = rs.acc_a, acc_w = rs.acc_w;
+  // ---- checksum of the whole member
+  uint32_t ck = 0;
+  if (fmt == TBZ_ZLIB) {
+    unsigned long long a = acc_a % TBZ_ADLER_MOD, w = acc_w % TBZ_ADLER_MOD;
+#pragma unroll
+    for (int sft = 16; sft; sft >>= 1) { a += __shfl_xor_sync(TBZ_FULL, a, sft); w += __shfl_xor_sync(TBZ_FULL, w, sft); }
+    if (lane == 0) { sm.wsum[warp][0] = a; sm.wsum[warp][1] = w; }
+    __syncthreads();
+    a = 0; w = 0;
+    for (int k = 0; k < NWARP; k++) { a += sm.wsum[k][0]; w += sm.wsum[k][1]; }
+    const unsigned long long N = pos % TBZ_ADLER_MOD, S = a % TBZ_ADLER_MOD;
+    const uint32_t s1 = (uint32_t)((1 + S) % TBZ_ADLER_MOD);
+    const uint32_t s2 = (uint32_t)((N + N * S + (unsigned long long)TBZ_ADLER_MOD * 4096 - w % TBZ_ADLER_MOD) % TBZ_ADLER_MOD);
+    ck = s1 | (s2 << 16);
+  } else if (fmt == TBZ_GZIP) {
+    __syncthreads();
+    uint32_t c = sm.crc;
+    if (rs.flushed < pos) {                  // the last partial unit (uniform: every thread computes the same value)
+      uint32_t t = 0xffffffffu;
+      for (uint32_t p = rs.flushed; p < pos; p++) t = (t >> 8) ^ sm.crc_tab[(t ^ sm.raw[FRONT + p - rs.bbase]) & 0xff];
+      c = crc_combine(c, t ^ 0xffffffffu, pos - rs.flushed);
+    }
+    ck = c;
+  }
+  // ---- trailer (zlib.lisp:80-96, gzip.lisp:82-106): any disagreement goes to the sequential kernel
+  uintptr_t a0 = (uintptr_t)mem.in;
+  const uint32_t mis = (uint32_t)(a0 & 3);
+  const uint8_t *base = mem.in - mis;
+  const uint32_t end = (mis + (uint32_t)mem.in_len) * 8;
+  uint32_t p = (rec.end_pos + 7) & ~7u;
+  if (fmt == TBZ_ZLIB) {
+    if (end - p < 32) return false;
+    const uint8_t *q = base + (p >> 3);
+    const uint32_t t = ((uint32_t)q[0] << 24) | ((uint32_t)q[1] << 16) | ((uint32_t)q[2] << 8) | q[3];
+    if (t != ck) return false;
+    p += 32;
+  } else if (fmt == TBZ_GZIP) {
+    if (end - p < 64) return false;
+    const uint8_t *q = base + (p >> 3);
+    const uint32_t t = q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24);
+    if (t != ck) return false;
+    p += 64;
+  }
+  if (tid == 0) {
+    res.out_len = pos;
+    res.in_used = (p - mis * 8 + 7) >> 3;
+    res.checksum = ck;
+    res.verdict = TBZ_FINISHED;
+    res.where = TBZ_AT_BODY;
+    res.path = 1;
+  }
+  return true;
+}
+
+}  // namespace tbzcp

@@ -19,6 +19,8 @@
 #include "inflate_seq.cuh"
 #include "inflate_decode.cuh"
 #include "inflate_resolve.cuh"
+#include "inflate_lockstep.cuh"
+#include "inflate_copy.cuh"
 #include "inflate_split.cuh"
 
 // =============================================================================================
@@ -64,16 +66,39 @@ k_inflate_decode(const DMember *members, uint32_t n, int fmt, tbzfast::P1Rec *re
 }
 
 // Phase two, persistent CTAs: one CTA per member resolves the token stream into bytes through a
-// shared-memory ring and checks the trailer.
-__global__ void __launch_bounds__(tbzres::NT, TBZ_RES_TPT > 2 ? 3 : 4)
+// shared-memory buffer and checks the trailer.  Three interchangeable implementations (TBZ_P2),
+// all bit-exact on the parity suite; per-launch times on BASELINE config 2 (4096 x 64 KiB), B200:
+//   0 (default) tbzres — byte-parallel rank queries + pointer jumping (inflate_resolve.cuh; also the
+//                        16-bit symbolic variant the split decode of one large member uses)  1.33 ms
+//   1           tbzls  — lock-step lanes over 16-byte chunks, pointer jumping (inflate_lockstep.cuh) 1.65 ms
+//   2           tbzcp  — one thread per token, dense word-wise copy queues, pending matches redirected
+//                        through their source tokens (inflate_copy.cuh)                              1.77 ms
+// The two token-walking variants execute fewer instructions on the bytes they copy but lose more to
+// divergent per-lane loops than they save (profiles/r1e_*): uniform control flow wins on this path.
+#ifndef TBZ_P2
+#define TBZ_P2 0
+#endif
+#if TBZ_P2 == 0
+namespace tbzp2 = tbzres;
+#define TBZ_P2_MINBLOCKS (TBZ_RES_TPT > 2 ? 3 : 4)
+#elif TBZ_P2 == 1
+namespace tbzp2 = tbzls;
+#define TBZ_P2_MINBLOCKS 3
+#else
+namespace tbzp2 = tbzcp;
+#ifndef TBZ_P2_MINBLOCKS
+#define TBZ_P2_MINBLOCKS 3
+#endif
+#endif
+__global__ void __launch_bounds__(tbzp2::NT, TBZ_P2_MINBLOCKS)
 k_inflate_resolve(const DMember *members, tbz_result *results, uint32_t n, int fmt,
                   const tbzfast::P1Rec *recs, const uint32_t *slabs, uint32_t *counters, uint32_t *todo) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  tbzres::Smem &sm = *reinterpret_cast<tbzres::Smem *>(smem_raw);
+  tbzp2::Smem &sm = *reinterpret_cast<tbzp2::Smem *>(smem_raw);
   const int tid = threadIdx.x;
   if (fmt == TBZ_GZIP) {
-    crc_table_init(sm.crc_tab, tid, tbzres::NT);
-    for (uint32_t k = tid; k < tbzres::WB / 16 + 4; k += tbzres::NT) sm.x16[k] = crc_x8n(16ull * k);
+    crc_table_init(sm.crc_tab, tid, tbzp2::NT);
+    for (uint32_t k = tid; k < tbzp2::WB / 16 + 4; k += tbzp2::NT) sm.x16[k] = crc_x8n(16ull * k);
   }
   for (;;) {
     __syncthreads();
@@ -82,7 +107,7 @@ k_inflate_resolve(const DMember *members, tbz_result *results, uint32_t n, int f
     const uint32_t i = sm.member;
     if (i >= n) break;
     if (!recs[i].status) continue;
-    const bool ok = tbzres::resolve_member(members[i], fmt, recs[i], slabs, results[i], sm, tid);
+    const bool ok = tbzp2::resolve_member(members[i], fmt, recs[i], slabs, results[i], sm, tid);
     if (!ok && tid == 0) todo[atomicAdd(&counters[1], 1u)] = i;
   }
 }
@@ -432,8 +457,8 @@ extern "C" int32_t tbz_batch_prepare(tbz_ctx *ctx, int32_t format, const tbz_mem
     cudaFuncSetAttribute(k_inflate_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(tbzfast::WSmem) * tbzfast::WPC));
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_inflate_decode, tbzfast::NT, sizeof(tbzfast::WSmem) * tbzfast::WPC);
     b->fast_grid = (int)std::min<uint64_t>((n + tbzfast::WPC - 1) / tbzfast::WPC, (uint64_t)ctx->sm_count * std::max(1, occ));
-    cudaFuncSetAttribute(k_inflate_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tbzres::Smem));
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_inflate_resolve, tbzres::NT, sizeof(tbzres::Smem));
+    cudaFuncSetAttribute(k_inflate_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tbzp2::Smem));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_inflate_resolve, tbzp2::NT, sizeof(tbzp2::Smem));
     b->res_grid = (int)std::min<uint64_t>(n, (uint64_t)ctx->sm_count * std::max(1, occ));
     // token slabs: one per round; a round covers at most ~31 KiB of compressed input and never
     // crosses a block boundary.  Members that find the pool empty go to the sequential kernel.
@@ -771,8 +796,8 @@ static int32_t launch_kernels(tbz_batch *b) {
     ctx->launches++;
     CK(ctx, cudaGetLastError());
     if (ctx->ktime) CK(ctx, cudaEventRecord(ctx->kev[1], ctx->stream));
-    CK(ctx, cudaFuncSetAttribute(k_inflate_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tbzres::Smem)));
-    k_inflate_resolve<<<b->res_grid, tbzres::NT, sizeof(tbzres::Smem), ctx->stream>>>(
+    CK(ctx, cudaFuncSetAttribute(k_inflate_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tbzp2::Smem)));
+    k_inflate_resolve<<<b->res_grid, tbzp2::NT, sizeof(tbzp2::Smem), ctx->stream>>>(
         (const DMember *)b->d_members, (tbz_result *)b->d_results, n, b->format,
         (const tbzfast::P1Rec *)b->d_recs, (const uint32_t *)b->d_slabs, (uint32_t *)b->d_counters, (uint32_t *)b->d_todo);
     ctx->launches++;
