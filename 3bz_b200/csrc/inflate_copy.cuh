@@ -5,19 +5,18 @@
 // shared-memory buffer (positions never wrap; when the buffer is full its last 32 KiB slide down).
 // A window is the next <= WT tokens (<= WCAP bytes); tokens are never split.  Per window:
 //   1. the tokens are loaded (TPT consecutive tokens per thread), a CTA prefix sum over their
-//      lengths gives every token its byte offset; a small table maps every 16-byte chunk of the
-//      window to the token that covers its first byte
+//      lengths gives every token its byte offset
 //   2. every thread writes its literals and sorts its matches into two dense job queues (warp scan,
 //      one shared-memory atomic per warp): READY = the source lies entirely below the window (final
 //      history), PENDING = the source reaches into the window
 //   3. the ready queue is copied by all threads, one job per thread and step, so the lanes of a
 //      warp all run the same straight-line copy: byte moves for the <= 3 bytes up to the first
 //      aligned destination word and after the last one, in between one aligned word load per 4
-//      source bytes and a funnel shift.  No atomics, no per-byte token search
-//   4. the pending queue (about a fifth of the tokens on text, in token order) is worked off in
-//      rounds: a job looks up the tokens that produce its source (chunk table + walk) and tests
-//      their done flags; when all are set it copies, fences and sets its own flag, so chains can
-//      also resolve inside one round.  Rounds end at a CTA barrier and stop when nothing is pending
+//      source bytes and a funnel shift.  No atomics, no per-byte token search.  The pending queue is
+//      expanded to bytes: val[byte] = window offset of its source, and a dense list of those bytes
+//   4. the pending bytes (about a third of the bytes on text) are resolved by pointer jumping with
+//      uniform control flow: a byte whose source is final copies it; otherwise it adopts the
+//      source's pointer (equal bytes).  Chains halve per level; a level ends at a CTA barrier
 //   5. the window is flushed to global memory with 16-byte stores; Adler-32 is folded in with dp4a
 //      (order-independent form), CRC-32 per 16-byte unit with x^(8n) combines
 // The trailer is checked as zlib.lisp:80-96 / gzip.lisp:82-106 do; any disagreement sends the member
@@ -40,25 +39,32 @@ using tbzfast::TOK_MATCH;
 constexpr int NT = 256;
 constexpr int NWARP = NT / 32;
 #ifndef TBZ_CP_TPT
-#define TBZ_CP_TPT 4
+#define TBZ_CP_TPT 3
+#endif
+#ifndef TBZ_CP_WCAP
+#define TBZ_CP_WCAP 5120
+#endif
+#ifndef TBZ_CP_ROOM
+#define TBZ_CP_ROOM 12288
 #endif
 constexpr int TPT = TBZ_CP_TPT;                 // tokens per thread and window
 constexpr uint32_t WT = (uint32_t)NT * TPT;     // window tokens
 constexpr uint32_t HIST = 32768u;
-constexpr uint32_t WCAP = 8192u;                // window bytes
-constexpr uint32_t LB = HIST + 16384u;          // linear buffer: history + room for two full windows
+constexpr uint32_t WCAP = TBZ_CP_WCAP;          // window bytes
+constexpr uint32_t LB = HIST + TBZ_CP_ROOM;     // linear buffer: history + room for new windows
 constexpr uint32_t WB = WCAP;                   // (name shared with the other phase-two variants: sizes the x16 table)
 constexpr uint32_t FRONT = 16u;                 // slack on both sides: word reads next to a source stay inside
+constexpr uint32_t V_FINAL = 0xffffu;
+static_assert(WT <= 1024u && WCAP <= 8192u && WCAP % 16u == 0 && TBZ_CP_ROOM >= WCAP, "queue entry fields");
 
 struct Smem {
   alignas(16) uint8_t raw[FRONT + LB + 16];    // buf = raw + FRONT
+  alignas(16) uint16_t val[WCAP];              // per window byte: V_FINAL, or the window offset of an equal byte
+  uint16_t pbytes[WCAP];                       // the bytes of the pending matches
   uint16_t tokoff[WT < 1024u ? 1026u : WT + 2u]; // window offset of every token; [tokens used] = window size (>= 2 KiB: CRC scratch)
-  uint16_t ctok[WCAP / 16 + 2];                // per 16-byte chunk of the window: the token that covers its first byte
-  uint32_t jobs[WT];                           // ready matches: token | (distance - 1) << 10
-  uint16_t pjobs[WT];                          // pending matches (token index), in token order
-  alignas(8) uint16_t tsrc[WT + 2];            // per token: 0 = its bytes are in the buffer once the ready queue is done
-                                               // (literal, or match from final history); else 0x8000 | (distance - 1)
-  uint32_t nready, npend;
+  uint32_t jobs[WT];                           // ready matches from [0] up, pending from [WT - 1] down: token | (distance - 1) << 10
+  uint16_t pq[WT];                             // per pending match: where its bytes start in pbytes
+  uint32_t nready, npend, npbytes;
   uint32_t hdr[SLAB_HDR_WORDS];
   uint32_t segstart[NL + 1];                   // flat index of the first token of every list of the current slab
   uint32_t segptr[NL];                         // word offset of that token in the slab
@@ -157,11 +163,41 @@ struct RState {
   unsigned long long acc_a, acc_w;        // per thread: Adler sum d, sum i*d over the bytes it flushed
 };
 
+// The slab's tokens [f, f + n) in flat order: thread tid gets tokens f + TPT tid + q (0 where there is none).
+__device__ __forceinline__ void load_tokens(const uint32_t *__restrict__ slab, uint32_t f, uint32_t n, const Smem &sm, int tid, uint32_t (&tk)[TPT]) {
+  // the list that holds the thread's first token: last j with segstart[j] <= g
+  const uint32_t g0 = f + tid * TPT;
+  uint32_t j = 0;
+  if ((uint32_t)tid * TPT < n) {
+#pragma unroll
+    for (int stp = NL / 2; stp; stp >>= 1)
+      if (sm.segstart[j + stp] <= g0) j += stp;
+  }
+  const uint32_t last = tid * TPT + TPT;                 // one past the thread's last token
+  if (last <= n && f + last <= sm.segstart[j + 1]) {     // common: all of them in one list
+    const uint32_t *src = slab + sm.segptr[j] + (g0 - sm.segstart[j]);
+#pragma unroll
+    for (int q = 0; q < TPT; q++) tk[q] = __ldg(src + q);
+  } else {
+#pragma unroll
+    for (int q = 0; q < TPT; q++) {
+      const uint32_t idx = tid * TPT + q;
+      tk[q] = 0u;
+      if (idx < n) {
+        const uint32_t g = f + idx;
+        while (g >= sm.segstart[j + 1]) j++;
+        tk[q] = __ldg(slab + sm.segptr[j] + (g - sm.segstart[j]));
+      }
+    }
+  }
+}
+
 // One window: the slab's tokens [f, f + n) in flat order (n <= WT); consumes as many whole tokens
 // as fit, returns the number consumed (0xffffffff = the member must go to the sequential kernel).
-// All threads must call; the result is uniform.
+// tk: in, this window's tokens (load_tokens); out, the next window's — of the `total` tokens of the
+// slab — loaded while this one is being copied.  All threads must call; the result is uniform.
 __device__ inline uint32_t resolve_window(uint8_t *__restrict__ out, int fmt, const uint32_t *__restrict__ slab, uint32_t f, uint32_t n,
-                                          RState &rs, Smem &sm, int tid) {
+                                          uint32_t total_tokens, uint32_t (&tk)[TPT], RState &rs, Smem &sm, int tid) {
   const int lane = tid & 31, warp = tid >> 5;
   uint8_t *const buf = sm.raw + FRONT;
   // ---- 0. room for a full window: slide the last 32 KiB down
@@ -189,41 +225,12 @@ __device__ inline uint32_t resolve_window(uint8_t *__restrict__ out, int fmt, co
   const uint32_t pos = rs.pos;
   const uint32_t wb = pos - rs.bbase;                   // buffer offset of the window's first byte
   // ---- 1. tokens and their offsets
-  uint32_t tk[TPT], ln[TPT];
+  uint32_t ln[TPT];
   uint32_t mine = 0;
-  {
-    // the list that holds the thread's first token: last j with segstart[j] <= g
-    const uint32_t g0 = f + tid * TPT;
-    uint32_t j = 0;
-    if ((uint32_t)tid * TPT < n) {
 #pragma unroll
-      for (int stp = NL / 2; stp; stp >>= 1)
-        if (sm.segstart[j + stp] <= g0) j += stp;
-    }
-    const uint32_t last = tid * TPT + TPT;               // one past the thread's last token
-    if (last <= n && f + last <= sm.segstart[j + 1]) {   // common: all of them in one list
-      const uint32_t *src = slab + sm.segptr[j] + (g0 - sm.segstart[j]);
-#pragma unroll
-      for (int q = 0; q < TPT; q++) {
-        tk[q] = __ldg(src + q);
-        ln[q] = tok_len(tk[q]);
-        mine += ln[q];
-      }
-    } else {
-#pragma unroll
-      for (int q = 0; q < TPT; q++) {
-        const uint32_t idx = tid * TPT + q;
-        const bool have = idx < n;
-        tk[q] = 0u;
-        if (have) {
-          const uint32_t g = f + idx;
-          while (g >= sm.segstart[j + 1]) j++;
-          tk[q] = __ldg(slab + sm.segptr[j] + (g - sm.segstart[j]));
-        }
-        ln[q] = have ? tok_len(tk[q]) : 0u;
-        mine += ln[q];
-      }
-    }
+  for (int q = 0; q < TPT; q++) {
+    ln[q] = (uint32_t)tid * TPT + q < n ? tok_len(tk[q]) : 0u;
+    mine += ln[q];
   }
   uint32_t x = mine;
 #pragma unroll
@@ -232,7 +239,9 @@ __device__ inline uint32_t resolve_window(uint8_t *__restrict__ out, int fmt, co
     if (lane >= sft) x += u;
   }
   if (lane == 31) sm.wscan[warp] = x;
-  if (tid == 0) { sm.nready = 0; sm.npend = 0; }
+  if (tid == 0) { sm.nready = 0; sm.npend = 0; sm.npbytes = 0; }
+  for (uint32_t i = tid; i < WCAP / 8u; i += NT)        // (the previous window's levels ended at a barrier)
+    reinterpret_cast<uint4 *>(sm.val)[i] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
   __syncthreads();
   uint32_t off = 0, total = 0;
 #pragma unroll
@@ -250,16 +259,6 @@ __device__ inline uint32_t resolve_window(uint8_t *__restrict__ out, int fmt, co
         sm.tokoff[idx] = (uint16_t)s;                   // (the first token that does not fit: its offset is the window size)
         if (s + ln[q] <= WCAP) {
           used |= 1u << q;
-          {                                             // the chunk boundaries this token covers: at most one unless it is long
-            const uint32_t bl = (s + ln[q] - 1u) & ~15u;
-            if (bl >= s) {
-              sm.ctok[bl >> 4] = (uint16_t)idx;
-              if (__builtin_expect(bl >= s + 16u, 0)) {
-#pragma unroll 1
-                for (uint32_t b = bl - 16u; b >= s && b < bl; b -= 16u) sm.ctok[b >> 4] = (uint16_t)idx;
-              }
-            }
-          }
           if ((tk[q] & TOK_MATCH) && ((tk[q] >> 8) & 0x7fffu) + 1u > pos + s) bad = true;   // deflate.lisp:343-345
         } else sm.wsize = s;
       }
@@ -268,27 +267,16 @@ __device__ inline uint32_t resolve_window(uint8_t *__restrict__ out, int fmt, co
   }
   if (bad) sm.fail = 1;
   if (tid == 0 && total <= WCAP) { sm.tokoff[n] = (uint16_t)total; sm.wsize = total; }
-  uint32_t nused = n;
   if (total > WCAP) {                                   // count the tokens that fit
     uint32_t c = __popc(used);
 #pragma unroll
     for (int sft = 16; sft; sft >>= 1) c += __shfl_xor_sync(TBZ_FULL, c, sft);
     if (lane == 0) sm.wscan2[warp] = c;
   }
-  __syncthreads();
-  if (total > WCAP) {
-    nused = 0;
-#pragma unroll
-    for (int w = 0; w < NWARP; w++) nused += sm.wscan2[w];
-  }
-  if (sm.fail) return 0xffffffffu;
-  const uint32_t wsize = sm.wsize;
   // ---- 2. literals; matches into the ready / pending queues
-  uint32_t rmask = 0, pmask = 0;
-  uint32_t ts[TPT];
+  uint32_t rmask = 0, pmask = 0, pb = 0;
 #pragma unroll
   for (int q = 0; q < TPT; q++) {
-    ts[q] = 0;
     if (used & (1u << q)) {
       const uint32_t t = tk[q], dst = wb + st[q];
       if (!(t & TOK_MATCH)) {
@@ -298,85 +286,89 @@ __device__ inline uint32_t resolve_window(uint8_t *__restrict__ out, int fmt, co
         const uint32_t d = ((t >> 8) & 0x7fffu) + 1u;
         const uint32_t reach = d < ln[q] ? d : ln[q];    // source bytes that are not the token's own output
         if (d >= st[q] + reach) rmask |= 1u << q;        // entirely below the window
-        else { pmask |= 1u << q; ts[q] = 0x8000u | (d - 1u); }
+        else { pmask |= 1u << q; pb += ln[q]; }
       }
     }
   }
-  if (TPT == 4) *reinterpret_cast<uint2 *>(&sm.tsrc[tid * 4]) = make_uint2(ts[0] | (ts[1] << 16), ts[2] | (ts[3] << 16));
-  else {
-#pragma unroll
-    for (int q = 0; q < TPT; q++) sm.tsrc[tid * TPT + q] = (uint16_t)ts[q];
-  }
   {
     const uint32_t c = __popc(rmask) | (__popc(pmask) << 16);
-    uint32_t incl = c;
+    uint32_t incl = c, incb = pb;
 #pragma unroll
     for (int sft = 1; sft < 32; sft <<= 1) {
-      const uint32_t u = __shfl_up_sync(TBZ_FULL, incl, sft);
-      if (lane >= sft) incl += u;
+      const uint32_t u = __shfl_up_sync(TBZ_FULL, incl, sft), ub = __shfl_up_sync(TBZ_FULL, incb, sft);
+      if (lane >= sft) { incl += u; incb += ub; }
     }
-    uint32_t br = 0, bp = 0;
+    uint32_t br = 0, bp = 0, bb = 0;
     if (lane == 31) {
       if (incl & 0xffffu) br = atomicAdd(&sm.nready, incl & 0xffffu);
-      if (incl >> 16) bp = atomicAdd(&sm.npend, incl >> 16);
+      if (incl >> 16) { bp = atomicAdd(&sm.npend, incl >> 16); bb = atomicAdd(&sm.npbytes, incb); }
     }
-    br = __shfl_sync(TBZ_FULL, br, 31); bp = __shfl_sync(TBZ_FULL, bp, 31);
-    uint32_t ri = br + ((incl - c) & 0xffffu), pi = bp + ((incl - c) >> 16);
+    br = __shfl_sync(TBZ_FULL, br, 31); bp = __shfl_sync(TBZ_FULL, bp, 31); bb = __shfl_sync(TBZ_FULL, bb, 31);
+    uint32_t ri = br + ((incl - c) & 0xffffu), pi = bp + ((incl - c) >> 16), qb = bb + incb - pb;
 #pragma unroll
     for (int q = 0; q < TPT; q++) {
-      if (rmask & (1u << q)) sm.jobs[ri++] = (tid * TPT + q) | (((tk[q] >> 8) & 0x7fffu) << 10);
-      if (pmask & (1u << q)) sm.pjobs[pi++] = (uint16_t)(tid * TPT + q);
+      const uint32_t job = (tid * TPT + q) | (((tk[q] >> 8) & 0x7fffu) << 10);
+      if (rmask & (1u << q)) sm.jobs[ri++] = job;
+      if (pmask & (1u << q)) { sm.jobs[WT - 1u - pi] = job; sm.pq[pi] = (uint16_t)qb; pi++; qb += ln[q]; }
     }
   }
   __syncthreads();
-  // ---- 3. the ready queue: one job per thread and step
+  uint32_t nused = n;
+  if (total > WCAP) {
+    nused = 0;
+#pragma unroll
+    for (int w = 0; w < NWARP; w++) nused += sm.wscan2[w];
+  }
+  if (sm.fail) return 0xffffffffu;
+  const uint32_t wsize = sm.wsize;
+  // ---- 3. the ready queue: one job per thread and step; the pending queue becomes bytes with pointers
+  {                                                     // the next window's tokens travel while this one is copied
+    const uint32_t fn = f + nused;
+    const uint32_t nn = total_tokens - fn < WT ? total_tokens - fn : WT;
+    load_tokens(slab, fn, nn, sm, tid, tk);
+  }
   {
-    const uint32_t nr = sm.nready;
+    const uint32_t nr = sm.nready, np = sm.npend;
     for (uint32_t j = tid; j < nr; j += NT) {
       const uint32_t job = sm.jobs[j], idx = job & 1023u;
       const uint32_t o = sm.tokoff[idx];
       copy_match(buf, wb + o, (job >> 10) + 1u, sm.tokoff[idx + 1] - o);
     }
-  }
-  __syncthreads();
-  // ---- 4. the pending queue: no waiting.  A source piece that lies in a pending token T is an
-  // equal run of bytes dist(T) further back (through the period, if T overlaps itself); it is
-  // redirected until it reaches bytes that exist: final history, a literal, or a ready match.
-  {
-    const uint32_t np = sm.npend;
     for (uint32_t j = tid; j < np; j += NT) {
-      const uint32_t idx = sm.pjobs[j];
-      const uint32_t s0 = sm.tokoff[idx], n_ = sm.tokoff[idx + 1] - s0, d = (sm.tsrc[idx] & 0x7fffu) + 1u;
-      uint32_t left = d < n_ ? d : n_;                    // bytes with a source outside the token
-      int cur = (int)s0 - (int)d;                         // window offset of the next source byte (negative: history)
-      uint32_t o = wb + s0;                               // buffer offset of the next output byte
-      while (left) {
-        int src = cur;
-        uint32_t m = left;
-        while (src >= 0) {
-          uint32_t k = sm.ctok[(uint32_t)src >> 4];       // the token that holds the byte
-          while (sm.tokoff[k + 1] <= (uint32_t)src) k++;
-          const uint32_t sT = sm.tokoff[k], eT = sm.tokoff[k + 1];
-          if (eT - (uint32_t)src < m) m = eT - (uint32_t)src;
-          const uint32_t tsv = sm.tsrc[k];
-          if (!tsv) break;                                // its bytes exist
-          const uint32_t dT = (tsv & 0x7fffu) + 1u;
-          if (dT < eT - sT) {                             // T overlaps itself: go through its period
-            const uint32_t o2 = ((uint32_t)src - sT) % dT;
-            if (dT - o2 < m) m = dT - o2;
-            src = (int)sT - (int)dT + (int)o2;
-          } else src -= (int)dT;
-        }
-        if (src < 0 && (uint32_t)(-src) < m) m = (uint32_t)(-src);   // the rest of the piece starts inside the window
-        const uint32_t sb = (uint32_t)((int)wb + src);
-        for (uint32_t b = 0; b < m; b++) buf[o + b] = buf[sb + b];
-        o += m; cur += (int)m; left -= m;
+      const uint32_t job = sm.jobs[WT - 1u - j], idx = job & 1023u, d = (job >> 10) + 1u;
+      const uint32_t s0 = sm.tokoff[idx], n_ = sm.tokoff[idx + 1] - s0;
+      uint16_t *qp = sm.pbytes + sm.pq[j];
+      for (uint32_t k = 0; k < n_; k++) {
+        const uint32_t r = s0 + k;
+        qp[k] = (uint16_t)r;
+        if (r < d) buf[wb + r] = buf[wb + r - d];         // the source is below the window: final
+        else sm.val[r] = (uint16_t)(r - d);
       }
-      for (uint32_t b = d; b < n_; b++) buf[wb + s0 + b] = buf[wb + s0 + b - d];   // the token's own period
     }
   }
   __syncthreads();
-  // ---- 4. flush complete 16-byte units, fold them into the checksum
+  // ---- 4. pointer jumping over the pending bytes
+  {
+    const uint32_t nb = sm.npbytes;
+    for (;;) {
+      int unresolved = 0;
+      for (uint32_t i = tid; i < nb; i += NT) {
+        const uint32_t r = sm.pbytes[i];
+        volatile uint16_t *vp = reinterpret_cast<volatile uint16_t *>(&sm.val[r]);
+        const uint32_t s2 = *vp;
+        if (s2 != V_FINAL) {
+          const uint32_t vs = *reinterpret_cast<volatile uint16_t *>(&sm.val[s2]);
+          if (vs == V_FINAL) {
+            buf[wb + r] = *reinterpret_cast<volatile uint8_t *>(&buf[wb + s2]);
+            __threadfence_block();
+            *vp = (uint16_t)V_FINAL;
+          } else { *vp = (uint16_t)vs; unresolved = 1; }   // equal bytes: adopt the source's pointer
+        }
+      }
+      if (!__syncthreads_or(unresolved)) break;
+    }
+  }
+  // ---- 5. flush complete 16-byte units, fold them into the checksum
   const bool aligned_out = (((uintptr_t)out) & 15) == 0;
   if (fmt == TBZ_GZIP && !aligned_out) crc_window(sm, buf, wb, wsize, tid);
   if (aligned_out) {
@@ -459,9 +451,11 @@ __device__ inline bool resolve_stream(uint8_t *__restrict__ out, int fmt, const 
     __syncthreads();
     const uint32_t total = sm.segstart[32];
     uint32_t f = 0;
+    uint32_t tk[TPT];
+    load_tokens(slab, 0, total < WT ? total : WT, sm, tid, tk);
     while (f < total) {
       const uint32_t n = total - f < WT ? total - f : WT;
-      const uint32_t used = resolve_window(out, fmt, slab, f, n, rs, sm, tid);
+      const uint32_t used = resolve_window(out, fmt, slab, f, n, total, tk, rs, sm, tid);
       if (used == 0xffffffffu || used == 0) return false;
       f += used;
     }
