@@ -39,13 +39,13 @@ using tbzfast::TOK_MATCH;
 constexpr int NT = 256;
 constexpr int NWARP = NT / 32;
 #ifndef TBZ_CP_TPT
-#define TBZ_CP_TPT 3
+#define TBZ_CP_TPT 4
 #endif
 #ifndef TBZ_CP_WCAP
-#define TBZ_CP_WCAP 5120
+#define TBZ_CP_WCAP 6000
 #endif
 #ifndef TBZ_CP_ROOM
-#define TBZ_CP_ROOM 12288
+#define TBZ_CP_ROOM 8192
 #endif
 constexpr int TPT = TBZ_CP_TPT;                 // tokens per thread and window
 constexpr uint32_t WT = (uint32_t)NT * TPT;     // window tokens

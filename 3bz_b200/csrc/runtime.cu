@@ -68,15 +68,13 @@ k_inflate_decode(const DMember *members, uint32_t n, int fmt, tbzfast::P1Rec *re
 // Phase two, persistent CTAs: one CTA per member resolves the token stream into bytes through a
 // shared-memory buffer and checks the trailer.  Three interchangeable implementations (TBZ_P2),
 // all bit-exact on the parity suite; per-launch times on BASELINE config 2 (4096 x 64 KiB), B200:
-//   0 (default) tbzres — byte-parallel rank queries + pointer jumping (inflate_resolve.cuh; also the
-//                        16-bit symbolic variant the split decode of one large member uses)  1.33 ms
+//   2 (default) tbzcp  — one thread per token: dense word-wise copy queue for matches from final
+//                        history, byte pointer jumping for the rest (inflate_copy.cuh)            1.00 ms
+//   0           tbzres — byte-parallel rank queries + pointer jumping for every byte (inflate_resolve.cuh;
+//                        its 16-bit symbolic variant serves the split decode of one large member) 1.33 ms
 //   1           tbzls  — lock-step lanes over 16-byte chunks, pointer jumping (inflate_lockstep.cuh) 1.65 ms
-//   2           tbzcp  — one thread per token, dense word-wise copy queues, pending matches redirected
-//                        through their source tokens (inflate_copy.cuh)                              1.77 ms
-// The two token-walking variants execute fewer instructions on the bytes they copy but lose more to
-// divergent per-lane loops than they save (profiles/r1e_*): uniform control flow wins on this path.
 #ifndef TBZ_P2
-#define TBZ_P2 0
+#define TBZ_P2 2
 #endif
 #if TBZ_P2 == 0
 namespace tbzp2 = tbzres;
