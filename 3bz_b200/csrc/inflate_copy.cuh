@@ -357,9 +357,11 @@ __device__ inline uint32_t resolve_window(uint8_t *__restrict__ out, int fmt, co
         volatile uint16_t *vp = reinterpret_cast<volatile uint16_t *>(&sm.val[r]);
         const uint32_t s2 = *vp;
         if (s2 != V_FINAL) {
-          const uint32_t vs = *reinterpret_cast<volatile uint16_t *>(&sm.val[s2]);
+          uint32_t sp = s2;
+          uint32_t vs = *reinterpret_cast<volatile uint16_t *>(&sm.val[sp]);
+          if (vs != V_FINAL) { sp = vs; vs = *reinterpret_cast<volatile uint16_t *>(&sm.val[sp]); }   // two hops per level
           if (vs == V_FINAL) {
-            buf[wb + r] = *reinterpret_cast<volatile uint8_t *>(&buf[wb + s2]);
+            buf[wb + r] = *reinterpret_cast<volatile uint8_t *>(&buf[wb + sp]);
             __threadfence_block();
             *vp = (uint16_t)V_FINAL;
           } else { *vp = (uint16_t)vs; unresolved = 1; }   // equal bytes: adopt the source's pointer
@@ -421,7 +423,7 @@ __device__ inline uint32_t resolve_window(uint8_t *__restrict__ out, int fmt, co
   }
   if (__builtin_expect((rs.acc_w >> 62) != 0, 0)) rs.acc_w %= TBZ_ADLER_MOD;
   rs.pos = pos + wsize;
-  __syncthreads();
+  // no barrier here: the next window (or the slide) reaches one before it writes anything this flush reads
   return nused;
 }
 
