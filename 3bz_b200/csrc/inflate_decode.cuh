@@ -20,12 +20,13 @@
 // is queued for the sequential kernel, which reproduces the reference's exact verdict.
 // Replaces deflate.lisp:465-509,673-702 (decode) and huffman-tree.lisp:99-218 (tables).
 #pragma once
+#include <cstddef>
 #include "tbz_device.cuh"
 
 namespace tbzfast {
 
 #ifndef TBZ_DEC_TOKCAP
-#define TBZ_DEC_TOKCAP 768
+#define TBZ_DEC_TOKCAP 736
 #endif
 #ifndef TBZ_DEC_CKSTEP
 #define TBZ_DEC_CKSTEP 32
@@ -62,7 +63,7 @@ struct P1Rec {
   uint32_t end_pos;     // bit position (relative to the 4-byte aligned input base) after the last block
 };
 
-constexpr uint32_t E_LONG = 0x00000300u, E_INVALID = 0x00010300u;   // table specials (code length 0)
+constexpr uint32_t E_LONG = 0xc000u, E_INVALID = 0x8000u;   // table specials (code length 0)
 // token: one literal = byte value; two literals = TOK_LIT2 | second << 8 | first;
 // match = TOK_MATCH | (distance - 1) << 8 | (length - 3).  End of block is not a token.
 constexpr uint32_t TOK_MATCH = 0x80000000u, TOK_LIT2 = 0x40000000u;
@@ -79,16 +80,22 @@ struct HdrScratch {                      // only alive while a block header is p
   uint16_t run[16];
 };
 struct WSmem {                           // one per warp
-  uint32_t lut_ll[1 << KLL];
-  uint32_t lut_d[1 << KD];
+  uint16_t lut_ll[1 << KLL];             // 16-bit entries: 7 KB per warp in all, 8 CTAs (32 warps) per SM
+  uint16_t lut_d[1 << KD];               // (directly behind lut_ll: the second lookup of a token indexes either)
   union {
     uint32_t ckpt[NCK][NL];              // [checkpoint][lane]: (bit offset in the sub-chunk) | (output bytes << 13)
     HdrScratch h;
   };
   Canon16 c_ll, c_d;
   uint16_t sorted_ll[288], sorted_d[32];
+  uint16_t lenbase[32], distbase[32];    // constants.lisp:36-61 base values, next to the tables that index them
+#ifdef TBZ_DEC_PAD
+  uint8_t pad[TBZ_DEC_PAD];            // occupancy experiments
+#endif
 };
 static_assert(sizeof(HdrScratch) <= sizeof(uint32_t) * NCK * NL, "header scratch must fit under the checkpoints");
+static_assert(offsetof(WSmem, lut_d) == offsetof(WSmem, lut_ll) + sizeof(uint16_t) * (1 << KLL), "lut_d must follow lut_ll");
+static_assert(sizeof(WSmem) * WPC + 1024 <= 233472 / 8, "eight CTAs per SM");
 
 struct In {
   const uint32_t *w; uint32_t nwords; uint32_t pos0, end;
@@ -102,18 +109,21 @@ __device__ __forceinline__ uint32_t byte_at(const In &in, uint32_t bytepos) {
   return (ldw(in, bytepos >> 2) >> (8 * (bytepos & 3))) & 0xff;
 }
 
-// ---- table entries ---------------------------------------------------------------------------
-// lit/len: [3:0] code length, [6:4] extra bits, [9:8] kind (0 literal, 1 length, 2 end of block), [31:16] value
-// dist   : [3:0] code length, [7:4] extra bits, [9:8] = 1, [31:16] base
+// ---- table entries (16 bit) -----------------------------------------------------------------
+// lit/len: [3:0] code length (0 = special), [6:4] extra bits, then
+//            literal      : bit 15 = 0, [14:7] the byte
+//            length       : bit 15 = 1, bit 14 = 0, [11:7] length symbol - 257 (base value in lenbase[])
+//            end of block : bits 15 and 14 = 1
+// dist   : [3:0] code length, [7:4] extra bits, [12:8] distance symbol (base value in distbase[])
 __device__ __forceinline__ uint32_t ll_entry(uint32_t sym, uint32_t L) {
-  if (sym < 256) return (sym << 16) | L;
-  if (sym == 256) return (2u << 8) | L;
+  if (sym < 256) return (sym << 7) | L;
+  if (sym == 256) return 0xc000u | L;
   if (sym > 285) return E_INVALID;                          // huffman-tree.lisp:176-177
-  return ((uint32_t)c_len_base[sym - 257] << 16) | (1u << 8) | ((uint32_t)c_len_extra[sym - 257] << 4) | L;
+  return 0x8000u | ((sym - 257) << 7) | ((uint32_t)c_len_extra[sym - 257] << 4) | L;
 }
 __device__ __forceinline__ uint32_t d_entry(uint32_t sym, uint32_t L) {
   if (sym > 29) return E_INVALID;                           // huffman-tree.lisp:172-175
-  return ((uint32_t)c_dist_base[sym] << 16) | (1u << 8) | ((uint32_t)c_dist_extra[sym] << 4) | L;
+  return (sym << 8) | ((uint32_t)c_dist_extra[sym] << 4) | L;
 }
 
 // canonical decode of the code that starts at bit 0 of `bits`, lengths lo..hi; returns (sym<<4)|L or 0
@@ -208,14 +218,19 @@ __device__ __forceinline__ int decode_token(Bits &b, const In &in, const WSmem &
     e = ll_entry(r >> 4, r & 15);
     if ((e & 15) == 0) return 3;
   }
-  const uint32_t L = e & 15, kind = (e >> 8) & 3, xb = (e >> 4) & 7;
-  const uint32_t val = (e >> 16) + ((w >> L) & ((1u << xb) - 1));   // literal byte / match length
+  const uint32_t L = e & 15, xb = (e >> 4) & 7, t2 = e >> 14;
+  const uint32_t kind = (t2 < 1u ? 1u : t2) - 1u;            // 0 literal, 1 length, 2 end of block
+  const bool ism = kind == 1;
+  const uint32_t pay = (e >> 7) & 255u;                      // the byte, or the length symbol
+  uint32_t val = pay;
+  if (ism) val = sm.lenbase[pay & 31u] + ((w >> L) & ((1u << xb) - 1));   // match length
   const uint32_t n1 = L + xb;
   bits_skip(b, n1);
-  const bool ism = kind == 1;
   if (ism && b.bc < 28) bits_refill(b, in);                  // a literal leaves >= 18 bits: enough for any code
   const uint32_t w2 = (uint32_t)b.bb;
-  uint32_t d = ism ? sm.lut_d[w2 & ((1u << KD) - 1)] : sm.lut_ll[w2 & ((1u << KLL) - 1)];
+  // one load for either table: lut_d lies directly behind lut_ll
+  const uint16_t *const lut = sm.lut_ll;
+  uint32_t d = lut[ism ? (1u << KLL) + (w2 & ((1u << KD) - 1)) : (w2 & ((1u << KLL) - 1))];
   if (ism && (d & 15) == 0) {
     if (d != E_LONG) return 3;
     uint32_t r = canon_lookup(sm.c_d, sm.sorted_d, w2, KD + 1, 15);
@@ -224,10 +239,11 @@ __device__ __forceinline__ int decode_token(Bits &b, const In &in, const WSmem &
     if ((d & 15) == 0) return 3;
   }
   // after a literal: keep the second symbol only if it is a literal with a short code
-  const bool two = kind == 0 && (d & 0x30f) != 0 && (d & 0x300) == 0;
-  if (!ism && !two) d = 0;
-  const uint32_t DL = d & 15, dxb = (d >> 4) & 15;          // a literal entry has no extra bits
-  const uint32_t dv = (d >> 16) + ((w2 >> DL) & ((1u << dxb) - 1));   // distance / second literal
+  const bool two = kind == 0 && (d & 15) != 0 && (d >> 15) == 0;
+  const uint32_t DL = (ism || two) ? (d & 15) : 0u;
+  const uint32_t dxb = ism ? (d >> 4) & 15 : 0u;             // a literal has no extra bits
+  uint32_t dv = (d >> 7) & 255u;                             // second literal
+  if (ism) dv = sm.distbase[(d >> 8) & 31u] + ((w2 >> DL) & ((1u << dxb) - 1));   // distance
   const uint32_t n2 = DL + dxb;
   bits_skip(b, n2);
   tok = ism ? (TOK_MATCH | ((dv - 1) << 8) | (val - 3)) : two ? (TOK_LIT2 | (dv << 8) | val) : val;
@@ -262,6 +278,7 @@ struct TokW {
 __device__ inline bool decode_blocks(const In &in, uint32_t pos, uint32_t stop_bit, unsigned long long out_cap, P1Rec &rec,
                                      WSmem &sm, uint32_t *__restrict__ slabs, uint32_t nslabs, uint32_t *slab_counter, int lane) {
   unsigned long long A = 0;    // output bytes so far
+  sm.lenbase[lane] = c_len_base[lane]; sm.distbase[lane] = c_dist_base[lane];
   uint32_t first_slab = NO_SLAB, prev_slab = NO_SLAB;
   uint32_t prev_block_bits = 0;   // size of the previous block of this member: predicts this one
   bool last = false;
@@ -342,11 +359,11 @@ __device__ inline bool decode_blocks(const In &in, uint32_t pos, uint32_t stop_b
     if (sm.c_ll.nsyms == 0) return false;
     for (int e = lane; e < (1 << KLL); e += 32) {
       uint32_t r = canon_lookup(sm.c_ll, sm.sorted_ll, (uint32_t)e, 1, KLL);
-      sm.lut_ll[e] = r ? ll_entry(r >> 4, r & 15) : (sm.c_ll.maxlen > KLL ? E_LONG : E_INVALID);
+      sm.lut_ll[e] = (uint16_t)(r ? ll_entry(r >> 4, r & 15) : (sm.c_ll.maxlen > KLL ? E_LONG : E_INVALID));
     }
     for (int e = lane; e < (1 << KD); e += 32) {
       uint32_t r = canon_lookup(sm.c_d, sm.sorted_d, (uint32_t)e, 1, KD);
-      sm.lut_d[e] = r ? d_entry(r >> 4, r & 15) : (sm.c_d.maxlen > KD ? E_LONG : E_INVALID);
+      sm.lut_d[e] = (uint16_t)(r ? d_entry(r >> 4, r & 15) : (sm.c_d.maxlen > KD ? E_LONG : E_INVALID));
     }
     __syncwarp();
 

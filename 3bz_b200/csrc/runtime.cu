@@ -48,7 +48,7 @@ k_inflate_seq(const DMember *members, tbz_result *results, uint32_t n, int fmt,
 // Phase one, persistent CTAs of WPC independent warps: each warp pulls the next member from a
 // global counter and decodes it into token slabs; members it cannot prove clean are queued for
 // k_inflate_seq.
-__global__ void __launch_bounds__(tbzfast::NT)
+__global__ void __launch_bounds__(tbzfast::NT, 8)
 k_inflate_decode(const DMember *members, uint32_t n, int fmt, tbzfast::P1Rec *recs,
                  uint32_t *slabs, uint32_t nslabs, uint32_t *counters, uint32_t *todo) {
   extern __shared__ __align__(16) unsigned char smem_raw[];

@@ -16,7 +16,7 @@ for l in out.splitlines():
         print(l)
 src = open(srcf).read().splitlines()
 base = os.path.basename(srcf)
-marks = [(i + 1, l.strip()) for i, l in enumerate(src) if l.strip().startswith('// ----') or re.match(r'^(__device__|template|__global__)', l)]
+marks = [(i + 1, l.strip()) for i, l in enumerate(src) if l.strip().startswith('// ----') or l.strip().startswith('// ====') or re.match(r'^(__device__|template|__global__)', l)]
 def sec(f, l):
     if base not in f:
         return 'other: ' + f
