@@ -213,7 +213,7 @@ __device__ __forceinline__ int decode_token(Bits &b, const In &in, const WSmem &
   uint32_t e = sm.lut_ll[w & ((1u << KLL) - 1)];
   if ((e & 15) == 0) {
     if (e != E_LONG) return 3;
-    uint32_t r = canon_lookup(sm.c_ll, sm.sorted_ll, w, KLL + 1, 15);
+        uint32_t r = canon_lookup(sm.c_ll, sm.sorted_ll, w, KLL + 1, 15);
     if (!r) return 3;
     e = ll_entry(r >> 4, r & 15);
     if ((e & 15) == 0) return 3;
@@ -222,8 +222,8 @@ __device__ __forceinline__ int decode_token(Bits &b, const In &in, const WSmem &
   const uint32_t kind = (t2 < 1u ? 1u : t2) - 1u;            // 0 literal, 1 length, 2 end of block
   const bool ism = kind == 1;
   const uint32_t pay = (e >> 7) & 255u;                      // the byte, or the length symbol
-  uint32_t val = pay;
-  if (ism) val = sm.lenbase[pay & 31u] + ((w >> L) & ((1u << xb) - 1));   // match length
+  const uint32_t lb = sm.lenbase[pay & 31u];                  // (loaded by every lane: no divergence)
+  const uint32_t val = ism ? lb + ((w >> L) & ((1u << xb) - 1)) : pay;   // match length / the byte
   const uint32_t n1 = L + xb;
   bits_skip(b, n1);
   if (ism && b.bc < 28) bits_refill(b, in);                  // a literal leaves >= 18 bits: enough for any code
@@ -233,7 +233,7 @@ __device__ __forceinline__ int decode_token(Bits &b, const In &in, const WSmem &
   uint32_t d = lut[ism ? (1u << KLL) + (w2 & ((1u << KD) - 1)) : (w2 & ((1u << KLL) - 1))];
   if (ism && (d & 15) == 0) {
     if (d != E_LONG) return 3;
-    uint32_t r = canon_lookup(sm.c_d, sm.sorted_d, w2, KD + 1, 15);
+        uint32_t r = canon_lookup(sm.c_d, sm.sorted_d, w2, KD + 1, 15);
     if (!r) return 3;
     d = d_entry(r >> 4, r & 15);
     if ((d & 15) == 0) return 3;
@@ -242,8 +242,8 @@ __device__ __forceinline__ int decode_token(Bits &b, const In &in, const WSmem &
   const bool two = kind == 0 && (d & 15) != 0 && (d >> 15) == 0;
   const uint32_t DL = (ism || two) ? (d & 15) : 0u;
   const uint32_t dxb = ism ? (d >> 4) & 15 : 0u;             // a literal has no extra bits
-  uint32_t dv = (d >> 7) & 255u;                             // second literal
-  if (ism) dv = sm.distbase[(d >> 8) & 31u] + ((w2 >> DL) & ((1u << dxb) - 1));   // distance
+  const uint32_t db = sm.distbase[(d >> 8) & 31u];
+  const uint32_t dv = ism ? db + ((w2 >> DL) & ((1u << dxb) - 1)) : (d >> 7) & 255u;   // distance / second literal
   const uint32_t n2 = DL + dxb;
   bits_skip(b, n2);
   tok = ism ? (TOK_MATCH | ((dv - 1) << 8) | (val - 3)) : two ? (TOK_LIT2 | (dv << 8) | val) : val;
