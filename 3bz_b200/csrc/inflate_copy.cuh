@@ -1,8 +1,8 @@
 // inflate_copy.cuh — phase two of the batched fast path for byte members: LZ77 resolution of a
 // token stream (deflate.lisp:244-359 `copy-history`), one thread per token.
 //
-// One CTA per member.  The last 32 KiB of output and the window being produced live in ONE linear
-// shared-memory buffer (positions never wrap; when the buffer is full its last 32 KiB slide down).
+// One CTA per member.  Shared memory holds the last 32 KiB of output as a ring (final history) and,
+// separately, the window being produced, so positions inside a window never wrap.
 // A window is the next <= WT tokens (<= WCAP bytes); tokens are never split.  Per window:
 //   1. the tokens are loaded (TPT consecutive tokens per thread), a CTA prefix sum over their
 //      lengths gives every token its byte offset
@@ -17,7 +17,7 @@
 //   4. the pending bytes (about a third of the bytes on text) are resolved by pointer jumping with
 //      uniform control flow: a byte whose source is final copies it; otherwise it adopts the
 //      source's pointer (equal bytes).  Chains halve per level; a level ends at a CTA barrier
-//   5. the window is flushed to global memory with 16-byte stores; Adler-32 is folded in with dp4a
+//   5. the window is flushed to global memory and appended to the ring with 16-byte stores; Adler-32 is folded in with dp4a
 //      (order-independent form), CRC-32 per 16-byte unit with x^(8n) combines
 // The trailer is checked as zlib.lisp:80-96 / gzip.lisp:82-106 do; any disagreement sends the member
 // to the sequential kernel, which owns the verdict rules.
@@ -44,27 +44,25 @@ constexpr int NWARP = NT / 32;
 #ifndef TBZ_CP_WCAP
 #define TBZ_CP_WCAP 6000
 #endif
-#ifndef TBZ_CP_ROOM
-#define TBZ_CP_ROOM 8192
-#endif
 constexpr int TPT = TBZ_CP_TPT;                 // tokens per thread and window
 constexpr uint32_t WT = (uint32_t)NT * TPT;     // window tokens
 constexpr uint32_t HIST = 32768u;
 constexpr uint32_t WCAP = TBZ_CP_WCAP;          // window bytes
-constexpr uint32_t LB = HIST + TBZ_CP_ROOM;     // linear buffer: history + room for new windows
+constexpr uint32_t HMASK = HIST - 1u;
 constexpr uint32_t WB = WCAP;                   // (name shared with the other phase-two variants: sizes the x16 table)
-constexpr uint32_t FRONT = 16u;                 // slack on both sides: word reads next to a source stay inside
 constexpr uint32_t V_FINAL = 0xffffu;
-static_assert(WT <= 1024u && WCAP <= 8192u && WCAP % 16u == 0 && TBZ_CP_ROOM >= WCAP, "queue entry fields");
+static_assert(WT <= 1024u && WCAP <= 8192u && WCAP % 16u == 0, "queue entry fields");
 
 struct Smem {
-  alignas(16) uint8_t raw[FRONT + LB + 16];    // buf = raw + FRONT
+  alignas(16) uint8_t ring[HIST];              // final history: absolute output offset p lives at ring[p & HMASK]
+  alignas(16) uint8_t win[16 + WCAP + 16];     // the window: offset r (absolute pos + r) lives at win[(pos & 15) + r], so that
+                                               // 16-byte units of the output are 16-byte units here
   alignas(16) uint16_t val[WCAP];              // per window byte: V_FINAL, or the window offset of an equal byte
   uint16_t pbytes[WCAP];                       // the bytes of the pending matches
   uint16_t tokoff[WT < 1024u ? 1026u : WT + 2u]; // window offset of every token; [tokens used] = window size (>= 2 KiB: CRC scratch)
   uint32_t jobs[WT];                           // ready matches from [0] up, pending from [WT - 1] down: token | (distance - 1) << 10
   uint16_t pq[WT];                             // per pending match: where its bytes start in pbytes
-  uint32_t nready, npend, npbytes;
+  uint32_t nready, npk;                        // npk: pending matches | their bytes << 16
   uint32_t hdr[SLAB_HDR_WORDS];
   uint32_t segstart[NL + 1];                   // flat index of the first token of every list of the current slab
   uint32_t segptr[NL];                         // word offset of that token in the slab
@@ -81,46 +79,44 @@ struct Smem {
 
 __device__ __forceinline__ uint32_t tok_len(uint32_t t) { return (t & TOK_MATCH) ? (t & 255u) + 3u : 1u + ((t >> 30) & 1u); }
 
-// One match: n bytes from d bytes back, dst a buffer offset.  Straight-line for n <= 19 when the
-// source does not overlap the destination closely (d >= n, or d >= 8: the one-word lookahead of the
-// funnel stays behind the bytes this thread has already stored); bytewise otherwise.
-__device__ __forceinline__ void copy_match(uint8_t *buf, uint32_t dst, uint32_t d, uint32_t n) {
-  if (__builtin_expect(d >= n || d >= 8u, 1)) {
-    const uint32_t src = dst - d, dend = dst + n;
-    uint32_t hb = (0u - dst) & 3u;                       // bytes up to the first aligned destination word
-    if (hb > n) hb = n;
+// One match whose source is final history: n bytes from ring offset src (wraps) to win[dst, dst+n).
+// Straight-line for n <= 19: byte moves up to the first aligned destination word and after the last
+// one, in between one aligned word load per 4 source bytes and a funnel shift.
+__device__ __forceinline__ void copy_hist(uint8_t *win, uint32_t dst, const uint8_t *ring, uint32_t src, uint32_t n) {
+  const uint32_t dend = dst + n;
+  uint32_t hb = (0u - dst) & 3u;                         // bytes up to the first aligned destination word
+  if (hb > n) hb = n;
 #pragma unroll
-    for (uint32_t b = 0; b < 3; b++)
-      if (b < hb) buf[dst + b] = buf[src + b];
-    uint32_t p = dst + hb;                               // aligned (or the end)
-    const uint32_t sa = src + hb;
-    const uint32_t sh = (sa & 3u) * 8u;
-    const uint32_t *sw = reinterpret_cast<const uint32_t *>(buf + (sa & ~3u));
-    uint32_t lo = sw[0];
+  for (uint32_t b = 0; b < 3; b++)
+    if (b < hb) win[dst + b] = ring[(src + b) & HMASK];
+  uint32_t p = dst + hb;                                 // aligned (or the end)
+  const uint32_t sa = src + hb;
+  const uint32_t sh = (sa & 3u) * 8u;
+  const uint32_t *rw = reinterpret_cast<const uint32_t *>(ring);
+  uint32_t wi = sa >> 2;
+  uint32_t lo = rw[wi & (HMASK >> 2)];
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-      if (p + 4u <= dend) {
-        const uint32_t hi = sw[i + 1];
-        *reinterpret_cast<uint32_t *>(buf + p) = __funnelshift_r(lo, hi, sh);
-        lo = hi;
-        p += 4u;
-      }
+  for (int i = 0; i < 4; i++) {
+    if (p + 4u <= dend) {
+      const uint32_t hi = rw[(wi + 1u + i) & (HMASK >> 2)];
+      *reinterpret_cast<uint32_t *>(win + p) = __funnelshift_r(lo, hi, sh);
+      lo = hi;
+      p += 4u;
     }
-    if (__builtin_expect(p + 4u <= dend, 0)) {           // long matches
-      sw += 4;
-      do {
-        const uint32_t hi = sw[1];
-        *reinterpret_cast<uint32_t *>(buf + p) = __funnelshift_r(lo, hi, sh);
-        lo = hi; sw++;
-        p += 4u;
-      } while (p + 4u <= dend);
-    }
-#pragma unroll
-    for (uint32_t b = 0; b < 3; b++)
-      if (p + b < dend) buf[p + b] = buf[p + b - d];
-  } else {                                               // close overlap: the thread's own stores are its sources
-    for (uint32_t k = 0; k < n; k++) buf[dst + k] = buf[dst + k - d];
   }
+  if (__builtin_expect(p + 4u <= dend, 0)) {             // long matches
+    wi += 4u;
+    do {
+      wi++;
+      const uint32_t hi = rw[wi & (HMASK >> 2)];
+      *reinterpret_cast<uint32_t *>(win + p) = __funnelshift_r(lo, hi, sh);
+      lo = hi;
+      p += 4u;
+    } while (p + 4u <= dend);
+  }
+#pragma unroll
+  for (uint32_t b = 0; b < 3; b++)
+    if (p + b < dend) win[p + b] = ring[(src + (p + b - dst)) & HMASK];
 }
 
 // CRC-32 of buf[a, a+m): every thread takes one contiguous slice; slices are merged pairwise with
@@ -158,7 +154,6 @@ __device__ inline void crc_window(Smem &sm, const uint8_t *buf, uint32_t a, uint
 // per-member state that lives in registers (uniform unless noted)
 struct RState {
   uint32_t pos;                           // output bytes produced so far (window base)
-  uint32_t bbase;                         // absolute output offset of buf[0] (a multiple of 16)
   uint32_t flushed;                       // output bytes already stored to global memory
   unsigned long long acc_a, acc_w;        // per thread: Adler sum d, sum i*d over the bytes it flushed
 };
@@ -199,31 +194,10 @@ __device__ __forceinline__ void load_tokens(const uint32_t *__restrict__ slab, u
 __device__ inline uint32_t resolve_window(uint8_t *__restrict__ out, int fmt, const uint32_t *__restrict__ slab, uint32_t f, uint32_t n,
                                           uint32_t total_tokens, uint32_t (&tk)[TPT], RState &rs, Smem &sm, int tid) {
   const int lane = tid & 31, warp = tid >> 5;
-  uint8_t *const buf = sm.raw + FRONT;
-  // ---- 0. room for a full window: slide the last 32 KiB down
-  if (rs.pos - rs.bbase + WCAP > LB) {
-    const uint32_t nb = (rs.pos - HIST) & ~15u;
-    const uint32_t shift = nb - rs.bbase;               // a multiple of 16, > 0
-    const uint32_t units = (rs.pos - nb + 15u) >> 4;    // 16-byte units to keep
-    for (uint32_t u0 = 0; u0 < units; u0 += 4u * NT) {  // reads of a batch precede its writes; later batches read above them
-      uint4 v[4];
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        const uint32_t u = u0 + (uint32_t)k * NT + tid;
-        if (u < units) v[k] = *reinterpret_cast<const uint4 *>(buf + shift + 16u * u);
-      }
-      __syncthreads();
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        const uint32_t u = u0 + (uint32_t)k * NT + tid;
-        if (u < units) *reinterpret_cast<uint4 *>(buf + 16u * u) = v[k];
-      }
-    }
-    rs.bbase = nb;
-    __syncthreads();
-  }
   const uint32_t pos = rs.pos;
-  const uint32_t wb = pos - rs.bbase;                   // buffer offset of the window's first byte
+  const uint32_t mis = pos & 15u;
+  uint8_t *const buf = sm.win;
+  const uint32_t wb = mis;                              // index of the window's first byte in win[]
   // ---- 1. tokens and their offsets
   uint32_t ln[TPT];
   uint32_t mine = 0;
@@ -239,10 +213,11 @@ __device__ inline uint32_t resolve_window(uint8_t *__restrict__ out, int fmt, co
     if (lane >= sft) x += u;
   }
   if (lane == 31) sm.wscan[warp] = x;
-  if (tid == 0) { sm.nready = 0; sm.npend = 0; sm.npbytes = 0; }
+  if (tid == 0) { sm.nready = 0; sm.npk = 0; }
   for (uint32_t i = tid; i < WCAP / 8u; i += NT)        // (the previous window's levels ended at a barrier)
     reinterpret_cast<uint4 *>(sm.val)[i] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
   __syncthreads();
+  if (tid < (int)mis) sm.win[tid] = sm.ring[(pos - mis + tid) & HMASK];   // the unit the previous window ended in
   uint32_t off = 0, total = 0;
 #pragma unroll
   for (int w = 0; w < NWARP; w++) { const uint32_t c = sm.wscan[w]; if (w < warp) off += c; total += c; }
@@ -291,20 +266,22 @@ __device__ inline uint32_t resolve_window(uint8_t *__restrict__ out, int fmt, co
     }
   }
   {
-    const uint32_t c = __popc(rmask) | (__popc(pmask) << 16);
-    uint32_t incl = c, incb = pb;
+    // one warp scan for three counts: ready matches | pending matches << 8 | pending bytes << 16
+    const uint32_t c = __popc(rmask) | (__popc(pmask) << 8) | (pb << 16);
+    uint32_t incl = c;
 #pragma unroll
     for (int sft = 1; sft < 32; sft <<= 1) {
-      const uint32_t u = __shfl_up_sync(TBZ_FULL, incl, sft), ub = __shfl_up_sync(TBZ_FULL, incb, sft);
-      if (lane >= sft) { incl += u; incb += ub; }
+      const uint32_t u = __shfl_up_sync(TBZ_FULL, incl, sft);
+      if (lane >= sft) incl += u;
     }
-    uint32_t br = 0, bp = 0, bb = 0;
+    uint32_t br = 0, bpk = 0;
     if (lane == 31) {
-      if (incl & 0xffffu) br = atomicAdd(&sm.nready, incl & 0xffffu);
-      if (incl >> 16) { bp = atomicAdd(&sm.npend, incl >> 16); bb = atomicAdd(&sm.npbytes, incb); }
+      if (incl & 0xffu) br = atomicAdd(&sm.nready, incl & 0xffu);
+      if (incl >> 8) bpk = atomicAdd(&sm.npk, ((incl >> 8) & 0xffu) | ((incl >> 16) << 16));   // matches | bytes << 16: one order for both
     }
-    br = __shfl_sync(TBZ_FULL, br, 31); bp = __shfl_sync(TBZ_FULL, bp, 31); bb = __shfl_sync(TBZ_FULL, bb, 31);
-    uint32_t ri = br + ((incl - c) & 0xffffu), pi = bp + ((incl - c) >> 16), qb = bb + incb - pb;
+    br = __shfl_sync(TBZ_FULL, br, 31); bpk = __shfl_sync(TBZ_FULL, bpk, 31);
+    const uint32_t ex = incl - c;
+    uint32_t ri = br + (ex & 0xffu), pi = (bpk & 0xffffu) + ((ex >> 8) & 0xffu), qb = (bpk >> 16) + (ex >> 16);
 #pragma unroll
     for (int q = 0; q < TPT; q++) {
       const uint32_t job = (tid * TPT + q) | (((tk[q] >> 8) & 0x7fffu) << 10);
@@ -328,11 +305,12 @@ __device__ inline uint32_t resolve_window(uint8_t *__restrict__ out, int fmt, co
     load_tokens(slab, fn, nn, sm, tid, tk);
   }
   {
-    const uint32_t nr = sm.nready, np = sm.npend;
+    const uint32_t nr = sm.nready, np = sm.npk & 0xffffu;
     for (uint32_t j = tid; j < nr; j += NT) {
       const uint32_t job = sm.jobs[j], idx = job & 1023u;
-      const uint32_t o = sm.tokoff[idx];
-      copy_match(buf, wb + o, (job >> 10) + 1u, sm.tokoff[idx + 1] - o);
+      const uint32_t o = sm.tokoff[idx], d = (job >> 10) + 1u, n_ = sm.tokoff[idx + 1] - o;
+      copy_hist(buf, wb + o, sm.ring, pos + o - d, d < n_ ? d : n_);
+      for (uint32_t k = d; k < n_; k++) buf[wb + o + k] = buf[wb + o + k - d];   // (first token of the window only) its own period
     }
     for (uint32_t j = tid; j < np; j += NT) {
       const uint32_t job = sm.jobs[WT - 1u - j], idx = job & 1023u, d = (job >> 10) + 1u;
@@ -341,7 +319,7 @@ __device__ inline uint32_t resolve_window(uint8_t *__restrict__ out, int fmt, co
       for (uint32_t k = 0; k < n_; k++) {
         const uint32_t r = s0 + k;
         qp[k] = (uint16_t)r;
-        if (r < d) buf[wb + r] = buf[wb + r - d];         // the source is below the window: final
+        if (r < d) buf[wb + r] = sm.ring[(pos + r - d) & HMASK];   // the source is below the window: final
         else sm.val[r] = (uint16_t)(r - d);
       }
     }
@@ -349,7 +327,7 @@ __device__ inline uint32_t resolve_window(uint8_t *__restrict__ out, int fmt, co
   __syncthreads();
   // ---- 4. pointer jumping over the pending bytes
   {
-    const uint32_t nb = sm.npbytes;
+    const uint32_t nb = sm.npk >> 16;
     for (;;) {
       int unresolved = 0;
       for (uint32_t i = tid; i < nb; i += NT) {
@@ -375,11 +353,12 @@ __device__ inline uint32_t resolve_window(uint8_t *__restrict__ out, int fmt, co
   if (fmt == TBZ_GZIP && !aligned_out) crc_window(sm, buf, wb, wsize, tid);
   if (aligned_out) {
     const uint32_t upto = (pos + wsize) & ~15u;
-    const uint8_t *b0 = buf - rs.bbase;                  // b0 + absolute offset
+    const uint8_t *b0 = buf - (pos - mis);               // b0 + absolute offset (16-byte units stay aligned)
     uint32_t myc = 0;                                    // gzip: CRCs of this thread's units, shifted to the end of the flushed range
     for (uint32_t p = rs.flushed + 16u * tid; p < upto; p += 16u * NT) {
       const uint4 v = *reinterpret_cast<const uint4 *>(b0 + p);
       *reinterpret_cast<uint4 *>(out + p) = v;
+      *reinterpret_cast<uint4 *>(&sm.ring[p & HMASK]) = v;
       if (fmt == TBZ_GZIP) {
         // crc(A || B) = crc(A) * x^(8 |B|) + crc(B) for finalized CRCs: one table CRC per unit, one
         // multiplication by the power for the bytes that follow it, XOR over all units
@@ -400,6 +379,7 @@ __device__ inline uint32_t resolve_window(uint8_t *__restrict__ out, int fmt, co
         rs.acc_w += (unsigned long long)p * sd + wj;
       }
     }
+    if (upto + tid < pos + wsize) sm.ring[(upto + tid) & HMASK] = b0[upto + tid];   // the unit the window ends in: history too
     if (fmt == TBZ_GZIP) {
 #pragma unroll
       for (int sft = 16; sft; sft >>= 1) myc ^= __shfl_xor_sync(TBZ_FULL, myc, sft);
@@ -415,15 +395,16 @@ __device__ inline uint32_t resolve_window(uint8_t *__restrict__ out, int fmt, co
     if (upto > rs.flushed) rs.flushed = upto;
   } else {
     for (uint32_t p = pos + tid; p < pos + wsize; p += NT) {
-      const uint32_t d = buf[p - rs.bbase];
+      const uint32_t d = buf[wb + p - pos];
       out[p] = (uint8_t)d;
+      sm.ring[p & HMASK] = (uint8_t)d;
       rs.acc_a += d; rs.acc_w += (unsigned long long)p * d;
     }
     rs.flushed = pos + wsize;
   }
   if (__builtin_expect((rs.acc_w >> 62) != 0, 0)) rs.acc_w %= TBZ_ADLER_MOD;
   rs.pos = pos + wsize;
-  // no barrier here: the next window (or the slide) reaches one before it writes anything this flush reads
+  // no barrier here: the next window reaches one before it reads the ring or writes anything this flush reads
   return nused;
 }
 
@@ -466,7 +447,7 @@ __device__ inline bool resolve_stream(uint8_t *__restrict__ out, int fmt, const 
   if (sm.fail) return false;
   if (rs.flushed + tid < rs.pos) {         // the last partial 16-byte unit
     const uint32_t p = rs.flushed + tid;
-    const uint32_t d = sm.raw[FRONT + p - rs.bbase];
+    const uint32_t d = sm.ring[p & HMASK];
     out[p] = (uint8_t)d;
     rs.acc_a += d; rs.acc_w += (unsigned long long)p * d;
   }
@@ -477,7 +458,7 @@ __device__ inline bool resolve_member(const DMember &mem, int fmt, const P1Rec &
                                       tbz_result &res, Smem &sm, int tid) {
   const int lane = tid & 31, warp = tid >> 5;
   RState rs;
-  rs.pos = 0; rs.bbase = 0; rs.flushed = 0; rs.acc_a = 0; rs.acc_w = 0;
+  rs.pos = 0; rs.flushed = 0; rs.acc_a = 0; rs.acc_w = 0;
   if (!resolve_stream(mem.out, fmt, rec, slabs, rs, sm, tid)) return false;
   const uint32_t pos = rs.pos;
   if (pos != rec.out_len) return false;
@@ -501,7 +482,7 @@ __device__ inline bool resolve_member(const DMember &mem, int fmt, const P1Rec &
     uint32_t c = sm.crc;
     if (rs.flushed < pos) {                  // the last partial unit (uniform: every thread computes the same value)
       uint32_t t = 0xffffffffu;
-      for (uint32_t p = rs.flushed; p < pos; p++) t = (t >> 8) ^ sm.crc_tab[(t ^ sm.raw[FRONT + p - rs.bbase]) & 0xff];
+      for (uint32_t p = rs.flushed; p < pos; p++) t = (t >> 8) ^ sm.crc_tab[(t ^ sm.ring[p & HMASK]) & 0xff];
       c = crc_combine(c, t ^ 0xffffffffu, pos - rs.flushed);
     }
     ck = c;
