@@ -48,25 +48,34 @@ __device__ __forceinline__ tbzfast::In chunk_input(const uint32_t *words, uint64
   return in;
 }
 
-// found[c] = first dynamic-block start in [c * chunk_bits, (c + 1) * chunk_bits) + body_bit, c >= 1
+// found[c] = first dynamic-block start in [c * chunk_bits, (c + 1) * chunk_bits) + body_bit, c >= 1.
+// The chunk's bits are searched in pieces of FPIECE bits, dealt round-robin to FSUB warps, so the
+// warps of a chunk advance through it together; the earliest hit wins (atomicMin), and a warp stops
+// once a hit below its next piece is known.
+constexpr uint32_t FSUB = 8, FPIECE = 4096;
 __global__ void __launch_bounds__(tbzfast::NT)
 k_split_find(const uint32_t *words, uint64_t end_bit, uint64_t body_bit, uint64_t chunk_bits, uint32_t nchunks, uint64_t *found) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   tbzfast::WSmem &sm = reinterpret_cast<tbzfast::WSmem *>(smem_raw)[warp];
-  const uint32_t c = blockIdx.x * tbzfast::WPC + warp + 1;
+  const uint32_t gw = blockIdx.x * tbzfast::WPC + warp;
+  const uint32_t c = gw / FSUB + 1, sub = gw % FSUB;
   if (c >= nchunks) return;
-  const uint64_t from = body_bit + chunk_bits * c;
-  uint64_t to = from + chunk_bits;
-  if (to > end_bit) to = end_bit;
-  uint64_t res = NONE64;
-  if (from < to) {
+  const uint64_t cfrom = body_bit + chunk_bits * c;
+  uint64_t cto = cfrom + chunk_bits;
+  if (cto > end_bit) cto = end_bit;
+  for (uint64_t from = cfrom + (uint64_t)FPIECE * sub; from < cto; from += (uint64_t)FPIECE * FSUB) {
+    if (*reinterpret_cast<volatile unsigned long long *>(&found[c]) < from) break;   // an earlier hit exists
+    uint64_t pe = from + FPIECE;
+    if (pe > cto) pe = cto;
     uint32_t rel;
     const tbzfast::In in = chunk_input(words, end_bit, from, rel);
-    const uint32_t r = tbzfast::find_block_start(in, rel, rel + (uint32_t)(to - from), sm, lane);
-    if (r != 0xffffffffu) res = from + (r - rel);
+    const uint32_t r = tbzfast::find_block_start(in, rel, rel + (uint32_t)(pe - from), sm, lane);
+    if (r != 0xffffffffu) {
+      if (lane == 0) atomicMin(reinterpret_cast<unsigned long long *>(&found[c]), (unsigned long long)(from + (r - rel)));
+      break;
+    }
   }
-  if (lane == 0) found[c] = res;
 }
 
 // todo[i]: index of a chunk to decode

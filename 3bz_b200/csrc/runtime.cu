@@ -608,7 +608,7 @@ static int32_t split_inflate(tbz_ctx *ctx, int fmt, const DMember &m, tbz_result
   // ---- K0: block starts
   SCK(cudaFuncSetAttribute(tbzsplit::k_split_find, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dec_smem));
   SCK(cudaMemsetAsync(d_found, 0xff, (size_t)nchunks * 8, st));
-  tbzsplit::k_split_find<<<(nchunks + tbzfast::WPC - 1) / tbzfast::WPC, tbzfast::NT, dec_smem, st>>>(
+  tbzsplit::k_split_find<<<((uint64_t)nchunks * tbzsplit::FSUB + tbzfast::WPC - 1) / tbzfast::WPC, tbzfast::NT, dec_smem, st>>>(
       words, end_bit, body_bit, chunk_bits, nchunks, (uint64_t *)d_found);
   ctx->launches++;
   std::vector<uint64_t> found(nchunks);
