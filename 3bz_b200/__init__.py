@@ -6,11 +6,12 @@ package `3bz`), or through the `threebz_b200` alias module at the repo root.
 from .api import (ThreeBzError, Ctx, default_ctx, decompress, decompress_vector, decompress_batch,  # noqa: F401
                   with_octet_pointer, make_octet_vector_context, make_octet_stream_context,
                   make_octet_pointer_context, make_deflate_state, make_zlib_state, make_gzip_state,
-                  finished, input_underrun, output_overflow, replace_output_buffer)
+                  finished, input_underrun, output_overflow, replace_output_buffer,
+                  gzip_header, decompress_gzip_members)
 from . import _ffi, shard  # noqa: F401
 
 # package.lisp:13-27 — the exported symbols, plus the new batch entry point
 __all__ = ["decompress", "decompress_vector", "with_octet_pointer", "make_octet_vector_context",
            "make_octet_stream_context", "make_octet_pointer_context", "make_deflate_state",
            "make_zlib_state", "make_gzip_state", "finished", "input_underrun", "output_overflow",
-           "replace_output_buffer", "decompress_batch"]
+           "replace_output_buffer", "decompress_batch", "gzip_header", "decompress_gzip_members"]

@@ -29,6 +29,7 @@ SYMBOLS = [
     "tbz_inflate_batch_multi", "tbz_partition",
     "tbz_session_create", "tbz_session_destroy", "tbz_session_set_output",
     "tbz_session_rebind_output", "tbz_session_replace_output", "tbz_session_decompress", "tbz_session_flags",
+    "tbz_gzip_header_parse", "tbz_inflate_gzip_members",
 ]
 
 
@@ -39,6 +40,13 @@ class Member(C.Structure):
 class Result(C.Structure):
     _fields_ = [("out_len", C.c_uint64), ("in_used", C.c_uint64), ("checksum", C.c_uint32),
                 ("verdict", C.c_int32), ("where", C.c_uint32), ("path", C.c_uint32)]
+
+
+class GzipHeader(C.Structure):
+    _fields_ = [("verdict", C.c_int32), ("flags", C.c_uint32), ("mtime", C.c_uint32), ("xfl", C.c_uint32),
+                ("os", C.c_uint32), ("header_crc", C.c_uint32),
+                ("extra_off", C.c_uint64), ("extra_len", C.c_uint64), ("name_off", C.c_uint64), ("name_len", C.c_uint64),
+                ("comment_off", C.c_uint64), ("comment_len", C.c_uint64), ("header_len", C.c_uint64)]
 
 
 class EngineError(RuntimeError):
@@ -101,6 +109,8 @@ def lib():
         "tbz_session_replace_output": (i32, [vp, vp, u64]),
         "tbz_session_decompress": (i32, [vp, vp, u64, P(C.c_int64), P(i32)]),
         "tbz_session_flags": (i32, [vp, P(i32), P(i32), P(i32)]),
+        "tbz_gzip_header_parse": (i32, [vp, u64, P(GzipHeader)]),
+        "tbz_inflate_gzip_members": (i32, [vp, vp, u64, vp, u64, P(Result), u64, P(u64), P(u64)]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)

@@ -285,6 +285,57 @@ def decompress_vector(compressed, format="zlib", start=0, end=None, output=None,
 
 
 # ---- decompress-batch: the new entry point for many independent members -------------------------
+_GZ_OS = ("fat", "amiga", "vms", "unix", "vm/cms", "atari-tos", "hpfs", "macintosh", "z-system", "cp/m",
+          "tops-20", "ntfs", "qdos", "acorn-riscos")          # gzip.lisp:169-176
+
+
+def gzip_header(compressed, start=0, end=None):
+    """The gzip-state slots decompress-gzip fills from the member header (gzip.lisp:17-28, :113-260):
+    flags, extra, name, comment, operating-system, mtime/unix, mtime/universal, compression-level.
+    Returns a dict, or None while the header is incomplete (input-underrun); header errors raise."""
+    data = bytes(compressed[start:end])
+    h = _ffi.GzipHeader()
+    _ffi.check(_ffi.lib().tbz_gzip_header_parse(data, len(data), C.byref(h)))
+    if h.verdict == 1:
+        return None
+    if h.verdict != 0:
+        raise ThreeBzError(_ffi.verdict_name(h.verdict), h.verdict)
+
+    def text(off, n):
+        raw = data[off:off + n]
+        try:
+            return raw.decode("utf-8")                       # "rfc says 8859-1, but try utf8 anyway" (gzip.lisp:214-217)
+        except UnicodeDecodeError:
+            return raw.decode("iso8859-1")
+    names = ((1, "text"), (2, "header-crc"), (4, "extra"), (8, "name"), (16, "comment"))
+    return {
+        "compression-method": "deflate",
+        "flags": [n for bit, n in names if h.flags & bit],
+        "extra": data[h.extra_off:h.extra_off + h.extra_len] if h.flags & 4 else None,
+        "name": text(h.name_off, h.name_len) if h.flags & 8 else None,
+        "comment": text(h.comment_off, h.comment_len) if h.flags & 16 else None,
+        "operating-system": _GZ_OS[h.os] if h.os <= 13 else ("unknown", h.os),
+        "mtime/unix": h.mtime or None,
+        "mtime/universal": h.mtime + 2208988800 if h.mtime else None,   # (encode-universal-time 0 0 0 1 1 1970 0)
+        "compression-level": {2: "maximum", 4: "fastest"}.get(h.xfl, h.xfl),
+        "header-length": h.header_len,
+    }
+
+
+def decompress_gzip_members(compressed, output, max_members=1 << 20, ctx=None):
+    """New entry point (the reference stops after the first member, gzip.lisp:279-286): decodes the
+    concatenated gzip members of `compressed` back to back into `output`.  Returns
+    (list of (out_len, in_used, crc32, verdict) per member, compressed bytes consumed)."""
+    ctx = ctx or default_ctx()
+    data = bytes(compressed)
+    n = min(max_members, max(1, len(data) // 18 + 1))
+    res = (_ffi.Result * n)()
+    nm, used = C.c_uint64(), C.c_uint64()
+    keep, addr = _addr(output)
+    _ffi.check(ctx.L.tbz_inflate_gzip_members(ctx.h, data, len(data), addr, len(output), res, n, C.byref(nm), C.byref(used)), ctx.h)
+    return [(r.out_len, r.in_used, r.checksum, r.verdict) for r in res[:nm.value]], used.value
+
+
 def decompress_batch(members, format="zlib", capacities=None, ctx=None, flags=0):
     """members: sequence of octet vectors; capacities: per-member output size (int or sequence).
     Returns a list of (buffer, count, verdict_code); a bad member never poisons the batch."""

@@ -1202,3 +1202,83 @@ extern "C" int32_t tbz_session_decompress(tbz_session *s, const uint8_t *in, uin
   } else { s->error = v; *ret = -1; }
   return TBZ_OK;
 }
+
+// =============================================================================================
+// gzip metadata and concatenated members.  Header rules as gzip.lisp:113-260.
+// =============================================================================================
+static uint32_t host_crc32(const uint8_t *p, uint64_t n) {
+  uint32_t c = 0xffffffffu;
+  for (uint64_t i = 0; i < n; i++) {
+    c ^= p[i];
+    for (int k = 0; k < 8; k++) c = (c >> 1) ^ ((c & 1) ? 0xedb88320u : 0);
+  }
+  return c ^ 0xffffffffu;
+}
+
+extern "C" int32_t tbz_gzip_header_parse(const uint8_t *in, uint64_t in_len, tbz_gzip_header *h) {
+  if (!h || (in_len && !in)) return TBZ_E_ARG;
+  memset(h, 0, sizeof *h);
+  h->verdict = TBZ_INPUT_UNDERRUN;
+  uint64_t p = 0;
+  if (in_len < 2) return TBZ_OK;
+  if (in[0] != 0x1f || in[1] != 0x8b) { h->verdict = TBZ_ERR_GZIP_MAGIC; return TBZ_OK; }
+  if (in_len < 4) return TBZ_OK;
+  if (in[2] != 8) { h->verdict = TBZ_ERR_GZIP_METHOD; return TBZ_OK; }
+  const uint32_t flg = in[3];
+  if (flg >> 5) { h->verdict = TBZ_ERR_GZIP_RESERVED; return TBZ_OK; }
+  h->flags = flg & 31u;
+  if (in_len < 8) return TBZ_OK;
+  h->mtime = in[4] | ((uint32_t)in[5] << 8) | ((uint32_t)in[6] << 16) | ((uint32_t)in[7] << 24);
+  if (in_len < 10) return TBZ_OK;
+  h->xfl = in[8]; h->os = in[9];
+  p = 10;
+  if (flg & TBZ_GZ_EXTRA) {
+    if (in_len - p < 2) return TBZ_OK;
+    const uint64_t xlen = in[p] | ((uint64_t)in[p + 1] << 8);
+    p += 2;
+    if (in_len - p < xlen) return TBZ_OK;
+    h->extra_off = p; h->extra_len = xlen;
+    p += xlen;
+  }
+  if (flg & TBZ_GZ_NAME) {
+    h->name_off = p;
+    while (p < in_len && in[p]) p++;
+    if (p >= in_len) return TBZ_OK;
+    h->name_len = p - h->name_off;
+    p++;
+  }
+  if (flg & TBZ_GZ_COMMENT) {
+    h->comment_off = p;
+    while (p < in_len && in[p]) p++;
+    if (p >= in_len) return TBZ_OK;
+    h->comment_len = p - h->comment_off;
+    p++;
+  }
+  if (flg & TBZ_GZ_HCRC) {
+    if (in_len - p < 2) return TBZ_OK;
+    h->header_crc = in[p] | ((uint32_t)in[p + 1] << 8);
+    if ((host_crc32(in, p) & 0xffffu) != h->header_crc) { h->verdict = TBZ_ERR_GZIP_HCRC; return TBZ_OK; }   // gzip.lisp:247-255
+    p += 2;
+  }
+  h->header_len = p;
+  h->verdict = TBZ_FINISHED;
+  return TBZ_OK;
+}
+
+extern "C" int32_t tbz_inflate_gzip_members(tbz_ctx *ctx, const uint8_t *in, uint64_t in_len, uint8_t *out,
+                                            uint64_t out_cap, tbz_result *r, uint64_t max_members,
+                                            uint64_t *n_members, uint64_t *in_used) {
+  if (!ctx || !r || !n_members || (in_len && !in) || (out_cap && !out)) return fail(ctx, TBZ_E_ARG, "tbz_inflate_gzip_members: bad argument");
+  uint64_t ip = 0, op = 0, k = 0;
+  while (k < max_members && ip < in_len) {
+    int32_t rc = tbz_inflate_single(ctx, TBZ_GZIP, in + ip, in_len - ip, out + op, out_cap - op, &r[k], 0, nullptr);
+    if (rc != TBZ_OK) return rc;
+    k++;
+    if (r[k - 1].verdict != TBZ_FINISHED) break;
+    ip += r[k - 1].in_used;
+    op += r[k - 1].out_len;
+  }
+  *n_members = k;
+  if (in_used) *in_used = ip;
+  return TBZ_OK;
+}

@@ -172,6 +172,33 @@ int32_t tbz_session_decompress(tbz_session *s, const uint8_t *in, uint64_t n,
 int32_t tbz_session_flags(tbz_session *s, int32_t *finished, int32_t *input_underrun,
                           int32_t *output_overflow);
 
+/* ---- gzip member metadata: the gzip-state slots flags / extra / name / comment / operating-system /
+ * mtime/unix / compression-level that decompress-gzip fills while it reads the header
+ * (gzip.lisp:17-28, :113-260).  Host-side only: no device work.  Offsets are from `in`. ---- */
+enum { TBZ_GZ_TEXT = 1, TBZ_GZ_HCRC = 2, TBZ_GZ_EXTRA = 4, TBZ_GZ_NAME = 8, TBZ_GZ_COMMENT = 16 };
+typedef struct tbz_gzip_header {
+  int32_t  verdict;      /* TBZ_FINISHED = header complete; TBZ_INPUT_UNDERRUN; TBZ_ERR_GZIP_* */
+  uint32_t flags;        /* TBZ_GZ_* (gzip.lisp:136-144) */
+  uint32_t mtime;        /* mtime/unix; 0 = not set (gzip.lisp:154-157) */
+  uint32_t xfl;          /* 2 = :maximum, 4 = :fastest (gzip.lisp:166-168) */
+  uint32_t os;           /* 0..13 index the reference's keyword table, else (:unknown os) (gzip.lisp:169-176) */
+  uint32_t header_crc;   /* the stored CRC16 when TBZ_GZ_HCRC */
+  uint64_t extra_off, extra_len;     /* FEXTRA payload */
+  uint64_t name_off, name_len;       /* FNAME without the terminating zero */
+  uint64_t comment_off, comment_len; /* FCOMMENT without the terminating zero */
+  uint64_t header_len;   /* the deflate body starts here */
+} tbz_gzip_header;
+int32_t tbz_gzip_header_parse(const uint8_t *in, uint64_t in_len, tbz_gzip_header *h);
+
+/* Concatenated gzip members (RFC 1952 2.2).  The reference stops after the first member and reports
+ * :done (gzip.lisp:279-286); that stays the default everywhere else.  This *new* entry point walks
+ * them: member i is decoded to out + sum of the earlier out_len, r[i].in_used is its compressed size.
+ * Stops at the first member that is not TBZ_FINISHED (its result is the last one written) or when
+ * max_members are done.  *n_members = results written; *in_used = bytes of `in` consumed by finished members. */
+int32_t tbz_inflate_gzip_members(tbz_ctx *ctx, const uint8_t *in, uint64_t in_len, uint8_t *out,
+                                 uint64_t out_cap, tbz_result *r, uint64_t max_members,
+                                 uint64_t *n_members, uint64_t *in_used);
+
 #ifdef __cplusplus
 }
 #endif

@@ -6,7 +6,7 @@
 ;;; through the Python mirror 3bz_b200/api.py, which issues the same C-ABI call sequences.
 (defsystem :3bz-cuda
   :description "deflate/zlib/gzip decompressor: 3bz API over a CUDA (sm_100a) engine"
-  :depends-on (alexandria cffi trivial-features)
+  :depends-on (alexandria cffi trivial-features babel)
   :serial t
   :license "MIT"
   :components

@@ -125,3 +125,52 @@ name for the place where the reference would have signalled.  A bad member never
             collect (list o (cffi:foreign-slot-value e '(:struct tbz-result) 'out-len)
                           (case v (0 :finished) (1 :input-underrun) (2 :output-overflow)
                             (t (tbz-verdict-name v))))))))
+
+(defun gzip-header (octets &key (start 0) (end (length octets)))
+  "The slots DECOMPRESS-GZIP fills from a member header in the reference's GZIP-STATE
+\(gzip.lisp:17-28, :113-260), as a plist: :flags :extra :name :comment :operating-system
+:mtime/unix :mtime/universal :compression-level :header-length.  NIL while the header is
+incomplete (the reference's input-underrun); header errors signal like the reference."
+  (cffi:with-foreign-object (h '(:struct tbz-gzip-header))
+    (cffi:with-pointer-to-vector-data (pin octets)
+      (check (tbz-gzip-header-parse (cffi:inc-pointer pin start) (- end start) h)))
+    (flet ((f (slot) (cffi:foreign-slot-value h '(:struct tbz-gzip-header) slot)))
+      (let ((v (f 'verdict)) (flg (f 'flags)) (mtime (f 'mtime)) (os (f 'os)) (xfl (f 'xfl)))
+        (cond
+          ((= v +tbz-input-underrun+) nil)
+          ((/= v +tbz-finished+) (%verdict-error v :gzip))
+          (t
+           (flet ((text (off len)
+                    (let ((raw (subseq octets (+ start off) (+ start off len))))
+                      ;; rfc says 8859-1, but try utf8 anyway (gzip.lisp:214-217)
+                      (or (ignore-errors (babel:octets-to-string raw :encoding :utf-8 :errorp t))
+                          (babel:octets-to-string raw :encoding :iso-8859-1)))))
+             (list :flags (loop for (bit name) in '((1 :text) (2 :header-crc) (4 :extra) (8 :name) (16 :comment))
+                                when (logtest bit flg) collect name)
+                   :extra (when (logtest 4 flg) (subseq octets (+ start (f 'extra-off)) (+ start (f 'extra-off) (f 'extra-len))))
+                   :name (when (logtest 8 flg) (text (f 'name-off) (f 'name-len)))
+                   :comment (when (logtest 16 flg) (text (f 'comment-off) (f 'comment-len)))
+                   :operating-system (if (<= 0 os 13)
+                                         (aref #(:fat :amiga :vms :unix :vm/cms :atari-tos :hpfs :macintosh
+                                                 :z-system :cp/m :tops-20 :ntfs :qdos :acorn-riscos) os)
+                                         (list :unknown os))
+                   :mtime/unix (unless (zerop mtime) mtime)
+                   :mtime/universal (unless (zerop mtime) (+ mtime (encode-universal-time 0 0 0 1 1 1970 0)))
+                   :compression-level (or (case xfl (2 :maximum) (4 :fastest)) xfl)
+                   :header-length (f 'header-len)))))))))
+
+(defun decompress-gzip-members (octets output &key (max-members (ash 1 20)))
+  "NEW: the reference stops after the first member of a gzip file (gzip.lisp:279-286); this walks
+all concatenated members into OUTPUT.  Returns (values list-of-(count in-used crc32 verdict) octets-consumed)."
+  (let ((n (min max-members (1+ (floor (length octets) 18)))))
+    (cffi:with-foreign-objects ((r '(:struct tbz-result) n) (nm :uint64) (used :uint64))
+      (cffi:with-pointer-to-vector-data (pi octets)
+        (cffi:with-pointer-to-vector-data (po output)
+          (check (tbz-inflate-gzip-members (ctx) pi (length octets) po (length output) r n nm used))))
+      (values (loop for i below (cffi:mem-ref nm :uint64)
+                    for e = (cffi:mem-aptr r '(:struct tbz-result) i)
+                    collect (list (cffi:foreign-slot-value e '(:struct tbz-result) 'out-len)
+                                  (cffi:foreign-slot-value e '(:struct tbz-result) 'in-used)
+                                  (cffi:foreign-slot-value e '(:struct tbz-result) 'checksum)
+                                  (cffi:foreign-slot-value e '(:struct tbz-result) 'verdict)))
+              (cffi:mem-ref used :uint64)))))

@@ -63,3 +63,13 @@
 
 (defun format-code (format)
   (ecase format (:deflate +tbz-deflate+) (:zlib +tbz-zlib+) (:gzip +tbz-gzip+)))
+
+;;; gzip member metadata (gzip.lisp:17-28) and the new walker over concatenated members
+(cffi:defcstruct tbz-gzip-header
+  (verdict :int32) (flags :uint32) (mtime :uint32) (xfl :uint32) (os :uint32) (header-crc :uint32)
+  (extra-off :uint64) (extra-len :uint64) (name-off :uint64) (name-len :uint64)
+  (comment-off :uint64) (comment-len :uint64) (header-len :uint64))
+(cffi:defcfun "tbz_gzip_header_parse" :int32 (in :pointer) (in-len :uint64) (h :pointer))
+(cffi:defcfun "tbz_inflate_gzip_members" :int32
+  (ctx :pointer) (in :pointer) (in-len :uint64) (out :pointer) (out-cap :uint64) (results :pointer)
+  (max-members :uint64) (n-members :pointer) (in-used :pointer))

@@ -20,4 +20,6 @@
    #:replace-output-buffer
    ;; new
    #:decompress-batch
+   #:gzip-header
+   #:decompress-gzip-members
    #:*device*))

@@ -79,3 +79,56 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 src = open(os.path.join(dp, f), errors="replace").read()
                 assert "oracle" not in src.lower().replace("no cpu oracle", ""), os.path.join(dp, f)
+
+
+def _gz(payload, **kw):
+    """A gzip member with optional header fields, assembled by hand (RFC 1952 2.3)."""
+    import struct
+    import zlib
+    flg = 0
+    extra, name, comment, hcrc, text = kw.get("extra"), kw.get("name"), kw.get("comment"), kw.get("hcrc"), kw.get("text")
+    flg |= 1 if text else 0
+    flg |= 2 if hcrc else 0
+    flg |= 4 if extra is not None else 0
+    flg |= 8 if name is not None else 0
+    flg |= 16 if comment is not None else 0
+    h = bytes([0x1f, 0x8b, 8, flg]) + struct.pack("<I", kw.get("mtime", 0)) + bytes([kw.get("xfl", 0), kw.get("os", 3)])
+    if extra is not None:
+        h += struct.pack("<H", len(extra)) + extra
+    if name is not None:
+        h += name + b"\0"
+    if comment is not None:
+        h += comment + b"\0"
+    if hcrc:
+        h += struct.pack("<H", (zlib.crc32(h) & 0xffff) ^ (1 if hcrc == "bad" else 0))
+    co = zlib.compressobj(6, zlib.DEFLATED, -15)
+    body = co.compress(payload) + co.flush()
+    return h, h + body + struct.pack("<II", zlib.crc32(payload), len(payload) & 0xffffffff)
+
+
+def test_gzip_header_metadata(engine):
+    """gzip-state slots (gzip.lisp:17-28) from the host-side header parser; no device involved."""
+    import threebz_b200 as t
+    h, m = _gz(b"hello", name=b"a.txt", comment="gr\xfc\xdfe".encode("latin-1"), extra=b"\x01\x02\x03", hcrc=True,
+               mtime=1234567890, xfl=2, os=3, text=True)
+    g = t.gzip_header(m)
+    assert g["flags"] == ["text", "header-crc", "extra", "name", "comment"]
+    assert g["name"] == "a.txt" and g["comment"] == "gr\xfc\xdfe" and g["extra"] == b"\x01\x02\x03"
+    assert g["mtime/unix"] == 1234567890 and g["mtime/universal"] == 1234567890 + 2208988800
+    assert g["operating-system"] == "unix" and g["compression-level"] == "maximum"
+    assert g["header-length"] == len(h)
+    # plain header: nothing optional, mtime 0 -> unset, unknown OS, numeric xfl
+    h2, m2 = _gz(b"x", os=77, xfl=9)
+    g2 = t.gzip_header(m2)
+    assert g2["flags"] == [] and g2["name"] is None and g2["mtime/unix"] is None
+    assert g2["operating-system"] == ("unknown", 77) and g2["compression-level"] == 9 and g2["header-length"] == 10
+    # every strict prefix of the header is an underrun, never an error
+    for k in range(len(h)):
+        assert t.gzip_header(m[:k]) is None, k
+    # the reference's error sites: magic, method, reserved flag bits, header CRC
+    for bad, verdict in ((b"\x1f\x8c" + m[2:], 28), (m[:2] + b"\x07" + m[3:], 29),       # TBZ_ERR_GZIP_MAGIC, _METHOD
+                         (m[:3] + bytes([m[3] | 0x20]) + m[4:], 30),                        # _RESERVED
+                         (_gz(b"y", name=b"n", hcrc="bad")[1], 31)):                        # _HCRC
+        with pytest.raises(t.ThreeBzError) as e:
+            t.gzip_header(bad)
+        assert e.value.verdict == verdict, (e.value.verdict, verdict)

@@ -285,3 +285,27 @@ def test_split_single_member(engine, ctx, oracle):
         compare(g, oracle.decompress_vector(v, "gzip", out_cap=n), "split variant")
     got, _ = run_batch(ctx, "gzip", [comp], n - 1000)
     compare(got[0], oracle.decompress_vector(comp, "gzip", out_cap=n - 1000), "split overflow")
+
+
+def test_gzip_concatenated_members(engine, ctx, oracle):
+    """New entry point: the members of a multi-member gzip file, back to back; the default
+    one-member behaviour (gzip.lisp:279-286) is what decompress_vector keeps doing."""
+    parts = [datagen.text(40000, 71), b"", datagen.text(3, 72), datagen.text(150000, 73)]
+    blobs = [datagen.compress(p, "gzip") for p in parts]
+    data = b"".join(blobs)
+    out = bytearray(sum(map(len, parts)))
+    res, used = engine.decompress_gzip_members(data, out, ctx=ctx)
+    assert used == len(data) and len(res) == len(parts)
+    assert bytes(out) == b"".join(parts)
+    for (n, iu, ck, v), p, b in zip(res, parts, blobs):
+        assert (n, iu, ck, v) == (len(p), len(b), zlib.crc32(p), 0)
+        w = oracle.decompress_vector(b, "gzip", out_cap=max(1, len(p)))
+        assert w["verdict"] == 0 and w["checksum"] == ck and w["out_len"] == n
+    # a damaged third member stops the walk there and reports its verdict; the first two stand
+    bad = bytearray(data)
+    bad[len(blobs[0]) + len(blobs[1]) + len(blobs[2]) - 8] ^= 1          # CRC-32 of member 2
+    res, used = engine.decompress_gzip_members(bytes(bad), out, ctx=ctx)
+    assert len(res) == 3 and [r[3] for r in res[:2]] == [0, 0] and res[2][3] == 32 and used == len(blobs[0]) + len(blobs[1])
+    # the reference-compatible call still stops after the first member
+    buf, n = engine.decompress_vector(data, format="gzip", output=bytearray(len(out)))
+    assert n == len(parts[0]) and bytes(buf[:n]) == parts[0]
