@@ -11,8 +11,11 @@
 //                        re-decoded) and prefix-sums the output sizes
 //   K2 k_split_resolve   a CTA per chunk resolves its tokens with 16-bit symbols: bytes, or markers
 //                        "byte i of the 32 KiB before this chunk" for what it cannot know yet
-//   K3 k_split_tails     one CTA walks the chunks in order and makes the last 32 KiB of every chunk
-//                        final (the only sequential step: 32 KiB per chunk)
+//   K3 k_tail_*          the last 32 KiB of output up to the end of every chunk become final by a
+//                        parallel scan: per chunk a 32 Ki-entry map "window after the chunk, in terms
+//                        of the window before it"; maps compose associatively (Hillis-Steele over the
+//                        chunks, log2(chunks) rounds, every round fully parallel).  k_split_tails is the
+//                        sequential form of the same step (one CTA walks the chunks), kept for comparison
 //   K4 k_split_translate every other symbol becomes a byte, all chunks in parallel
 //   K5 k_split_checksum  CRC-32 / Adler-32 partials per 4 KiB segment; the host combines them
 #pragma once
@@ -191,6 +194,48 @@ k_split_tails(const Chunk *__restrict__ chunks, uint32_t nchunks, const uint16_t
     for (int j = 0; j < 32; j++) nxt[tid + 1024u * j] = nx[j];
     __syncthreads();
     start = nstart; lo = nlo; end = nend;
+  }
+}
+
+// ---- K3 as a scan --------------------------------------------------------------------------------
+// map[v][j], j < 32768: the byte at absolute output offset end_v - 32768 + j as a symbol relative to
+// the 32 KiB window that precedes chunk v: a byte, or SYM_MARK | i = "entry i of that window".
+constexpr uint32_t TAILW = 32768;
+__global__ void __launch_bounds__(256)
+k_tail_init(const Chunk *__restrict__ chunks, const uint16_t *__restrict__ sym, uint16_t *__restrict__ map) {
+  const uint32_t v = blockIdx.x;
+  const long long start = (long long)chunks[v].out_off, len = (long long)chunks[v].rec.out_len, end = start + len;
+  uint16_t *mv = map + (size_t)v * TAILW;
+  for (uint32_t j = blockIdx.y * 1024u + threadIdx.x; j < blockIdx.y * 1024u + 1024u; j += 256u) {
+    const long long a = end - (long long)TAILW + j;
+    uint32_t s = 0;
+    if (a >= start) s = sym[a];
+    else if (a >= 0) s = tbzres::SYM_MARK | (uint32_t)(len + j);   // the chunk is shorter than the window: an older byte
+    mv[j] = (uint16_t)s;
+  }
+}
+// out[v] = in[v] o in[v - stride]: markers of map v are looked up in the map `stride` chunks back
+__global__ void __launch_bounds__(256)
+k_tail_compose(const uint16_t *__restrict__ in, uint16_t *__restrict__ outm, uint32_t stride) {
+  const uint32_t v = blockIdx.x;
+  const uint16_t *mv = in + (size_t)v * TAILW;
+  uint16_t *ov = outm + (size_t)v * TAILW;
+  const uint16_t *pv = v >= stride ? in + (size_t)(v - stride) * TAILW : nullptr;
+  for (uint32_t j = blockIdx.y * 1024u + threadIdx.x; j < blockIdx.y * 1024u + 1024u; j += 256u) {
+    uint32_t s = mv[j];
+    if (pv && (s & tbzres::SYM_MARK)) s = pv[s & 0x7fffu];
+    ov[j] = (uint16_t)s;
+  }
+}
+// the final windows go to the output: chunk v owns [max(end - 32768, start), end)
+__global__ void __launch_bounds__(256)
+k_tail_write(const Chunk *__restrict__ chunks, const uint16_t *__restrict__ map, uint8_t *__restrict__ out) {
+  const uint32_t v = blockIdx.x;
+  const long long start = (long long)chunks[v].out_off, end = start + (long long)chunks[v].rec.out_len;
+  const uint16_t *mv = map + (size_t)v * TAILW;
+  for (uint32_t j = blockIdx.y * 1024u + threadIdx.x; j < blockIdx.y * 1024u + 1024u; j += 256u) {
+    const long long a = end - (long long)TAILW + j;
+    if (a >= start) out[a] = (uint8_t)mv[j];
   }
 }
 

@@ -701,8 +701,29 @@ static int32_t split_inflate(tbz_ctx *ctx, int fmt, const DMember &m, tbz_result
   for (const Chunk &c : vch) if (!c.ok) { cleanup(); return TBZ_OK; }
   stage("resolve");
   // ---- K3, K4: bytes
-  SCK(cudaFuncSetAttribute(tbzsplit::k_split_tails, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tbzsplit::TailSmem)));
-  tbzsplit::k_split_tails<<<1, 1024, sizeof(tbzsplit::TailSmem), st>>>((const Chunk *)d_chunks, nv, (const uint16_t *)d_sym, m.out);
+  {
+    static const bool seq_tails = getenv("TBZ_SEQ_TAILS") != nullptr;   // the one-CTA walk, for comparison
+    void *d_maps = nullptr;
+    const size_t map_bytes = (size_t)nv * tbzsplit::TAILW * 2;
+    if (!seq_tails && nv > 1 && dev_alloc(ctx, 2 * map_bytes, &d_maps) == TBZ_OK) {
+      uint16_t *ma = (uint16_t *)d_maps, *mb = ma + (size_t)nv * tbzsplit::TAILW;
+      const dim3 grid(nv, tbzsplit::TAILW / 1024);
+      tbzsplit::k_tail_init<<<grid, 256, 0, st>>>((const Chunk *)d_chunks, (const uint16_t *)d_sym, ma);
+      ctx->launches++;
+      for (uint32_t stride = 1; stride < nv; stride <<= 1) {
+        tbzsplit::k_tail_compose<<<grid, 256, 0, st>>>(ma, mb, stride);
+        ctx->launches++;
+        std::swap(ma, mb);
+      }
+      tbzsplit::k_tail_write<<<grid, 256, 0, st>>>((const Chunk *)d_chunks, ma, m.out);
+      cudaError_t e_ = cudaStreamSynchronize(st);
+      dev_release(ctx, d_maps);
+      if (e_ != cudaSuccess) { cleanup(); return fail(ctx, TBZ_E_CUDA, "tail scan", e_); }
+    } else {
+      SCK(cudaFuncSetAttribute(tbzsplit::k_split_tails, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tbzsplit::TailSmem)));
+      tbzsplit::k_split_tails<<<1, 1024, sizeof(tbzsplit::TailSmem), st>>>((const Chunk *)d_chunks, nv, (const uint16_t *)d_sym, m.out);
+    }
+  }
   stage("tails");
   {
     std::vector<uint64_t> offs(nv + 1);
