@@ -122,7 +122,8 @@ struct DevBlock { void *p; size_t size; bool used; };
 struct tbz_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;          // the stream new work is enqueued on (main_stream, or a pipeline stream)
-  cudaStream_t main_stream = nullptr, pstream[3] = {nullptr, nullptr, nullptr};
+  static const int kPipeStreams = 8;
+  cudaStream_t main_stream = nullptr, pstream[kPipeStreams] = {};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, tev0 = nullptr, tev1 = nullptr;
   cudaEvent_t kev[4] = {nullptr, nullptr, nullptr, nullptr};   // TBZ_KTIME=1: events between the kernels of a launch
   bool ktime = false, ktime_quiet = false;
@@ -948,7 +949,7 @@ static int32_t batch_device_ms(tbz_batch *b, float *ms) {
   return TBZ_OK;
 }
 
-// Host buffers, many members: the batch is cut into contiguous sub-batches that travel down three
+// Host buffers, many members: the batch is cut into contiguous sub-batches that travel down several
 // streams, so the H2D copy of one, the kernels of another and the D2H copy of a third overlap (the
 // copy engines and the SMs are separate units).  Needs dense inputs and adjacent outputs (the DMA
 // then runs straight on the caller's memory); anything else takes the one-piece path.
@@ -961,7 +962,9 @@ static int32_t inflate_batch_pipelined(tbz_ctx *ctx, int32_t format, const tbz_m
     bytes += m[i].in_len + m[i].out_cap;
   }
   if (bytes < (32ull << 20)) return TBZ_OK;
-  const uint64_t parts = std::min<uint64_t>(16, std::max<uint64_t>(2, n / 256));
+  static const uint64_t max_parts = getenv("TBZ_PIPE_PARTS") ? strtoull(getenv("TBZ_PIPE_PARTS"), nullptr, 10) : 12;
+  static const uint64_t npipe = std::min<uint64_t>(tbz_ctx::kPipeStreams, getenv("TBZ_PIPE_STREAMS") ? std::max<uint64_t>(1, strtoull(getenv("TBZ_PIPE_STREAMS"), nullptr, 10)) : 6);
+  const uint64_t parts = std::min<uint64_t>(max_parts, std::max<uint64_t>(2, n / 256));
   std::vector<tbz_batch *> sub(parts, nullptr);
   {
     int32_t src = ensure_stage(ctx, &ctx->stage_res, &ctx->stage_res_cap, n * sizeof(tbz_result));
@@ -973,7 +976,7 @@ static int32_t inflate_batch_pipelined(tbz_ctx *ctx, int32_t format, const tbz_m
   bool ok = true;
   for (uint64_t p = 0; p < parts && !rc; p++) {
     const uint64_t lo = n * p / parts, hi = n * (p + 1) / parts;
-    ctx->stream = ctx->pstream[p % 3];
+    ctx->stream = ctx->pstream[p % npipe];
     rc = tbz_batch_prepare(ctx, format, m + lo, hi - lo, flags, &sub[p]);
     if (!rc && !(sub[p]->in_direct && sub[p]->out_direct)) { ok = false; break; }
     if (!rc) { sub[p]->eager_res = pinned + lo; rc = tbz_batch_launch(sub[p]); }

@@ -328,6 +328,12 @@ def _main(real_stdout):
                              "algorithmic_bytes_per_launch": C_total + U_total + B_total,
                              "kernel_ms": ms_per_step,
                              "kernels_ms": kernel_ms,
+                             "per_kernel": {
+                                 "k_inflate_decode": {"algorithmic_bytes": C_total, "achieved": C_total / (kernel_ms["k_inflate_decode"] * 1e-3) / 1e9,
+                                                      "note": "compressed bytes in (token scratch is not algorithmic)"},
+                                 "k_inflate_resolve": {"algorithmic_bytes": U_total + B_total,
+                                                       "achieved": (U_total + B_total) / (kernel_ms["k_inflate_resolve"] * 1e-3) / 1e9,
+                                                       "note": "decompressed bytes out + back-reference bytes read: the dominant kernel"}},
                              "note": "achieved = (C + U + B) of one launch of the hot path (decode + resolve kernels) / its "
                                      "CUDA-event time; traffic = ncu dram bytes of the dominant kernel (k_inflate_resolve)"},
                 "cpu_baseline": {"value": sample * size / cpu_t / 1e9, "unit": "GB/s", "cores": cores, "kind": "port",
