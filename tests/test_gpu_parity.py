@@ -309,3 +309,40 @@ def test_gzip_concatenated_members(engine, ctx, oracle):
     # the reference-compatible call still stops after the first member
     buf, n = engine.decompress_vector(data, format="gzip", output=bytearray(len(out)))
     assert n == len(parts[0]) and bytes(buf[:n]) == parts[0]
+
+
+@pytest.mark.parametrize("fmt", ["deflate", "zlib", "gzip"])
+def test_device_pointers_any_alignment(ctx, oracle, fmt):
+    """Caller-owned device memory at every input / output misalignment: the fast kernels' byte-wise
+    flush (output not 16-byte aligned) and word-misaligned bit readers, through TBZ_FLAG_DEVICE_PTRS."""
+    import ctypes as C
+    from threebz_b200 import _ffi
+    L = _ffi.lib()
+    size = 70000
+    plains = [datagen.text(size, 4200 + i) for i in range(16)]
+    comps = [datagen.compress(p, fmt) for p in plains]
+    stride_in = max(map(len, comps)) + 64
+    stride_out = size + 64
+    d_in, d_out = C.c_void_p(), C.c_void_p()
+    _ffi.check(L.tbz_device_alloc(ctx.h, 16 * stride_in, C.byref(d_in)), ctx.h)
+    _ffi.check(L.tbz_device_alloc(ctx.h, 16 * stride_out, C.byref(d_out)), ctx.h)
+    try:
+        marr = (_ffi.Member * 16)()
+        for i, c in enumerate(comps):
+            a_in = d_in.value + i * stride_in + i            # input misalignment 0..15
+            a_out = d_out.value + i * stride_out + (i * 7) % 16   # output misalignment, all residues mod 16
+            _ffi.check(L.tbz_memcpy_h2d(ctx.h, a_in, c, len(c)), ctx.h)
+            marr[i] = _ffi.Member(a_in, len(c), a_out, size)
+        rarr = (_ffi.Result * 16)()
+        _ffi.check(L.tbz_inflate_batch(ctx.h, _ffi.fmt_code(fmt), marr, 16, rarr, _ffi.FLAG_DEVICE_PTRS, None), ctx.h)
+        for i, (p, c) in enumerate(zip(plains, comps)):
+            w = oracle.decompress_vector(c, fmt, out_cap=size)
+            host = C.create_string_buffer(size)
+            _ffi.check(L.tbz_memcpy_d2h(ctx.h, host, marr[i].out, size), ctx.h)
+            r = rarr[i]
+            assert (r.verdict, r.out_len, r.checksum, r.in_used) == (0, size, w["checksum"], len(c)), (i, r.verdict, r.out_len)
+            assert host.raw == p, i
+            assert r.path == 1, (i, r.path)                  # the fast kernels, not the sequential one
+    finally:
+        L.tbz_device_free(ctx.h, d_in)
+        L.tbz_device_free(ctx.h, d_out)
