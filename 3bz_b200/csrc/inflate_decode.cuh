@@ -269,6 +269,18 @@ struct TokW {
   }
 };
 
+// Candidate block starts of a split member, ascending absolute bit positions (chunk decode only):
+// the decode of a chunk ends on the first candidate it lands on EXACTLY; candidates it passes over
+// were not block starts (false positives of the search) and are simply skipped.
+struct StopList {
+  const unsigned long long *starts; uint32_t n, next; unsigned long long base;   // base: absolute bit of in.w
+  __device__ __forceinline__ uint32_t rel(uint32_t i) const {
+    if (i >= n) return 0xffffffffu;
+    const unsigned long long r = starts[i] - base;
+    return r > 0xf0000000ull ? 0xf0000000u : (uint32_t)r;
+  }
+};
+
 // ------------------------------------------------------------------------------------------------
 // Blocks from bit `pos` (a block start) on, one warp.  Stops after the final block, or — for a
 // chunk of a split member — after the first block that ends at or beyond `stop_bit`.  Returns
@@ -276,7 +288,9 @@ struct TokW {
 // Every return value is warp-uniform.
 // ------------------------------------------------------------------------------------------------
 __device__ inline bool decode_blocks(const In &in, uint32_t pos, uint32_t stop_bit, unsigned long long out_cap, P1Rec &rec,
-                                     WSmem &sm, uint32_t *__restrict__ slabs, uint32_t nslabs, uint32_t *slab_counter, int lane) {
+                                     WSmem &sm, uint32_t *__restrict__ slabs, uint32_t nslabs, uint32_t *slab_counter, int lane,
+                                     const StopList *stops = nullptr) {
+  uint32_t stop_i = stops ? stops->next : 0u;
   unsigned long long A = 0;    // output bytes so far
   sm.lenbase[lane] = c_len_base[lane]; sm.distbase[lane] = c_dist_base[lane];
   uint32_t first_slab = NO_SLAB, prev_slab = NO_SLAB;
@@ -506,7 +520,10 @@ __device__ inline bool decode_blocks(const In &in, uint32_t pos, uint32_t stop_b
       __syncwarp();
     }
     prev_block_bits = pos - data_start;
-    if (pos >= stop_bit) break;
+    if (stops) {                              // skip the candidates this block ran past; stop on an exact landing
+      while (pos > stop_bit) stop_bit = stops->rel(++stop_i);
+      if (pos == stop_bit) break;
+    } else if (pos >= stop_bit) break;
   }
   if (lane == 0) {
     rec.first_slab = first_slab;
@@ -555,6 +572,16 @@ __device__ inline bool decode_member(const DMember &mem, int fmt, P1Rec &rec, WS
 // false positive is caught later: the previous chunk's decoder must land exactly on this bit.
 // ------------------------------------------------------------------------------------------------
 __device__ inline uint32_t find_block_start(const In &in, uint32_t from, uint32_t to, WSmem &sm, int lane) {
+  // Kraft sums of three 3-bit code lengths at a time (the root table's memory is free during a search)
+  uint16_t *const kraft = sm.lut_ll;
+  __syncwarp();
+  for (uint32_t x = lane; x < 512u; x += 32u) {
+    uint32_t sum3 = 0;
+#pragma unroll
+    for (int k = 0; k < 3; k++) { const uint32_t l = (x >> (3 * k)) & 7u; if (l) sum3 += 128u >> l; }
+    kraft[x] = (uint16_t)sum3;
+  }
+  __syncwarp();
   for (uint32_t base = from; base < to; base += 32) {
     const uint32_t p = base + lane;
     bool cand = p < to && p + 17 + 12 <= in.end;
@@ -563,17 +590,14 @@ __device__ inline uint32_t find_block_start(const In &in, uint32_t from, uint32_
       h = peek32(in, p);
       cand = ((h >> 1) & 3) == 2 && ((h >> 3) & 31) <= 29 && ((h >> 8) & 31) <= 29;
     }
-    if (cand) {                                        // Kraft sum of the code-length code
-      const uint32_t ncl = ((h >> 13) & 15) + 4;
-      uint32_t sum = 0, q = p + 17;
-      for (uint32_t i = 0; i < ncl; i += 10) {
-        const uint32_t w = peek32(in, q + 3 * i);
-        for (uint32_t k = 0; k < 10 && i + k < ncl; k++) {
-          const uint32_t l = (w >> (3 * k)) & 7;
-          if (l) sum += 128u >> l;
-        }
-      }
-      cand = sum == 128u && p + 17 + 3 * ncl <= in.end;
+    if (cand) {                                        // Kraft sum of the code-length code: 3 ncl <= 57 bits
+      const uint32_t ncl = ((h >> 13) & 15) + 4, nb = 3u * ncl, q = p + 17;
+      uint32_t lo = peek32(in, q), hi = peek32(in, q + 32);
+      if (nb < 32u) { lo &= (1u << nb) - 1u; hi = 0u; } else hi &= (1u << (nb - 32u)) - 1u;
+      const uint32_t sum = (uint32_t)kraft[lo & 511u] + kraft[(lo >> 9) & 511u] + kraft[(lo >> 18) & 511u] +
+                           kraft[((lo >> 27) | (hi << 5)) & 511u] + kraft[(hi >> 4) & 511u] + kraft[(hi >> 13) & 511u] +
+                           kraft[(hi >> 22) & 511u];
+      cand = sum == 128u && p + 17 + nb <= in.end;
     }
     uint32_t m = __ballot_sync(TBZ_FULL, cand);
     while (m) {                                        // full validation, one survivor at a time

@@ -4,11 +4,11 @@
 //
 //   K0 k_split_find      the compressed body is cut at fixed offsets; a warp per chunk searches for the
 //                        first dynamic-block start inside its chunk (find_block_start)
-//   K1 k_split_decode    a warp per chunk decodes blocks from its start until the first block that
-//                        ends at or beyond the next chunk's start: token slabs, output size and the
-//                        bit it landed on.  The host validates the chain (every chunk must land exactly
-//                        on its successor's start; a false positive is dropped and its predecessor
-//                        re-decoded) and prefix-sums the output sizes
+//   K1 k_split_decode    a warp per chunk decodes blocks from its start until it lands EXACTLY on a later
+//                        candidate start (candidates it runs past were false positives of the search and
+//                        are skipped): token slabs, output size and the bit it landed on.  The host follows
+//                        the chain of landings from chunk 0 (chunks nobody lands on are dropped) and
+//                        prefix-sums the output sizes; one pass, no re-decoding
 //   K2 k_split_resolve   a CTA per chunk resolves its tokens with 16-bit symbols: bytes, or markers
 //                        "byte i of the 32 KiB before this chunk" for what it cannot know yet
 //   K3 k_tail_*          the last 32 KiB of output up to the end of every chunk become final by a
@@ -81,10 +81,11 @@ k_split_find(const uint32_t *words, uint64_t end_bit, uint64_t body_bit, uint64_
   }
 }
 
-// todo[i]: index of a chunk to decode
+// todo[i]: index of a chunk to decode.  cands: the ncands candidate starts in ascending order;
+// chunks[c].pad = position of the chunk's own start in cands.
 __global__ void __launch_bounds__(tbzfast::NT)
 k_split_decode(const uint32_t *words, uint64_t end_bit, Chunk *chunks, const uint32_t *todo, uint32_t ntodo,
-               uint32_t *slabs, uint32_t nslabs, uint32_t *counters) {
+               uint32_t *slabs, uint32_t nslabs, uint32_t *counters, const unsigned long long *cands, uint32_t ncands) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   tbzfast::WSmem &sm = reinterpret_cast<tbzfast::WSmem *>(smem_raw)[warp];
@@ -97,12 +98,9 @@ k_split_decode(const uint32_t *words, uint64_t end_bit, Chunk *chunks, const uin
     uint32_t rel;
     const tbzfast::In in = chunk_input(words, end_bit, ch.start_bit, rel);
     const uint64_t base = ch.start_bit - rel;
-    uint32_t stop = 0xffffffffu;
-    if (ch.stop_bit != NONE64) {
-      const uint64_t s = ch.stop_bit - base;
-      stop = s > 0xf0000000ull ? 0xf0000000u : (uint32_t)s;
-    }
-    const bool ok = tbzfast::decode_blocks(in, rel, stop, 0xffffffffull, ch.rec, sm, slabs, nslabs, &counters[2], lane);
+    tbzfast::StopList sl;
+    sl.starts = cands; sl.n = ncands; sl.next = ch.pad + 1u; sl.base = base;
+    const bool ok = tbzfast::decode_blocks(in, rel, sl.rel(sl.next), 0xffffffffull, ch.rec, sm, slabs, nslabs, &counters[2], lane, &sl);
     __syncwarp();
     if (lane == 0) {
       if (!ok) ch.rec.status = 0;
@@ -244,11 +242,18 @@ k_tail_write(const Chunk *__restrict__ chunks, const uint16_t *__restrict__ map,
 __global__ void __launch_bounds__(256)
 k_split_translate(const uint64_t *__restrict__ offs, uint32_t nchunks, const uint16_t *__restrict__ sym, uint8_t *out, uint64_t total) {
   const uint64_t nunits = (total + 7) / 8;
-  for (uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; u < nunits; u += (uint64_t)gridDim.x * blockDim.x) {
+  // every block takes one contiguous range of units, so a thread stays inside one chunk for many
+  // steps and the chunk lookup is two cached loads instead of a binary search
+  const uint64_t per_block = (nunits + gridDim.x - 1) / gridDim.x;
+  const uint64_t u_end = per_block * (blockIdx.x + 1) < nunits ? per_block * (blockIdx.x + 1) : nunits;
+  uint32_t k = 0xffffffffu;
+  for (uint64_t u = per_block * blockIdx.x + threadIdx.x; u < u_end; u += blockDim.x) {
     const uint64_t a0 = u * 8;
-    uint32_t k = 0;                                    // last chunk with offs[k] <= a0
-    for (uint32_t stp = 1u << 15; stp; stp >>= 1)
-      if (k + stp < nchunks && offs[k + stp] <= a0) k += stp;
+    if (k == 0xffffffffu || a0 < offs[k] || a0 >= offs[k + 1]) {
+      k = 0;                                             // last chunk with offs[k] <= a0
+      for (uint32_t stp = 1u << 15; stp; stp >>= 1)
+        if (k + stp < nchunks && offs[k + stp] <= a0) k += stp;
+    }
     uint64_t start = offs[k], next = offs[k + 1];
     if (a0 + 8 <= total && a0 + 8 <= next) {
       const uint4 v = *reinterpret_cast<const uint4 *>(sym + a0);

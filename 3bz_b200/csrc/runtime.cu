@@ -115,7 +115,8 @@ k_inflate_resolve(const DMember *members, tbz_result *results, uint32_t n, int f
 // =============================================================================================
 static const uint64_t kSlabPoolBytes = 6ull << 30;   // upper bound of the token slab pool per batch
 static const uint64_t kSplitMinBytes = 4ull << 20;   // members at least this large are split across the GPU
-static const uint64_t kSplitChunkBytes = 128ull << 10;
+static const uint64_t kSplitChunkBytes =      // compressed bytes per chunk of a split member (TBZ_SPLIT_CHUNK_KB: tuning)
+    (getenv("TBZ_SPLIT_CHUNK_KB") ? std::max<uint64_t>(16, strtoull(getenv("TBZ_SPLIT_CHUNK_KB"), nullptr, 10)) : 160ull) << 10;
 
 struct DevBlock { void *p; size_t size; bool used; };
 
@@ -628,52 +629,47 @@ static int32_t split_inflate(tbz_ctx *ctx, int fmt, const DMember &m, tbz_result
   std::vector<uint32_t> valid;                       // chunk indices that start a decode, ascending
   for (uint32_t c = 0; c < nchunks; c++) if (found[c] != tbzsplit::NONE64) valid.push_back(c);
   std::vector<Chunk> ch(nchunks);
-  std::vector<uint32_t> todo = valid;
-  SCK(cudaMemsetAsync(d_cnt, 0, 256, st));
-  bool chain_ok = false;
-  for (int pass = 0; pass < 6 && !chain_ok; pass++) {
+  {
+    // one pass: every candidate chunk decodes until it lands exactly on a later candidate start
+    std::vector<unsigned long long> cands(valid.size());
     for (size_t v = 0; v < valid.size(); v++) {
       Chunk &c = ch[valid[v]];
+      cands[v] = found[valid[v]];
       c.start_bit = found[valid[v]];
       c.stop_bit = v + 1 < valid.size() ? found[valid[v + 1]] : tbzsplit::NONE64;
+      c.pad = (uint32_t)v;
     }
-    if (todo.size() > 8) SCK(cudaMemcpyAsync(d_chunks, ch.data(), (size_t)nchunks * sizeof(Chunk), cudaMemcpyHostToDevice, st));
-    else for (uint32_t t : todo) SCK(cudaMemcpyAsync((Chunk *)d_chunks + t, &ch[t], sizeof(Chunk), cudaMemcpyHostToDevice, st));
-    SCK(cudaMemcpyAsync(d_todo, todo.data(), todo.size() * 4, cudaMemcpyHostToDevice, st));
-    SCK(cudaMemsetAsync(d_cnt, 0, 4, st));             // work counter only: slabs keep accumulating
+    void *d_cands = nullptr;
+    SRC(dev_alloc(ctx, cands.size() * 8 + 8, &d_cands));
+    SCK(cudaMemcpyAsync(d_cands, cands.data(), cands.size() * 8, cudaMemcpyHostToDevice, st));
+    SCK(cudaMemcpyAsync(d_chunks, ch.data(), (size_t)nchunks * sizeof(Chunk), cudaMemcpyHostToDevice, st));
+    SCK(cudaMemcpyAsync(d_todo, valid.data(), valid.size() * 4, cudaMemcpyHostToDevice, st));
+    SCK(cudaMemsetAsync(d_cnt, 0, 256, st));
     int occ = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tbzsplit::k_split_decode, tbzfast::NT, dec_smem);
-    const int grid = (int)std::min<uint64_t>((todo.size() + tbzfast::WPC - 1) / tbzfast::WPC, (uint64_t)ctx->sm_count * std::max(1, occ));
+    const int grid = (int)std::min<uint64_t>((valid.size() + tbzfast::WPC - 1) / tbzfast::WPC, (uint64_t)ctx->sm_count * std::max(1, occ));
     tbzsplit::k_split_decode<<<grid, tbzfast::NT, dec_smem, st>>>(words, end_bit, (Chunk *)d_chunks, (const uint32_t *)d_todo,
-                                                                  (uint32_t)todo.size(), (uint32_t *)d_slabs, nslabs, (uint32_t *)d_cnt);
+                                                                  (uint32_t)valid.size(), (uint32_t *)d_slabs, nslabs, (uint32_t *)d_cnt,
+                                                                  (const unsigned long long *)d_cands, (uint32_t)cands.size());
     ctx->launches++;
-    if (todo.size() > 8) SCK(cudaMemcpyAsync(ch.data(), d_chunks, (size_t)nchunks * sizeof(Chunk), cudaMemcpyDeviceToHost, st));
-    else for (uint32_t t : todo) SCK(cudaMemcpyAsync(&ch[t], (Chunk *)d_chunks + t, sizeof(Chunk), cudaMemcpyDeviceToHost, st));
-    SCK(cudaStreamSynchronize(st));
-    // walk the chain from chunk 0; the first broken link decides what is decoded again
-    todo.clear();
-    chain_ok = true;
-    for (size_t v = 0; v < valid.size(); v++) {
+    cudaError_t e1 = cudaMemcpyAsync(ch.data(), d_chunks, (size_t)nchunks * sizeof(Chunk), cudaMemcpyDeviceToHost, st);
+    cudaError_t e2 = cudaStreamSynchronize(st);
+    dev_release(ctx, d_cands);
+    if (e1 != cudaSuccess || e2 != cudaSuccess) { cleanup(); return fail(ctx, TBZ_E_CUDA, "split decode", e1 != cudaSuccess ? e1 : e2); }
+    // follow the landings from chunk 0; a chunk nobody lands on did not start at a block start
+    std::vector<uint32_t> chain;
+    size_t v = 0;
+    for (;;) {
       const Chunk &c = ch[valid[v]];
-      const bool is_last = v + 1 == valid.size();
-      if (c.rec.status == 0) {                          // this chunk did not decode: its start was not a block start
-        if (v == 0) { cleanup(); return TBZ_OK; }
-        todo.push_back(valid[v - 1]);
-        valid.erase(valid.begin() + v);
-        chain_ok = false;
-        break;
-      }
-      if (is_last) { if (c.rec.status != 1) { cleanup(); return TBZ_OK; } break; }
-      if (c.rec.status == 1) { valid.resize(v + 1); break; }   // final block reached: later "starts" are not this member's deflate data
-      if (c.land_bit != c.stop_bit) {                       // missed the successor: it was not a block start
-        valid.erase(valid.begin() + v + 1);
-        todo.push_back(valid[v]);
-        chain_ok = false;
-        break;
-      }
+      if (c.rec.status == 0) { cleanup(); return TBZ_OK; }      // a chunk on the chain did not decode: the sequential path owns the verdict
+      chain.push_back(valid[v]);
+      if (c.rec.status == 1) break;                               // the final block
+      auto it = std::lower_bound(cands.begin() + v + 1, cands.end(), (unsigned long long)c.land_bit);
+      if (it == cands.end() || *it != c.land_bit) { cleanup(); return TBZ_OK; }
+      v = (size_t)(it - cands.begin());
     }
+    valid.swap(chain);
   }
-  if (!chain_ok) { cleanup(); return TBZ_OK; }
   stage("decode");
   // ---- output offsets
   std::vector<Chunk> vch(valid.size());
