@@ -51,6 +51,10 @@ constexpr uint32_t WCAP = TBZ_CP_WCAP;          // window bytes
 constexpr uint32_t HMASK = HIST - 1u;
 constexpr uint32_t WB = WCAP;                   // (name shared with the other phase-two variants: sizes the x16 table)
 constexpr uint32_t V_FINAL = 0xffffu;
+#ifndef TBZ_CP_CRC_UPT
+#define TBZ_CP_CRC_UPT 2
+#endif
+constexpr int CRC_UPT = TBZ_CP_CRC_UPT;         // gzip: consecutive 16-byte units per thread between two GF(2) multiplications
 static_assert(WT <= 1024u && WCAP <= 8192u && WCAP % 16u == 0, "queue entry fields");
 
 struct Smem {
@@ -355,28 +359,41 @@ __device__ inline uint32_t resolve_window(uint8_t *__restrict__ out, int fmt, co
     const uint32_t upto = (pos + wsize) & ~15u;
     const uint8_t *b0 = buf - (pos - mis);               // b0 + absolute offset (16-byte units stay aligned)
     uint32_t myc = 0;                                    // gzip: CRCs of this thread's units, shifted to the end of the flushed range
-    for (uint32_t p = rs.flushed + 16u * tid; p < upto; p += 16u * NT) {
-      const uint4 v = *reinterpret_cast<const uint4 *>(b0 + p);
-      *reinterpret_cast<uint4 *>(out + p) = v;
-      *reinterpret_cast<uint4 *>(&sm.ring[p & HMASK]) = v;
-      if (fmt == TBZ_GZIP) {
-        // crc(A || B) = crc(A) * x^(8 |B|) + crc(B) for finalized CRCs: one table CRC per unit, one
-        // multiplication by the power for the bytes that follow it, XOR over all units
-        const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
-        uint32_t c = 0xffffffffu;
+    if (fmt == TBZ_GZIP) {
+      // crc(A || B) = crc(A) * x^(8 |B|) + crc(B) for finalized CRCs: a thread runs the table CRC over
+      // CRC_UPT consecutive 16-byte units, then multiplies once by the power for the bytes that follow
+      // them (no carry-less multiply on sm_100a: 32 shift-and-xor steps); XOR over all threads
+      for (uint32_t p = rs.flushed + 16u * CRC_UPT * tid; p < upto; p += 16u * CRC_UPT * NT) {
+        uint32_t c = 0xffffffffu, pe = p;
 #pragma unroll
-        for (int q = 0; q < 4; q++)
+        for (int j = 0; j < CRC_UPT; j++) {
+          if (p + 16u * j < upto) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(b0 + p + 16u * j);
+            *reinterpret_cast<uint4 *>(out + p + 16u * j) = v;
+            *reinterpret_cast<uint4 *>(&sm.ring[(p + 16u * j) & HMASK]) = v;
+            const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-          for (int b8 = 0; b8 < 4; b8++) c = (c >> 8) ^ sm.crc_tab[(c ^ (w4[q] >> (8 * b8))) & 0xff];
-        myc ^= crc_mulmod(sm.x16[(upto - p - 16u) >> 4], c ^ 0xffffffffu);
+            for (int q = 0; q < 4; q++)
+#pragma unroll
+              for (int b8 = 0; b8 < 4; b8++) c = (c >> 8) ^ sm.crc_tab[(c ^ (w4[q] >> (8 * b8))) & 0xff];
+            pe = p + 16u * j + 16u;
+          }
+        }
+        myc ^= crc_mulmod(sm.x16[(upto - pe) >> 4], c ^ 0xffffffffu);
       }
-      if (fmt == TBZ_ZLIB) {
-        uint32_t sd = __dp4a(v.x, 0x01010101u, 0u); sd = __dp4a(v.y, 0x01010101u, sd);
-        sd = __dp4a(v.z, 0x01010101u, sd); sd = __dp4a(v.w, 0x01010101u, sd);
-        uint32_t wj = __dp4a(v.x, 0x03020100u, 0u); wj = __dp4a(v.y, 0x07060504u, wj);
-        wj = __dp4a(v.z, 0x0b0a0908u, wj); wj = __dp4a(v.w, 0x0f0e0d0cu, wj);
-        rs.acc_a += sd;
-        rs.acc_w += (unsigned long long)p * sd + wj;
+    } else {
+      for (uint32_t p = rs.flushed + 16u * tid; p < upto; p += 16u * NT) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(b0 + p);
+        *reinterpret_cast<uint4 *>(out + p) = v;
+        *reinterpret_cast<uint4 *>(&sm.ring[p & HMASK]) = v;
+        if (fmt == TBZ_ZLIB) {
+          uint32_t sd = __dp4a(v.x, 0x01010101u, 0u); sd = __dp4a(v.y, 0x01010101u, sd);
+          sd = __dp4a(v.z, 0x01010101u, sd); sd = __dp4a(v.w, 0x01010101u, sd);
+          uint32_t wj = __dp4a(v.x, 0x03020100u, 0u); wj = __dp4a(v.y, 0x07060504u, wj);
+          wj = __dp4a(v.z, 0x0b0a0908u, wj); wj = __dp4a(v.w, 0x0f0e0d0cu, wj);
+          rs.acc_a += sd;
+          rs.acc_w += (unsigned long long)p * sd + wj;
+        }
       }
     }
     if (upto + tid < pos + wsize) sm.ring[(upto + tid) & HMASK] = b0[upto + tid];   // the unit the window ends in: history too
