@@ -54,6 +54,10 @@ constexpr uint32_t V_FINAL = 0xffffu;
 #ifndef TBZ_CP_CRC_UPT
 #define TBZ_CP_CRC_UPT 2
 #endif
+#ifndef TBZ_CP_HOPS
+#define TBZ_CP_HOPS 4
+#endif
+constexpr int PJ_HOPS = TBZ_CP_HOPS;           // pointer hops per level of the pending-byte resolution
 constexpr int CRC_UPT = TBZ_CP_CRC_UPT;         // gzip: consecutive 16-byte units per thread between two GF(2) multiplications
 static_assert(WT <= 1024u && WCAP <= 8192u && WCAP % 16u == 0, "queue entry fields");
 
@@ -341,7 +345,9 @@ __device__ inline uint32_t resolve_window(uint8_t *__restrict__ out, int fmt, co
         if (s2 != V_FINAL) {
           uint32_t sp = s2;
           uint32_t vs = *reinterpret_cast<volatile uint16_t *>(&sm.val[sp]);
-          if (vs != V_FINAL) { sp = vs; vs = *reinterpret_cast<volatile uint16_t *>(&sm.val[sp]); }   // two hops per level
+#pragma unroll
+          for (int hop = 1; hop < PJ_HOPS; hop++)         // several hops per level: fewer levels, fewer barriers
+            if (vs != V_FINAL) { sp = vs; vs = *reinterpret_cast<volatile uint16_t *>(&sm.val[sp]); }
           if (vs == V_FINAL) {
             buf[wb + r] = *reinterpret_cast<volatile uint8_t *>(&buf[wb + sp]);
             __threadfence_block();
