@@ -15,8 +15,8 @@
 //       proven token and the round's output size
 // Measured on the level-6 text of BASELINE config 2: a mis-aligned start re-synchronises after
 // 117 bits on average (p99 595), against S ~ 6000 bits per lane, so ~95 % of decode work is kept.
-// Phase two (inflate_resolve.cuh) turns the token stream into bytes.  Anything this kernel cannot
-// prove clean (stored blocks, malformed codes, truncated input, too small an output buffer ...)
+// Phase two (inflate_copy.cuh) turns the token stream into bytes.  Stored blocks travel as literal
+// tokens.  Anything this kernel cannot prove clean (malformed codes, truncated input, too small an output buffer ...)
 // is queued for the sequential kernel, which reproduces the reference's exact verdict.
 // Replaces deflate.lisp:465-509,673-702 (decode) and huffman-tree.lisp:99-218 (tables).
 #pragma once
@@ -363,8 +363,56 @@ __device__ inline bool decode_blocks(const In &in, uint32_t pos, uint32_t stop_b
       err = __shfl_sync(TBZ_FULL, err, 0);
       if (err) return false;
       pos = __shfl_sync(TBZ_FULL, p, 0);
+    } else if (btype == 0) {
+      // ================= stored block (deflate.lisp:532-573) =================
+      // LEN, NLEN, then LEN bytes as they are.  They travel as literal tokens, two bytes each, the
+      // lanes taking consecutive slices; anything irregular is left to the sequential kernel.
+      pos = (pos + 7u) & ~7u;
+      if (in.end < pos || in.end - pos < 32u) return false;
+      const uint32_t v = peek32(in, pos);
+      uint32_t slen = v & 0xffffu;
+      if ((slen ^ 0xffffu) != (v >> 16)) return false;                 // deflate.lisp:535
+      pos += 32u;
+      if (in.end - pos < 8u * slen) return false;                      // the input ends inside the block
+      uint32_t bp = pos >> 3;                                          // byte offset of the payload from in.w
+      pos += 8u * slen;
+      while (slen) {
+        uint32_t slab_id = 0;
+        if (lane == 0) slab_id = atomicAdd(slab_counter, 1u);
+        slab_id = __shfl_sync(TBZ_FULL, slab_id, 0);
+        if (slab_id >= nslabs) return false;
+        uint32_t *slab = slabs + (size_t)slab_id * SLAB_WORDS;
+        SlabHdr *sh = reinterpret_cast<SlabHdr *>(slab);
+        const uint32_t nb = slen < (uint32_t)(NL * TOKCAP * 2) ? slen : (uint32_t)(NL * TOKCAP * 2);
+        const uint32_t per = ((nb + NL - 1) / NL + 1u) & ~1u;          // bytes per lane, even
+        const uint32_t lo = per * lane < nb ? per * lane : nb, hi = lo + per < nb ? lo + per : nb;
+        const uint32_t cnt = (hi - lo + 1u) / 2u;
+        uint32_t *list = slab + SLAB_HDR_WORDS + lane * TOKCAP;
+        for (uint32_t t = 0; t < cnt; t++) {
+          const uint32_t a = bp + lo + 2u * t;
+          const uint32_t b0 = byte_at(in, a);
+          list[t] = lo + 2u * t + 1u < hi ? (TOK_LIT2 | (byte_at(in, a + 1u) << 8) | b0) : b0;
+        }
+        A += nb;
+        if (A > out_cap || A >= (1ull << 32)) return false;            // overflow: sequential kernel
+        sh->fc[lane] = cnt << 16;
+        if (lane == 0) {
+          sh->next = NO_SLAB; sh->out_bytes = nb;
+          if (prev_slab != NO_SLAB) reinterpret_cast<SlabHdr *>(slabs + (size_t)prev_slab * SLAB_WORDS)->next = slab_id;
+        }
+        if (first_slab == NO_SLAB) first_slab = slab_id;
+        prev_slab = slab_id;
+        bp += nb; slen -= nb;
+        __syncwarp();
+      }
+      prev_block_bits = 0;
+      if (stops) {
+        while (pos > stop_bit) stop_bit = stops->rel(++stop_i);
+        if (pos == stop_bit) break;
+      } else if (pos >= stop_bit) break;
+      continue;
     } else {
-      return false;                        // stored / reserved block type: sequential kernel
+      return false;                        // reserved block type: sequential kernel
     }
     __syncwarp();
     // ================= tables (huffman-tree.lisp:99-218) =================

@@ -346,3 +346,30 @@ def test_device_pointers_any_alignment(ctx, oracle, fmt):
     finally:
         L.tbz_device_free(ctx.h, d_in)
         L.tbz_device_free(ctx.h, d_out)
+
+
+def test_stored_blocks_take_the_fast_path(ctx, oracle):
+    """Stored blocks (deflate.lisp:532-573) travel through the token kernels as literal tokens:
+    level-0 streams, incompressible data (libz falls back to stored blocks), streams that mix stored
+    and Huffman blocks (Z_FULL_FLUSH emits an empty stored block), in all three formats."""
+    text, rnd = datagen.text(200000, 5), datagen.random_bytes(150000, 9)
+    for fmt in cases.FMTS:
+        mixed = zlib.compressobj(6, zlib.DEFLATED, datagen.WBITS[fmt])
+        blob = mixed.compress(text[:70000]) + mixed.flush(zlib.Z_FULL_FLUSH) + mixed.compress(rnd[:80000]) + \
+            mixed.flush(zlib.Z_SYNC_FLUSH) + mixed.compress(text[70000:]) + mixed.flush()
+        plain_mixed = text[:70000] + rnd[:80000] + text[70000:]
+        items = [(datagen.compress(text, fmt, level=0), text), (datagen.compress(rnd, fmt), rnd), (blob, plain_mixed),
+                 (datagen.compress(b"", fmt, level=0), b""), (datagen.compress(b"x", fmt, level=0), b"x")]
+        got, _ = run_batch(ctx, fmt, [c for c, _ in items], [max(1, len(p)) for _, p in items])
+        for k, ((comp, plain), g) in enumerate(zip(items, got)):
+            compare(g, oracle.decompress_vector(comp, fmt, out_cap=max(1, len(plain))), (fmt, k))
+            assert g["verdict"] == 0 and g["out"] == plain and g["path"] == 1, (fmt, k, g["verdict"], g["path"])
+        # a stored block cut short, a bad NLEN and a too small buffer keep the reference's verdicts (sequential kernel)
+        comp = datagen.compress(rnd[:5000], fmt, level=0)
+        hdr = {"deflate": 0, "zlib": 2, "gzip": 10}[fmt]
+        bad = bytearray(comp); bad[hdr + 3] ^= 0x40
+        ins = [comp[:hdr + 1000], bytes(bad), comp]
+        got, _ = run_batch(ctx, fmt, ins, [5000, 5000, 4999])
+        for k, g in enumerate(got):
+            compare(g, oracle.decompress_vector(ins[k], fmt, out_cap=[5000, 5000, 4999][k]), (fmt, "bad", k))
+        assert [g["verdict"] for g in got] == [1, 17, 2], [g["verdict"] for g in got]
