@@ -605,8 +605,25 @@ __device__ inline bool decode_member(const DMember &mem, int fmt, P1Rec &rec, WS
   } else if (fmt == TBZ_GZIP) {
     if (in.end - pos < 80) return false;
     uint32_t bp = pos >> 3;
-    if (byte_at(in, bp) != 0x1f || byte_at(in, bp + 1) != 0x8b || byte_at(in, bp + 2) != 8 || byte_at(in, bp + 3) != 0) return false;
-    pos += 80;
+    if (byte_at(in, bp) != 0x1f || byte_at(in, bp + 1) != 0x8b || byte_at(in, bp + 2) != 8) return false;
+    const uint32_t flg = byte_at(in, bp + 3);
+    if (flg & 0xe2u) return false;                      // reserved bits (an error) or a header CRC: sequential kernel
+    // optional fields (gzip.lisp:178-240): FEXTRA, FNAME, FCOMMENT are skipped here — `gzip file` always
+    // writes a name; every lane walks the same bytes
+    const uint32_t endb = in.end >> 3;
+    uint32_t q = bp + 10;
+    if (flg & 4u) {
+      if (q + 2 > endb) return false;
+      q += 2u + (byte_at(in, q) | (byte_at(in, q + 1) << 8));
+    }
+    for (uint32_t field = 8u; field <= 16u; field <<= 1) {
+      if (flg & field) {
+        while (q < endb && byte_at(in, q)) q++;
+        q++;
+      }
+    }
+    if (q >= endb) return false;                        // the header does not end inside the input
+    pos = q * 8;
   }
   return decode_blocks(in, pos, 0xffffffffu, mem.out_cap, rec, sm, slabs, nslabs, slab_counter, lane);
 }

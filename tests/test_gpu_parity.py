@@ -166,6 +166,14 @@ def test_gzip_header_fields(ctx, oracle):
     got, _ = run_batch(ctx, "gzip", variants, 5000)
     for i, g in enumerate(got):
         compare(g, oracle.decompress_vector(variants[i], "gzip", out_cap=5000), i)
+    # name / comment / extra are skipped by the fast kernels (path 1); a header CRC goes to the sequential one
+    assert [got[i]["path"] for i in range(4)] == [0, 0, 1, 0], [got[i]["path"] for i in range(4)]
+    fast = [cases.gzip_with_header_fields(plain, hcrc=False), cases.gzip_with_header_fields(plain, extra=None, hcrc=False),
+            cases.gzip_with_header_fields(plain, extra=b"", name=b"", comment=b"", hcrc=False)]
+    got, _ = run_batch(ctx, "gzip", fast, 5000)
+    for i, g in enumerate(got):
+        compare(g, oracle.decompress_vector(fast[i], "gzip", out_cap=5000), ("fast", i))
+        assert g["verdict"] == 0 and g["out"] == plain and g["path"] == 1, ("fast", i, g["path"])
 
 
 def _drain_both(engine, oracle, comp, fmt, sizes, start=0):
