@@ -58,7 +58,11 @@ constexpr uint32_t V_FINAL = 0xffffu;
 #define TBZ_CP_HOPS 4
 #endif
 constexpr int PJ_HOPS = TBZ_CP_HOPS;           // pointer hops per level of the pending-byte resolution
-constexpr int CRC_UPT = TBZ_CP_CRC_UPT;         // gzip: consecutive 16-byte units per thread between two GF(2) multiplications
+constexpr int CRC_UPT = TBZ_CP_CRC_UPT;
+#ifndef TBZ_CP_CRC_SEPARATE
+#define TBZ_CP_CRC_SEPARATE 1
+#endif
+constexpr bool CRC_SEPARATE = TBZ_CP_CRC_SEPARATE != 0;   // gzip: CRC-32 and trailer compare in k_member_crc (inflate_crc.cuh)         // gzip: consecutive 16-byte units per thread between two GF(2) multiplications
 static_assert(WT <= 1024u && WCAP <= 8192u && WCAP % 16u == 0, "queue entry fields");
 
 struct Smem {
@@ -360,12 +364,13 @@ __device__ inline uint32_t resolve_window(uint8_t *__restrict__ out, int fmt, co
   }
   // ---- 5. flush complete 16-byte units, fold them into the checksum
   const bool aligned_out = (((uintptr_t)out) & 15) == 0;
-  if (fmt == TBZ_GZIP && !aligned_out) crc_window(sm, buf, wb, wsize, tid);
+  const bool crc_here = fmt == TBZ_GZIP && !CRC_SEPARATE;
+  if (crc_here && !aligned_out) crc_window(sm, buf, wb, wsize, tid);
   if (aligned_out) {
     const uint32_t upto = (pos + wsize) & ~15u;
     const uint8_t *b0 = buf - (pos - mis);               // b0 + absolute offset (16-byte units stay aligned)
     uint32_t myc = 0;                                    // gzip: CRCs of this thread's units, shifted to the end of the flushed range
-    if (fmt == TBZ_GZIP) {
+    if (crc_here) {
       // crc(A || B) = crc(A) * x^(8 |B|) + crc(B) for finalized CRCs: a thread runs the table CRC over
       // CRC_UPT consecutive 16-byte units, then multiplies once by the power for the bytes that follow
       // them (no carry-less multiply on sm_100a: 32 shift-and-xor steps); XOR over all threads
@@ -403,7 +408,7 @@ __device__ inline uint32_t resolve_window(uint8_t *__restrict__ out, int fmt, co
       }
     }
     if (upto + tid < pos + wsize) sm.ring[(upto + tid) & HMASK] = b0[upto + tid];   // the unit the window ends in: history too
-    if (fmt == TBZ_GZIP) {
+    if (crc_here) {
 #pragma unroll
       for (int sft = 16; sft; sft >>= 1) myc ^= __shfl_xor_sync(TBZ_FULL, myc, sft);
       if (lane == 0) sm.crcw[warp] = myc;
@@ -500,7 +505,7 @@ __device__ inline bool resolve_member(const DMember &mem, int fmt, const P1Rec &
     const uint32_t s1 = (uint32_t)((1 + S) % TBZ_ADLER_MOD);
     const uint32_t s2 = (uint32_t)((N + N * S + (unsigned long long)TBZ_ADLER_MOD * 4096 - w % TBZ_ADLER_MOD) % TBZ_ADLER_MOD);
     ck = s1 | (s2 << 16);
-  } else if (fmt == TBZ_GZIP) {
+  } else if (fmt == TBZ_GZIP && !CRC_SEPARATE) {
     __syncthreads();
     uint32_t c = sm.crc;
     if (rs.flushed < pos) {                  // the last partial unit (uniform: every thread computes the same value)
@@ -526,7 +531,7 @@ __device__ inline bool resolve_member(const DMember &mem, int fmt, const P1Rec &
     if (end - p < 64) return false;
     const uint8_t *q = base + (p >> 3);
     const uint32_t t = q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24);
-    if (t != ck) return false;
+    if (!CRC_SEPARATE && t != ck) return false;        // (separate CRC kernel: it compares, and fills in the checksum)
     p += 64;
   }
   if (tid == 0) {

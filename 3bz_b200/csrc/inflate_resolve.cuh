@@ -38,6 +38,7 @@ using tbzfast::TOK_MATCH;
 constexpr int NT = 256;
 constexpr int NWARP = NT / 32;
 constexpr uint32_t HIST = 32768u, HMASK = HIST - 1u;
+constexpr bool CRC_SEPARATE = false;    // CRC-32 inside the kernel
 #ifndef TBZ_RES_TPT
 #define TBZ_RES_TPT 4
 #endif

@@ -21,6 +21,7 @@
 #include "inflate_resolve.cuh"
 #include "inflate_lockstep.cuh"
 #include "inflate_copy.cuh"
+#include "inflate_crc.cuh"
 #include "inflate_split.cuh"
 
 // =============================================================================================
@@ -44,7 +45,7 @@ k_inflate_seq(const DMember *members, tbz_result *results, uint32_t n, int fmt,
 }
 
 // counters: [0] next member for phase one, [1] members queued for the sequential kernel,
-//           [2] slabs handed out, [3] next member for phase two
+//           [2] slabs handed out, [3] next member for phase two, [4] next member for the gzip CRC kernel
 // Phase one, persistent CTAs of WPC independent warps: each warp pulls the next member from a
 // global counter and decodes it into token slabs; members it cannot prove clean are queued for
 // k_inflate_seq.
@@ -107,6 +108,7 @@ k_inflate_resolve(const DMember *members, tbz_result *results, uint32_t n, int f
     if (!recs[i].status) continue;
     const bool ok = tbzp2::resolve_member(members[i], fmt, recs[i], slabs, results[i], sm, tid);
     if (!ok && tid == 0) todo[atomicAdd(&counters[1], 1u)] = i;
+    if (ok && tid == 0 && tbzp2::CRC_SEPARATE && fmt == TBZ_GZIP) const_cast<tbzfast::P1Rec *>(recs)[i].status = tbzcrc::ST_CRC_PENDING;
   }
 }
 
@@ -818,6 +820,14 @@ static int32_t launch_kernels(tbz_batch *b) {
         (const tbzfast::P1Rec *)b->d_recs, (const uint32_t *)b->d_slabs, (uint32_t *)b->d_counters, (uint32_t *)b->d_todo);
     ctx->launches++;
     CK(ctx, cudaGetLastError());
+    if (tbzp2::CRC_SEPARATE && b->format == TBZ_GZIP) {   // gzip: CRC-32 of the finished members + trailer compare
+      const int crc_grid = (int)std::min<uint64_t>(n, (uint64_t)ctx->sm_count * 6);
+      tbzcrc::k_member_crc<<<crc_grid, tbzcrc::NT, 0, ctx->stream>>>(
+          (const DMember *)b->d_members, (tbz_result *)b->d_results, n, (const tbzfast::P1Rec *)b->d_recs,
+          (uint32_t *)b->d_counters, (uint32_t *)b->d_todo);
+      ctx->launches++;
+      CK(ctx, cudaGetLastError());
+    }
     if (ctx->ktime) CK(ctx, cudaEventRecord(ctx->kev[2], ctx->stream));
     k_inflate_seq<<<(n + SEQ_WARPS - 1) / SEQ_WARPS, SEQ_WARPS * 32, 0, ctx->stream>>>(
         (const DMember *)b->d_members, (tbz_result *)b->d_results, n, b->format,
