@@ -132,3 +132,18 @@ def test_gzip_header_metadata(engine):
         with pytest.raises(t.ThreeBzError) as e:
             t.gzip_header(bad)
         assert e.value.verdict == verdict, (e.value.verdict, verdict)
+
+
+@pytest.mark.parametrize("p2", [0, 1])
+def test_phase_two_alternatives_still_compile(p2, tmp_path):
+    """The measured alternatives of phase two (byte-parallel rank queries, lock-step lanes)
+    stay buildable behind -DTBZ_P2; nvcc cross-compiles for sm_100a without a GPU."""
+    import importlib
+    import shutil
+    b = importlib.import_module("3bz_b200.build")
+    if not shutil.which(b.NVCC) and not os.path.exists(b.NVCC):
+        pytest.skip("no nvcc")
+    out = str(tmp_path / ("p2_%d.so" % p2))
+    b.build(force=True, extra=["-DTBZ_P2=%d" % p2], out=out)
+    L = C.CDLL(out)
+    assert L.tbz_abi_version() == 1
