@@ -42,7 +42,7 @@ constexpr int NWARP = NT / 32;
 #define TBZ_CP_TPT 4
 #endif
 #ifndef TBZ_CP_WCAP
-#define TBZ_CP_WCAP 6000
+#define TBZ_CP_WCAP 6400
 #endif
 constexpr int TPT = TBZ_CP_TPT;                 // tokens per thread and window
 constexpr uint32_t WT = (uint32_t)NT * TPT;     // window tokens
