@@ -62,11 +62,16 @@ constexpr int CRC_UPT = TBZ_CP_CRC_UPT;
 #ifndef TBZ_CP_CRC_SEPARATE
 #define TBZ_CP_CRC_SEPARATE 1
 #endif
+#ifndef TBZ_CP_GHIST
+#define TBZ_CP_GHIST 0
+#endif
+constexpr bool GHIST = TBZ_CP_GHIST != 0;       // experiment: final history is read back from the output in global memory
+                                                // (L2) instead of a 32 KiB shared-memory ring: 43 KB per CTA, 5 CTAs/SM
 constexpr bool CRC_SEPARATE = TBZ_CP_CRC_SEPARATE != 0;   // gzip: CRC-32 and trailer compare in k_member_crc (inflate_crc.cuh)         // gzip: consecutive 16-byte units per thread between two GF(2) multiplications
 static_assert(WT <= 1024u && WCAP <= 8192u && WCAP % 16u == 0, "queue entry fields");
 
 struct Smem {
-  alignas(16) uint8_t ring[HIST];              // final history: absolute output offset p lives at ring[p & HMASK]
+  alignas(16) uint8_t ring[GHIST ? 16 : HIST]; // final history: absolute output offset p lives at ring[p & HMASK]
   alignas(16) uint8_t win[16 + WCAP + 16];     // the window: offset r (absolute pos + r) lives at win[(pos & 15) + r], so that
                                                // 16-byte units of the output are 16-byte units here
   alignas(16) uint16_t val[WCAP];              // per window byte: V_FINAL, or the window offset of an equal byte
@@ -91,26 +96,38 @@ struct Smem {
 
 __device__ __forceinline__ uint32_t tok_len(uint32_t t) { return (t & TOK_MATCH) ? (t & 255u) + 3u : 1u + ((t >> 30) & 1u); }
 
-// One match whose source is final history: n bytes from ring offset src (wraps) to win[dst, dst+n).
+// Final history: the ring in shared memory, or (GHIST) the member's own output in global memory, read
+// through L2 (__ldcg: the bytes were stored by this CTA before a barrier).
+struct Hist {
+  const uint8_t *ring; const uint8_t *out;
+  __device__ __forceinline__ uint32_t byte(uint32_t p) const { return GHIST ? (uint32_t)__ldcg(out + p) : (uint32_t)ring[p & HMASK]; }
+  // the aligned 32-bit word number wi of the history (byte offsets 4 wi .. 4 wi + 3 relative to the word grid of `out` / the ring)
+  __device__ __forceinline__ uint32_t word(uint32_t wi, uint32_t lim) const {
+    if (GHIST) { return wi < lim ? __ldcg(reinterpret_cast<const uint32_t *>(out - ((uintptr_t)out & 3u)) + wi) : 0u; }
+    return reinterpret_cast<const uint32_t *>(ring)[wi & (HMASK >> 2)];
+  }
+};
+
+// One match whose source is final history: n bytes from history offset src to win[dst, dst+n).
 // Straight-line for n <= 19: byte moves up to the first aligned destination word and after the last
-// one, in between one aligned word load per 4 source bytes and a funnel shift.
-__device__ __forceinline__ void copy_hist(uint8_t *win, uint32_t dst, const uint8_t *ring, uint32_t src, uint32_t n) {
+// one, in between one aligned word load per 4 source bytes and a funnel shift.  lim: (GHIST) number of
+// history words that may be read (nothing beyond the bytes produced so far).
+__device__ __forceinline__ void copy_hist(uint8_t *win, uint32_t dst, const Hist &h, uint32_t src, uint32_t n, uint32_t lim) {
   const uint32_t dend = dst + n;
   uint32_t hb = (0u - dst) & 3u;                         // bytes up to the first aligned destination word
   if (hb > n) hb = n;
 #pragma unroll
   for (uint32_t b = 0; b < 3; b++)
-    if (b < hb) win[dst + b] = ring[(src + b) & HMASK];
+    if (b < hb) win[dst + b] = (uint8_t)h.byte(src + b);
   uint32_t p = dst + hb;                                 // aligned (or the end)
-  const uint32_t sa = src + hb;
+  const uint32_t sa = src + hb + (GHIST ? (uint32_t)((uintptr_t)h.out & 3u) : 0u);   // offset on the history's word grid
   const uint32_t sh = (sa & 3u) * 8u;
-  const uint32_t *rw = reinterpret_cast<const uint32_t *>(ring);
   uint32_t wi = sa >> 2;
-  uint32_t lo = rw[wi & (HMASK >> 2)];
+  uint32_t lo = h.word(wi, lim);
 #pragma unroll
   for (int i = 0; i < 4; i++) {
     if (p + 4u <= dend) {
-      const uint32_t hi = rw[(wi + 1u + i) & (HMASK >> 2)];
+      const uint32_t hi = h.word(wi + 1u + i, lim);
       *reinterpret_cast<uint32_t *>(win + p) = __funnelshift_r(lo, hi, sh);
       lo = hi;
       p += 4u;
@@ -120,7 +137,7 @@ __device__ __forceinline__ void copy_hist(uint8_t *win, uint32_t dst, const uint
     wi += 4u;
     do {
       wi++;
-      const uint32_t hi = rw[wi & (HMASK >> 2)];
+      const uint32_t hi = h.word(wi, lim);
       *reinterpret_cast<uint32_t *>(win + p) = __funnelshift_r(lo, hi, sh);
       lo = hi;
       p += 4u;
@@ -128,7 +145,7 @@ __device__ __forceinline__ void copy_hist(uint8_t *win, uint32_t dst, const uint
   }
 #pragma unroll
   for (uint32_t b = 0; b < 3; b++)
-    if (p + b < dend) win[p + b] = ring[(src + (p + b - dst)) & HMASK];
+    if (p + b < dend) win[p + b] = (uint8_t)h.byte(src + (p + b - dst));
 }
 
 // CRC-32 of buf[a, a+m): every thread takes one contiguous slice; slices are merged pairwise with
@@ -229,7 +246,10 @@ __device__ inline uint32_t resolve_window(uint8_t *__restrict__ out, int fmt, co
   for (uint32_t i = tid; i < WCAP / 8u; i += NT)        // (the previous window's levels ended at a barrier)
     reinterpret_cast<uint4 *>(sm.val)[i] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
   __syncthreads();
-  if (tid < (int)mis) sm.win[tid] = sm.ring[(pos - mis + tid) & HMASK];   // the unit the previous window ended in
+  Hist hist;
+  hist.ring = sm.ring; hist.out = out;
+  const uint32_t hlim = (pos + (uint32_t)((uintptr_t)out & 3u) + 3u) >> 2;   // history words that hold produced bytes
+  if (tid < (int)mis) sm.win[tid] = (uint8_t)hist.byte(pos - mis + tid);   // the unit the previous window ended in
   uint32_t off = 0, total = 0;
 #pragma unroll
   for (int w = 0; w < NWARP; w++) { const uint32_t c = sm.wscan[w]; if (w < warp) off += c; total += c; }
@@ -321,7 +341,7 @@ __device__ inline uint32_t resolve_window(uint8_t *__restrict__ out, int fmt, co
     for (uint32_t j = tid; j < nr; j += NT) {
       const uint32_t job = sm.jobs[j], idx = job & 1023u;
       const uint32_t o = sm.tokoff[idx], d = (job >> 10) + 1u, n_ = sm.tokoff[idx + 1] - o;
-      copy_hist(buf, wb + o, sm.ring, pos + o - d, d < n_ ? d : n_);
+      copy_hist(buf, wb + o, hist, pos + o - d, d < n_ ? d : n_, hlim);
       for (uint32_t k = d; k < n_; k++) buf[wb + o + k] = buf[wb + o + k - d];   // (first token of the window only) its own period
     }
     for (uint32_t j = tid; j < np; j += NT) {
@@ -331,7 +351,7 @@ __device__ inline uint32_t resolve_window(uint8_t *__restrict__ out, int fmt, co
       for (uint32_t k = 0; k < n_; k++) {
         const uint32_t r = s0 + k;
         qp[k] = (uint16_t)r;
-        if (r < d) buf[wb + r] = sm.ring[(pos + r - d) & HMASK];   // the source is below the window: final
+        if (r < d) buf[wb + r] = (uint8_t)hist.byte(pos + r - d);   // the source is below the window: final
         else sm.val[r] = (uint16_t)(r - d);
       }
     }
@@ -381,7 +401,7 @@ __device__ inline uint32_t resolve_window(uint8_t *__restrict__ out, int fmt, co
           if (p + 16u * j < upto) {
             const uint4 v = *reinterpret_cast<const uint4 *>(b0 + p + 16u * j);
             *reinterpret_cast<uint4 *>(out + p + 16u * j) = v;
-            *reinterpret_cast<uint4 *>(&sm.ring[(p + 16u * j) & HMASK]) = v;
+            if (!GHIST) *reinterpret_cast<uint4 *>(&sm.ring[(p + 16u * j) & HMASK]) = v;
             const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
             for (int q = 0; q < 4; q++)
@@ -396,7 +416,7 @@ __device__ inline uint32_t resolve_window(uint8_t *__restrict__ out, int fmt, co
       for (uint32_t p = rs.flushed + 16u * tid; p < upto; p += 16u * NT) {
         const uint4 v = *reinterpret_cast<const uint4 *>(b0 + p);
         *reinterpret_cast<uint4 *>(out + p) = v;
-        *reinterpret_cast<uint4 *>(&sm.ring[p & HMASK]) = v;
+        if (!GHIST) *reinterpret_cast<uint4 *>(&sm.ring[p & HMASK]) = v;
         if (fmt == TBZ_ZLIB) {
           uint32_t sd = __dp4a(v.x, 0x01010101u, 0u); sd = __dp4a(v.y, 0x01010101u, sd);
           sd = __dp4a(v.z, 0x01010101u, sd); sd = __dp4a(v.w, 0x01010101u, sd);
@@ -407,7 +427,9 @@ __device__ inline uint32_t resolve_window(uint8_t *__restrict__ out, int fmt, co
         }
       }
     }
-    if (upto + tid < pos + wsize) sm.ring[(upto + tid) & HMASK] = b0[upto + tid];   // the unit the window ends in: history too
+    if (upto + tid < pos + wsize) {                      // the unit the window ends in: history too
+      if (GHIST) out[upto + tid] = b0[upto + tid]; else sm.ring[(upto + tid) & HMASK] = b0[upto + tid];
+    }
     if (crc_here) {
 #pragma unroll
       for (int sft = 16; sft; sft >>= 1) myc ^= __shfl_xor_sync(TBZ_FULL, myc, sft);
@@ -425,7 +447,7 @@ __device__ inline uint32_t resolve_window(uint8_t *__restrict__ out, int fmt, co
     for (uint32_t p = pos + tid; p < pos + wsize; p += NT) {
       const uint32_t d = buf[wb + p - pos];
       out[p] = (uint8_t)d;
-      sm.ring[p & HMASK] = (uint8_t)d;
+      if (!GHIST) sm.ring[p & HMASK] = (uint8_t)d;
       rs.acc_a += d; rs.acc_w += (unsigned long long)p * d;
     }
     rs.flushed = pos + wsize;
@@ -475,7 +497,7 @@ __device__ inline bool resolve_stream(uint8_t *__restrict__ out, int fmt, const 
   if (sm.fail) return false;
   if (rs.flushed + tid < rs.pos) {         // the last partial 16-byte unit
     const uint32_t p = rs.flushed + tid;
-    const uint32_t d = sm.ring[p & HMASK];
+    const uint32_t d = GHIST ? (uint32_t)__ldcg(out + p) : (uint32_t)sm.ring[p & HMASK];
     out[p] = (uint8_t)d;
     rs.acc_a += d; rs.acc_w += (unsigned long long)p * d;
   }
@@ -510,7 +532,7 @@ __device__ inline bool resolve_member(const DMember &mem, int fmt, const P1Rec &
     uint32_t c = sm.crc;
     if (rs.flushed < pos) {                  // the last partial unit (uniform: every thread computes the same value)
       uint32_t t = 0xffffffffu;
-      for (uint32_t p = rs.flushed; p < pos; p++) t = (t >> 8) ^ sm.crc_tab[(t ^ sm.ring[p & HMASK]) & 0xff];
+      for (uint32_t p = rs.flushed; p < pos; p++) t = (t >> 8) ^ sm.crc_tab[(t ^ (GHIST ? (uint32_t)__ldcg(mem.out + p) : (uint32_t)sm.ring[p & HMASK])) & 0xff];
       c = crc_combine(c, t ^ 0xffffffffu, pos - rs.flushed);
     }
     ck = c;
