@@ -7,11 +7,11 @@ from .api import (ThreeBzError, Ctx, default_ctx, decompress, decompress_vector,
                   with_octet_pointer, make_octet_vector_context, make_octet_stream_context,
                   make_octet_pointer_context, make_deflate_state, make_zlib_state, make_gzip_state,
                   finished, input_underrun, output_overflow, replace_output_buffer,
-                  gzip_header, decompress_gzip_members)
+                  gzip_header, decompress_gzip_members, resync_file_stream)
 from . import _ffi, shard  # noqa: F401
 
 # package.lisp:13-27 — the exported symbols, plus the new batch entry point
 __all__ = ["decompress", "decompress_vector", "with_octet_pointer", "make_octet_vector_context",
            "make_octet_stream_context", "make_octet_pointer_context", "make_deflate_state",
            "make_zlib_state", "make_gzip_state", "finished", "input_underrun", "output_overflow",
-           "replace_output_buffer", "decompress_batch", "gzip_header", "decompress_gzip_members"]
+           "replace_output_buffer", "decompress_batch", "gzip_header", "decompress_gzip_members", "resync_file_stream"]

@@ -140,8 +140,38 @@ def make_octet_pointer_context(octet_pointer, start=0, offset=0, end=None):
     return OctetPointerContext(octet_pointer, start, offset, end)
 
 
-def make_octet_stream_context(*a, **k):
-    raise NotImplementedError("octet-stream-context is out of scope for the device engine (SURVEY.md §8f.4)")
+class OctetStreamContext:
+    """octet-stream-context (io-common.lisp:47-63, io.lisp:61-104): the octets [offset, end) of a
+    seekable binary stream.  The reference pulls 4/8 octets at a time through FILE-POSITION and
+    READ-BYTE ("very slow", README.md:13); here the unread octets are read into one host buffer per
+    `decompress` call and travel like an octet vector."""
+
+    def __init__(self, stream, start=0, offset=0, end=None):
+        if not (hasattr(stream, "read") and hasattr(stream, "seek") and getattr(stream, "readable", lambda: True)()):
+            raise ThreeBzError("not a valid octet stream")            # (assert (valid-octet-stream stream)), io.lisp:69
+        self.stream, self.start, self.offset = stream, start, offset
+        if end is None:                                               # (file-length file-stream)
+            here = stream.tell()
+            end = stream.seek(0, 2)
+            stream.seek(here)
+        self.end = end
+        self._keep = None
+
+    def _unread(self):
+        self.stream.seek(self.offset)
+        data = self.stream.read(max(0, self.end - self.offset))
+        self._keep, base = _addr(data)
+        return base, len(data)
+
+
+def make_octet_stream_context(file_stream, start=0, offset=0, end=None):
+    return OctetStreamContext(file_stream, start, offset, end)
+
+
+def resync_file_stream(context):
+    """%resync-file-stream (io-common.lisp:51-56): put the stream where the context's offset is."""
+    if isinstance(context, OctetStreamContext):
+        context.stream.seek(context.offset)
 
 
 # ---- states (deflate.lisp:4-62, zlib.lisp:3-12, gzip.lisp:3-28) ------------------------------

@@ -51,11 +51,24 @@
                  :op octet-pointer :pointer (base octet-pointer)
                  :boxes (make-context-boxes :start start :offset offset :end end)))
 
-;; Stream input stays with the reference's CPU path (README.md:13 "very slow"); out of scope here.
-(defun make-octet-stream-context (file-stream &key start offset end)
-  (declare (ignore file-stream start offset end))
-  (error "octet-stream contexts are not served by the CUDA engine; read the stream into an octet-vector"))
-(defgeneric %resync-file-stream (context) (:method (context) (declare (ignore context)) nil))
+;; octet-stream-context (io-common.lisp:47-63, io.lisp:61-104).  The reference pulls 4 / 8 octets at a
+;; time through FILE-POSITION and READ-BYTE (README.md:13 "very slow"); here the unread octets
+;; [offset, end) are read with one READ-SEQUENCE per DECOMPRESS call and travel like an octet vector.
+(defclass octet-stream-context ()
+  ((octet-stream :reader octet-stream :initarg :octet-stream)
+   (boxes :reader boxes :initarg :boxes)))
+
+(defun valid-octet-stream (os)
+  (and (typep os 'stream) (subtypep (stream-element-type os) 'octet) (open-stream-p os) (input-stream-p os)))
+
+(defun make-octet-stream-context (file-stream &key (start 0) (offset 0) (end (file-length file-stream)))
+  (make-instance 'octet-stream-context :octet-stream file-stream
+                 :boxes (make-context-boxes :start start :offset offset :end end)))
+
+(defgeneric %resync-file-stream (context)
+  (:method (context) (declare (ignore context)) nil)
+  (:method ((context octet-stream-context))
+    (file-position (octet-stream context) (cb-offset (boxes context)))))
 
 (defgeneric call-with-unread-octets (context function)
   (:documentation "Calls FUNCTION with a foreign pointer to the unread octets and their count."))
@@ -68,3 +81,13 @@
     (error "trying to use octet-pointer outside scope of with-octet-pointer"))
   (let ((b (boxes c)))
     (funcall function (cffi:inc-pointer (%pointer c) (cb-offset b)) (- (cb-end b) (cb-offset b)))))
+
+(defmethod call-with-unread-octets ((c octet-stream-context) function)
+  (let* ((b (boxes c)) (n (max 0 (- (cb-end b) (cb-offset b))))
+         (s (octet-stream c))
+         (v (make-array n :element-type 'octet)))
+    (assert (valid-octet-stream s))
+    (file-position s (cb-offset b))
+    (let ((got (read-sequence v s)))
+      (cffi:with-pointer-to-vector-data (p v)
+        (funcall function p got)))))

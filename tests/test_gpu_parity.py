@@ -381,3 +381,32 @@ def test_stored_blocks_take_the_fast_path(ctx, oracle):
         for k, g in enumerate(got):
             compare(g, oracle.decompress_vector(ins[k], fmt, out_cap=[5000, 5000, 4999][k]), (fmt, "bad", k))
         assert [g["verdict"] for g in got] == [1, 17, 2], [g["verdict"] for g in got]
+
+
+def test_octet_stream_context(engine, ctx, tmp_path):
+    """octet-stream-context (io-common.lisp:47-63, io.lisp:61-104): a member that lies
+    somewhere inside a file, read through a stream context; %resync-file-stream puts the file
+    position where the context says."""
+    import io
+    plain = datagen.text(300000, 77)
+    comp = datagen.compress(plain, "gzip")
+    blob = b"HEAD" * 25 + comp + b"TAIL" * 10
+    path = tmp_path / "blob.bin"
+    path.write_bytes(blob)
+    for f in (open(path, "rb"), io.BytesIO(blob)):
+        with f:
+            st = engine.make_gzip_state(output_buffer=bytearray(len(plain)))
+            c = engine.make_octet_stream_context(f, start=100, offset=100, end=100 + len(comp))
+            n = engine.decompress(c, st)
+            assert n == len(plain) and engine.finished(st) and bytes(st.output_buffer[:n]) == plain
+            engine.resync_file_stream(c)
+            assert f.tell() == c.offset == 100 + len(comp) and f.read(4) == b"TAIL"
+            # chunked input through the stream: first half, then the rest (test-chunked-input.lisp:27-44)
+            st = engine.make_gzip_state(output_buffer=bytearray(len(plain)))
+            half = 100 + len(comp) // 2
+            engine.decompress(engine.make_octet_stream_context(f, start=100, offset=100, end=half), st)
+            assert engine.input_underrun(st) and not engine.finished(st)
+            n = engine.decompress(engine.make_octet_stream_context(f, start=half, offset=half, end=100 + len(comp)), st)
+            assert n == len(plain) and engine.finished(st) and bytes(st.output_buffer[:n]) == plain
+    with pytest.raises(engine.ThreeBzError):
+        engine.make_octet_stream_context(object())
