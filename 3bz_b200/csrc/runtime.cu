@@ -115,7 +115,7 @@ k_inflate_resolve(const DMember *members, tbz_result *results, uint32_t n, int f
 // =============================================================================================
 // host objects
 // =============================================================================================
-static const uint64_t kSlabPoolBytes = 6ull << 30;   // upper bound of the token slab pool per batch
+static const uint64_t kSlabPoolBytes = 24ull << 30;  // upper bound of the token slab pool per batch (B200: 180 GB)
 static const uint64_t kSplitMinBytes = 4ull << 20;   // members at least this large are split across the GPU
 static const uint64_t kSplitChunkBytes =      // compressed bytes per chunk of a split member (TBZ_SPLIT_CHUNK_KB: tuning)
     (getenv("TBZ_SPLIT_CHUNK_KB") ? std::max<uint64_t>(16, strtoull(getenv("TBZ_SPLIT_CHUNK_KB"), nullptr, 10)) : 160ull) << 10;

@@ -30,7 +30,8 @@ METRIC = "decompressed GB/s (device-timed)"
 WORKLOADS = {
     # name: (members per GPU, member size, format, first seed)
     "zlib64k": (4096, 65536, "zlib", 1000),     # BASELINE.json configs[1]
-    "gzip1m": (2048, 1 << 20, "gzip", 5000),    # configs[3] shape: 1 MiB gzip members (2 GiB per GPU)
+    "gzip1m": (8192, 1 << 20, "gzip", 5000),    # configs[3]: 1 MiB gzip members, 8 GiB of output per GPU (64 GiB over 8 GPUs;
+                                                # SURVEY.md 8d config 4); all members unique
     "gzip1g": (1, 1 << 30, "gzip", 3),          # configs[2]: one 1 GiB gzip member, speculative split decode
     "gzip256m": (1, 1 << 28, "gzip", 3),        # the same shape, smaller (quick runs)
 }
@@ -308,6 +309,13 @@ def _main(real_stdout):
         _, b_sample = oracle_pass(comps[:sample], fmt, size, cores)            # warm
         cpu_t, b_sample = oracle_pass(comps[:sample], fmt, size, cores)
         B_total = sum(b_sample) * n / sample
+        # second stand-in named by SURVEY.md 8d: system libz `inflate` on the same sample and threads
+        wb = {"deflate": -15, "zlib": 15, "gzip": 31}[fmt]
+        with ThreadPoolExecutor(cores) as ex:
+            t0 = time.perf_counter()
+            outs = list(ex.map(lambda cdata: len(zlib.decompress(cdata, wb)), comps[:sample]))
+            libz_t = time.perf_counter() - t0
+        assert all(o == size for o in outs)
         peak, how = peaks()
         achieved = (C_total + U_total + B_total) / (ms_per_step * 1e-3) / 1e9
         line = {"metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
@@ -337,7 +345,9 @@ def _main(real_stdout):
                              "note": "achieved = (C + U + B) of one launch of the hot path (decode + resolve kernels) / its "
                                      "CUDA-event time; traffic = ncu dram bytes of the dominant kernel (k_inflate_resolve)"},
                 "cpu_baseline": {"value": sample * size / cpu_t / 1e9, "unit": "GB/s", "cores": cores, "kind": "port",
-                                 "sample": "%d of %d members, one pass, %d threads" % (sample, n, cores)}}
+                                 "sample": "%d of %d members, one pass, %d threads" % (sample, n, cores),
+                                 "libz": {"value": sample * size / libz_t / 1e9, "unit": "GB/s",
+                                          "what": "system libz inflate (python zlib, GIL released) on the same sample and threads"}}}
     L.tbz_batch_destroy(batch)
     L.tbz_device_free(ctx.h, d_in); L.tbz_device_free(ctx.h, d_out)
     L.tbz_host_free(h_in); L.tbz_host_free(h_out)
