@@ -16,9 +16,11 @@
 //      expanded to bytes: val[byte] = window offset of its source, and a dense list of those bytes
 //   4. the pending bytes (about a third of the bytes on text) are resolved by pointer jumping with
 //      uniform control flow: a byte whose source is final copies it; otherwise it adopts the
-//      source's pointer (equal bytes).  Chains halve per level; a level ends at a CTA barrier
-//   5. the window is flushed to global memory and appended to the ring with 16-byte stores; Adler-32 is folded in with dp4a
-//      (order-independent form), CRC-32 per 16-byte unit with x^(8n) combines
+//      source's pointer (equal bytes), PJ_HOPS hops per level; a level ends at a CTA barrier
+//   5. the window is flushed to global memory and appended to the ring with 16-byte stores;
+//      Adler-32 is folded in with dp4a (order-independent form).  gzip's CRC-32 and its trailer
+//      compare are a kernel of their own (inflate_crc.cuh; -DTBZ_CP_CRC_SEPARATE=0 keeps them here:
+//      a table CRC per 16-byte unit with x^(8n) combines)
 // The trailer is checked as zlib.lisp:80-96 / gzip.lisp:82-106 do; any disagreement sends the member
 // to the sequential kernel, which owns the verdict rules.
 #pragma once

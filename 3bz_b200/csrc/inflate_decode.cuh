@@ -14,7 +14,7 @@
 //   1c  a walk over "who synchronised into whom" from lane 0 gives the proven lanes, their first
 //       proven token and the round's output size
 // Measured on the level-6 text of BASELINE config 2: a mis-aligned start re-synchronises after
-// 117 bits on average (p99 595), against S ~ 6000 bits per lane, so ~95 % of decode work is kept.
+// 117 bits on average (p99 595), against S ~ 3000 - 4000 bits per lane, so ~95 % of decode work is kept.
 // Phase two (inflate_copy.cuh) turns the token stream into bytes.  Stored blocks travel as literal
 // tokens.  Anything this kernel cannot prove clean (malformed codes, truncated input, too small an output buffer ...)
 // is queued for the sequential kernel, which reproduces the reference's exact verdict.
