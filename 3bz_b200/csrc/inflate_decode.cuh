@@ -196,7 +196,9 @@ __device__ __forceinline__ void bits_refill(Bits &b, const In &in) {
     b.bc += 32;
     b.nw = ldw(in, b.wn);
     b.wn++;
+#ifndef TBZ_EMU
     if ((b.wn & 31u) == 0u && b.wn + 32u < in.nwords) asm volatile("prefetch.global.L1 [%0];" ::"l"(in.w + b.wn + 32));
+#endif
   }
 }
 __device__ __forceinline__ void bits_skip(Bits &b, uint32_t n) { b.bb >>= n; b.bc -= n; }

@@ -58,7 +58,7 @@ __device__ __forceinline__ tbzfast::In chunk_input(const uint32_t *words, uint64
 constexpr uint32_t FSUB = 8, FPIECE = 4096;
 __global__ void __launch_bounds__(tbzfast::NT)
 k_split_find(const uint32_t *words, uint64_t end_bit, uint64_t body_bit, uint64_t chunk_bits, uint32_t nchunks, uint64_t *found) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  TBZ_DYN_SMEM(smem_raw);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   tbzfast::WSmem &sm = reinterpret_cast<tbzfast::WSmem *>(smem_raw)[warp];
   const uint32_t gw = blockIdx.x * tbzfast::WPC + warp;
@@ -86,7 +86,7 @@ k_split_find(const uint32_t *words, uint64_t end_bit, uint64_t body_bit, uint64_
 __global__ void __launch_bounds__(tbzfast::NT)
 k_split_decode(const uint32_t *words, uint64_t end_bit, Chunk *chunks, const uint32_t *todo, uint32_t ntodo,
                uint32_t *slabs, uint32_t nslabs, uint32_t *counters, const unsigned long long *cands, uint32_t ncands) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  TBZ_DYN_SMEM(smem_raw);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   tbzfast::WSmem &sm = reinterpret_cast<tbzfast::WSmem *>(smem_raw)[warp];
   for (;;) {
@@ -113,7 +113,7 @@ typedef tbzres::SmemT<uint16_t> SymSmem;
 
 __global__ void __launch_bounds__(tbzres::NT)
 k_split_resolve(Chunk *chunks, uint32_t nchunks, const uint32_t *slabs, uint16_t *sym, uint32_t *counters) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  TBZ_DYN_SMEM(smem_raw);
   SymSmem &sm = *reinterpret_cast<SymSmem *>(smem_raw);
   const int tid = threadIdx.x;
   for (;;) {
@@ -153,7 +153,7 @@ __device__ __forceinline__ void tail_range(const Chunk *chunks, uint32_t nchunks
 
 __global__ void __launch_bounds__(1024)
 k_split_tails(const Chunk *__restrict__ chunks, uint32_t nchunks, const uint16_t *__restrict__ sym, uint8_t *__restrict__ out) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  TBZ_DYN_SMEM(smem_raw);
   TailSmem &sm = *reinterpret_cast<TailSmem *>(smem_raw);
   const uint32_t tid = threadIdx.x;
   uint64_t start, lo, end;

@@ -19,102 +19,18 @@
 #include "inflate_seq.cuh"
 #include "inflate_decode.cuh"
 #include "inflate_resolve.cuh"
-#include "inflate_lockstep.cuh"
 #include "inflate_copy.cuh"
 #include "inflate_crc.cuh"
+#include "kernels.cuh"
 #include "inflate_split.cuh"
-
-// =============================================================================================
-// kernels
-// =============================================================================================
-#define SEQ_WARPS 4
-
-__global__ void __launch_bounds__(SEQ_WARPS * 32)
-k_inflate_seq(const DMember *members, tbz_result *results, uint32_t n, int fmt,
-              const uint32_t *todo, const uint32_t *todo_count) {
-  __shared__ tbzseq::WarpSmem sm[SEQ_WARPS];
-  __shared__ uint32_t crc_tab[256];
-  crc_table_init(crc_tab, threadIdx.x, blockDim.x);
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint32_t i = blockIdx.x * SEQ_WARPS + warp;
-  if (todo_count) n = *todo_count;
-  if (i >= n) return;
-  if (todo) i = todo[i];
-  tbzseq::inflate_member(members[i], fmt, results[i], sm[warp], crc_tab, lane);
-}
-
-// counters: [0] next member for phase one, [1] members queued for the sequential kernel,
-//           [2] slabs handed out, [3] next member for phase two, [4] next member for the gzip CRC kernel
-// Phase one, persistent CTAs of WPC independent warps: each warp pulls the next member from a
-// global counter and decodes it into token slabs; members it cannot prove clean are queued for
-// k_inflate_seq.
-__global__ void __launch_bounds__(tbzfast::NT, 8)
-k_inflate_decode(const DMember *members, uint32_t n, int fmt, tbzfast::P1Rec *recs,
-                 uint32_t *slabs, uint32_t nslabs, uint32_t *counters, uint32_t *todo) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  tbzfast::WSmem &sm = reinterpret_cast<tbzfast::WSmem *>(smem_raw)[warp];
-  for (;;) {
-    uint32_t i = 0;
-    if (lane == 0) i = atomicAdd(&counters[0], 1u);
-    i = __shfl_sync(TBZ_FULL, i, 0);
-    if (i >= n) break;
-    const bool ok = tbzfast::decode_member(members[i], fmt, recs[i], sm, slabs, nslabs, &counters[2], lane);
-    __syncwarp();
-    if (!ok && lane == 0) { recs[i].status = 0; todo[atomicAdd(&counters[1], 1u)] = i; }
-  }
-}
-
-// Phase two, persistent CTAs: one CTA per member resolves the token stream into bytes through a
-// shared-memory buffer and checks the trailer.  Three interchangeable implementations (TBZ_P2),
-// all bit-exact on the parity suite; per-launch times on BASELINE config 2 (4096 x 64 KiB), B200:
-//   2 (default) tbzcp  — one thread per token: dense word-wise copy queue for matches from final
-//                        history, byte pointer jumping for the rest (inflate_copy.cuh)            1.00 ms
-//   0           tbzres — byte-parallel rank queries + pointer jumping for every byte (inflate_resolve.cuh;
-//                        its 16-bit symbolic variant serves the split decode of one large member) 1.33 ms
-//   1           tbzls  — lock-step lanes over 16-byte chunks, pointer jumping (inflate_lockstep.cuh) 1.65 ms
-#ifndef TBZ_P2
-#define TBZ_P2 2
-#endif
-#if TBZ_P2 == 0
-namespace tbzp2 = tbzres;
-#define TBZ_P2_MINBLOCKS (TBZ_RES_TPT > 2 ? 3 : 4)
-#elif TBZ_P2 == 1
-namespace tbzp2 = tbzls;
-#define TBZ_P2_MINBLOCKS 3
-#else
-namespace tbzp2 = tbzcp;
-#ifndef TBZ_P2_MINBLOCKS
-#define TBZ_P2_MINBLOCKS 3
-#endif
-#endif
-__global__ void __launch_bounds__(tbzp2::NT, TBZ_P2_MINBLOCKS)
-k_inflate_resolve(const DMember *members, tbz_result *results, uint32_t n, int fmt,
-                  const tbzfast::P1Rec *recs, const uint32_t *slabs, uint32_t *counters, uint32_t *todo) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  tbzp2::Smem &sm = *reinterpret_cast<tbzp2::Smem *>(smem_raw);
-  const int tid = threadIdx.x;
-  if (fmt == TBZ_GZIP) {
-    crc_table_init(sm.crc_tab, tid, tbzp2::NT);
-    for (uint32_t k = tid; k < tbzp2::WB / 16 + 4; k += tbzp2::NT) sm.x16[k] = crc_x8n(16ull * k);
-  }
-  for (;;) {
-    __syncthreads();
-    if (tid == 0) sm.member = atomicAdd(&counters[3], 1u);
-    __syncthreads();
-    const uint32_t i = sm.member;
-    if (i >= n) break;
-    if (!recs[i].status) continue;
-    const bool ok = tbzp2::resolve_member(members[i], fmt, recs[i], slabs, results[i], sm, tid);
-    if (!ok && tid == 0) todo[atomicAdd(&counters[1], 1u)] = i;
-    if (ok && tid == 0 && tbzp2::CRC_SEPARATE && fmt == TBZ_GZIP) const_cast<tbzfast::P1Rec *>(recs)[i].status = tbzcrc::ST_CRC_PENDING;
-  }
-}
 
 // =============================================================================================
 // host objects
 // =============================================================================================
+#ifndef TBZ_RESOLVE
+#define TBZ_RESOLVE 2                  // phase two: 2 = one warp per member (inflate_resolve2.cuh), 1 = the round-1 CTA kernel (inflate_copy.cuh)
+#endif
+static const size_t kResolve2Smem = (size_t)tbzr2::WPC * tbzr2::H;
 static const uint64_t kSlabPoolBytes = 24ull << 30;  // upper bound of the token slab pool per batch (B200: 180 GB)
 static const uint64_t kSplitMinBytes = 4ull << 20;   // members at least this large are split across the GPU
 static const uint64_t kSplitChunkBytes =      // compressed bytes per chunk of a split member (TBZ_SPLIT_CHUNK_KB: tuning)
@@ -459,9 +375,15 @@ extern "C" int32_t tbz_batch_prepare(tbz_ctx *ctx, int32_t format, const tbz_mem
     cudaFuncSetAttribute(k_inflate_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(tbzfast::WSmem) * tbzfast::WPC));
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_inflate_decode, tbzfast::NT, sizeof(tbzfast::WSmem) * tbzfast::WPC);
     b->fast_grid = (int)std::min<uint64_t>((n + tbzfast::WPC - 1) / tbzfast::WPC, (uint64_t)ctx->sm_count * std::max(1, occ));
+#if TBZ_RESOLVE == 1
     cudaFuncSetAttribute(k_inflate_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tbzp2::Smem));
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_inflate_resolve, tbzp2::NT, sizeof(tbzp2::Smem));
     b->res_grid = (int)std::min<uint64_t>(n, (uint64_t)ctx->sm_count * std::max(1, occ));
+#else
+    cudaFuncSetAttribute(k_inflate_resolve2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kResolve2Smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_inflate_resolve2, tbzr2::NT, kResolve2Smem);
+    b->res_grid = (int)std::min<uint64_t>((n + tbzr2::WPC - 1) / tbzr2::WPC, (uint64_t)ctx->sm_count * std::max(1, occ));
+#endif
     // token slabs: one per round; a round covers at most ~31 KiB of compressed input and never
     // crosses a block boundary.  Members that find the pool empty go to the sequential kernel.
     uint64_t want = 0;
@@ -814,13 +736,20 @@ static int32_t launch_kernels(tbz_batch *b) {
     ctx->launches++;
     CK(ctx, cudaGetLastError());
     if (ctx->ktime) CK(ctx, cudaEventRecord(ctx->kev[1], ctx->stream));
+#if TBZ_RESOLVE == 1
     CK(ctx, cudaFuncSetAttribute(k_inflate_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tbzp2::Smem)));
     k_inflate_resolve<<<b->res_grid, tbzp2::NT, sizeof(tbzp2::Smem), ctx->stream>>>(
         (const DMember *)b->d_members, (tbz_result *)b->d_results, n, b->format,
         (const tbzfast::P1Rec *)b->d_recs, (const uint32_t *)b->d_slabs, (uint32_t *)b->d_counters, (uint32_t *)b->d_todo);
+#else
+    CK(ctx, cudaFuncSetAttribute(k_inflate_resolve2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kResolve2Smem));
+    k_inflate_resolve2<<<b->res_grid, tbzr2::NT, kResolve2Smem, ctx->stream>>>(
+        (const DMember *)b->d_members, (tbz_result *)b->d_results, n, b->format,
+        (const tbzfast::P1Rec *)b->d_recs, (const uint32_t *)b->d_slabs, (uint32_t *)b->d_counters, (uint32_t *)b->d_todo);
+#endif
     ctx->launches++;
     CK(ctx, cudaGetLastError());
-    if (tbzp2::CRC_SEPARATE && b->format == TBZ_GZIP) {   // gzip: CRC-32 of the finished members + trailer compare
+    if (b->format == TBZ_GZIP) {   // gzip: CRC-32 of the finished members + trailer compare
       const int crc_grid = (int)std::min<uint64_t>(n, (uint64_t)ctx->sm_count * 6);
       tbzcrc::k_member_crc<<<crc_grid, tbzcrc::NT, 0, ctx->stream>>>(
           (const DMember *)b->d_members, (tbz_result *)b->d_results, n, (const tbzfast::P1Rec *)b->d_recs,

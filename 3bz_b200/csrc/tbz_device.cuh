@@ -5,6 +5,9 @@
 #include "threebz_cuda.h"
 
 #define TBZ_FULL 0xffffffffu
+#ifndef TBZ_EMU   // (tests/emu defines its own: the dynamic shared memory of the block)
+#define TBZ_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#endif
 
 // RFC 1951 tables in the reference's order: constants.lisp:36-61 (lengths at +32 there; split here)
 __device__ __constant__ uint16_t c_len_base[32] = {3,4,5,6,7,8,9,10,11,13,15,17,19,23,27,31,35,43,51,59,67,83,99,

@@ -1,0 +1,44 @@
+// emu_driver.cpp — runs the batched kernel sequence of runtime.cu::launch_kernels under the SIMT
+// emulator (tests/emu/cuda_emu.h).  TEST INFRASTRUCTURE ONLY: built and loaded by tests/test_emu.py.
+#include <cuda_runtime.h>
+#include <vector>
+#include "kernels.cuh"
+
+extern "C" int emu_inflate_batch(int fmt, const tbz_member *m, uint64_t n, tbz_result *r, uint32_t flags, int os_threads, int variant) {
+  // variant bit 0: the round-1 phase two (inflate_copy.cuh) instead of inflate_resolve2.cuh
+  emu_os_threads = os_threads > 0 ? os_threads : 1;
+  if (!n) return 0;
+  std::vector<DMember> dm(n);
+  for (uint64_t i = 0; i < n; i++) dm[i] = DMember{m[i].in, m[i].in_len, m[i].out, m[i].out_cap};
+  std::vector<uint32_t> counters(64, 0), todo(n, 0);
+  const uint32_t nn = (uint32_t)n;
+  if (flags & TBZ_FLAG_NO_FASTPATH) {
+    emu_launch(k_inflate_seq, dim3((nn + SEQ_WARPS - 1) / SEQ_WARPS), dim3(SEQ_WARPS * 32), 0,
+               (const DMember *)dm.data(), r, nn, fmt, (const uint32_t *)nullptr, (const uint32_t *)nullptr);
+    return 0;
+  }
+  std::vector<tbzfast::P1Rec> recs(n);
+  const uint64_t round_bytes = (uint64_t)tbzfast::NL * tbzfast::S_MAX / 8;
+  uint64_t want = 0;
+  for (uint64_t i = 0; i < n; i++) want += 2 * (m[i].in_len / round_bytes) + 4;
+  const uint32_t nslabs = (uint32_t)want;
+  std::vector<uint32_t> slabs((size_t)nslabs * tbzfast::SLAB_WORDS);
+  const unsigned dec_grid = std::min<unsigned>((nn + tbzfast::WPC - 1) / tbzfast::WPC, 16);
+  emu_launch(k_inflate_decode, dim3(dec_grid), dim3(tbzfast::NT), sizeof(tbzfast::WSmem) * tbzfast::WPC,
+             (const DMember *)dm.data(), nn, fmt, recs.data(), slabs.data(), nslabs, counters.data(), todo.data());
+  if (variant & 1)
+    emu_launch(k_inflate_resolve, dim3(std::min<unsigned>(nn, 16)), dim3(tbzp2::NT), sizeof(tbzp2::Smem),
+               (const DMember *)dm.data(), r, nn, fmt, (const tbzfast::P1Rec *)recs.data(), (const uint32_t *)slabs.data(),
+               counters.data(), todo.data());
+  else
+    emu_launch(k_inflate_resolve2, dim3(std::min<unsigned>((nn + tbzr2::WPC - 1) / tbzr2::WPC, 16)), dim3(tbzr2::NT), (size_t)tbzr2::WPC * tbzr2::H,
+               (const DMember *)dm.data(), r, nn, fmt, (const tbzfast::P1Rec *)recs.data(), (const uint32_t *)slabs.data(),
+               counters.data(), todo.data());
+  if (fmt == TBZ_GZIP)
+    emu_launch(tbzcrc::k_member_crc, dim3(std::min<unsigned>(nn, 16)), dim3(tbzcrc::NT), 0,
+               (const DMember *)dm.data(), r, nn, (const tbzfast::P1Rec *)recs.data(), counters.data(), todo.data());
+  if (!(variant & 2))          // (variant bit 1: leave the members the fast kernels gave up on as they are, for debugging)
+    emu_launch(k_inflate_seq, dim3((nn + SEQ_WARPS - 1) / SEQ_WARPS), dim3(SEQ_WARPS * 32), 0,
+               (const DMember *)dm.data(), r, nn, fmt, (const uint32_t *)todo.data(), (const uint32_t *)counters.data() + 1);
+  return (int)counters[1];     // members that took the sequential kernel
+}

@@ -1,0 +1,65 @@
+"""Runs the batched kernels under the CPU SIMT emulator (tests/emu): the same device source nvcc compiles,
+executed on the host so that `-m "not gpu"` can check kernel logic against the oracle.  Test infrastructure
+only — the product has no CPU path."""
+import ctypes as C
+import os
+import subprocess
+
+from threebz_b200 import _ffi
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+EMU = os.path.join(HERE, "emu")
+ROOT = os.path.dirname(HERE)
+SO = os.path.join(EMU, "_emu.so")
+_lib = None
+
+
+def build(force=False):
+    srcs = [os.path.join(EMU, f) for f in ("emu_driver.cpp", "cuda_emu.cpp")]
+    csrc = os.path.join(ROOT, "3bz_b200", "csrc")
+    deps = srcs + [os.path.join(EMU, "cuda_emu.h"), os.path.join(ROOT, "include", "threebz_cuda.h")] + \
+        [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith(".cuh")]
+    if force or not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
+        subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-fsanitize=alignment",
+                               "-fno-sanitize-recover=alignment", "-I", os.path.join(EMU, "shim"),
+                               "-I", os.path.join(ROOT, "include"), "-I", csrc, "-o", SO] + srcs + ["-lpthread"])
+    return SO
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+        _lib.emu_inflate_batch.argtypes = [C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_int, C.c_int]
+        _lib.emu_inflate_batch.restype = C.c_int
+    return _lib
+
+
+def run_batch(fmt, inputs, caps, flags=0, threads=None, in_mis=0, out_mis=0, variant=0):
+    """Like tests.gpuutil.run_batch, on the emulator.  Returns (results, members that took the sequential kernel)."""
+    L = lib()
+    n = len(inputs)
+    caps = [caps] * n if isinstance(caps, int) else list(caps)
+    # every member 16-byte aligned (+ the requested misalignment), like the product's device arenas
+    ioff, ooff, io, oo = [], [], 0, 0
+    for d, c in zip(inputs, caps):
+        ioff.append(io + in_mis); io += (len(d) + in_mis + 15 + 16) & ~15
+        ooff.append(oo + out_mis); oo += (c + out_mis + 15 + 16) & ~15
+    inbuf = (C.c_uint8 * (io + 64))()
+    outbuf = (C.c_uint8 * (oo + 64))()
+    ibase = (C.addressof(inbuf) + 15) & ~15
+    obase = (C.addressof(outbuf) + 15) & ~15
+    marr = (_ffi.Member * max(1, n))()
+    for i, (d, c) in enumerate(zip(inputs, caps)):
+        C.memmove(ibase + ioff[i], d, len(d))
+        marr[i] = _ffi.Member(ibase + ioff[i], len(d), obase + ooff[i], c)
+    rarr = (_ffi.Result * max(1, n))()
+    nseq = L.emu_inflate_batch(_ffi.fmt_code(fmt), marr, n, rarr, flags, threads or (os.cpu_count() or 1), variant)
+    res = []
+    for i in range(n):
+        r = rarr[i]
+        res.append({"verdict": r.verdict, "out_len": r.out_len, "checksum": r.checksum, "where": r.where,
+                    "in_used": r.in_used, "path": r.path,
+                    "out": C.string_at(obase + ooff[i], r.out_len),
+                    "raw": C.string_at(obase + ooff[i], caps[i])})     # the whole buffer (debugging a member that fell back)
+    return res, nseq

@@ -134,16 +134,15 @@ def test_gzip_header_metadata(engine):
         assert e.value.verdict == verdict, (e.value.verdict, verdict)
 
 
-@pytest.mark.parametrize("p2", [0, 1])
-def test_phase_two_alternatives_still_compile(p2, tmp_path):
-    """The measured alternatives of phase two (byte-parallel rank queries, lock-step lanes)
-    stay buildable behind -DTBZ_P2; nvcc cross-compiles for sm_100a without a GPU."""
+def test_round1_phase_two_still_compiles(tmp_path):
+    """The round-1 phase two (one CTA per member, inflate_copy.cuh) stays selectable with -DTBZ_RESOLVE=1 as the
+    measured baseline of DESIGN.md 4.2; nvcc cross-compiles for sm_100a without a GPU."""
     import importlib
     import shutil
     b = importlib.import_module("3bz_b200.build")
     if not shutil.which(b.NVCC) and not os.path.exists(b.NVCC):
         pytest.skip("no nvcc")
-    out = str(tmp_path / ("p2_%d.so" % p2))
-    b.build(force=True, extra=["-DTBZ_P2=%d" % p2], out=out)
+    out = str(tmp_path / "resolve1.so")
+    b.build(force=True, extra=["-DTBZ_RESOLVE=1"], out=out)
     L = C.CDLL(out)
     assert L.tbz_abi_version() == 1

@@ -1,0 +1,115 @@
+"""Kernel logic on the CPU: the batched kernels' device source (3bz_b200/csrc/*.cuh, the same text nvcc compiles
+for sm_100a) runs under tests/emu — a SIMT emulator with fibers for threads, checked warp collectives and
+-fsanitize=alignment — and is compared with the oracle.  The -m gpu suite repeats all of this on the B200
+through the C ABI; this suite exists so that a kernel bug is found before GPU time is spent.
+Test infrastructure only: the product has no CPU path."""
+import random
+import zlib
+
+import pytest
+
+import datagen
+from oracle import o3bz
+from tests import cases, emuutil
+from tests.gpuutil import compare
+
+VARIANTS = [0, 1]       # 0: round-2 phase two (inflate_resolve2.cuh), 1: round-1 phase two (inflate_copy.cuh)
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    emuutil.build()
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_emu_config2_members(variant):
+    ms = datagen.members(6, 65536, 1000, "zlib")
+    got, nseq = emuutil.run_batch("zlib", [c for _, c in ms], 65536, variant=variant)
+    assert nseq == 0
+    for (p, c), g in zip(ms, got):
+        compare(g, o3bz.decompress_vector(c, "zlib", out_cap=65536), "cfg2")
+        assert g["out"] == p and g["path"] == 1 and g["checksum"] == zlib.adler32(p)
+
+
+def test_emu_config4_member():
+    p, c = datagen.member(1 << 20, 5000, "gzip")
+    got, nseq = emuutil.run_batch("gzip", [c], [len(p)])
+    assert nseq == 0 and got[0]["out"] == p and got[0]["checksum"] == zlib.crc32(p) and got[0]["path"] == 1
+
+
+@pytest.mark.parametrize("fmt", cases.FMTS)
+def test_emu_edge_mix(fmt):
+    items = [(n, c, p) for n, f, c, p in cases.edge_streams() if f == fmt]
+    got, nseq = emuutil.run_batch(fmt, [c for _, c, _ in items], [len(p) for _, _, p in items])
+    for (name, comp, plain), g in zip(items, got):
+        compare(g, o3bz.decompress_vector(comp, fmt, out_cap=len(plain)), (name, fmt))
+        assert g["verdict"] == 0 and g["out"] == plain and g["path"] == 1, (name, fmt, g["path"])
+
+
+def test_emu_nayuki_vectors():
+    vs = cases.nayuki()
+    ins = [bytes.fromhex(v["input_hex"]) for v in vs]
+    got, _ = emuutil.run_batch("deflate", ins, 1024)
+    for v, d, g in zip(vs, ins, got):
+        compare(g, o3bz.decompress_vector(d, "deflate", out_cap=1024), v["line"])
+
+
+def test_emu_fixture_and_truncations():
+    raw, meta = cases.test_deflated()
+    payload = raw[8:]
+    ks = sorted(set(list(range(0, 40)) + list(range(40, len(payload), 97)) + list(range(len(payload) - 12, len(payload) + 1))))
+    ins = [payload[:k] for k in ks]
+    got, _ = emuutil.run_batch("deflate", ins, 22728)
+    for k, d, g in zip(ks, ins, got):
+        compare(g, o3bz.decompress_vector(d, "deflate", out_cap=22728), k)
+    assert got[-1]["out_len"] == 22728 and got[-1]["path"] == 1
+
+
+def test_emu_capacity_sweep():
+    """an output buffer that is too small: the fast kernels give the member up, the sequential kernel reports
+    output-overflow with exactly the bytes that fit (deflate.lisp:239-241, :254-269, :693-697)"""
+    for name, fmt, comp, plain in cases.edge_streams():
+        if name not in ("text64k", "zeros", "period3") or fmt != "zlib":
+            continue
+        n = len(plain)
+        caps = sorted(set([0, 1, 3, 257, 258, 259, 4096, n // 2, n - 259, n - 1, n, n + 1, n + 100]))
+        got, _ = emuutil.run_batch(fmt, [comp] * len(caps), caps)
+        for cap, g in zip(caps, got):
+            compare(g, o3bz.decompress_vector(comp, fmt, out_cap=cap), (name, cap))
+
+
+def test_emu_any_alignment():
+    """members and outputs at every 16-byte residue (caller-owned device memory need not be aligned)"""
+    p, c = datagen.member(40000, 321, "zlib")
+    z = datagen.compress(bytes(5000) + p[:3000] + b"ab" * 3000, "zlib")
+    zp = bytes(5000) + p[:3000] + b"ab" * 3000
+    for mis in (1, 2, 3, 4, 7, 8, 13, 15):
+        got, nseq = emuutil.run_batch("zlib", [c, z], [len(p), len(zp)], in_mis=mis, out_mis=(mis * 5) % 16)
+        assert nseq == 0
+        assert got[0]["out"] == p and got[1]["out"] == zp and got[0]["path"] == 1 and got[1]["path"] == 1
+
+
+def test_emu_corruption_fuzz():
+    """mutated streams: whatever the fast kernels make of them, the verdict and bytes are the oracle's"""
+    rnd = random.Random(5)
+    p, c = datagen.member(20000, 99, "zlib")
+    ins = []
+    for _ in range(60):
+        b = bytearray(c)
+        for _ in range(rnd.randint(1, 3)):
+            b[rnd.randrange(len(b))] ^= 1 << rnd.randrange(8)
+        ins.append(bytes(b))
+    got, _ = emuutil.run_batch("zlib", ins, 20000)
+    for d, g in zip(ins, got):
+        compare(g, o3bz.decompress_vector(d, "zlib", out_cap=20000), "fuzz")
+
+
+def test_emu_long_distances_and_lengths():
+    """distances up to 32 KiB (older than the 16 KiB ring: read back from the output) and 258-byte matches"""
+    rnd = random.Random(7)
+    block = bytes(rnd.randrange(256) for _ in range(33000))
+    plain = block + block[:32768][::-1][:100] + block[100:30000] + block[:258] * 3 + block[5:32700]
+    for level in (6, 9):
+        comp = datagen.compress(plain, "zlib", level=level)
+        got, nseq = emuutil.run_batch("zlib", [comp], [len(plain)])
+        assert nseq == 0 and got[0]["out"] == plain and got[0]["path"] == 1
