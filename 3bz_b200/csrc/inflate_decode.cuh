@@ -584,10 +584,9 @@ __device__ inline bool decode_blocks(const In &in, uint32_t pos, uint32_t stop_b
   return true;
 }
 
-// One member, one warp: wrapper header, then every block.
-__device__ inline bool decode_member(const DMember &mem, int fmt, P1Rec &rec, WSmem &sm,
-                                     uint32_t *__restrict__ slabs, uint32_t nslabs, uint32_t *slab_counter, int lane) {
-  In in;
+// Where a member's deflate body starts: the input window (4-byte aligned base at or below the first byte) and the
+// wrapper header (zlib.lisp:108-126, gzip.lisp:113-240).  false: the sequential kernel owns the verdict.
+__device__ inline bool member_start(const DMember &mem, int fmt, In &in, uint32_t &pos) {
   {
     uintptr_t a = (uintptr_t)mem.in;
     uint32_t mis = (uint32_t)(a & 3);
@@ -597,8 +596,7 @@ __device__ inline bool decode_member(const DMember &mem, int fmt, P1Rec &rec, WS
     in.end = (mis + (uint32_t)mem.in_len) * 8;
     in.nwords = (in.end + 31) >> 5;
   }
-  uint32_t pos = in.pos0;
-  // ---- wrapper header (zlib.lisp:108-126, gzip.lisp:113-177; optional gzip fields -> sequential kernel)
+  pos = in.pos0;
   if (fmt == TBZ_ZLIB) {
     if (in.end - pos < 16) return false;
     uint32_t cmf = byte_at(in, pos >> 3), flg = byte_at(in, (pos >> 3) + 1);
@@ -627,6 +625,15 @@ __device__ inline bool decode_member(const DMember &mem, int fmt, P1Rec &rec, WS
     if (q >= endb) return false;                        // the header does not end inside the input
     pos = q * 8;
   }
+  return true;
+}
+
+// One member, one warp: wrapper header, then every block.
+__device__ inline bool decode_member(const DMember &mem, int fmt, P1Rec &rec, WSmem &sm,
+                                     uint32_t *__restrict__ slabs, uint32_t nslabs, uint32_t *slab_counter, int lane) {
+  In in;
+  uint32_t pos;
+  if (!member_start(mem, fmt, in, pos)) return false;
   return decode_blocks(in, pos, 0xffffffffu, mem.out_cap, rec, sm, slabs, nslabs, slab_counter, lane);
 }
 

@@ -6,16 +6,19 @@
 // their source inside the window, and every window rebuilt offsets, queues and pointers.  On deflate text
 // distances are long (level-6 text of BASELINE config 2: 4 % of the matches reach back less than 128 bytes,
 // the median distance is 3.8 KB), so a SMALL unit of work has almost no internal dependency.  Here the unit
-// is a step of 64 tokens (two per lane, about 270 output bytes):
-//   1. the lane's two tokens arrive with one 8-byte load (prefetched a step ahead); a warp scan of their
+// is a step of 32 tokens — one per lane, each `up to four literals + one match` (inflate_decode2.cuh), about
+// 280 output bytes:
+//   1. the lane's token arrives with one 8-byte load (prefetched a step ahead); a warp scan of the token
 //      lengths gives every token its output offset
-//   2. literals are stored; a match whose source lies entirely below the step is READY and is copied by
-//      its own lane with one straight-line sequence — aligned 4-byte loads of the source, one funnel shift
-//      per destination word, 32-bit stores between a <= 3-byte head and tail — the same instructions for
-//      every lane whatever the length (<= NFAST bytes) or alignment
+//   2. literals are stored; a match whose source lies entirely below the step is READY and is copied by its
+//      own lane with one straight-line, branch-free sequence — aligned 4-byte loads of the source at
+//      immediate offsets, one funnel shift per destination word, 32-bit stores between a <= 3-byte head and
+//      tail — the same instructions for every lane whatever the length (<= NFAST bytes) or alignment.
+//      Every lane has exactly one match, so no copy slot idles on a literal
 //   3. the few matches that reach into the step itself (or overlap their own output: distance < length, the
-//      RLE case; or are longer than NFAST) are then copied in stream order by the whole warp, 32 bytes per
-//      pass, the usable distance doubling per pass for overlapping copies (the period trick)
+//      RLE case; or are longer than NFAST; or touch the ring's wrap-around) are then copied in stream order
+//      by the whole warp, 32 bytes per pass, the usable distance doubling per pass for overlapping copies
+//      (the period trick)
 //   4. every 512 finished bytes leave with one 16-byte store per lane; Adler-32 is folded in with dp4a on the
 //      way out (order-independent form); gzip's CRC-32 is k_member_crc's job (inflate_crc.cuh)
 // The last H bytes of output live in a shared-memory ring per warp (H = 16 KiB: 14 members per SM); a source
@@ -24,7 +27,7 @@
 // trailer that disagrees — sends the member to the sequential kernel, which owns the verdict rules.
 #pragma once
 #include "tbz_device.cuh"
-#include "inflate_decode.cuh"
+#include "inflate_decode2.cuh"
 
 namespace tbzr2 {
 
@@ -34,14 +37,13 @@ namespace tbzr2 {
 #define TBZ_R2_WHY(...) do { } while (0)
 #endif
 
+using tbzd2::T2_MATCH;
+using tbzd2::TOKCAP2;
 using tbzfast::NO_SLAB;
 using tbzfast::P1Rec;
 using tbzfast::SLAB_HDR_WORDS;
 using tbzfast::SLAB_WORDS;
 using tbzfast::SlabHdr;
-using tbzfast::TOKCAP;
-using tbzfast::TOK_LIT2;
-using tbzfast::TOK_MATCH;
 
 #ifndef TBZ_R2_RING
 #define TBZ_R2_RING 16384
@@ -50,21 +52,49 @@ using tbzfast::TOK_MATCH;
 #define TBZ_R2_WPC 7
 #endif
 #ifndef TBZ_R2_NFAST
-#define TBZ_R2_NFAST 16
+#define TBZ_R2_NFAST 24
 #endif
 constexpr uint32_t H = TBZ_R2_RING, M = H - 1u;   // ring bytes per warp: absolute output offset p lives at ring[p & M]
 constexpr int WPC = TBZ_R2_WPC;                    // warps (members in flight) per CTA
 constexpr int NT = WPC * 32;
 constexpr uint32_t NFAST = TBZ_R2_NFAST;           // longest match the per-lane straight-line copy takes
 constexpr uint32_t NW = NFAST / 4;                 // full destination words of such a match, at most
-constexpr uint32_t SBMAX = 1024;                   // a step that produces more than this goes token by token
+constexpr uint32_t SBMAX = 32 * (NFAST + 4);       // a step that produces more than this goes token by token
 constexpr uint32_t FLUSH = 512;                    // bytes per flush: one 16-byte unit per lane
+constexpr uint32_t EDGE = 4 * (NW + 3);            // a token this close to the ring's end takes the ordered path (the fast copy never wraps)
+constexpr uint32_t PAD = 16, TAIL = 64;            // shared memory before the first / after the last ring that a fast copy may read (never uses)
 static_assert((H & M) == 0 && H >= 4096 && H >= FLUSH + 2 * SBMAX + 1024, "ring margins");
-static_assert(NFAST % 4 == 0 && NFAST >= 8 && NFAST <= 32, "straight-line copy length");
-static_assert(TOKCAP % 2 == 0 && SLAB_HDR_WORDS % 2 == 0, "token pairs are loaded with 8-byte loads");
+static_assert(NFAST % 4 == 0 && NFAST >= 8 && NFAST <= 32 && EDGE <= TAIL, "straight-line copy length");
+constexpr size_t SMEM_BYTES = PAD + (size_t)WPC * H + TAIL;
+
+// The ring is addressed by 32-bit shared-space addresses through ld.shared / st.shared, not through a generic pointer:
+// every access of the straight-line copy is then `register + immediate` with no address arithmetic (with a uint8_t*
+// the compiler recomputed a window base + offset for each predicated store: +30 % instructions in the copy).
+#ifdef TBZ_EMU
+__device__ __forceinline__ uint32_t smem_base() { return 0u; }                      // (the emulator: offsets into the block's buffer)
+template <class T> __device__ __forceinline__ T lds(uint32_t a) { return *reinterpret_cast<const T *>(::emu::dyn_smem() + a); }
+template <class T> __device__ __forceinline__ void sts(uint32_t a, T v) { *reinterpret_cast<T *>(::emu::dyn_smem() + a) = v; }
+__device__ __forceinline__ void sts_low8(uint32_t a, uint32_t v) { sts<uint8_t>(a, (uint8_t)v); }
+__device__ __forceinline__ void sts_low16(uint32_t a, uint32_t v) { sts<uint16_t>(a, (uint16_t)v); }
+#else
+extern __shared__ __align__(16) unsigned char tbz_r2_smem[];
+__device__ __forceinline__ uint32_t smem_base() { return (uint32_t)__cvta_generic_to_shared(tbz_r2_smem); }
+template <class T> __device__ __forceinline__ T lds(uint32_t a);
+template <> __device__ __forceinline__ uint8_t lds<uint8_t>(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return (uint8_t)v; }
+template <> __device__ __forceinline__ uint32_t lds<uint32_t>(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+template <> __device__ __forceinline__ uint4 lds<uint4>(uint32_t a) {
+  uint4 v; asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory"); return v;
+}
+template <class T> __device__ __forceinline__ void sts(uint32_t a, T v);
+template <> __device__ __forceinline__ void sts<uint8_t>(uint32_t a, uint8_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"((uint32_t)v) : "memory"); }
+__device__ __forceinline__ void sts_low8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }     // the low byte of v
+__device__ __forceinline__ void sts_low16(uint32_t a, uint32_t v) { asm volatile("st.shared.b16 [%0], %1;" ::"r"(a), "h"((uint16_t)v) : "memory"); }
+template <> __device__ __forceinline__ void sts<uint16_t>(uint32_t a, uint16_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"(v) : "memory"); }
+template <> __device__ __forceinline__ void sts<uint32_t>(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+#endif
 
 struct WState {
-  uint8_t *ring;                          // this warp's ring
+  uint32_t ring;                          // this warp's ring: shared-space address of its first byte
   uint8_t *out;                           // the member's output
   unsigned long long cap;                 // bytes the output may take (capped below 2^32)
   uint32_t pos;                           // output bytes produced so far
@@ -72,88 +102,95 @@ struct WState {
   unsigned long long acc_a, acc_w;        // per lane: sum d and sum i*d over the bytes it flushed (Adler-32)
 };
 
-__device__ __forceinline__ uint32_t tok_len(uint32_t t) { return (t & TOK_MATCH) ? (t & 255u) + 3u : 1u + ((t >> 30) & 1u); }
-__device__ __forceinline__ uint32_t ring_word(const uint8_t *ring, uint32_t p) { return *reinterpret_cast<const uint32_t *>(ring + (p & M & ~3u)); }
-
-// One READY match, copied by its own lane: n <= NFAST bytes from absolute offset src to dst, the source entirely
-// below the current step (so it never overlaps the destination).  `far`: the source is older than the ring and
-// is read from `out`.  Straight-line, no data-dependent branch: head bytes up to the first aligned destination
-// word, NW word slots, tail bytes; the source words are aligned loads, one funnel shift per word aligns them.
+// One READY match, copied by its own lane: 3 <= n <= NFAST bytes from absolute offset src to dst; the source lies
+// entirely below the current step, so it never overlaps the destination, and neither range comes within EDGE bytes of
+// the end of the ring.  far: the source is older than the ring and is read from the member's output instead.
+// Straight-line: no data-dependent branch, every shared-memory access at an immediate offset.  Lanes without a ready
+// match run along (act = false): they load unused words from wherever their garbage points inside the warp's ring.
 template <bool AL>
-__device__ __forceinline__ void copy_ready(const WState &w, bool act, uint32_t dst, uint32_t src, uint32_t n, bool far) {
-  uint8_t *const ring = w.ring;
-  const uint32_t hb0 = (0u - dst) & 3u;
-  const uint32_t hb = hb0 < n ? hb0 : n;            // head bytes
-  const uint32_t nw = (n - hb) >> 2;                 // full words
-  const uint32_t tb = (n - hb) & 3u;                 // tail bytes
+__device__ __forceinline__ void copy_ready(uint32_t ring, const uint8_t *out, bool act, bool far, uint32_t dst, uint32_t src, uint32_t n) {
+  const uint32_t hb = (0u - dst) & 3u;               // head bytes up to the first aligned destination word (n >= 3 >= hb)
   const uint32_t as = src & 3u;
-  const uint32_t q = as + hb;                        // offset of the first full word's source inside the word grid of src
+  const uint32_t q = as + hb;                        // offset of the first full word's source on the word grid of src
   const uint32_t sh = (q & 3u) * 8u;
   const uint32_t s0 = (src & ~3u) + (q & 4u);        // aligned source offset of word slot 0
-  const uint32_t lim = src + n;                      // source words at or beyond this offset hold nothing that is needed
-  // source words S[0..NW+1): slot j needs S[j], S[j+1]
-  uint32_t S[NW + 2];
-#pragma unroll
-  for (uint32_t i = 0; i < NW + 2; i++) {
-    const uint32_t a = s0 + 4u * i;
-    uint32_t v = 0;
-    if (act && a < lim) {
-      if (!far) v = ring_word(ring, a);
-      else if (AL) v = __ldcg(reinterpret_cast<const uint32_t *>(w.out + a));
-      else {
-#pragma unroll
-        for (int b = 0; b < 4; b++) v |= (uint32_t)__ldcg(w.out + a + b) << (8 * b);   // (reads <= 3 bytes beyond lim - 1: inside the output produced so far or its 16-byte slack)
-      }
-    }
-    S[i] = v;
-  }
-  // head: the first hb bytes of the stream = the bytes at src
+  const uint32_t rest = act ? n - hb : 0u;           // bytes in full words and the tail (none for a lane that only runs along)
+  // source words: E = the word before slot 0 (the head may start there); S[j], S[j+1] feed word slot j
+  uint32_t E, S[NW + 2];
   {
-    uint32_t e = 0;                                   // the word before slot 0 (only when the head starts in it: q >= 4)
-    if (act && (q & 4u)) {
-      const uint32_t a = src & ~3u;
-      if (!far) e = ring_word(ring, a);
-      else if (AL) e = __ldcg(reinterpret_cast<const uint32_t *>(w.out + a));
-      else {
+    const uint32_t rp = ring + (s0 & M);
+    E = lds<uint32_t>(rp - 4u);
 #pragma unroll
-        for (int b = 0; b < 4; b++) e |= (uint32_t)__ldcg(w.out + a + b) << (8 * b);
+    for (uint32_t i = 0; i < NW + 2; i++) S[i] = lds<uint32_t>(rp + 4u * i);
+  }
+  if (__builtin_expect(__any_sync(TBZ_FULL, act && far), 0)) {        // a source older than the ring: the same words from `out`
+    if (act && far) {
+      const uint32_t need = src + n - s0;                              // words at or beyond this byte offset hold nothing needed
+      if (AL) {
+        const uint32_t *gp = reinterpret_cast<const uint32_t *>(out + s0);
+        if (q & 4u) E = __ldcg(gp - 1);
+#pragma unroll
+        for (uint32_t i = 0; i < NW + 2; i++) if (4u * i < need) S[i] = __ldcg(gp + i);
+      } else {                                                         // `out` is not aligned: byte by byte
+        E = 0;
+        if (q & 4u)
+          for (int b = 0; b < 4; b++) E |= (uint32_t)__ldcg(out + s0 - 4 + b) << (8 * b);
+#pragma unroll
+        for (uint32_t i = 0; i < NW + 2; i++) {
+          uint32_t v = 0;
+          for (uint32_t b = 0; b < 4; b++) if (4u * i + b < need) v |= (uint32_t)__ldcg(out + s0 + 4u * i + b) << (8 * b);
+          S[i] = v;
+        }
       }
     }
-    const uint32_t lo = (q & 4u) ? e : S[0], hi = (q & 4u) ? S[0] : S[1];
-    const uint32_t hd = __funnelshift_r(lo, hi, as * 8u);            // stream bytes 0..3
-    if (act && (hb & 1u)) ring[dst & M] = (uint8_t)hd;
-    if (act && (hb & 2u)) *reinterpret_cast<uint16_t *>(ring + ((dst + (hb & 1u)) & M)) = (uint16_t)(hd >> (8u * (hb & 1u)));
+  }
+  // head: stream bytes 0..hb-1 = the bytes at src
+  {
+    const uint32_t lo = (q & 4u) ? E : S[0], hi = (q & 4u) ? S[0] : S[1];
+    const uint32_t hd = __funnelshift_r(lo, hi, as * 8u);
+    const uint32_t hp = ring + (dst & M);
+    if (act && (hb & 1u)) sts_low8(hp, hd);
+    if (act && (hb & 2u)) sts_low16(hp + (hb & 1u), hd >> (8u * (hb & 1u)));
   }
   // full words, and the word the tail lies in
-  const uint32_t d0 = dst + hb;                                      // aligned
+  const uint32_t wp = ring + ((dst + hb) & M);
   uint32_t tw = 0;
 #pragma unroll
   for (uint32_t j = 0; j <= NW; j++) {
     const uint32_t v = __funnelshift_r(S[j], S[j + 1], sh);
-    if (j < NW && act && j < nw) *reinterpret_cast<uint32_t *>(ring + ((d0 + 4u * j) & M)) = v;
-    if (j == nw) tw = v;
+    if (j < NW && rest >= 4u * (j + 1u)) sts<uint32_t>(wp + 4u * j, v);
+    if (j == 0) tw = v;
+    else if (rest >= 4u * j) tw = v;                                   // tw = word slot (rest / 4)
   }
   {
-    const uint32_t ta = d0 + 4u * nw;
-    if (act && (tb & 2u)) *reinterpret_cast<uint16_t *>(ring + (ta & M)) = (uint16_t)tw;
-    if (act && (tb & 1u)) ring[(ta + (tb & 2u)) & M] = (uint8_t)(tw >> (8u * (tb & 2u)));
+    const uint32_t tp = wp + (rest & ~3u);
+    if (rest & 2u) sts_low16(tp, tw);
+    if (rest & 1u) sts_low8(tp + (rest & 2u), tw >> (8u * (rest & 2u)));
   }
 }
 
-// One match copied by the whole warp (warp-uniform arguments): n bytes at absolute offset p, distance d.  A pass
-// moves up to `back` bytes from `back` bytes earlier; for an overlapping copy (d < n) everything written so far
-// repeats with period d, so the usable distance doubles after every pass (deflate.lisp:286-326 special-cases the
-// short periods for the same reason).  A source byte older than the ring is read from `out`.
-// ring_lo: offsets below it are not in the ring any more (they are in `out`).
+// n bytes at absolute offset p copied by the whole warp from distance d (warp-uniform arguments).  A pass moves up
+// to `back` bytes from `back` bytes earlier; for an overlapping copy (d < n) everything written so far repeats with
+// period d, so the usable distance doubles after every pass (deflate.lisp:286-326 special-cases the short periods for
+// the same reason).  ring_lo: offsets below it are not in the ring any more (they are in `out`).
 __device__ __forceinline__ void copy_warp(const WState &w, uint32_t p, uint32_t n, uint32_t d, uint32_t ring_lo, int lane) {
-  uint8_t *const ring = w.ring;
+  const uint32_t ring = w.ring;
+  if (n <= 32u && d >= n) {                                            // the common case: one pass
+    if ((uint32_t)lane < n) {
+      const uint32_t a = p + lane - d;
+      const uint32_t v = a < ring_lo ? (uint32_t)__ldcg(w.out + a) : (uint32_t)lds<uint8_t>(ring + (a & M));
+      sts<uint8_t>(ring + ((p + lane) & M), (uint8_t)v);
+    }
+    __syncwarp();
+    return;
+  }
   uint32_t done = 0, back = d;
   while (done < n) {
     const uint32_t c = back < n - done ? back : n - done;
     for (uint32_t k = lane; k < c; k += 32u) {
       const uint32_t a = p + done + k - back;
-      const uint32_t v = a < ring_lo ? (uint32_t)__ldcg(w.out + a) : (uint32_t)ring[a & M];
-      ring[(p + done + k) & M] = (uint8_t)v;
+      const uint32_t v = a < ring_lo ? (uint32_t)__ldcg(w.out + a) : (uint32_t)lds<uint8_t>(ring + (a & M));
+      sts<uint8_t>(ring + ((p + done + k) & M), (uint8_t)v);
     }
     __syncwarp();
     done += c;
@@ -161,11 +198,19 @@ __device__ __forceinline__ void copy_warp(const WState &w, uint32_t p, uint32_t 
   }
 }
 
+// One whole token by the whole warp, in stream order: its literals, then its match.
+__device__ __forceinline__ void token_warp(const WState &w, uint32_t p, uint32_t lo, uint32_t hi, uint32_t ring_lo, int lane) {
+  const uint32_t nl = tbzd2::t2_nlit(hi);
+  if ((uint32_t)lane < nl) sts<uint8_t>(w.ring + ((p + lane) & M), (uint8_t)(lo >> (8 * lane)));
+  __syncwarp();                                  // the match may start with these very bytes
+  if (hi & T2_MATCH) copy_warp(w, p + nl, (hi & 255u) + 3u, ((hi >> 8) & 0x7fffu) + 1u, ring_lo, lane);
+}
+
 // 16-byte units [w.flushed, upto) leave the ring: stored to `out`, folded into the Adler-32 sums.  upto is a multiple of 16.
 template <bool AL>
 __device__ __forceinline__ void flush_to(WState &w, uint32_t upto, bool adler, int lane) {
   for (uint32_t u = w.flushed + 16u * lane; u < upto; u += FLUSH) {
-    const uint4 v = *reinterpret_cast<const uint4 *>(w.ring + (u & M));
+    const uint4 v = lds<uint4>(w.ring + (u & M));
     if (AL) *reinterpret_cast<uint4 *>(w.out + u) = v;
     else {
       const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
@@ -186,14 +231,16 @@ __device__ __forceinline__ void flush_to(WState &w, uint32_t upto, bool adler, i
   __syncwarp();                     // the stores are ordered before any later read of `out` by another lane
 }
 
-// One step: the lane's tokens t0, t1 (tokens 2 lane and 2 lane + 1 of the step's nvalid).  Returns false when the
-// member must go to the sequential kernel.  Warp-uniform result.
+// One step: the lane's token (lo, hi), valid for lanes below nvalid.  Returns false when the member must go to the
+// sequential kernel.  Warp-uniform result.
 template <bool AL>
-__device__ __forceinline__ bool step(WState &w, uint32_t t0, uint32_t t1, uint32_t nvalid, bool adler, int lane) {
-  uint8_t *const ring = w.ring;
-  const bool v0 = 2u * lane < nvalid, v1 = 2u * lane + 1u < nvalid;
-  const uint32_t l0 = v0 ? tok_len(t0) : 0u, l1 = v1 ? tok_len(t1) : 0u;
-  const uint32_t mine = l0 + l1;
+__device__ __forceinline__ bool step(WState &w, uint32_t lo, uint32_t hi, uint32_t nvalid, bool adler, int lane) {
+  const uint32_t ring = w.ring;
+  const bool v = (uint32_t)lane < nvalid;
+  const bool m = v && (hi & T2_MATCH);
+  const uint32_t nl = v ? tbzd2::t2_nlit(hi) : 0u;
+  const uint32_t n = m ? (hi & 255u) + 3u : 0u;
+  const uint32_t mine = nl + n;
   uint32_t x = mine;
 #pragma unroll
   for (int sft = 1; sft < 32; sft <<= 1) {
@@ -202,82 +249,78 @@ __device__ __forceinline__ bool step(WState &w, uint32_t t0, uint32_t t1, uint32
   }
   const uint32_t total = __shfl_sync(TBZ_FULL, x, 31);
   const uint32_t base = w.pos;
-  const uint32_t p0 = base + x - mine, p1 = p0 + l0;
-  if ((unsigned long long)base + total > w.cap) { TBZ_R2_WHY("overflow base %u total %u cap %llu\n", base, total, w.cap); return false; }                 // output overflow: the sequential kernel reports it
-  const bool m0 = v0 && (t0 & TOK_MATCH), m1 = v1 && (t1 & TOK_MATCH);
-  const uint32_t d0 = ((t0 >> 8) & 0x7fffu) + 1u, d1 = ((t1 >> 8) & 0x7fffu) + 1u;
-  if (__any_sync(TBZ_FULL, (m0 && d0 > p0) || (m1 && d1 > p1))) { TBZ_R2_WHY("distance too far at %u\n", base); return false; }   // deflate.lisp:343-345
+  const uint32_t p = base + x - mine;            // the token's first byte
+  const uint32_t dst = p + nl;                   // the match's first byte
+  if ((unsigned long long)base + total > w.cap) { TBZ_R2_WHY("overflow base %u total %u cap %llu\n", base, total, w.cap); return false; }   // output overflow: the sequential kernel reports it
+  const uint32_t d = ((hi >> 8) & 0x7fffu) + 1u;
+  if (__any_sync(TBZ_FULL, m && d > dst)) { TBZ_R2_WHY("distance too far at %u\n", base); return false; }   // deflate.lisp:343-345
   const uint32_t end = base + total;
-  uint32_t pm0, pm1;
-  if (total <= SBMAX) {
-    // literals
-    if (v0 && !m0) { ring[p0 & M] = (uint8_t)t0; if (t0 & TOK_LIT2) ring[(p0 + 1u) & M] = (uint8_t)(t0 >> 8); }
-    if (v1 && !m1) { ring[p1 & M] = (uint8_t)t1; if (t1 & TOK_LIT2) ring[(p1 + 1u) & M] = (uint8_t)(t1 >> 8); }
-    // ready matches, each by its own lane
-    const uint32_t s0 = p0 - d0, s1 = p1 - d1;
-    const bool r0 = m0 && s0 + l0 <= base && l0 <= NFAST, r1 = m1 && s1 + l1 <= base && l1 <= NFAST;
+  if (__builtin_expect(total <= SBMAX, 1)) {
     const uint32_t ring_lo = end > H ? end - H : 0u;
-    copy_ready<AL>(w, r0, p0, s0, l0, s0 < ring_lo);
-    copy_ready<AL>(w, r1, p1, s1, l1, s1 < ring_lo);
+    const uint32_t src = dst - d;
+    const bool far = src < ring_lo;
+    // a token near the ring's end (its bytes, or its source, would wrap) takes the ordered path as a whole
+    const bool edge = v && ((p & M) > H - EDGE - 4u || (m && !far && (src & M) > H - EDGE));
+    const bool ready = m && !edge && src + n <= base && n <= NFAST;
+    // literals
+    {
+      const uint32_t lp = ring + (p & M), nle = edge ? 0u : nl;
+      if (nle > 0u) sts_low8(lp, lo);
+      if (nle > 1u) sts_low8(lp + 1u, lo >> 8);
+      if (nle > 2u) sts_low8(lp + 2u, lo >> 16);
+      if (nle > 3u) sts_low8(lp + 3u, lo >> 24);
+    }
+    copy_ready<AL>(ring, w.out, ready, far, dst, src, n);
     __syncwarp();
-    pm0 = __ballot_sync(TBZ_FULL, m0 && !r0);
-    pm1 = __ballot_sync(TBZ_FULL, m1 && !r1);
     // the rest in stream order, by the whole warp
-    uint32_t pm = pm0 | pm1;
+    uint32_t pm = __ballot_sync(TBZ_FULL, edge || (m && !ready));
+    const uint32_t em = __ballot_sync(TBZ_FULL, edge);
     while (pm) {
       const int l = __ffs(pm) - 1;
       pm &= pm - 1u;
-      const uint32_t pa = __shfl_sync(TBZ_FULL, p0, l), na = __shfl_sync(TBZ_FULL, l0 | (d0 << 16), l);
-      const uint32_t pb = __shfl_sync(TBZ_FULL, p1, l), nb = __shfl_sync(TBZ_FULL, l1 | (d1 << 16), l);
-      if ((pm0 >> l) & 1u) copy_warp(w, pa, na & 0xffffu, na >> 16, ring_lo, lane);      // (the ring already holds the whole step)
-      if ((pm1 >> l) & 1u) copy_warp(w, pb, nb & 0xffffu, nb >> 16, ring_lo, lane);
+      const uint32_t pa = __shfl_sync(TBZ_FULL, p, l), ha = __shfl_sync(TBZ_FULL, hi, l);
+      if ((em >> l) & 1u) token_warp(w, pa, __shfl_sync(TBZ_FULL, lo, l), ha, ring_lo, lane);      // (literals too)
+      else copy_warp(w, pa + tbzd2::t2_nlit(ha), (ha & 255u) + 3u, ((ha >> 8) & 0x7fffu) + 1u, ring_lo, lane);
     }
     w.pos = end;
     if (end - w.flushed >= FLUSH) flush_to<AL>(w, w.flushed + ((end - w.flushed) / FLUSH) * FLUSH, adler, lane);
   } else {
-    // a step of long matches (RLE, zeros): token by token, the ring never holds more than one token of unflushed slack
+    // a step of long matches (RLE, zeros): token by token, so that the ring never runs more than one token ahead of `out`
     for (int l = 0; l < 32; l++) {
-#pragma unroll
-      for (int s = 0; s < 2; s++) {
-        const uint32_t t = __shfl_sync(TBZ_FULL, s ? t1 : t0, l), p = __shfl_sync(TBZ_FULL, s ? p1 : p0, l);
-        if (2u * l + s >= nvalid) continue;
-        const uint32_t e = p + tok_len(t);
-        if (t & TOK_MATCH) copy_warp(w, p, (t & 255u) + 3u, ((t >> 8) & 0x7fffu) + 1u, e > H ? e - H : 0u, lane);
-        else {
-          if (lane == 0) { ring[p & M] = (uint8_t)t; if (t & TOK_LIT2) ring[(p + 1u) & M] = (uint8_t)(t >> 8); }
-          __syncwarp();
-        }
-        if (e - w.flushed >= FLUSH) flush_to<AL>(w, w.flushed + ((e - w.flushed) / FLUSH) * FLUSH, adler, lane);
-      }
+      const uint32_t pa = __shfl_sync(TBZ_FULL, p, l), la = __shfl_sync(TBZ_FULL, lo, l), ha = __shfl_sync(TBZ_FULL, hi, l);
+      if ((uint32_t)l >= nvalid) break;
+      const uint32_t e = pa + tbzd2::t2_outlen(ha);
+      token_warp(w, pa, la, ha, e > H ? e - H : 0u, lane);
+      if (e - w.flushed >= FLUSH) flush_to<AL>(w, w.flushed + ((e - w.flushed) / FLUSH) * FLUSH, adler, lane);
     }
     w.pos = end;
   }
   return true;
 }
 
-// The member's token stream, step by step: slabs in chain order, the 32 lists of a slab in lane order, 64 tokens at a time.
+// The member's token stream, step by step: slabs in chain order, the 32 lists of a slab in lane order, 32 tokens at a time.
 struct Cursor {
-  const uint32_t *slabs, *slab, *list;
+  const uint32_t *slabs, *slab;
+  const uint2 *list;
   uint32_t fc, next_slab, cnt, i0;
   int j;
-  __device__ __forceinline__ void open(const uint32_t *slabs_, uint32_t first, int lane) {
+  __device__ __forceinline__ void open(const uint32_t *slabs_, uint32_t first) {
     slabs = slabs_; slab = nullptr; list = nullptr; cnt = 0; i0 = 0; j = 32; next_slab = first; fc = 0;
-    (void)lane;
   }
-  // the next step: its first token and how many tokens it has (<= 64); false at the end of the stream.  Uniform.
-  __device__ __forceinline__ bool next(const uint32_t *&ptr, uint32_t &nvalid, int lane) {
+  // the next step: its first token and how many tokens it has (<= 32); false at the end of the stream.  Uniform.
+  __device__ __forceinline__ bool next(const uint2 *&ptr, uint32_t &nvalid, int lane) {
     for (;;) {
       if (i0 < cnt) {
         ptr = list + i0;
-        nvalid = cnt - i0 < 64u ? cnt - i0 : 64u;
-        i0 += 64u;
+        nvalid = cnt - i0 < 32u ? cnt - i0 : 32u;
+        i0 += 32u;
         return true;
       }
       if (j < 31) {
         j++;
         const uint32_t f = __shfl_sync(TBZ_FULL, fc, j);
         cnt = f >> 16; i0 = 0;
-        list = slab + SLAB_HDR_WORDS + (uint32_t)j * TOKCAP + (f & 0xffffu);
+        list = reinterpret_cast<const uint2 *>(slab + SLAB_HDR_WORDS) + (uint32_t)j * TOKCAP2 + (f & 0xffffu);
         continue;
       }
       if (next_slab == NO_SLAB) return false;
@@ -290,36 +333,29 @@ struct Cursor {
   }
 };
 
-__device__ __forceinline__ void load_pair(const uint32_t *ptr, uint32_t nvalid, int lane, uint32_t &t0, uint32_t &t1) {
-  t0 = 0; t1 = 0;
-  const uint32_t i = 2u * lane;
-  if (i + 1u < nvalid) {
-    const uint2 v = __ldg(reinterpret_cast<const uint2 *>(ptr + i));      // lists, first proven tokens and steps are all even
-    t0 = v.x; t1 = v.y;
-  } else if (i < nvalid) t0 = __ldg(ptr + i);
-}
-
 template <bool AL>
 __device__ inline bool resolve_stream(WState &w, const P1Rec &rec, const uint32_t *__restrict__ slabs, bool adler, int lane) {
   Cursor cur;
-  cur.open(slabs, rec.first_slab, lane);
-  const uint32_t *ptr = nullptr;
-  uint32_t nvalid = 0, t0 = 0, t1 = 0;
+  cur.open(slabs, rec.first_slab);
+  const uint2 *ptr = nullptr;
+  uint32_t nvalid = 0;
+  uint2 t = make_uint2(0u, 0u);
   bool have = cur.next(ptr, nvalid, lane);
-  if (have) load_pair(ptr, nvalid, lane, t0, t1);
+  if (have && (uint32_t)lane < nvalid) t = __ldg(ptr + lane);
   while (have) {
-    const uint32_t *nptr = nullptr;
-    uint32_t nn = 0, n0 = 0, n1 = 0;
+    const uint2 *nptr = nullptr;
+    uint32_t nn = 0;
+    uint2 tn = make_uint2(0u, 0u);
     const bool have_n = cur.next(nptr, nn, lane);
-    if (have_n) load_pair(nptr, nn, lane, n0, n1);                        // travels while this step is copied
-    if (!step<AL>(w, t0, t1, nvalid, adler, lane)) return false;
-    t0 = n0; t1 = n1; nvalid = nn; have = have_n;
+    if (have_n && (uint32_t)lane < nn) tn = __ldg(nptr + lane);          // travels while this step is copied
+    if (!step<AL>(w, t.x, t.y, nvalid, adler, lane)) return false;
+    t = tn; nvalid = nn; have = have_n;
   }
   // what is left in the ring: whole units, then the last partial one byte by byte
   flush_to<AL>(w, w.pos & ~15u, adler, lane);
   if (w.flushed + lane < w.pos) {
     const uint32_t p = w.flushed + lane;
-    const uint32_t d = w.ring[p & M];
+    const uint32_t d = lds<uint8_t>(w.ring + (p & M));
     w.out[p] = (uint8_t)d;
     w.acc_a += d; w.acc_w += (unsigned long long)p * d;
   }
@@ -329,7 +365,7 @@ __device__ inline bool resolve_stream(WState &w, const P1Rec &rec, const uint32_
 
 // One member, one warp.  Returns false when the caller must queue the member for the sequential kernel.
 __device__ inline bool resolve_member(const DMember &mem, int fmt, const P1Rec &rec, const uint32_t *__restrict__ slabs,
-                                      tbz_result &res, uint8_t *ring, int lane) {
+                                      tbz_result &res, uint32_t ring, int lane) {
   WState w;
   w.ring = ring; w.out = mem.out;
   w.cap = mem.out_cap < 0xffffffffull ? mem.out_cap : 0xffffffffull;

@@ -6,6 +6,7 @@
 #include "inflate_seq.cuh"
 #include "inflate_decode.cuh"
 #include "inflate_copy.cuh"
+#include "inflate_decode2.cuh"
 #include "inflate_resolve2.cuh"
 #include "inflate_crc.cuh"
 
@@ -83,14 +84,33 @@ k_inflate_resolve(const DMember *members, tbz_result *results, uint32_t n, int f
 }
 
 
+// Phase one, round-2 decoder (the default): 64-bit tokens, lean symbol loop (inflate_decode2.cuh).  scratch: SCRATCH_U16
+// 16-bit words per warp of the grid (the sorted symbol lists of the canonical codes).
+__global__ void __launch_bounds__(tbzd2::NT, 7)
+k_inflate_decode2(const DMember *members, uint32_t n, int fmt, tbzfast::P1Rec *recs,
+                  uint32_t *slabs, uint32_t nslabs, uint32_t *counters, uint32_t *todo, uint16_t *scratch) {
+  TBZ_DYN_SMEM(smem_raw);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  tbzd2::WSmem &sm = reinterpret_cast<tbzd2::WSmem *>(smem_raw)[warp];
+  uint16_t *gs = scratch + ((size_t)blockIdx.x * tbzd2::WPC + warp) * tbzd2::SCRATCH_U16;
+  for (;;) {
+    uint32_t i = 0;
+    if (lane == 0) i = atomicAdd(&counters[0], 1u);
+    i = __shfl_sync(TBZ_FULL, i, 0);
+    if (i >= n) break;
+    const bool ok = tbzd2::decode_member(members[i], fmt, recs[i], sm, gs, slabs, nslabs, &counters[2], lane);
+    __syncwarp();
+    if (!ok && lane == 0) { recs[i].status = 0; todo[atomicAdd(&counters[1], 1u)] = i; }
+  }
+}
+
 // Phase two, round-2 design (the default): persistent CTAs of WPC independent warps, ONE WARP per member, a
 // 16 KiB history ring per warp, no CTA barrier (inflate_resolve2.cuh).
 __global__ void __launch_bounds__(tbzr2::NT, 2)
 k_inflate_resolve2(const DMember *members, tbz_result *results, uint32_t n, int fmt,
                    const tbzfast::P1Rec *recs, const uint32_t *slabs, uint32_t *counters, uint32_t *todo) {
-  TBZ_DYN_SMEM(smem_raw);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint8_t *ring = reinterpret_cast<uint8_t *>(smem_raw) + (size_t)warp * tbzr2::H;
+  const uint32_t ring = tbzr2::smem_base() + tbzr2::PAD + (uint32_t)warp * tbzr2::H;   // shared-space address of this warp's ring
   for (;;) {
     uint32_t i = 0;
     if (lane == 0) i = atomicAdd(&counters[3], 1u);

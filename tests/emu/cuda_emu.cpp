@@ -59,7 +59,7 @@ static void run_block(Block *b, unsigned bx, dim3 grid, dim3 block, size_t smem,
   b->body = body;
   if (b->fibers.size() < n) b->fibers.resize(n);
   b->warps.assign((n + 31) / 32, Warp());
-  b->dyn.assign(smem + 16, 0xcd);                      // shared memory is not zero-initialised on hardware either
+  b->dyn.assign(smem, 0xcd);       // exactly the bytes the launch asked for; shared memory is not zero-initialised on hardware either
   b->bar_arrived = 0; b->bar_alive = n; b->bar_gen = 0; b->bar_or = 0; b->epoch = 0;
   for (unsigned t = 0; t < n; t++) {
     Fiber &f = b->fibers[t];

@@ -5,7 +5,7 @@
 #include "kernels.cuh"
 
 extern "C" int emu_inflate_batch(int fmt, const tbz_member *m, uint64_t n, tbz_result *r, uint32_t flags, int os_threads, int variant) {
-  // variant bit 0: the round-1 phase two (inflate_copy.cuh) instead of inflate_resolve2.cuh
+  // variant bit 0: the round-1 kernels (inflate_decode.cuh + inflate_copy.cuh) instead of inflate_decode2.cuh + inflate_resolve2.cuh
   emu_os_threads = os_threads > 0 ? os_threads : 1;
   if (!n) return 0;
   std::vector<DMember> dm(n);
@@ -23,17 +23,22 @@ extern "C" int emu_inflate_batch(int fmt, const tbz_member *m, uint64_t n, tbz_r
   for (uint64_t i = 0; i < n; i++) want += 2 * (m[i].in_len / round_bytes) + 4;
   const uint32_t nslabs = (uint32_t)want;
   std::vector<uint32_t> slabs((size_t)nslabs * tbzfast::SLAB_WORDS);
-  const unsigned dec_grid = std::min<unsigned>((nn + tbzfast::WPC - 1) / tbzfast::WPC, 16);
-  emu_launch(k_inflate_decode, dim3(dec_grid), dim3(tbzfast::NT), sizeof(tbzfast::WSmem) * tbzfast::WPC,
-             (const DMember *)dm.data(), nn, fmt, recs.data(), slabs.data(), nslabs, counters.data(), todo.data());
-  if (variant & 1)
+  if (variant & 1) {           // the round-1 pair: 32-bit tokens, one CTA per member in phase two
+    const unsigned dec_grid = std::min<unsigned>((nn + tbzfast::WPC - 1) / tbzfast::WPC, 16);
+    emu_launch(k_inflate_decode, dim3(dec_grid), dim3(tbzfast::NT), sizeof(tbzfast::WSmem) * tbzfast::WPC,
+               (const DMember *)dm.data(), nn, fmt, recs.data(), slabs.data(), nslabs, counters.data(), todo.data());
     emu_launch(k_inflate_resolve, dim3(std::min<unsigned>(nn, 16)), dim3(tbzp2::NT), sizeof(tbzp2::Smem),
                (const DMember *)dm.data(), r, nn, fmt, (const tbzfast::P1Rec *)recs.data(), (const uint32_t *)slabs.data(),
                counters.data(), todo.data());
-  else
-    emu_launch(k_inflate_resolve2, dim3(std::min<unsigned>((nn + tbzr2::WPC - 1) / tbzr2::WPC, 16)), dim3(tbzr2::NT), (size_t)tbzr2::WPC * tbzr2::H,
+  } else {
+    const unsigned dec_grid = std::min<unsigned>((nn + tbzd2::WPC - 1) / tbzd2::WPC, 16);
+    std::vector<uint16_t> scratch((size_t)dec_grid * tbzd2::WPC * tbzd2::SCRATCH_U16);
+    emu_launch(k_inflate_decode2, dim3(dec_grid), dim3(tbzd2::NT), sizeof(tbzd2::WSmem) * tbzd2::WPC,
+               (const DMember *)dm.data(), nn, fmt, recs.data(), slabs.data(), nslabs, counters.data(), todo.data(), scratch.data());
+    emu_launch(k_inflate_resolve2, dim3(std::min<unsigned>((nn + tbzr2::WPC - 1) / tbzr2::WPC, 16)), dim3(tbzr2::NT), tbzr2::SMEM_BYTES,
                (const DMember *)dm.data(), r, nn, fmt, (const tbzfast::P1Rec *)recs.data(), (const uint32_t *)slabs.data(),
                counters.data(), todo.data());
+  }
   if (fmt == TBZ_GZIP)
     emu_launch(tbzcrc::k_member_crc, dim3(std::min<unsigned>(nn, 16)), dim3(tbzcrc::NT), 0,
                (const DMember *)dm.data(), r, nn, (const tbzfast::P1Rec *)recs.data(), counters.data(), todo.data());
