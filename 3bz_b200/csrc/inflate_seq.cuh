@@ -125,9 +125,20 @@ __device__ __forceinline__ void lz_copy(Out &o, uint32_t n, uint32_t d, int lane
   o.pos += n;
 }
 
-// One member, one warp.  fmt = TBZ_DEFLATE / TBZ_ZLIB / TBZ_GZIP.
+// What a session keeps between two `decompress` calls (deflate.lisp:4-62 keeps every register of its state machine;
+// here a call resumes at the last block boundary): everything below is relative to the first octet of the stream.
+struct Resume {
+  unsigned long long blk_bit;    // bit offset of the next block header (valid once header_done)
+  unsigned long long blk_out;    // output bytes produced by the blocks before it
+  unsigned long long ck_pos;     // output bytes the running checksum covers
+  uint32_t ck;                   // Adler-32 (s1 | s2 << 16) or finalised CRC-32 of out[0, ck_pos)
+  uint32_t header_done;          // the wrapper header has been parsed and accepted
+};
+
+// One member, one warp.  fmt = TBZ_DEFLATE / TBZ_ZLIB / TBZ_GZIP.  rs (sessions only): resume at the last block
+// boundary, leave the new one behind; the checksum then runs over the new output bytes only.
 __device__ inline void inflate_member(const DMember &m, int fmt, tbz_result &res, WarpSmem &sm,
-                                      const uint32_t *crc_tab, int lane) {
+                                      const uint32_t *crc_tab, int lane, Resume *rs = nullptr) {
   BitIn in;
   {
     uintptr_t a = (uintptr_t)m.in;
@@ -144,7 +155,11 @@ __device__ inline void inflate_member(const DMember &m, int fmt, tbz_result &res
   uint32_t hcrc_state = 0xffffffffu;   // gzip FHCRC over the header bytes
 
   // ---------------- wrapper headers ----------------
-  if (fmt == TBZ_ZLIB) {                                   // zlib.lisp:108-126, :14-37
+  const bool resumed = rs && rs->header_done;
+  if (resumed) {                                           // (a session that is past its header)
+    in.pos = pos0 + rs->blk_bit;
+    out.pos = rs->blk_out;
+  } else if (fmt == TBZ_ZLIB) {                            // zlib.lisp:108-126, :14-37
     if (avail(in) < 16) verdict = TBZ_INPUT_UNDERRUN;
     else {
       uint32_t cmf = byte_at(in, in.pos >> 3), flg = byte_at(in, (in.pos >> 3) + 1);
@@ -206,6 +221,7 @@ __device__ inline void inflate_member(const DMember &m, int fmt, tbz_result &res
   // ---------------- deflate blocks (deflate.lisp:516-726) ----------------
   Canon ll, dd, cl;
   if (verdict < 0) where = TBZ_AT_BODY;
+  if (rs && !resumed && verdict < 0 && lane == 0) { rs->header_done = 1; rs->blk_bit = in.pos - pos0; rs->blk_out = 0; }
   while (verdict < 0) {
     // :start-of-block
     if (avail(in) < 3) { verdict = TBZ_INPUT_UNDERRUN; break; }
@@ -334,12 +350,20 @@ __device__ inline void inflate_member(const DMember &m, int fmt, tbz_result &res
       if (verdict >= 0) break;
     }
     if (last) { verdict = TBZ_FINISHED; break; }
+    if (rs && lane == 0) { rs->blk_bit = in.pos - pos0; rs->blk_out = out.pos; }     // a block is complete: the next call starts here
   }
 
   // ---------------- checksum + trailer ----------------
   __syncwarp();
   uint32_t ck = 0;
-  if (fmt == TBZ_ZLIB) ck = adler32_warp(out.p, out.pos, lane);
+  if (rs) {                                                // a session: only the bytes that are new since the last call
+    const unsigned long long from = rs->ck_pos, n = out.pos - from;
+    ck = rs->ck;
+    if (fmt == TBZ_ZLIB) ck = adler32_warp(out.p + from, n, lane, from ? (ck & 0xffffu) : 1u, from ? (ck >> 16) : 0u);
+    else if (fmt == TBZ_GZIP) { const uint32_t c2 = crc32_warp(out.p + from, n, crc_tab, lane); ck = from ? (n ? crc_combine(ck, c2, n) : ck) : c2; }
+    __syncwarp();
+    if (lane == 0) { rs->ck = ck; rs->ck_pos = out.pos; }
+  } else if (fmt == TBZ_ZLIB) ck = adler32_warp(out.p, out.pos, lane);
   else if (fmt == TBZ_GZIP) ck = crc32_warp(out.p, out.pos, crc_tab, lane);
   if (verdict == TBZ_FINISHED && fmt != TBZ_DEFLATE) {
     in.pos = (in.pos + 7) & ~7ull;                          // byte-align (zlib.lisp:139, gzip.lisp:273)

@@ -19,7 +19,6 @@
 #include "inflate_seq.cuh"
 #include "inflate_decode.cuh"
 #include "inflate_resolve.cuh"
-#include "inflate_copy.cuh"
 #include "inflate_crc.cuh"
 #include "kernels.cuh"
 #include "inflate_split.cuh"
@@ -27,11 +26,8 @@
 // =============================================================================================
 // host objects
 // =============================================================================================
-#ifndef TBZ_RESOLVE
-#define TBZ_RESOLVE 2                  // batched kernels: 2 = round 2 (inflate_decode2.cuh + inflate_resolve2.cuh), 1 = round 1 (inflate_decode.cuh + inflate_copy.cuh)
-#endif
-static const size_t kResolve2Smem = tbzr2::SMEM_BYTES;
-static const size_t kDecode2Smem = sizeof(tbzd2::WSmem) * tbzd2::WPC;
+static const size_t kResolveSmem = tbzlz::SMEM_BYTES;
+static const size_t kDecodeSmem = sizeof(tbzhd::WSmem) * tbzhd::WPC;
 static const uint64_t kSlabPoolBytes = 24ull << 30;  // upper bound of the token slab pool per batch (B200: 180 GB)
 static const uint64_t kSplitMinBytes = 4ull << 20;   // members at least this large are split across the GPU
 static const uint64_t kSplitChunkBytes =      // compressed bytes per chunk of a split member (TBZ_SPLIT_CHUNK_KB: tuning)
@@ -122,7 +118,7 @@ struct tbz_batch {
   bool out_direct = false;             // caller's outputs are exactly adjacent: DMA straight into them
   const uint8_t *in_span = nullptr; uint8_t *out_span = nullptr;
   void *d_in = nullptr, *d_out = nullptr, *d_members = nullptr, *d_results = nullptr;
-  void *d_slabs = nullptr, *d_counters = nullptr, *d_todo = nullptr, *d_recs = nullptr, *d_scratch = nullptr;
+  void *d_slabs = nullptr, *d_counters = nullptr, *d_todo = nullptr, *d_recs = nullptr;
   int fast_grid = 0, res_grid = 0;
   uint32_t nslabs = 0;
   bool launched = false;
@@ -353,7 +349,6 @@ extern "C" int32_t tbz_batch_destroy(tbz_batch *b) {
   dev_release(ctx, b->d_in); dev_release(ctx, b->d_out);
   dev_release(ctx, b->d_members); dev_release(ctx, b->d_results);
   dev_release(ctx, b->d_slabs); dev_release(ctx, b->d_counters); dev_release(ctx, b->d_todo); dev_release(ctx, b->d_recs);
-  dev_release(ctx, b->d_scratch);
   delete b;
   return TBZ_OK;
 }
@@ -374,41 +369,26 @@ extern "C" int32_t tbz_batch_prepare(tbz_ctx *ctx, int32_t format, const tbz_mem
   PCK(dev_alloc(ctx, std::max<uint64_t>(1, n) * sizeof(tbz_result), &b->d_results));
   if (!(flags & TBZ_FLAG_NO_FASTPATH) && n) {
     int occ = 0;
-#if TBZ_RESOLVE == 1
-    cudaFuncSetAttribute(k_inflate_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(tbzfast::WSmem) * tbzfast::WPC));
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_inflate_decode, tbzfast::NT, sizeof(tbzfast::WSmem) * tbzfast::WPC);
-    b->fast_grid = (int)std::min<uint64_t>((n + tbzfast::WPC - 1) / tbzfast::WPC, (uint64_t)ctx->sm_count * std::max(1, occ));
-#else
-    cudaFuncSetAttribute(k_inflate_decode2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDecode2Smem);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_inflate_decode2, tbzd2::NT, kDecode2Smem);
-    b->fast_grid = (int)std::min<uint64_t>((n + tbzd2::WPC - 1) / tbzd2::WPC, (uint64_t)ctx->sm_count * std::max(1, occ));
-#endif
-#if TBZ_RESOLVE == 1
-    cudaFuncSetAttribute(k_inflate_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tbzp2::Smem));
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_inflate_resolve, tbzp2::NT, sizeof(tbzp2::Smem));
-    b->res_grid = (int)std::min<uint64_t>(n, (uint64_t)ctx->sm_count * std::max(1, occ));
-#else
-    cudaFuncSetAttribute(k_inflate_resolve2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kResolve2Smem);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_inflate_resolve2, tbzr2::NT, kResolve2Smem);
-    b->res_grid = (int)std::min<uint64_t>((n + tbzr2::WPC - 1) / tbzr2::WPC, (uint64_t)ctx->sm_count * std::max(1, occ));
-#endif
+    cudaFuncSetAttribute(k_inflate_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDecodeSmem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_inflate_decode, tbzhd::NT, kDecodeSmem);
+    b->fast_grid = (int)std::min<uint64_t>((n + tbzhd::WPC - 1) / tbzhd::WPC, (uint64_t)ctx->sm_count * std::max(1, occ));
+    cudaFuncSetAttribute(k_inflate_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kResolveSmem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_inflate_resolve, tbzlz::NT, kResolveSmem);
+    b->res_grid = (int)std::min<uint64_t>((n + tbzlz::WPC - 1) / tbzlz::WPC, (uint64_t)ctx->sm_count * std::max(1, occ));
     // token slabs: one per round; a round covers at most ~31 KiB of compressed input and never
     // crosses a block boundary.  Members that find the pool empty go to the sequential kernel.
     uint64_t want = 0;
     // a round covers up to NL * S_MAX bits; blocks end rounds early and a lane that fills its token
     // list shortens them, hence the factor 2 and the slack
-    const uint64_t round_bytes = (uint64_t)tbzfast::NL * tbzfast::S_MAX / 8;
-    for (uint64_t i = 0; i < n; i++) want += 2 * (m[i].in_len / round_bytes) + 4;
-    const uint64_t slab_bytes = (uint64_t)tbzfast::SLAB_WORDS * 4;
+    const uint64_t round_bytes = (uint64_t)tbzhd::NL * tbzhd::S_MAX / 8;
+    for (uint64_t i = 0; i < n; i++) want += 4 * (m[i].in_len / round_bytes) + 6;
+    const uint64_t slab_bytes = tbzhd::SLAB_BYTES;
     const uint64_t cap = std::max<uint64_t>(64, kSlabPoolBytes / slab_bytes);
     b->nslabs = (uint32_t)std::min<uint64_t>(want, cap);
     PCK(dev_alloc(ctx, (size_t)b->nslabs * slab_bytes, &b->d_slabs));
     PCK(dev_alloc(ctx, 256, &b->d_counters));
     PCK(dev_alloc(ctx, n * 4, &b->d_todo));
     PCK(dev_alloc(ctx, n * sizeof(tbzfast::P1Rec), &b->d_recs));
-#if TBZ_RESOLVE != 1
-    PCK(dev_alloc(ctx, (size_t)b->fast_grid * tbzd2::WPC * tbzd2::SCRATCH_U16 * 2, &b->d_scratch));
-#endif
   }
   std::vector<DMember> &dm = b->dm;
   dm.resize(n);
@@ -739,32 +719,17 @@ static int32_t launch_kernels(tbz_batch *b) {
   if (b->fast_grid) {
     CK(ctx, cudaMemsetAsync(b->d_counters, 0, 256, ctx->stream));
     if (ctx->ktime) CK(ctx, cudaEventRecord(ctx->kev[0], ctx->stream));
-#if TBZ_RESOLVE == 1
-    const size_t dec_smem = sizeof(tbzfast::WSmem) * tbzfast::WPC;
-    CK(ctx, cudaFuncSetAttribute(k_inflate_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dec_smem));
-    k_inflate_decode<<<b->fast_grid, tbzfast::NT, dec_smem, ctx->stream>>>(
+    CK(ctx, cudaFuncSetAttribute(k_inflate_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDecodeSmem));
+    k_inflate_decode<<<b->fast_grid, tbzhd::NT, kDecodeSmem, ctx->stream>>>(
         (const DMember *)b->d_members, n, b->format, (tbzfast::P1Rec *)b->d_recs,
-        (uint32_t *)b->d_slabs, b->nslabs, (uint32_t *)b->d_counters, (uint32_t *)b->d_todo);
-#else
-    CK(ctx, cudaFuncSetAttribute(k_inflate_decode2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDecode2Smem));
-    k_inflate_decode2<<<b->fast_grid, tbzd2::NT, kDecode2Smem, ctx->stream>>>(
-        (const DMember *)b->d_members, n, b->format, (tbzfast::P1Rec *)b->d_recs,
-        (uint32_t *)b->d_slabs, b->nslabs, (uint32_t *)b->d_counters, (uint32_t *)b->d_todo, (uint16_t *)b->d_scratch);
-#endif
+        (unsigned char *)b->d_slabs, b->nslabs, (uint32_t *)b->d_counters, (uint32_t *)b->d_todo);
     ctx->launches++;
     CK(ctx, cudaGetLastError());
     if (ctx->ktime) CK(ctx, cudaEventRecord(ctx->kev[1], ctx->stream));
-#if TBZ_RESOLVE == 1
-    CK(ctx, cudaFuncSetAttribute(k_inflate_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tbzp2::Smem)));
-    k_inflate_resolve<<<b->res_grid, tbzp2::NT, sizeof(tbzp2::Smem), ctx->stream>>>(
+    CK(ctx, cudaFuncSetAttribute(k_inflate_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kResolveSmem));
+    k_inflate_resolve<<<b->res_grid, tbzlz::NT, kResolveSmem, ctx->stream>>>(
         (const DMember *)b->d_members, (tbz_result *)b->d_results, n, b->format,
-        (const tbzfast::P1Rec *)b->d_recs, (const uint32_t *)b->d_slabs, (uint32_t *)b->d_counters, (uint32_t *)b->d_todo);
-#else
-    CK(ctx, cudaFuncSetAttribute(k_inflate_resolve2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kResolve2Smem));
-    k_inflate_resolve2<<<b->res_grid, tbzr2::NT, kResolve2Smem, ctx->stream>>>(
-        (const DMember *)b->d_members, (tbz_result *)b->d_results, n, b->format,
-        (const tbzfast::P1Rec *)b->d_recs, (const uint32_t *)b->d_slabs, (uint32_t *)b->d_counters, (uint32_t *)b->d_todo);
-#endif
+        (const tbzfast::P1Rec *)b->d_recs, (const unsigned char *)b->d_slabs, (uint32_t *)b->d_counters, (uint32_t *)b->d_todo);
     ctx->launches++;
     CK(ctx, cudaGetLastError());
     if (b->format == TBZ_GZIP) {   // gzip: CRC-32 of the finished members + trailer compare

@@ -101,8 +101,7 @@ __device__ inline uint32_t crc32_warp(const uint8_t *p, uint64_t n, const uint32
 
 // warp-parallel Adler-32 of p[0,n): returns s1 | s2<<16 starting from (1,0).
 // s1 = 1 + sum d_i ; s2 = n + sum (n-i) d_i   (mod 65521); tiles of 4096 bytes keep sums in 32 bits.
-__device__ inline uint32_t adler32_warp(const uint8_t *p, uint64_t n, int lane) {
-  uint32_t s1 = 1, s2 = 0;
+__device__ inline uint32_t adler32_warp(const uint8_t *p, uint64_t n, int lane, uint32_t s1 = 1, uint32_t s2 = 0) {
   for (uint64_t base = 0; base < n; base += 4096) {
     uint32_t m = (uint32_t)((n - base) < 4096 ? (n - base) : 4096);
     uint32_t a = 0, w = 0;   // a = sum d ; w = sum (m - j) d   over this lane's bytes

@@ -13,13 +13,20 @@
 //     lane and step; literals are gathered in a register until a match closes the token
 //   * no output offsets are tracked here (phase two scans the lengths anyway; it also owns the overflow verdict)
 // Codes longer than the root tables (10 bits lit/len, 9 bits distance: ~1 % of the symbols on text) take a canonical
-// search whose sorted symbol lists live in a small global scratch area per warp (L1/L2): shared memory is what limits
-// the number of members in flight (7.6 KB per warp, 28 warps per SM).
+// search.  Shared memory is what limits the number of members in flight: 7.8 KB per warp, 28 warps per SM.  (A first
+// version kept the sorted symbol lists of that search in global memory: with all of shared memory taken L1 is 4 KB,
+// every search was an L2 round trip, and half of all loop iterations have a lane that searches: 0.79 ms against 0.62.)
 #pragma once
 #include "tbz_device.cuh"
 #include "inflate_decode.cuh"
 
 namespace tbzd2 {
+
+#if defined(TBZ_EMU) && defined(TBZ_EMU_TRACE)
+#define TBZ_D2_WHY(what) do { if (lane == 0) fprintf(stderr, "[d2] %s (line %d)\n", what, __LINE__); } while (0)
+#else
+#define TBZ_D2_WHY(what) do { } while (0)
+#endif
 
 using tbzfast::byte_at;
 using tbzfast::Canon16;
@@ -39,13 +46,13 @@ using tbzfast::warp_canon;
 constexpr int WPC = 4;                              // warps (members in flight) per CTA
 constexpr int NT = WPC * 32;
 constexpr int KLL = 10, KD = 9;                     // root table bits
-constexpr uint32_t TOKCAP2 = tbzfast::TOKCAP / 2;   // 64-bit tokens per list (same slab geometry as the 32-bit lists)
+constexpr uint32_t TOKCAP2 = tbzfast::TOKCAP / 2;   // 64-bit tokens a list has room for (same slab geometry as the 32-bit lists)
+constexpr uint32_t LANECAP = 256;                   // tokens a lane emits per round before it ends the round early
 constexpr uint32_t CKSTEP2 = 16;                    // a checkpoint about every 16 tokens
-constexpr uint32_t NCK2 = TOKCAP2 / CKSTEP2;
+constexpr uint32_t NCK2 = LANECAP / CKSTEP2;
 constexpr uint32_t S_MAX = 4000, S_MIN = 64;        // sub-chunk size in bits (12-bit field in a checkpoint: < 4095)
 constexpr uint16_t CK_NONE = 0xffffu;
-constexpr uint32_t SCRATCH_U16 = 512;               // global scratch per warp: sorted_ll[288], sorted_d[32]
-static_assert(tbzfast::TOKCAP % 2 == 0 && TOKCAP2 % CKSTEP2 == 0 && S_MAX < 4095, "token list geometry");
+static_assert(tbzfast::TOKCAP % 2 == 0 && LANECAP % CKSTEP2 == 0 && LANECAP <= TOKCAP2 && S_MAX < 4095, "token list geometry");
 
 // ---- 64-bit token: lo = up to four literal bytes (first byte lowest); hi: [7:0] match length - 3, [22:8] distance - 1,
 //      [25:23] number of literals, bit 31 = a match follows the literals
@@ -83,7 +90,8 @@ struct WSmem {                           // one per warp
     uint16_t ckpt[NCK2][NL];             // [checkpoint][lane]: bit offset in the sub-chunk | (token index - 16 c) << 12
     HdrScratch h;
   };
-  Canon16 c_ll, c_d;                     // first code / count / base per length: the search for codes beyond the root tables
+  Canon16 c_ll, c_d;                     // first code / count / base per length, and the symbols sorted by (length, symbol):
+  uint16_t sorted_ll[288], sorted_d[32]; // the search for codes beyond the root tables (~1 % of the symbols on text)
 };
 static_assert(sizeof(HdrScratch) <= sizeof(uint16_t) * NCK2 * NL, "header scratch must fit under the checkpoints");
 static_assert((sizeof(WSmem) * WPC + 1024) * 7 <= 232448, "seven CTAs = 28 warps per SM");
@@ -124,12 +132,12 @@ __device__ __forceinline__ void flush_literals(Lane &s) {
 // same instructions for either.  Returns 0 = go on, 2 = end of block (its bits dropped), 3 = no such code.
 // stop_at: a bit position a second literal must not start at... it ends the item instead (phase 1b: the place where
 // this lane may synchronise with the next one has to be the start of an item, whatever the pairing was so far).
-__device__ __forceinline__ int item(Lane &s, const In &in, const WSmem &sm, const uint16_t *gs, uint32_t stop_at) {
+__device__ __forceinline__ int item(Lane &s, const In &in, const WSmem &sm, uint32_t stop_at) {
   const uint32_t w = br_peek(s.b);
   uint32_t e = sm.lut[w & ((1u << KLL) - 1u)];
   if (__builtin_expect((e & K_SPECIAL) != 0, 0)) {
     if ((e & K_MASK) == K_LONG) {
-      const uint32_t r = canon_lookup(sm.c_ll, gs, w, KLL + 1, 15);
+      const uint32_t r = canon_lookup(sm.c_ll, sm.sorted_ll, w, KLL + 1, 15);
       e = r ? ll_entry(r >> 4, r & 15u) : K_INVALID;
     }
     if ((e & K_MASK) == K_EOB) { s.p += e & 31u; return 2; }
@@ -143,7 +151,7 @@ __device__ __forceinline__ int item(Lane &s, const In &in, const WSmem &sm, cons
   uint32_t e2 = sm.lut[ism ? (1u << KLL) + (w2 & ((1u << KD) - 1u)) : (w2 & ((1u << KLL) - 1u))];
   if (__builtin_expect(ism && (e2 & K_SPECIAL) != 0, 0)) {
     if ((e2 & K_MASK) == K_LONG) {
-      const uint32_t r = canon_lookup(sm.c_d, gs + 288, w2, KD + 1, 15);
+      const uint32_t r = canon_lookup(sm.c_d, sm.sorted_d, w2, KD + 1, 15);
       e2 = r ? d_entry(r >> 4, r & 15u) : K_INVALID;
     }
     if (e2 & K_SPECIAL) return 3;
@@ -172,16 +180,16 @@ enum { ST_RUN = 0, ST_OVER, ST_END, ST_SYNC, ST_EOB, ST_CAP, ST_BAD, ST_IDLE }; 
 // Every block of a member from bit `pos` on, one warp.  Returns true when the token stream is complete (rec filled in),
 // false when the member goes to the sequential kernel.  Every return value is warp-uniform.
 // ------------------------------------------------------------------------------------------------
-__device__ inline bool decode_blocks(const In &in, uint32_t pos, P1Rec &rec, WSmem &sm, uint16_t *gs,
+__device__ inline bool decode_blocks(const In &in, uint32_t pos, P1Rec &rec, WSmem &sm,
                                      uint32_t *__restrict__ slabs, uint32_t nslabs, uint32_t *slab_counter, int lane) {
   uint32_t first_slab = NO_SLAB, prev_slab = NO_SLAB;
   uint32_t prev_block_bits = 0;   // size of the previous block of this member: predicts this one
   bool last = false;
-  uint16_t *const sorted_ll = gs, *const sorted_d = gs + 288;
+  uint16_t *const sorted_ll = sm.sorted_ll, *const sorted_d = sm.sorted_d;
 
   while (!last) {
     // ================= block header (deflate.lisp:518-528, :577-669) =================
-    if (in.end - pos < 3) return false;
+    if (in.end - pos < 3) { TBZ_D2_WHY("give up"); return false; }
     const uint32_t hdr = peek32(in, pos) & 7;
     pos += 3;
     last = hdr & 1;
@@ -192,18 +200,18 @@ __device__ inline bool decode_blocks(const In &in, uint32_t pos, P1Rec &rec, WSm
       hlit = 288; hdist = 32;
       for (int i = lane; i < 320; i += 32) sm.h.lens[32 + i] = i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : i < 288 ? 8 : 5;
     } else if (btype == 2) {
-      if (in.end - pos < 14) return false;
+      if (in.end - pos < 14) { TBZ_D2_WHY("give up"); return false; }
       const uint32_t v = peek32(in, pos);
       hlit = (v & 31) + 257; hdist = ((v >> 5) & 31) + 1;
       const int ncl = ((v >> 10) & 15) + 4;
-      if (in.end - pos < 14u + 3u * ncl) return false;
+      if (in.end - pos < 14u + 3u * ncl) { TBZ_D2_WHY("give up"); return false; }
       if (lane < 19) sm.h.lens[lane] = 0;
       __syncwarp();
       if (lane < ncl) sm.h.lens[c_clen_order[lane]] = peek32(in, pos + 14 + 3 * lane) & 7;
       __syncwarp();
       int err = warp_canon(sm.h.lens, 19, sm.h.c_cl, sm.h.sorted_cl, sm.h.run, lane);
       if (!err && sm.h.c_cl.nsyms == 0) err = TBZ_ERR_INVALID_SYMBOL;
-      if (err) return false;
+      if (err) { TBZ_D2_WHY("give up"); return false; }
       // entry: [3:0] code length, [7:4] extra bits, [12:8] symbol; 0 = no code
       for (int e = lane; e < 128; e += 32) {
         const uint32_t r = canon_lookup(sm.h.c_cl, sm.h.sorted_cl, (uint32_t)e, 1, 7);
@@ -238,25 +246,25 @@ __device__ inline bool decode_blocks(const In &in, uint32_t pos, P1Rec &rec, WSm
         }
       }
       err = __shfl_sync(TBZ_FULL, err, 0);
-      if (err) return false;
+      if (err) { TBZ_D2_WHY("give up"); return false; }
       pos = __shfl_sync(TBZ_FULL, p, 0);
     } else if (btype == 0) {
       // ================= stored block (deflate.lisp:532-573): LEN, NLEN, then LEN bytes as they are =================
       // They travel as literal tokens, four bytes each, the lanes taking consecutive slices.
       pos = (pos + 7u) & ~7u;
-      if (in.end < pos || in.end - pos < 32u) return false;
+      if (in.end < pos || in.end - pos < 32u) { TBZ_D2_WHY("give up"); return false; }
       const uint32_t v = peek32(in, pos);
       uint32_t slen = v & 0xffffu;
-      if ((slen ^ 0xffffu) != (v >> 16)) return false;                 // deflate.lisp:535
+      if ((slen ^ 0xffffu) != (v >> 16)) { TBZ_D2_WHY("give up"); return false; }                 // deflate.lisp:535
       pos += 32u;
-      if (in.end - pos < 8u * slen) return false;                      // the input ends inside the block
+      if (in.end - pos < 8u * slen) { TBZ_D2_WHY("give up"); return false; }                      // the input ends inside the block
       uint32_t bp = pos >> 3;                                          // byte offset of the payload from in.w
       pos += 8u * slen;
       while (slen) {
         uint32_t slab_id = 0;
         if (lane == 0) slab_id = atomicAdd(slab_counter, 1u);
         slab_id = __shfl_sync(TBZ_FULL, slab_id, 0);
-        if (slab_id >= nslabs) return false;
+        if (slab_id >= nslabs) { TBZ_D2_WHY("give up"); return false; }
         uint32_t *slab = slabs + (size_t)slab_id * SLAB_WORDS;
         SlabHdr *sh = reinterpret_cast<SlabHdr *>(slab);
         const uint32_t nb = slen < (uint32_t)(NL * TOKCAP2 * 4) ? slen : (uint32_t)(NL * TOKCAP2 * 4);
@@ -283,13 +291,13 @@ __device__ inline bool decode_blocks(const In &in, uint32_t pos, P1Rec &rec, WSm
       prev_block_bits = 0;
       continue;
     } else {
-      return false;                        // reserved block type: sequential kernel
+      { TBZ_D2_WHY("give up"); return false; }                        // reserved block type: sequential kernel
     }
     __syncwarp();
     // ================= tables (huffman-tree.lisp:99-218) =================
-    if (warp_canon(sm.h.lens + 32, hlit, sm.c_ll, sorted_ll, sm.h.run, lane)) return false;
-    if (warp_canon(sm.h.lens + 32 + hlit, hdist, sm.c_d, sorted_d, sm.h.run, lane)) return false;
-    if (sm.c_ll.nsyms == 0) return false;
+    if (warp_canon(sm.h.lens + 32, hlit, sm.c_ll, sorted_ll, sm.h.run, lane)) { TBZ_D2_WHY("give up"); return false; }
+    if (warp_canon(sm.h.lens + 32 + hlit, hdist, sm.c_d, sorted_d, sm.h.run, lane)) { TBZ_D2_WHY("give up"); return false; }
+    if (sm.c_ll.nsyms == 0) { TBZ_D2_WHY("give up"); return false; }
     for (int e = lane; e < (1 << KLL); e += 32) {
       const uint32_t r = canon_lookup(sm.c_ll, sorted_ll, (uint32_t)e, 1, KLL);
       sm.lut[e] = r ? ll_entry(r >> 4, r & 15) : (sm.c_ll.maxlen > KLL ? K_LONG : K_INVALID);
@@ -313,7 +321,7 @@ __device__ inline bool decode_blocks(const In &in, uint32_t pos, P1Rec &rec, WSm
       uint32_t slab_id = 0;
       if (lane == 0) slab_id = atomicAdd(slab_counter, 1u);
       slab_id = __shfl_sync(TBZ_FULL, slab_id, 0);
-      if (slab_id >= nslabs) return false;
+      if (slab_id >= nslabs) { TBZ_D2_WHY("give up"); return false; }
       // ---- geometry of this round
       const uint32_t P0 = pos;
       uint32_t left = in.end - P0;
@@ -343,14 +351,14 @@ __device__ inline bool decode_blocks(const In &in, uint32_t pos, P1Rec &rec, WSm
       while (__any_sync(TBZ_FULL, st == ST_RUN)) {
         if (st == ST_RUN) {
           if (s.p >= cend) st = ST_OVER;
-          else if (s.k + 2u >= TOKCAP2) st = ST_CAP;
+          else if (s.k + 2u >= LANECAP) st = ST_CAP;
           else {
             if (s.k >= nextck) {                                   // a checkpoint: literals still waiting close their token here
               flush_literals(s);
               if (s.k - nextck < 16u) sm.ckpt[nextck / CKSTEP2][lane] = (uint16_t)((s.p - cstart) | ((s.k - nextck) << 12));
               nextck = (s.k & ~(CKSTEP2 - 1u)) + CKSTEP2;
             }
-            const int r = item(s, in, sm, gs, 0xffffffffu);
+            const int r = item(s, in, sm, 0xffffffffu);
             if (r) st = r == 2 ? ST_EOB : ST_BAD;
           }
         }
@@ -377,9 +385,9 @@ __device__ inline bool decode_blocks(const In &in, uint32_t pos, P1Rec &rec, WSm
                   tgt = c < NCK2 ? (jend - S) + (ck & 0xfffu) : jend;
                 }
               }
-            } else if (s.k + 2u >= TOKCAP2) st = ST_CAP;
+            } else if (s.k + 2u >= LANECAP) st = ST_CAP;
             else {
-              const int r = item(s, in, sm, gs, tgt);
+              const int r = item(s, in, sm, tgt);
               if (r) st = r == 2 ? ST_EOB : ST_BAD;
             }
           }
@@ -406,7 +414,7 @@ __device__ inline bool decode_blocks(const In &in, uint32_t pos, P1Rec &rec, WSm
           cur = (int)nx_c;
         }
       }
-      if (term_st == ST_BAD || term_st == ST_IDLE || term_st == ST_OVER) return false;
+      if (term_st == ST_BAD || term_st == ST_IDLE || term_st == ST_OVER) { TBZ_D2_WHY("give up"); return false; }
       // a lane that ran into its token cap ends the round early: use shorter sub-chunks from here on
       if (term_st == ST_CAP && shrink < 6) shrink++;
       const uint32_t cnt = proven ? s.k - my_g : 0u;
@@ -417,8 +425,11 @@ __device__ inline bool decode_blocks(const In &in, uint32_t pos, P1Rec &rec, WSm
       }
       if (first_slab == NO_SLAB) first_slab = slab_id;
       prev_slab = slab_id;
+#if defined(TBZ_EMU) && defined(TBZ_EMU_TRACE)
+      if (lane == 0) fprintf(stderr, "[d2] round P0 %u S %u -> term_st %d pos %u (slab %u)\n", P0, S, term_st, term_pos, slab_id);
+#endif
       // ---- how did the round end?
-      if (term_pos <= pos && term_st != ST_EOB) return false;     // no progress (cannot happen; guards the loop)
+      if (term_pos <= pos && term_st != ST_EOB) { TBZ_D2_WHY("give up"); return false; }     // no progress (cannot happen; guards the loop)
       pos = term_pos;
       if (term_st == ST_EOB) block_done = true;
       __syncwarp();
@@ -435,12 +446,12 @@ __device__ inline bool decode_blocks(const In &in, uint32_t pos, P1Rec &rec, WSm
 }
 
 // One member, one warp: wrapper header, then every block.
-__device__ inline bool decode_member(const DMember &mem, int fmt, P1Rec &rec, WSmem &sm, uint16_t *gs,
+__device__ inline bool decode_member(const DMember &mem, int fmt, P1Rec &rec, WSmem &sm,
                                      uint32_t *__restrict__ slabs, uint32_t nslabs, uint32_t *slab_counter, int lane) {
   In in;
   uint32_t pos;
-  if (!member_start(mem, fmt, in, pos)) return false;
-  return decode_blocks(in, pos, rec, sm, gs, slabs, nslabs, slab_counter, lane);
+  if (!member_start(mem, fmt, in, pos)) { TBZ_D2_WHY("give up"); return false; }
+  return decode_blocks(in, pos, rec, sm, slabs, nslabs, slab_counter, lane);
 }
 
 }  // namespace tbzd2

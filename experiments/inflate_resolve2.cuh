@@ -102,51 +102,63 @@ struct WState {
   unsigned long long acc_a, acc_w;        // per lane: sum d and sum i*d over the bytes it flushed (Adler-32)
 };
 
+// Where a lane's source words come from, decided a step ahead (prepare) so that the words of a source older than the
+// ring — an L2 round trip — travel while the previous step is still being copied.
+struct Src {
+  uint32_t E, S[NW + 2];                  // E = the word before slot 0 (the head may start there); S[j], S[j+1] feed word slot j
+};
+
+// The geometry of a ready match: hb head bytes up to the first aligned destination word, then full words, then a tail.
+__device__ __forceinline__ uint32_t copy_s0(uint32_t dst, uint32_t src) {    // aligned source offset of word slot 0
+  return (src & ~3u) + (((src & 3u) + ((0u - dst) & 3u)) & 4u);
+}
+
+// The source words of a ready match whose source is older than the ring, read from the member's output (which has them
+// by now).  Only words that hold a needed byte are touched.
+template <bool AL>
+__device__ __forceinline__ void load_far(Src &f, const uint8_t *out, uint32_t dst, uint32_t src, uint32_t n) {
+  const uint32_t s0 = copy_s0(dst, src);
+  const uint32_t need = src + n - s0;                                  // words at or beyond this byte offset hold nothing needed
+  const bool pre = s0 > src;                                           // the head starts in the word before slot 0
+  if (AL) {
+    const uint32_t *gp = reinterpret_cast<const uint32_t *>(out + s0);
+    if (pre) f.E = __ldcg(gp - 1);
+#pragma unroll
+    for (uint32_t i = 0; i < NW + 2; i++) if (4u * i < need) f.S[i] = __ldcg(gp + i);
+  } else {                                                             // `out` is not aligned: byte by byte
+    f.E = 0;
+    if (pre)
+      for (int b = 0; b < 4; b++) f.E |= (uint32_t)__ldcg(out + s0 - 4 + b) << (8 * b);
+#pragma unroll
+    for (uint32_t i = 0; i < NW + 2; i++) {
+      uint32_t v = 0;
+      for (uint32_t b = 0; b < 4; b++) if (4u * i + b < need) v |= (uint32_t)__ldcg(out + s0 + 4u * i + b) << (8 * b);
+      f.S[i] = v;
+    }
+  }
+}
+
 // One READY match, copied by its own lane: 3 <= n <= NFAST bytes from absolute offset src to dst; the source lies
 // entirely below the current step, so it never overlaps the destination, and neither range comes within EDGE bytes of
-// the end of the ring.  far: the source is older than the ring and is read from the member's output instead.
+// the end of the ring.  far: the source is older than the ring; its words are in f already (load_far).
 // Straight-line: no data-dependent branch, every shared-memory access at an immediate offset.  Lanes without a ready
 // match run along (act = false): they load unused words from wherever their garbage points inside the warp's ring.
-template <bool AL>
-__device__ __forceinline__ void copy_ready(uint32_t ring, const uint8_t *out, bool act, bool far, uint32_t dst, uint32_t src, uint32_t n) {
+__device__ __forceinline__ void copy_ready(uint32_t ring, Src &f, bool act, bool far, uint32_t dst, uint32_t src, uint32_t n) {
   const uint32_t hb = (0u - dst) & 3u;               // head bytes up to the first aligned destination word (n >= 3 >= hb)
   const uint32_t as = src & 3u;
   const uint32_t q = as + hb;                        // offset of the first full word's source on the word grid of src
   const uint32_t sh = (q & 3u) * 8u;
   const uint32_t s0 = (src & ~3u) + (q & 4u);        // aligned source offset of word slot 0
   const uint32_t rest = act ? n - hb : 0u;           // bytes in full words and the tail (none for a lane that only runs along)
-  // source words: E = the word before slot 0 (the head may start there); S[j], S[j+1] feed word slot j
-  uint32_t E, S[NW + 2];
-  {
+  if (!far) {
     const uint32_t rp = ring + (s0 & M);
-    E = lds<uint32_t>(rp - 4u);
+    f.E = lds<uint32_t>(rp - 4u);
 #pragma unroll
-    for (uint32_t i = 0; i < NW + 2; i++) S[i] = lds<uint32_t>(rp + 4u * i);
-  }
-  if (__builtin_expect(__any_sync(TBZ_FULL, act && far), 0)) {        // a source older than the ring: the same words from `out`
-    if (act && far) {
-      const uint32_t need = src + n - s0;                              // words at or beyond this byte offset hold nothing needed
-      if (AL) {
-        const uint32_t *gp = reinterpret_cast<const uint32_t *>(out + s0);
-        if (q & 4u) E = __ldcg(gp - 1);
-#pragma unroll
-        for (uint32_t i = 0; i < NW + 2; i++) if (4u * i < need) S[i] = __ldcg(gp + i);
-      } else {                                                         // `out` is not aligned: byte by byte
-        E = 0;
-        if (q & 4u)
-          for (int b = 0; b < 4; b++) E |= (uint32_t)__ldcg(out + s0 - 4 + b) << (8 * b);
-#pragma unroll
-        for (uint32_t i = 0; i < NW + 2; i++) {
-          uint32_t v = 0;
-          for (uint32_t b = 0; b < 4; b++) if (4u * i + b < need) v |= (uint32_t)__ldcg(out + s0 + 4u * i + b) << (8 * b);
-          S[i] = v;
-        }
-      }
-    }
+    for (uint32_t i = 0; i < NW + 2; i++) f.S[i] = lds<uint32_t>(rp + 4u * i);
   }
   // head: stream bytes 0..hb-1 = the bytes at src
   {
-    const uint32_t lo = (q & 4u) ? E : S[0], hi = (q & 4u) ? S[0] : S[1];
+    const uint32_t lo = (q & 4u) ? f.E : f.S[0], hi = (q & 4u) ? f.S[0] : f.S[1];
     const uint32_t hd = __funnelshift_r(lo, hi, as * 8u);
     const uint32_t hp = ring + (dst & M);
     if (act && (hb & 1u)) sts_low8(hp, hd);
@@ -157,7 +169,7 @@ __device__ __forceinline__ void copy_ready(uint32_t ring, const uint8_t *out, bo
   uint32_t tw = 0;
 #pragma unroll
   for (uint32_t j = 0; j <= NW; j++) {
-    const uint32_t v = __funnelshift_r(S[j], S[j + 1], sh);
+    const uint32_t v = __funnelshift_r(f.S[j], f.S[j + 1], sh);
     if (j < NW && rest >= 4u * (j + 1u)) sts<uint32_t>(wp + 4u * j, v);
     if (j == 0) tw = v;
     else if (rest >= 4u * j) tw = v;                                   // tw = word slot (rest / 4)
@@ -231,64 +243,92 @@ __device__ __forceinline__ void flush_to(WState &w, uint32_t upto, bool adler, i
   __syncwarp();                     // the stores are ordered before any later read of `out` by another lane
 }
 
-// One step: the lane's token (lo, hi), valid for lanes below nvalid.  Returns false when the member must go to the
-// sequential kernel.  Warp-uniform result.
+// A step, prepared: the lane's token, where it goes, what kind of work its match is.
+struct Prep {
+  uint32_t lo, hi, nvalid;                // the token; lanes below nvalid have one
+  uint32_t p, nl, n, src;                 // first output byte, literals, match length (0 = none), source offset of the match
+  uint32_t base, total;                   // (uniform) where the step starts, how many bytes it produces
+  bool ready, far, edge, pend, have;      // match by its own lane / source older than the ring (f holds it) / token near the
+  bool fail;                              // ring's end / match for the ordered path / far words already loaded.  fail: uniform
+  Src f;
+};
+
+// Prepare a step that starts at output offset `base`: offsets by a warp scan, classification, and — for sources older
+// than the ring that `out` already holds — the loads of the source words.  flushed: what `out` holds right now.
 template <bool AL>
-__device__ __forceinline__ bool step(WState &w, uint32_t lo, uint32_t hi, uint32_t nvalid, bool adler, int lane) {
-  const uint32_t ring = w.ring;
+__device__ __forceinline__ void prepare(Prep &q, const WState &w, uint32_t base, uint32_t lo, uint32_t hi, uint32_t nvalid, int lane) {
+  q.lo = lo; q.hi = hi; q.nvalid = nvalid; q.base = base;
   const bool v = (uint32_t)lane < nvalid;
   const bool m = v && (hi & T2_MATCH);
-  const uint32_t nl = v ? tbzd2::t2_nlit(hi) : 0u;
-  const uint32_t n = m ? (hi & 255u) + 3u : 0u;
-  const uint32_t mine = nl + n;
+  q.nl = v ? tbzd2::t2_nlit(hi) : 0u;
+  q.n = m ? (hi & 255u) + 3u : 0u;
+  const uint32_t mine = q.nl + q.n;
   uint32_t x = mine;
 #pragma unroll
   for (int sft = 1; sft < 32; sft <<= 1) {
     const uint32_t u = __shfl_up_sync(TBZ_FULL, x, sft);
     if (lane >= sft) x += u;
   }
-  const uint32_t total = __shfl_sync(TBZ_FULL, x, 31);
-  const uint32_t base = w.pos;
-  const uint32_t p = base + x - mine;            // the token's first byte
-  const uint32_t dst = p + nl;                   // the match's first byte
-  if ((unsigned long long)base + total > w.cap) { TBZ_R2_WHY("overflow base %u total %u cap %llu\n", base, total, w.cap); return false; }   // output overflow: the sequential kernel reports it
+  q.total = __shfl_sync(TBZ_FULL, x, 31);
+  q.p = base + x - mine;
+  const uint32_t dst = q.p + q.nl;
   const uint32_t d = ((hi >> 8) & 0x7fffu) + 1u;
-  if (__any_sync(TBZ_FULL, m && d > dst)) { TBZ_R2_WHY("distance too far at %u\n", base); return false; }   // deflate.lisp:343-345
-  const uint32_t end = base + total;
-  if (__builtin_expect(total <= SBMAX, 1)) {
+  q.src = dst - d;
+  const uint32_t end = base + q.total;
+  // output overflow, or a distance that reaches before the start of the output (deflate.lisp:343-345): the sequential kernel reports it
+  q.fail = (unsigned long long)base + q.total > w.cap || __any_sync(TBZ_FULL, m && d > dst);
+  const uint32_t ring_lo = end > H ? end - H : 0u;
+  q.far = q.src < ring_lo;
+  // a token near the ring's end (its bytes, or its source, would wrap) takes the ordered path as a whole
+  q.edge = v && ((q.p & M) > H - EDGE - 4u || (m && !q.far && (q.src & M) > H - EDGE));
+  q.ready = m && !q.edge && q.src + q.n <= base && q.n <= NFAST && q.total <= SBMAX;
+  q.pend = m && !q.ready;
+  q.have = q.ready && q.far && q.src + q.n <= w.flushed;
+  if (q.have) load_far<AL>(q.f, w.out, dst, q.src, q.n);
+}
+
+// Execute a prepared step.  Returns false when the member must go to the sequential kernel.  Warp-uniform result.
+template <bool AL>
+__device__ __forceinline__ bool execute(WState &w, Prep &q, bool adler, int lane) {
+  if (q.fail) { TBZ_R2_WHY("overflow or distance too far at %u (+%u, cap %llu)\n", q.base, q.total, w.cap); return false; }
+  const uint32_t ring = w.ring;
+  const uint32_t end = q.base + q.total;
+  if (__builtin_expect(q.total <= SBMAX, 1)) {
     const uint32_t ring_lo = end > H ? end - H : 0u;
-    const uint32_t src = dst - d;
-    const bool far = src < ring_lo;
-    // a token near the ring's end (its bytes, or its source, would wrap) takes the ordered path as a whole
-    const bool edge = v && ((p & M) > H - EDGE - 4u || (m && !far && (src & M) > H - EDGE));
-    const bool ready = m && !edge && src + n <= base && n <= NFAST;
+    const uint32_t dst = q.p + q.nl;
     // literals
     {
-      const uint32_t lp = ring + (p & M), nle = edge ? 0u : nl;
-      if (nle > 0u) sts_low8(lp, lo);
-      if (nle > 1u) sts_low8(lp + 1u, lo >> 8);
-      if (nle > 2u) sts_low8(lp + 2u, lo >> 16);
-      if (nle > 3u) sts_low8(lp + 3u, lo >> 24);
+      const uint32_t lp = ring + (q.p & M), nle = q.edge ? 0u : q.nl;
+      if (nle > 0u) sts_low8(lp, q.lo);
+      if (nle > 1u) sts_low8(lp + 1u, q.lo >> 8);
+      if (nle > 2u) sts_low8(lp + 2u, q.lo >> 16);
+      if (nle > 3u) sts_low8(lp + 3u, q.lo >> 24);
     }
-    copy_ready<AL>(ring, w.out, ready, far, dst, src, n);
+    // a far source the preparation could not load yet (it was not in `out` then; it is now)
+    if (__builtin_expect(__any_sync(TBZ_FULL, q.ready && q.far && !q.have), 0)) {
+      if (q.ready && q.far && !q.have) load_far<AL>(q.f, w.out, dst, q.src, q.n);
+    }
+    copy_ready(ring, q.f, q.ready, q.far, dst, q.src, q.n);
     __syncwarp();
     // the rest in stream order, by the whole warp
-    uint32_t pm = __ballot_sync(TBZ_FULL, edge || (m && !ready));
-    const uint32_t em = __ballot_sync(TBZ_FULL, edge);
-    while (pm) {
-      const int l = __ffs(pm) - 1;
-      pm &= pm - 1u;
-      const uint32_t pa = __shfl_sync(TBZ_FULL, p, l), ha = __shfl_sync(TBZ_FULL, hi, l);
-      if ((em >> l) & 1u) token_warp(w, pa, __shfl_sync(TBZ_FULL, lo, l), ha, ring_lo, lane);      // (literals too)
-      else copy_warp(w, pa + tbzd2::t2_nlit(ha), (ha & 255u) + 3u, ((ha >> 8) & 0x7fffu) + 1u, ring_lo, lane);
+    uint32_t pm = __ballot_sync(TBZ_FULL, q.edge || q.pend);
+    if (pm) {
+      const uint32_t em = __ballot_sync(TBZ_FULL, q.edge);
+      do {
+        const int l = __ffs(pm) - 1;
+        pm &= pm - 1u;
+        const uint32_t pa = __shfl_sync(TBZ_FULL, q.p, l), ha = __shfl_sync(TBZ_FULL, q.hi, l);
+        if ((em >> l) & 1u) token_warp(w, pa, __shfl_sync(TBZ_FULL, q.lo, l), ha, ring_lo, lane);      // (literals too)
+        else copy_warp(w, pa + tbzd2::t2_nlit(ha), (ha & 255u) + 3u, ((ha >> 8) & 0x7fffu) + 1u, ring_lo, lane);
+      } while (pm);
     }
     w.pos = end;
     if (end - w.flushed >= FLUSH) flush_to<AL>(w, w.flushed + ((end - w.flushed) / FLUSH) * FLUSH, adler, lane);
   } else {
     // a step of long matches (RLE, zeros): token by token, so that the ring never runs more than one token ahead of `out`
     for (int l = 0; l < 32; l++) {
-      const uint32_t pa = __shfl_sync(TBZ_FULL, p, l), la = __shfl_sync(TBZ_FULL, lo, l), ha = __shfl_sync(TBZ_FULL, hi, l);
-      if ((uint32_t)l >= nvalid) break;
+      const uint32_t pa = __shfl_sync(TBZ_FULL, q.p, l), la = __shfl_sync(TBZ_FULL, q.lo, l), ha = __shfl_sync(TBZ_FULL, q.hi, l);
+      if ((uint32_t)l >= q.nvalid) break;
       const uint32_t e = pa + tbzd2::t2_outlen(ha);
       token_warp(w, pa, la, ha, e > H ? e - H : 0u, lane);
       if (e - w.flushed >= FLUSH) flush_to<AL>(w, w.flushed + ((e - w.flushed) / FLUSH) * FLUSH, adler, lane);
@@ -307,20 +347,15 @@ struct Cursor {
   __device__ __forceinline__ void open(const uint32_t *slabs_, uint32_t first) {
     slabs = slabs_; slab = nullptr; list = nullptr; cnt = 0; i0 = 0; j = 32; next_slab = first; fc = 0;
   }
-  // the next step: its first token and how many tokens it has (<= 32); false at the end of the stream.  Uniform.
-  __device__ __forceinline__ bool next(const uint2 *&ptr, uint32_t &nvalid, int lane) {
+  // the next list that has tokens, in the next slab when this one is done; false at the end of the stream.  Uniform.
+  __device__ __noinline__ bool next_list(int lane) {
     for (;;) {
-      if (i0 < cnt) {
-        ptr = list + i0;
-        nvalid = cnt - i0 < 32u ? cnt - i0 : 32u;
-        i0 += 32u;
-        return true;
-      }
       if (j < 31) {
         j++;
         const uint32_t f = __shfl_sync(TBZ_FULL, fc, j);
         cnt = f >> 16; i0 = 0;
         list = reinterpret_cast<const uint2 *>(slab + SLAB_HDR_WORDS) + (uint32_t)j * TOKCAP2 + (f & 0xffffu);
+        if (cnt) return true;
         continue;
       }
       if (next_slab == NO_SLAB) return false;
@@ -331,25 +366,33 @@ struct Cursor {
       j = -1; cnt = 0; i0 = 0;
     }
   }
+  // the next step: the lane's token (zero beyond the step's nvalid <= 32 tokens); false at the end of the stream.  Uniform.
+  __device__ __forceinline__ bool next(uint2 &t, uint32_t &nvalid, int lane) {
+    if (i0 >= cnt && !next_list(lane)) { nvalid = 0; t = make_uint2(0u, 0u); return false; }
+    nvalid = cnt - i0 < 32u ? cnt - i0 : 32u;
+    t = (uint32_t)lane < nvalid ? __ldg(list + i0 + lane) : make_uint2(0u, 0u);
+    i0 += 32u;
+    return true;
+  }
 };
 
+// Every step of the stream, software-pipelined: while step k is copied, step k + 1 is prepared (its far sources are
+// on their way) and the tokens of step k + 2 are loaded.
 template <bool AL>
 __device__ inline bool resolve_stream(WState &w, const P1Rec &rec, const uint32_t *__restrict__ slabs, bool adler, int lane) {
   Cursor cur;
   cur.open(slabs, rec.first_slab);
-  const uint2 *ptr = nullptr;
-  uint32_t nvalid = 0;
-  uint2 t = make_uint2(0u, 0u);
-  bool have = cur.next(ptr, nvalid, lane);
-  if (have && (uint32_t)lane < nvalid) t = __ldg(ptr + lane);
-  while (have) {
-    const uint2 *nptr = nullptr;
-    uint32_t nn = 0;
-    uint2 tn = make_uint2(0u, 0u);
-    const bool have_n = cur.next(nptr, nn, lane);
-    if (have_n && (uint32_t)lane < nn) tn = __ldg(nptr + lane);          // travels while this step is copied
-    if (!step<AL>(w, t.x, t.y, nvalid, adler, lane)) return false;
-    t = tn; nvalid = nn; have = have_n;
+  uint2 t1, t2;
+  uint32_t nv1 = 0, nv2 = 0;
+  Prep q, qn;
+  bool have0 = cur.next(t1, nv1, lane);
+  if (have0) prepare<AL>(q, w, 0u, t1.x, t1.y, nv1, lane);
+  bool have1 = have0 && cur.next(t1, nv1, lane);
+  while (have0) {
+    const bool have2 = have1 && cur.next(t2, nv2, lane);                   // the tokens two steps ahead travel
+    if (have1) prepare<AL>(qn, w, q.base + q.total, t1.x, t1.y, nv1, lane);  // the next step's far sources travel
+    if (!execute<AL>(w, q, adler, lane)) return false;
+    q = qn; have0 = have1; have1 = have2; t1 = t2; nv1 = nv2;
   }
   // what is left in the ring: whole units, then the last partial one byte by byte
   flush_to<AL>(w, w.pos & ~15u, adler, lane);

@@ -25,10 +25,12 @@ for ln in dis.splitlines():
         lines.append(cur)
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "regex:" + kern], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
-hi = [i for i, r in enumerate(rows) if len(r) > 3 and r[0] == "Address"][0]
+his = [i for i, r in enumerate(rows) if len(r) > 3 and r[0] == "Address"]
+hi = his[0]
 hdr = rows[hi]
 ix = {h: i for i, h in enumerate(hdr)}
-body = [r for r in rows[hi + 1:] if len(r) >= len(hdr) and r[0].startswith("0x")]
+# (a report that holds several launches of the kernel lists each of them: the first one is used)
+body = [r for r in rows[hi + 1:(his[1] if len(his) > 1 else len(rows))] if len(r) >= len(hdr) and r[0].startswith("0x")]
 n = min(len(body), len(lines))
 if len(body) != len(lines):
     print("warning: %d sass rows vs %d disassembled instructions" % (len(body), len(lines)), file=sys.stderr)

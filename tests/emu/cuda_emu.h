@@ -27,6 +27,7 @@
 #define __forceinline__ inline __attribute__((always_inline))
 #define __constant__ const
 #define __launch_bounds__(...)
+#define __noinline__ __attribute__((noinline))
 #define __align__(n) alignas(n)
 #define __shared__ static thread_local
 

@@ -5,7 +5,6 @@
 #include "kernels.cuh"
 
 extern "C" int emu_inflate_batch(int fmt, const tbz_member *m, uint64_t n, tbz_result *r, uint32_t flags, int os_threads, int variant) {
-  // variant bit 0: the round-1 kernels (inflate_decode.cuh + inflate_copy.cuh) instead of inflate_decode2.cuh + inflate_resolve2.cuh
   emu_os_threads = os_threads > 0 ? os_threads : 1;
   if (!n) return 0;
   std::vector<DMember> dm(n);
@@ -18,27 +17,19 @@ extern "C" int emu_inflate_batch(int fmt, const tbz_member *m, uint64_t n, tbz_r
     return 0;
   }
   std::vector<tbzfast::P1Rec> recs(n);
-  const uint64_t round_bytes = (uint64_t)tbzfast::NL * tbzfast::S_MAX / 8;
+  const uint64_t round_bytes = (uint64_t)tbzhd::NL * tbzhd::S_MAX / 8;
   uint64_t want = 0;
-  for (uint64_t i = 0; i < n; i++) want += 2 * (m[i].in_len / round_bytes) + 4;
+  for (uint64_t i = 0; i < n; i++) want += 4 * (m[i].in_len / round_bytes) + 6;
   const uint32_t nslabs = (uint32_t)want;
-  std::vector<uint32_t> slabs((size_t)nslabs * tbzfast::SLAB_WORDS);
-  if (variant & 1) {           // the round-1 pair: 32-bit tokens, one CTA per member in phase two
-    const unsigned dec_grid = std::min<unsigned>((nn + tbzfast::WPC - 1) / tbzfast::WPC, 16);
-    emu_launch(k_inflate_decode, dim3(dec_grid), dim3(tbzfast::NT), sizeof(tbzfast::WSmem) * tbzfast::WPC,
-               (const DMember *)dm.data(), nn, fmt, recs.data(), slabs.data(), nslabs, counters.data(), todo.data());
-    emu_launch(k_inflate_resolve, dim3(std::min<unsigned>(nn, 16)), dim3(tbzp2::NT), sizeof(tbzp2::Smem),
-               (const DMember *)dm.data(), r, nn, fmt, (const tbzfast::P1Rec *)recs.data(), (const uint32_t *)slabs.data(),
-               counters.data(), todo.data());
-  } else {
-    const unsigned dec_grid = std::min<unsigned>((nn + tbzd2::WPC - 1) / tbzd2::WPC, 16);
-    std::vector<uint16_t> scratch((size_t)dec_grid * tbzd2::WPC * tbzd2::SCRATCH_U16);
-    emu_launch(k_inflate_decode2, dim3(dec_grid), dim3(tbzd2::NT), sizeof(tbzd2::WSmem) * tbzd2::WPC,
-               (const DMember *)dm.data(), nn, fmt, recs.data(), slabs.data(), nslabs, counters.data(), todo.data(), scratch.data());
-    emu_launch(k_inflate_resolve2, dim3(std::min<unsigned>((nn + tbzr2::WPC - 1) / tbzr2::WPC, 16)), dim3(tbzr2::NT), tbzr2::SMEM_BYTES,
-               (const DMember *)dm.data(), r, nn, fmt, (const tbzfast::P1Rec *)recs.data(), (const uint32_t *)slabs.data(),
-               counters.data(), todo.data());
-  }
+  std::vector<unsigned char> slabs((size_t)nslabs * tbzhd::SLAB_BYTES + 16);
+  unsigned char *slab0 = (unsigned char *)(((uintptr_t)slabs.data() + 15) & ~(uintptr_t)15);
+  (void)variant;
+  const unsigned dec_grid = std::min<unsigned>((nn + tbzhd::WPC - 1) / tbzhd::WPC, 16);
+  emu_launch(k_inflate_decode, dim3(dec_grid), dim3(tbzhd::NT), sizeof(tbzhd::WSmem) * tbzhd::WPC,
+             (const DMember *)dm.data(), nn, fmt, recs.data(), slab0, nslabs, counters.data(), todo.data());
+  emu_launch(k_inflate_resolve, dim3(std::min<unsigned>((nn + tbzlz::WPC - 1) / tbzlz::WPC, 16)), dim3(tbzlz::NT), tbzlz::SMEM_BYTES,
+             (const DMember *)dm.data(), r, nn, fmt, (const tbzfast::P1Rec *)recs.data(), (const unsigned char *)slab0,
+             counters.data(), todo.data());
   if (fmt == TBZ_GZIP)
     emu_launch(tbzcrc::k_member_crc, dim3(std::min<unsigned>(nn, 16)), dim3(tbzcrc::NT), 0,
                (const DMember *)dm.data(), r, nn, (const tbzfast::P1Rec *)recs.data(), counters.data(), todo.data());

@@ -13,7 +13,7 @@ from oracle import o3bz
 from tests import cases, emuutil
 from tests.gpuutil import compare
 
-VARIANTS = [0, 1]       # 0: round-2 phase two (inflate_resolve2.cuh), 1: round-1 phase two (inflate_copy.cuh)
+VARIANTS = [0]          # (one pair of batched kernels: huff_decode.cuh + lz_resolve.cuh)
 
 
 @pytest.fixture(scope="module", autouse=True)
