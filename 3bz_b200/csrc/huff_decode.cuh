@@ -4,13 +4,15 @@
 // The compressed bits of a block are cut into 32 sub-chunks of S bits.  Lane i starts at the first bit of
 // sub-chunk i without knowing whether a symbol starts there (only lane 0 does) and relies on the
 // self-synchronisation of Huffman streams (117 bits on average on the text of BASELINE config 2, p99 595):
-//   * every lane decodes into its own token list (global memory) and records where its first tokens start
-//     (every token up to CK_DENSE, then every CK_STEP-th) in shared memory
+//   * every lane decodes into its own token list (a scratch area per warp, global memory) and records where its first
+//     tokens start (every token up to CK_DENSE, then every CK_STEP-th) in shared memory
 //   * a lane does not stop at the end of its sub-chunk: it decodes on until one of its token boundaries coincides
 //     with a recorded token start of the lane that owns those bits — from there on both decodes are identical
 //     (same tables, same bit), so the owner's list is proven from that token on and this lane is done.
 //     One loop does both: the owner of the next sub-chunk recorded its first token starts ~S bits ago
-//   * a walk over "who synchronised into whom" from lane 0 gives the proven lanes and their first proven token
+//   * a walk over "who synchronised into whom" from lane 0 gives the proven lanes and their first proven token; the
+//     proven tokens of the round are then copied, lane after lane, into one contiguous block of the token heap
+//     (allocated with one atomic add now that the count is known): phase two reads a member's tokens as plain arrays
 // What this kernel is bound by is its instruction count, so the loop body is branch-free for the common symbols:
 //   * 32-bit table entries carry everything a symbol needs: byte 0 = code length | kind flags, byte 1 = bits to
 //     drop (length + extra bits), bits 31..17 = the BASE VALUE (literal, length - 3, distance - 1); the extra bits
@@ -21,9 +23,12 @@
 //   * an iteration decodes one item with exactly two lookups, the same instructions for every lane: a length and
 //     its distance, or a literal and — if the next symbol is a literal too — that one as well
 //   * the bit reader keeps three stream words and a bit offset: a peek is a funnel shift, dropping bits an add,
-//     one refill point per iteration (deflate.lisp:142-231 keeps a shifted 64-bit accumulator instead)
-//   * a token is `up to four literals + one match` (8 bytes), written with one predicated store when a match (or a
-//     fifth literal) closes it: phase two (lz_resolve.cuh) has one back-reference per lane and step
+//     one refill point per iteration (deflate.lisp:142-231 keeps a shifted 64-bit accumulator instead).  The stream
+//     reaches every lane in 16-byte chunks, two of them waiting or on their way in shared-memory slots with cp.async
+//     (LDGSTS): a load into a register that the loop carries forward costs a move that waits for it whatever the
+//     distance to its first use, and one 16-byte request per four words is a quarter of the memory pipe's work
+//   * a token is `up to four literals + one match` (8 bytes), closed by a match (or a fifth literal); two tokens leave
+//     with one 16-byte store: phase two (lz_resolve.cuh) has one back-reference per lane and step
 // Stored blocks travel as literal tokens.  Output offsets are not tracked here: phase two scans the lengths anyway
 // and owns the overflow verdict.  Anything not provably clean (bad codes, truncation, a header this kernel does not
 // take) sends the member to the sequential kernel (inflate_seq.cuh), which reproduces the reference's verdict.
@@ -45,19 +50,18 @@ using tbzfast::Canon16;
 using tbzfast::canon_lookup;
 using tbzfast::In;
 using tbzfast::member_start;
-using tbzfast::NO_SLAB;
 using tbzfast::P1Rec;
 using tbzfast::peek32;
 using tbzfast::warp_canon;
 
 #ifndef TBZ_HD_SMAX
-#define TBZ_HD_SMAX 6144
+#define TBZ_HD_SMAX 8000
 #endif
 #ifndef TBZ_HD_KD
 #define TBZ_HD_KD 8
 #endif
 #ifndef TBZ_HD_SUBCAP
-#define TBZ_HD_SUBCAP 288
+#define TBZ_HD_SUBCAP 224
 #endif
 #ifndef TBZ_HD_MINBLOCKS
 #define TBZ_HD_MINBLOCKS 7
@@ -70,21 +74,28 @@ constexpr uint32_t SUBCAP = TBZ_HD_SUBCAP;          // second-level entries a bl
 constexpr uint32_t LUT_D = 1u << KLL, LUT_SUB = LUT_D + (1u << KD), LUT_N = LUT_SUB + SUBCAP;
 constexpr uint32_t LISTCAP = 512;                   // 64-bit tokens a lane may emit per round (sub-chunk + overrun)
 constexpr uint32_t S_MAX = TBZ_HD_SMAX, S_MIN = 256;  // sub-chunk size in bits
-constexpr uint32_t CK_DENSE = 16, CK_STEP = 16, NCK = 24;   // recorded token starts: tokens 0..15, then 16 + 16 i
-constexpr uint16_t CK_NONE = 0xffffu;
-static_assert(S_MAX < 0xffffu && NCK > CK_DENSE, "a recorded token start is a 16-bit offset into the sub-chunk");
+constexpr uint32_t CK_DENSE = 24, CK_EVERY = 16, CK_SPARSE = 24, NCK = CK_DENSE + CK_SPARSE;   // recorded token starts: tokens 0..23 (shared memory: the bits since the token before), then one every CK_EVERY iterations (global scratch: rarely looked at)
+constexpr uint16_t CK_NONE = 0xffffu, CK_END = 0xfffeu;     // not recorded (yet) / the lane records no more
+static_assert(S_MAX < 0xfffeu, "a recorded token start is a 16-bit offset into the sub-chunk");
 
-// A slab holds the token lists of one round: header, then NL lists of LISTCAP 64-bit tokens.
-struct SlabHdr {
-  uint32_t next;        // next slab of the member, or NO_SLAB
-  uint32_t pad[3];
-  uint32_t fc[NL];      // per lane: first proven token | (number of proven tokens << 16); 0 = nothing
-};
-constexpr uint32_t SLAB_HDR_BYTES = sizeof(SlabHdr);
-constexpr size_t SLAB_BYTES = SLAB_HDR_BYTES + (size_t)NL * LISTCAP * 8;
-static_assert(SLAB_HDR_BYTES % 16 == 0 && LISTCAP <= 0xffffu, "slab geometry");
-__device__ __forceinline__ uint2 *slab_list(unsigned char *slab, int lane) {
-  return reinterpret_cast<uint2 *>(slab + SLAB_HDR_BYTES) + (size_t)lane * LISTCAP;
+// The token heap: 16-byte units handed out by an atomic counter.  A block = one header unit {next block (unit index) or
+// NO_BLOCK, number of tokens, 0, 0} + its tokens; the blocks of a member form a chain in stream order.
+constexpr uint32_t NO_BLOCK = 0xffffffffu;
+constexpr size_t SCRATCH_BYTES = (size_t)NL * LISTCAP * 8 + (size_t)NL * (CK_SPARSE + 1) * 4;   // the per-warp lists a round decodes into + the sparse token starts
+__device__ __forceinline__ uint32_t block_units(uint32_t ntok) { return 1u + (ntok + 1u) / 2u; }
+// A new block of ntok tokens behind block `prev` of the chain (uniform arguments; lane 0 allocates and links).
+// Returns its unit index, or NO_BLOCK when the heap is exhausted.
+__device__ __forceinline__ uint32_t block_alloc(uint4 *heap, uint32_t heap_units, uint32_t *heap_top, uint32_t ntok, uint32_t prev, int lane) {
+  uint32_t u = 0;
+  if (lane == 0) {
+    u = atomicAdd(heap_top, block_units(ntok));
+    if (u + block_units(ntok) > heap_units || u + block_units(ntok) < u) u = NO_BLOCK;
+    else {
+      heap[u] = make_uint4(NO_BLOCK, ntok, 0u, 0u);
+      if (prev != NO_BLOCK) reinterpret_cast<uint32_t *>(heap + prev)[0] = u;
+    }
+  }
+  return __shfl_sync(TBZ_FULL, u, 0);
 }
 
 // ---- 64-bit token: lo = up to four literal bytes (first byte lowest); hi: [7:0] match length - 3, [22:8] distance - 1,
@@ -117,10 +128,25 @@ __device__ __forceinline__ uint32_t e_value(uint32_t e, uint32_t x, uint32_t n) 
   return (e >> 17) + __funnelshift_r(x & ~(0xffffffffu << n), 0u, e);                                     // (shift = e & 31 = L)
 }
 
+// ---- shared-space addressing and cp.async for the per-lane input slots
+#ifdef TBZ_EMU
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)((const unsigned char *)p - ::emu::dyn_smem()); }
+__device__ __forceinline__ uint32_t lds32(uint32_t a) { return *reinterpret_cast<const uint32_t *>(::emu::dyn_smem() + a); }
+__device__ __forceinline__ void cp_async16(uint32_t a, const void *g) { memcpy(::emu::dyn_smem() + a, g, 16); }
+__device__ __forceinline__ void cp_async_commit() {}
+template <int N> __device__ __forceinline__ void cp_async_wait() {}
+#else
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void cp_async16(uint32_t a, const void *g) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(a), "l"(g) : "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+#endif
+
 struct HdrScratch {                      // only alive while a block header is parsed and the tables are built
   uint16_t lut_cl[128];
   Canon16 c_cl, c_ll, c_d;
-  uint16_t sorted_cl[32], sorted_ll[288], sorted_d[32];
+  uint16_t sorted_cl[32], sorted_d[32];
   uint16_t run[16];
 };
 // The code lengths of a header ([0,19) code-length code, [32,352) lit/len + distance) live where the second-level
@@ -129,15 +155,33 @@ static_assert(SUBCAP * 4 >= 352, "code lengths under the second-level tables");
 struct WSmem {                           // one per warp
   uint32_t lut[LUT_N];                   // lit/len root table, distance root table, second-level tables
   union {
-    struct {
-      uint16_t ckpt[NCK][NL];            // [slot][lane]: bit offset in the lane's sub-chunk where that token starts
-      uint32_t own_done;                 // bit l: lane l has left its own sub-chunk (it records no more token starts)
-    };
+    uint4 inq[2][NL];                    // [slot][lane]: the lane's 16-byte chunk c of the stream waits in slot c % 2 (cp.async landing zone)
+    uint16_t sorted_ll[288];             // (while the tables are built: the lit/len symbols sorted by code)
+  };
+  union {
+    uint8_t ckd[CK_DENSE][NL];           // [token][lane]: the bits between the starts of this token and the one before; 0 = not recorded (yet), 1 = the lane records no more
     HdrScratch h;
   };
 };
-static_assert(sizeof(HdrScratch) <= sizeof(uint16_t) * NCK * NL + 4, "header scratch must fit under the checkpoints");
-static_assert((sizeof(WSmem) * WPC + 1024) * TBZ_HD_MINBLOCKS <= 232448, "CTAs per SM");
+static_assert(sizeof(HdrScratch) <= sizeof(uint8_t) * CK_DENSE * NL, "header scratch must fit under the checkpoints");
+static_assert((sizeof(WSmem) * WPC + 1024) * TBZ_HD_MINBLOCKS <= 233472, "CTAs per SM (228 KB, 1 KB of it reserved per CTA)");
+
+// recorded token starts: the dense ones in shared memory (slot = token index; the value is the distance from the start
+// recorded before), the sparse ones — offset | token index << 16 — in the warp's global scratch (written by their
+// lane, read by another lane of the same warp after a __syncwarp, past L1); the slot behind a sparse one is set to
+// "not yet" first
+__device__ __forceinline__ void ck_put(WSmem &sm, uint32_t *gck, uint32_t slot, int lane, uint32_t off, uint32_t tok, uint32_t lastoff) {
+  if (slot < CK_DENSE) sm.ckd[slot][lane] = (uint8_t)(off - lastoff);
+  else {
+    uint32_t *g = gck + lane * (CK_SPARSE + 1) + (slot - CK_DENSE);
+    g[1] = CK_NONE;
+    g[0] = off | (tok << 16);
+  }
+}
+__device__ __forceinline__ void ck_end(WSmem &sm, uint32_t *gck, uint32_t slot, int lane) {
+  if (slot < CK_DENSE) sm.ckd[slot][lane] = 1;
+  else gck[lane * (CK_SPARSE + 1) + (slot - CK_DENSE)] = CK_END;
+}
 
 enum { ST_RUN = 0, ST_END, ST_SYNC, ST_EOB, ST_CAP, ST_BAD, ST_IDLE };   // ST_IDLE: the lane had nothing to decode
 
@@ -186,13 +230,74 @@ __device__ inline bool build_sub(uint32_t *lut, uint32_t root, const Canon16 &c,
   return true;
 }
 
+// What a lane needs only at the rare token boundaries where something has to be looked at (a token start to record, a
+// full list, a place where it may synchronise): kept out of the decode loop's registers (the function below is not
+// inlined, so this lives in local memory), as is the code.
+struct Rare {
+  uint32_t cstart, cend, winend, S;                  // the lane's sub-chunk, the end of the round's window, the sub-chunk size
+  uint32_t slot;                                     // the next token start to record (token 0 starts at offset 0)
+  uint32_t lastoff;                                  // offset of the token start recorded last
+  uint32_t tgt;                                      // the next place where a synchronisation can happen
+  uint32_t j, jstart, c, dof;                        // the lane this one is compared with, its sub-chunk start, its recorded start c (dof: offset of start c - 1)
+  uint32_t nx, g_sync;                               // ST_SYNC: synchronised into token g_sync of lane nx
+  uint32_t endp;                                     // where the lane's list ends
+};
+struct RareOut { int st; uint32_t evk, tgt; };
+// k tokens are closed, the next one starts at bit pb (p1: where the reader is).  Returns the lane's new state, the token
+// count of its next event and the next place where it may synchronise.
+__device__ __noinline__ RareOut rare_event(Rare &r, WSmem &sm, uint32_t *gck, int lane, uint32_t k, uint32_t evk, uint32_t pb, uint32_t p1) {
+  int st = ST_RUN;
+  if (k == evk) {
+    if (k + 2u >= LISTCAP) { st = ST_CAP; r.endp = pb; }
+    else if (pb < r.cend && r.slot < NCK) {
+      // inside the own sub-chunk: record where this token starts
+      ck_put(sm, gck, r.slot, lane, pb - r.cstart, k, r.lastoff);
+      r.lastoff = pb - r.cstart;
+      r.slot++;
+      evk = r.slot < CK_DENSE ? r.slot : LISTCAP - 2u;       // (beyond the dense ones: when the iteration count says so)
+    } else evk = LISTCAP - 2u;
+  }
+  if (st == ST_RUN && pb >= r.tgt) {
+    // past the own sub-chunk: does a token of the lane that owns these bits start here?
+    if (r.tgt == r.cend && r.slot < NCK) ck_end(sm, gck, r.slot, lane);
+    if (pb >= r.winend) { st = ST_END; r.endp = p1; }
+    else {
+      while (pb >= r.jstart + r.S) { r.j++; r.jstart += r.S; r.c = 1; r.dof = 0; }
+      const uint32_t j = r.j, rel = pb - r.jstart;
+      uint32_t c = r.c, dof = r.dof;
+      // the first recorded start at or beyond rel: ck = its offset (or "not yet" / "no more"), c its slot
+      uint32_t ck = 0u, ckv = 0u;
+      if (rel) {
+        ck = CK_NONE;
+        while (c < CK_DENSE) {
+          const uint32_t d = sm.ckd[c][j];
+          if (d < 2u) { ck = d ? CK_END : CK_NONE; break; }
+          if (dof + d >= rel) { ck = dof + d; break; }
+          dof += d; c++;
+        }
+        if (c >= CK_DENSE)
+          while (c < NCK && (ck = (ckv = __ldcg(gck + j * (CK_SPARSE + 1) + (c - CK_DENSE))) & 0xffffu) < rel) c++;
+      }
+      r.c = c; r.dof = dof;
+      if (c < NCK && ck == rel) {
+        st = ST_SYNC; r.nx = j; r.g_sync = !rel ? 0u : c < CK_DENSE ? c : ckv >> 16; r.endp = pb;
+      } else if (c < NCK && ck < CK_END) r.tgt = r.jstart + ck;
+      else if (c >= NCK || ck == CK_END) r.tgt = r.jstart + r.S;                  // no more recorded starts in that sub-chunk
+      else r.tgt = pb;                                                            // its owner is not there yet: look again
+    }
+  }
+  if (st != ST_RUN && r.slot < NCK) ck_end(sm, gck, r.slot, lane);                // (whatever ended it: no more token starts from this lane)
+  RareOut o; o.st = st; o.evk = evk; o.tgt = r.tgt;
+  return o;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Every block of a member from bit `pos` on, one warp.  Returns true when the token stream is complete (rec filled in),
 // false when the member goes to the sequential kernel.  Every return value is warp-uniform.
 // ------------------------------------------------------------------------------------------------
-__device__ inline bool decode_blocks(const In &in, uint32_t pos, P1Rec &rec, WSmem &sm,
-                                     unsigned char *__restrict__ slabs, uint32_t nslabs, uint32_t *slab_counter, int lane) {
-  uint32_t first_slab = NO_SLAB, prev_slab = NO_SLAB;
+__device__ inline bool decode_blocks(const In &in, uint32_t pos, P1Rec &rec, WSmem &sm, uint2 *__restrict__ scratch,
+                                     uint4 *__restrict__ heap, uint32_t heap_units, uint32_t *heap_top, int lane) {
+  uint32_t first_blk = NO_BLOCK, prev_blk = NO_BLOCK;
   uint32_t prev_block_bits = 0;   // size of the previous block of this member: predicts this one
   uint32_t s_cap = S_MAX;         // longest sub-chunk a lane's token list has room for (learned when a list fills up)
   bool last = false;
@@ -276,30 +381,19 @@ __device__ inline bool decode_blocks(const In &in, uint32_t pos, P1Rec &rec, WSm
       uint32_t bp = pos >> 3;                                          // byte offset of the payload from in.w
       pos += 8u * slen;
       while (slen) {
-        uint32_t slab_id = 0;
-        if (lane == 0) slab_id = atomicAdd(slab_counter, 1u);
-        slab_id = __shfl_sync(TBZ_FULL, slab_id, 0);
-        if (slab_id >= nslabs) { TBZ_HD_WHY("give up"); return false; }
-        unsigned char *slab = slabs + (size_t)slab_id * SLAB_BYTES;
-        SlabHdr *sh = reinterpret_cast<SlabHdr *>(slab);
-        const uint32_t nb = slen < (uint32_t)(NL * LISTCAP * 4) ? slen : (uint32_t)(NL * LISTCAP * 4);
-        const uint32_t per = ((nb + NL - 1) / NL + 3u) & ~3u;          // bytes per lane, a multiple of four
-        const uint32_t lo = per * lane < nb ? per * lane : nb, hi = lo + per < nb ? lo + per : nb;
-        const uint32_t cnt = (hi - lo + 3u) / 4u;
-        uint2 *list = slab_list(slab, lane);
-        for (uint32_t t = 0; t < cnt; t++) {
-          const uint32_t a = lo + 4u * t, m = hi - a < 4u ? hi - a : 4u;
+        const uint32_t nb = slen < (1u << 20) ? slen : (1u << 20);      // bytes in this token block
+        const uint32_t ntok = (nb + 3u) / 4u;
+        const uint32_t blk = block_alloc(heap, heap_units, heap_top, ntok, prev_blk, lane);
+        if (blk == NO_BLOCK) { TBZ_HD_WHY("give up"); return false; }
+        uint2 *const tok = reinterpret_cast<uint2 *>(heap + blk + 1);
+        for (uint32_t t = lane; t < ntok; t += 32u) {
+          const uint32_t a = 4u * t, m = nb - a < 4u ? nb - a : 4u;
           uint32_t wv = peek32(in, (bp + a) * 8u);
           if (m < 4u) wv &= (1u << (8u * m)) - 1u;
-          list[t] = make_uint2(wv, m << 23);
+          tok[t] = make_uint2(wv, m << 23);
         }
-        sh->fc[lane] = cnt << 16;
-        if (lane == 0) {
-          sh->next = NO_SLAB;
-          if (prev_slab != NO_SLAB) reinterpret_cast<SlabHdr *>(slabs + (size_t)prev_slab * SLAB_BYTES)->next = slab_id;
-        }
-        if (first_slab == NO_SLAB) first_slab = slab_id;
-        prev_slab = slab_id;
+        if (first_blk == NO_BLOCK) first_blk = blk;
+        prev_blk = blk;
         bp += nb; slen -= nb;
         __syncwarp();
       }
@@ -310,13 +404,13 @@ __device__ inline bool decode_blocks(const In &in, uint32_t pos, P1Rec &rec, WSm
     }
     __syncwarp();
     // ================= tables (huffman-tree.lisp:99-218) =================
-    if (warp_canon(hlens + 32, hlit, sm.h.c_ll, sm.h.sorted_ll, sm.h.run, lane)) { TBZ_HD_WHY("give up"); return false; }
+    if (warp_canon(hlens + 32, hlit, sm.h.c_ll, sm.sorted_ll, sm.h.run, lane)) { TBZ_HD_WHY("give up"); return false; }
     if (warp_canon(hlens + 32 + hlit, hdist, sm.h.c_d, sm.h.sorted_d, sm.h.run, lane)) { TBZ_HD_WHY("give up"); return false; }
     if (sm.h.c_ll.nsyms == 0) { TBZ_HD_WHY("give up"); return false; }
     // a lone code longer than its root table would leave holes in a second-level table: nothing writes such a block
     if ((sm.h.c_ll.nsyms == 1 && sm.h.c_ll.maxlen > KLL) || (sm.h.c_d.nsyms == 1 && sm.h.c_d.maxlen > KD)) { TBZ_HD_WHY("give up"); return false; }
     for (int e = lane; e < (1 << KLL); e += 32) {
-      const uint32_t r = canon_lookup(sm.h.c_ll, sm.h.sorted_ll, (uint32_t)e, 1, KLL);
+      const uint32_t r = canon_lookup(sm.h.c_ll, sm.sorted_ll, (uint32_t)e, 1, KLL);
       lut[e] = r ? ll_entry(r >> 4, r & 15) : E_INVALID;
     }
     for (int e = lane; e < (1 << KD); e += 32) {
@@ -326,7 +420,7 @@ __device__ inline bool decode_blocks(const In &in, uint32_t pos, P1Rec &rec, WSm
     __syncwarp();
     {
       uint32_t sub = LUT_SUB;
-      if (sm.h.c_ll.maxlen > KLL && !build_sub<KLL, false>(lut, 0u, sm.h.c_ll, sm.h.sorted_ll, sub, lane)) { TBZ_HD_WHY("give up"); return false; }
+      if (sm.h.c_ll.maxlen > KLL && !build_sub<KLL, false>(lut, 0u, sm.h.c_ll, sm.sorted_ll, sub, lane)) { TBZ_HD_WHY("give up"); return false; }
       if (sm.h.c_d.maxlen > KD && !build_sub<KD, true>(lut, LUT_D, sm.h.c_d, sm.h.sorted_d, sub, lane)) { TBZ_HD_WHY("give up"); return false; }
     }
     __syncwarp();
@@ -339,11 +433,6 @@ __device__ inline bool decode_blocks(const In &in, uint32_t pos, P1Rec &rec, WSm
     if (prev_block_bits && prev_block_bits + prev_block_bits / 16 < expect) expect = prev_block_bits + prev_block_bits / 16;
     bool block_done = false;
     while (!block_done) {
-      // ---- a slab for this round's token lists
-      uint32_t slab_id = 0;
-      if (lane == 0) slab_id = atomicAdd(slab_counter, 1u);
-      slab_id = __shfl_sync(TBZ_FULL, slab_id, 0);
-      if (slab_id >= nslabs) { TBZ_HD_WHY("give up"); return false; }
       // ---- geometry of this round
       const uint32_t P0 = pos;
       uint32_t left = in.end - P0;
@@ -354,40 +443,52 @@ __device__ inline bool decode_blocks(const In &in, uint32_t pos, P1Rec &rec, WSm
       if (S < S_MIN) S = S_MIN;
       uint32_t winend = P0 + S * NL;
       if (winend > in.end) winend = in.end;
-#pragma unroll 4
-      for (uint32_t c = 0; c < NCK; c++) sm.ckpt[c][lane] = CK_NONE;
-      if (lane == 0) sm.own_done = 0u;
-      unsigned char *slab = slabs + (size_t)slab_id * SLAB_BYTES;
-      SlabHdr *sh = reinterpret_cast<SlabHdr *>(slab);
-      uint2 *const list = slab_list(slab, lane);
+      uint32_t *const gck = reinterpret_cast<uint32_t *>(scratch + (size_t)NL * LISTCAP);
+#pragma unroll
+      for (uint32_t c = 0; c < CK_DENSE; c++) sm.ckd[c][lane] = 0;
+      gck[lane * (CK_SPARSE + 1)] = CK_NONE;             // (a sparse slot is set to "not yet" before the one in front of it is filled)
+      uint2 *const list = scratch + (size_t)lane * LISTCAP;
       __syncwarp();
 
+      const uint32_t *const inw = in.w;
+      const uint32_t lastw = in.nwords - 1u;       // (words past the end repeat the last one: a lane that gets there is discarded)
+      const uint32_t woff = (uint32_t)(((uintptr_t)inw >> 2) & 3u);
+      const uint4 *const inb = reinterpret_cast<const uint4 *>(inw - woff);
+      const uint32_t lastc = (lastw + woff) >> 2;
       // ---- the lane's state
       const uint32_t cstart = P0 + S * lane, cend = cstart + S;
       uint32_t lb = 0, nl = 0;          // the literals of the open token
       uint32_t k = 0;                   // tokens closed
-      uint32_t slot = 1;                // the next token start to record (token 0 starts at offset 0) ...
-      uint32_t evk = 1;                 // ... is that of token evk; with nothing left to record: the token count of a full list
-      uint32_t tgt = cend;              // the next place where a synchronisation can happen,
-      uint32_t twi = (tgt >> 5) + 4u;   // and the reader's word index from which on it may have been reached
-      uint32_t j = lane + 1, jstart = cend, c = 0;   // the lane, its sub-chunk start and recorded start this lane is compared with
-      uint32_t nx = 0, g_sync = 0;      // ST_SYNC: synchronised into token g_sync of lane nx
-      uint32_t endp = cstart;           // where the lane's list ends
-      // the bit reader: three stream words, the next one on its way, a bit offset below 32 between iterations; the
-      // position of the reader is 32 (wi - 4) + bo
-      uint32_t w0 = 0, w1 = 0, w2 = 0, nw = 0, wi = 4, bo = 0;
-      const uint32_t *const inw = in.w;
-      const uint32_t lastw = in.nwords - 1u;       // (words past the end repeat the last one: a lane that gets there is discarded)
+      uint32_t evk = 1;                 // the token count at which something is to be done: a token start to record, a full list
+      uint32_t twi = (cend >> 5) + 3u + woff;   // the reader's word index from which on the next place to synchronise may have been reached
+      Rare rare;
+      rare.cstart = cstart; rare.cend = cend; rare.winend = winend; rare.S = S;
+      rare.slot = 1; rare.lastoff = 0; rare.tgt = cend;
+      rare.j = lane + 1; rare.jstart = cend; rare.c = 1; rare.dof = 0;
+      rare.nx = 0; rare.g_sync = 0; rare.endp = cstart;
+      // the bit reader: three stream words, a bit offset below 32 between iterations, word wi the next to move up (word
+      // indices count from the 16-byte aligned address at or below in.w; the chunk of word wi and the one behind it are
+      // in the lane's slots or on their way there); the reader is at bit 32 (wi - 3 - woff) + bo
+      uint32_t w0 = 0, w1 = 0, w2 = 0, wi = 3, bo = 0;
+      const uint32_t inq = smem_addr(&sm.inq[0][lane]);
+      uint32_t plo = 0, phi = 0;        // a closed token that waits for its neighbour (two tokens per store)
       int st = cstart < winend ? ST_RUN : ST_IDLE;
       if (st == ST_RUN) {
         const uint32_t q = cstart >> 5;
         w0 = __ldg(inw + min(q, lastw)); w1 = __ldg(inw + min(q + 1u, lastw)); w2 = __ldg(inw + min(q + 2u, lastw));
-        nw = __ldg(inw + min(q + 3u, lastw)); wi = q + 4u; bo = cstart & 31u;
-        sm.ckpt[0][lane] = 0;
+        wi = q + 3u + woff; bo = cstart & 31u;
+        cp_async16(inq + ((wi & 4u) << 7), inb + min(wi >> 2, lastc)); cp_async_commit();
+        cp_async16(inq + ((~wi & 4u) << 7), inb + min((wi >> 2) + 1u, lastc)); cp_async_commit();
       }
       __syncwarp();
 
+      uint32_t it = 0;                  // iterations of the loop (uniform)
+#ifdef TBZ_HD_TIMING
+      const long long t_loop0 = clock64();
+#endif
       while (__any_sync(TBZ_FULL, st == ST_RUN)) {
+        // every CK_EVERY iterations: the lanes still inside their own sub-chunk record the start of their next token
+        if ((++it & (CK_EVERY - 1u)) == 0u && evk >= LISTCAP - 2u) evk = k + 1u;       // (what there is to record, if anything, the event decides)
         if (st == ST_RUN) {
           // ---- first symbol: lit/len
           const uint32_t x = __funnelshift_r(w0, w1, bo);
@@ -396,7 +497,7 @@ __device__ inline bool decode_blocks(const In &in, uint32_t pos, P1Rec &rec, WSm
             if (e & K_SUB) e = lut[(e >> 17) + ((x >> KLL) & ~(0xffffffffu << (e & 31u)))];
             if (e & K_STOP) {
               if (e & K_LEN) st = ST_BAD;
-              else { st = ST_EOB; endp = ((wi - 4u) << 5) + bo + (e & 31u); }
+              else { st = ST_EOB; rare.endp = ((wi - 3u - woff) << 5) + bo + (e & 31u); }
             }
           }
           const uint32_t n1 = e_drop(e);
@@ -412,62 +513,54 @@ __device__ inline bool decode_blocks(const In &in, uint32_t pos, P1Rec &rec, WSm
           const uint32_t v1 = e_value(e, x, n1), v2 = e_value(e2, y, n2);
           if (__builtin_expect(ism && (e2 & K_STOP) != 0u && st == ST_RUN, 0)) st = ST_BAD;
           if (st == ST_RUN) {
-            // ---- drop the bits; one word moves up when the offset passes 32 (two, rarely)
+            // ---- drop the bits; the words move up by one when the offset passes 32, by two (rarely) when it passes
+            // 64.  Either way what is loaded now is not looked at before a later iteration.
             bo = o2 + n2;
-            if (__builtin_expect(bo >= 64u, 0)) { w0 = w1; w1 = w2; w2 = nw; nw = __ldg(inw + min(wi, lastw)); wi++; bo -= 32u; }
-            {
-              const bool r = bo >= 32u;
-              w0 = r ? w1 : w0; w1 = r ? w2 : w1; w2 = r ? nw : w2;
-              if (r) { nw = __ldg(inw + min(wi, lastw)); wi++; bo -= 32u; }
+#pragma unroll
+            for (int twice = 0; twice < 2; twice++) {
+              if (twice == 0 ? __builtin_expect(bo >= 64u, 0) : bo >= 32u) {
+                const uint32_t slot = inq + ((wi & 4u) << 7);
+                cp_async_wait<1>();                                    // (all but the newest chunk have landed)
+                w0 = w1; w1 = w2; w2 = lds32(slot + ((wi & 3u) << 2));
+                if ((wi & 3u) == 3u) { cp_async16(slot, inb + min((wi >> 2) + 2u, lastc)); cp_async_commit(); }   // the slot is free: the chunk after next
+                wi++; bo -= 32u;
+              }
             }
             // ---- the token: a match closes it; literals close it when it would hold more than four
             const uint32_t cnt = two ? 2u : 1u;
             const bool close = ism || nl + cnt > 4u;
-            if (close) list[k] = make_uint2(lb, (nl << 23) | (ism ? T_MATCH | (v2 << 8) | v1 : 0u));
+            if (close) {
+              const uint32_t th = (nl << 23) | (ism ? T_MATCH | (v2 << 8) | v1 : 0u);
+              if (k & 1u) *reinterpret_cast<uint4 *>(list + (k - 1u)) = make_uint4(plo, phi, lb, th);
+              plo = lb; phi = th;
+            }
             k += close ? 1u : 0u;
             lb = close ? 0u : lb; nl = close ? 0u : nl;
-            lb |= ism ? 0u : (two ? v1 | (v2 << 8) : v1) << (8u * nl);
-            nl += ism ? 0u : cnt;
+            {
+              const uint32_t keep = (uint32_t)ism - 1u;                   // all ones for literals
+              lb |= (((two ? v2 << 8 : 0u) | v1) << (8u * nl)) & keep;
+              nl += cnt & keep;
+            }
             // ---- rarely, at a token boundary: a token start to record, a full list, a place where this lane may synchronise
             if (__builtin_expect(close && (k == evk || wi >= twi), 0)) {
-              const uint32_t p1 = ((wi - 4u) << 5) + bo;
-              const uint32_t pb = ism ? p1 : p1 - n1 - n2;          // where the next token starts
-              if (k == evk) {
-                if (k + 2u >= LISTCAP) { st = ST_CAP; endp = pb; }
-                else if (pb < cend && slot < NCK) {
-                  // inside the own sub-chunk: record where this token starts
-                  sm.ckpt[slot][lane] = (uint16_t)(pb - cstart);
-                  slot++;
-                  evk = slot < NCK ? (slot <= CK_DENSE ? slot : CK_DENSE + (slot - CK_DENSE) * CK_STEP) : LISTCAP - 2u;
-                } else evk = LISTCAP - 2u;
-              }
-              if (st == ST_RUN && pb >= tgt) {
-                // past the own sub-chunk: does a token of the lane that owns these bits start here?
-                if (tgt == cend) atomicOr(&sm.own_done, 1u << lane);
-                if (pb >= winend) { st = ST_END; endp = p1; }
-                else {
-                  while (pb >= jstart + S) { j++; jstart += S; c = 0; }
-                  const uint32_t rel = pb - jstart;
-                  uint32_t ck = CK_NONE;
-                  while (c < NCK && (ck = sm.ckpt[c][j]) < rel) c++;
-                  if (c < NCK && ck == rel) {
-                    st = ST_SYNC; nx = j; g_sync = c < CK_DENSE ? c : CK_DENSE + (c - CK_DENSE) * CK_STEP; endp = pb;
-                  } else if (c < NCK && ck != CK_NONE) tgt = jstart + ck;
-                  else if (c >= NCK || ((sm.own_done >> j) & 1u)) tgt = jstart + S;      // no more recorded starts in that sub-chunk
-                  else tgt = pb;                                                        // its owner is not there yet: look again
-                  twi = (tgt >> 5) + 4u;
-                }
-              }
+              const uint32_t p1 = ((wi - 3u - woff) << 5) + bo;
+              const RareOut o = rare_event(rare, sm, gck, lane, k, evk, ism ? p1 : p1 - n1 - n2, p1);
+              st = o.st; evk = o.evk; twi = (o.tgt >> 5) + 3u + woff;
             }
           }
-          if (st != ST_RUN) atomicOr(&sm.own_done, 1u << lane);             // (whatever ended it: no more token starts from this lane)
+          if (__builtin_expect(st != ST_RUN && st != ST_SYNC && st != ST_END && st != ST_CAP, 0) && rare.slot < NCK) ck_end(sm, gck, rare.slot, lane);   // (end of block, bad code: no more token starts from this lane)
         }
         __syncwarp();
       }
+#ifdef TBZ_HD_TIMING
+      const long long t_loop1 = clock64();
+#endif
       // ---- the end of the lane's list: literals still waiting close a last token (not after a synchronisation or a
       // full list: the list ends at a token boundary there and the open literals belong to whoever continues)
+      if (k & 1u) list[k - 1u] = make_uint2(plo, phi);                 // (the last token of an odd count still waits for a neighbour)
       if ((st == ST_END || st == ST_EOB) && nl) { list[k] = make_uint2(lb, nl << 23); k++; }
       // a lane that decoded past the end of the input has nothing proven to offer (repeated words are read there)
+      const uint32_t endp = rare.endp, nx = rare.nx, g_sync = rare.g_sync;
       if (st != ST_IDLE && endp > in.end) st = ST_BAD;
       __syncwarp();
       // ---- lanes reachable from lane 0 through "synchronised into" edges are proven
@@ -494,17 +587,48 @@ __device__ inline bool decode_blocks(const In &in, uint32_t pos, P1Rec &rec, WSm
         if (s_cap > S_MAX) s_cap = S_MAX;
         if (s_cap < S_MIN) s_cap = S_MIN;
       }
-      const uint32_t cnt = proven && k > my_g ? k - my_g : 0u;
-      sh->fc[lane] = cnt ? (my_g | (cnt << 16)) : 0u;
-      if (lane == 0) {
-        sh->next = NO_SLAB;
-        if (prev_slab != NO_SLAB) reinterpret_cast<SlabHdr *>(slabs + (size_t)prev_slab * SLAB_BYTES)->next = slab_id;
+      // ---- the proven tokens of the round, lane after lane, become one block of the token heap
+      {
+        const uint32_t cnt = proven && k > my_g ? k - my_g : 0u;
+        uint32_t xs = cnt;
+#pragma unroll
+        for (int sft = 1; sft < 32; sft <<= 1) {
+          const uint32_t u = __shfl_up_sync(TBZ_FULL, xs, sft);
+          if (lane >= sft) xs += u;
+        }
+        const uint32_t total = __shfl_sync(TBZ_FULL, xs, 31);
+        if (total) {
+          const uint32_t blk = block_alloc(heap, heap_units, heap_top, total, prev_blk, lane);
+          if (blk == NO_BLOCK) { TBZ_HD_WHY("give up"); return false; }
+          __syncwarp();                                   // every lane's list is visible to the others from here
+          // list after list, the whole warp on each: coalesced loads and stores, up to eight per lane in flight
+          uint2 *const blk_tok = reinterpret_cast<uint2 *>(heap + blk + 1);
+          for (int L = 0; L < NL; L++) {
+            const uint32_t cntL = __shfl_sync(TBZ_FULL, cnt, L);
+            if (!cntL) continue;
+            const uint2 *src = scratch + (size_t)L * LISTCAP + __shfl_sync(TBZ_FULL, my_g, L);
+            uint2 *dst = blk_tok + (__shfl_sync(TBZ_FULL, xs, L) - cntL);
+            for (uint32_t i0 = lane; i0 < cntL; i0 += 256u) {
+              uint2 a[8];
+#pragma unroll
+              for (uint32_t u = 0; u < 8; u++) if (i0 + 32u * u < cntL) a[u] = __ldcg(src + i0 + 32u * u);
+#pragma unroll
+              for (uint32_t u = 0; u < 8; u++) if (i0 + 32u * u < cntL) dst[i0 + 32u * u] = a[u];
+            }
+          }
+          if (first_blk == NO_BLOCK) first_blk = blk;
+          prev_blk = blk;
+        }
       }
-      if (first_slab == NO_SLAB) first_slab = slab_id;
-      prev_slab = slab_id;
+#ifdef TBZ_HD_TIMING
+      if (lane == 0 && (P0 & 7u) == 0u) {
+        unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        printf("T sm %u S %u it %u loop %lld copy %lld start %lld\n", smid, S, it, t_loop1 - t_loop0, clock64() - t_loop1, t_loop0);
+      }
+#endif
 #if defined(TBZ_EMU) && defined(TBZ_EMU_TRACE)
       fprintf(stderr, "[hd]   lane %d st %d cstart %u endp %u k %u nx %u g %u proven %d\n", lane, st, cstart, endp, k, nx, g_sync, (int)proven);
-      if (lane == 0) fprintf(stderr, "[hd] round P0 %u S %u -> term_st %d pos %u (slab %u)\n", P0, S, term_st, term_pos, slab_id);
+      if (lane == 0) fprintf(stderr, "[hd] round P0 %u S %u -> term_st %d pos %u\n", P0, S, term_st, term_pos);
 #endif
       // ---- how did the round end?
       if (term_pos <= pos && term_st != ST_EOB) { TBZ_HD_WHY("give up"); return false; }     // no progress (cannot happen; guards the loop)
@@ -515,7 +639,7 @@ __device__ inline bool decode_blocks(const In &in, uint32_t pos, P1Rec &rec, WSm
     prev_block_bits = pos - data_start;
   }
   if (lane == 0) {
-    rec.first_slab = first_slab;
+    rec.first_slab = first_blk;
     rec.out_len = 0xffffffffu;             // not tracked here: phase two counts (and owns the overflow verdict)
     rec.end_pos = pos;
     rec.status = 1u;
@@ -524,12 +648,12 @@ __device__ inline bool decode_blocks(const In &in, uint32_t pos, P1Rec &rec, WSm
 }
 
 // One member, one warp: wrapper header, then every block.
-__device__ inline bool decode_member(const DMember &mem, int fmt, P1Rec &rec, WSmem &sm,
-                                     unsigned char *__restrict__ slabs, uint32_t nslabs, uint32_t *slab_counter, int lane) {
+__device__ inline bool decode_member(const DMember &mem, int fmt, P1Rec &rec, WSmem &sm, uint2 *__restrict__ scratch,
+                                     uint4 *__restrict__ heap, uint32_t heap_units, uint32_t *heap_top, int lane) {
   In in;
   uint32_t pos;
   if (!member_start(mem, fmt, in, pos)) { TBZ_HD_WHY("give up"); return false; }
-  return decode_blocks(in, pos, rec, sm, slabs, nslabs, slab_counter, lane);
+  return decode_blocks(in, pos, rec, sm, scratch, heap, heap_units, heap_top, lane);
 }
 
 }  // namespace tbzhd

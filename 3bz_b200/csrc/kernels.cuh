@@ -30,42 +30,43 @@ k_inflate_seq(const DMember *members, tbz_result *results, uint32_t n, int fmt,
 }
 
 // counters: [0] next member for phase one, [1] members queued for the sequential kernel,
-//           [2] slabs handed out, [3] next member for phase two, [4] next member for the gzip CRC kernel
+//           [2] 16-byte units of the token heap handed out, [3] next member for phase two, [4] next member for the gzip CRC kernel
 // Phase one (huff_decode.cuh), persistent CTAs of WPC independent warps: each warp pulls the next member from a
-// global counter and decodes it into token slabs; members it cannot prove clean are queued for k_inflate_seq.
+// global counter and decodes it into blocks of the token heap (through its own scratch lists: SCRATCH_BYTES per warp
+// of the grid); members it cannot prove clean are queued for k_inflate_seq.
 __global__ void __launch_bounds__(tbzhd::NT, TBZ_HD_MINBLOCKS)
-k_inflate_decode(const DMember *members, uint32_t n, int fmt, tbzfast::P1Rec *recs,
-                 unsigned char *slabs, uint32_t nslabs, uint32_t *counters, uint32_t *todo) {
+k_inflate_decode(const DMember *members, uint32_t n, int fmt, tbzfast::P1Rec *recs, unsigned char *scratch_all,
+                 uint4 *heap, uint32_t heap_units, uint32_t *counters, uint32_t *todo) {
   TBZ_DYN_SMEM(smem_raw);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   tbzhd::WSmem &sm = reinterpret_cast<tbzhd::WSmem *>(smem_raw)[warp];
+  uint2 *const scratch = reinterpret_cast<uint2 *>(scratch_all + ((size_t)blockIdx.x * tbzhd::WPC + warp) * tbzhd::SCRATCH_BYTES);
   for (;;) {
     uint32_t i = 0;
     if (lane == 0) i = atomicAdd(&counters[0], 1u);
     i = __shfl_sync(TBZ_FULL, i, 0);
     if (i >= n) break;
-    const bool ok = tbzhd::decode_member(members[i], fmt, recs[i], sm, slabs, nslabs, &counters[2], lane);
+    const bool ok = tbzhd::decode_member(members[i], fmt, recs[i], sm, scratch, heap, heap_units, &counters[2], lane);
     __syncwarp();
     if (!ok && lane == 0) { recs[i].status = 0; todo[atomicAdd(&counters[1], 1u)] = i; }
   }
 }
 
-// Phase two (lz_resolve.cuh), persistent CTAs of WPC independent warps: ONE WARP per member, a history ring and 32
-// staging slots per warp, no CTA barrier.  (The round-1 design — one CTA per member, windows, pointer jumping — and the
+// Phase two (lz_resolve.cuh), persistent CTAs of WPC independent warps: ONE WARP per member, a history ring per warp,
+// no CTA barrier.  (The round-1 design — one CTA per member, windows, pointer jumping — and the
 // first round-2 pair live under experiments/ with their numbers in profiles/.)
 __global__ void __launch_bounds__(tbzlz::NT, TBZ_LZ_MINBLOCKS)
 k_inflate_resolve(const DMember *members, tbz_result *results, uint32_t n, int fmt,
-                  const tbzfast::P1Rec *recs, const unsigned char *slabs, uint32_t *counters, uint32_t *todo) {
+                  const tbzfast::P1Rec *recs, const uint4 *heap, uint32_t *counters, uint32_t *todo) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t ring = tbzlz::smem_base() + tbzlz::PAD + (uint32_t)warp * tbzlz::H;   // shared-space address of this warp's ring
-  const uint32_t stg = tbzlz::smem_base() + tbzlz::PAD + (uint32_t)tbzlz::WPC * tbzlz::H + tbzlz::TAIL + (uint32_t)threadIdx.x * tbzlz::STG;
   for (;;) {
     uint32_t i = 0;
     if (lane == 0) i = atomicAdd(&counters[3], 1u);
     i = __shfl_sync(TBZ_FULL, i, 0);
     if (i >= n) break;
     if (!recs[i].status) continue;
-    const bool ok = tbzlz::resolve_member(members[i], fmt, recs[i], slabs, results[i], ring, stg, lane);
+    const bool ok = tbzlz::resolve_member(members[i], fmt, recs[i], heap, results[i], ring, lane);
     __syncwarp();
     if (!ok && lane == 0) todo[atomicAdd(&counters[1], 1u)] = i;
     if (ok && lane == 0 && fmt == TBZ_GZIP) const_cast<tbzfast::P1Rec *>(recs)[i].status = tbzcrc::ST_CRC_PENDING;

@@ -7,9 +7,9 @@
 // text of BASELINE config 2: 4 % of the matches reach back less than 128 bytes, the median distance is 3.8 KB), so a
 // SMALL unit of work has almost no internal dependency.  Here the unit is a step of 32 tokens — one per lane, each
 // `up to four literals + one match` (huff_decode.cuh), about 280 output bytes:
-//   1. the lane's token arrives with one 8-byte load (issued two steps ahead; a step takes its 32 tokens across the
-//      ends of the per-lane lists phase one wrote, so steps are full); a warp scan of the token lengths gives every
-//      token its output offset
+//   1. the lane's token arrives with one coalesced 8-byte load (issued two steps ahead; phase one leaves a member's
+//      tokens as contiguous blocks, so steps are full); a warp scan of the token lengths gives every token its
+//      output offset
 //   2. literals are stored; a match whose source lies entirely below the step is READY and is copied by its own lane
 //      with one straight-line, branch-free sequence — aligned 4-byte loads of the source at immediate offsets, one
 //      funnel shift per destination word, 32-bit stores between a <= 3-byte head and tail — the same instructions for
@@ -19,10 +19,10 @@
 //      32 bytes per pass, the usable distance doubling per pass for overlapping copies (the period trick)
 //   4. every 512 finished bytes leave with one 16-byte store per lane; Adler-32 is folded in with dp4a on the way out
 //      (order-independent form); gzip's CRC-32 is k_member_crc's job (inflate_crc.cuh)
-// The last H bytes of output live in a shared-memory ring per warp (H = 16 KiB).  A source older than that is in the
-// member's own output by then: its 16-byte pieces are fetched with cp.async (LDGSTS) into a 48-byte staging slot per
-// lane one step ahead — while the previous step's slow part runs — and the straight-line copy reads its source words
-// from there instead of the ring: same instructions, no registers held across the wait.
+// The last H bytes of output live in a shared-memory ring per warp (H = 16 KiB: 14 members per SM, which shared memory
+// limits — registers are plentiful at that occupancy).  A source older than that is in the member's own output by
+// then: its words are loaded into registers one step ahead, as soon as the scan of that step has placed its tokens,
+// and the straight-line copy takes them from there instead of the ring.
 // Anything irregular — a distance before the start of the output, an output buffer that is too small, a trailer that
 // disagrees — sends the member to the sequential kernel, which owns the verdict rules.
 #pragma once
@@ -37,19 +37,15 @@ namespace tbzlz {
 #define TBZ_LZ_WHY(...) do { } while (0)
 #endif
 
-using tbzfast::NO_SLAB;
 using tbzfast::P1Rec;
-using tbzhd::LISTCAP;
-using tbzhd::SLAB_BYTES;
-using tbzhd::SLAB_HDR_BYTES;
-using tbzhd::SlabHdr;
+using tbzhd::NO_BLOCK;
 using tbzhd::T_MATCH;
 
 #ifndef TBZ_LZ_RING
 #define TBZ_LZ_RING 16384
 #endif
 #ifndef TBZ_LZ_WPC
-#define TBZ_LZ_WPC 6
+#define TBZ_LZ_WPC 7
 #endif
 #ifndef TBZ_LZ_NFAST
 #define TBZ_LZ_NFAST 24
@@ -66,10 +62,9 @@ constexpr uint32_t SBMAX = 32 * (NFAST + 4);       // a step that produces more 
 constexpr uint32_t FLUSH = 512;                    // bytes per flush: one 16-byte unit per lane
 constexpr uint32_t EDGE = 4 * (NW + 3);            // a token this close to the ring's end takes the ordered path (the fast copy never wraps)
 constexpr uint32_t PAD = 16, TAIL = 64;            // shared memory before the first / after the last ring that a fast copy may read (never uses)
-constexpr uint32_t STG = 48;                       // staging bytes per lane: three 16-byte pieces of a far source
-static_assert((H & M) == 0 && H >= 4096 && H >= FLUSH + 4 * SBMAX + 1024, "ring margins (a far source is in `out` a step ahead)");
-static_assert(NFAST % 4 == 0 && NFAST >= 8 && NFAST <= 32 && EDGE <= TAIL && 4 * (NW + 3) + 12 <= STG, "straight-line copy length");
-constexpr size_t SMEM_BYTES = PAD + (size_t)WPC * H + TAIL + (size_t)WPC * 32 * STG;
+static_assert((H & M) == 0 && H >= 32 * 262 + SBMAX + FLUSH + 64, "ring margins: a far source is in `out` a step ahead, even behind a step of 258-byte matches");
+static_assert(NFAST % 4 == 0 && NFAST >= 8 && NFAST <= 32 && EDGE <= TAIL, "straight-line copy length");
+constexpr size_t SMEM_BYTES = PAD + (size_t)WPC * H + TAIL;
 static_assert((SMEM_BYTES + 1024) * TBZ_LZ_MINBLOCKS <= 233472, "CTAs per SM");
 
 // The ring is addressed by 32-bit shared-space addresses through ld.shared / st.shared, not through a generic pointer:
@@ -80,9 +75,6 @@ template <class T> __device__ __forceinline__ T lds(uint32_t a) { return *reinte
 template <class T> __device__ __forceinline__ void sts(uint32_t a, T v) { *reinterpret_cast<T *>(::emu::dyn_smem() + a) = v; }
 __device__ __forceinline__ void sts_low8(uint32_t a, uint32_t v) { sts<uint8_t>(a, (uint8_t)v); }
 __device__ __forceinline__ void sts_low16(uint32_t a, uint32_t v) { sts<uint16_t>(a, (uint16_t)v); }
-__device__ __forceinline__ void cp_async16(uint32_t a, const void *g) { memcpy(::emu::dyn_smem() + a, g, 16); }
-__device__ __forceinline__ void cp_async_commit() {}
-__device__ __forceinline__ void cp_async_wait_all() {}
 #else
 extern __shared__ __align__(16) unsigned char tbz_lz_smem[];
 __device__ __forceinline__ uint32_t smem_base() { return (uint32_t)__cvta_generic_to_shared(tbz_lz_smem); }
@@ -97,15 +89,10 @@ template <> __device__ __forceinline__ void sts<uint8_t>(uint32_t a, uint8_t v) 
 __device__ __forceinline__ void sts_low8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }     // the low byte of v
 __device__ __forceinline__ void sts_low16(uint32_t a, uint32_t v) { asm volatile("st.shared.b16 [%0], %1;" ::"r"(a), "h"((uint16_t)v) : "memory"); }
 template <> __device__ __forceinline__ void sts<uint32_t>(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
-// 16 bytes global -> shared, asynchronously, past L1 (the source was written by other lanes of this warp)
-__device__ __forceinline__ void cp_async16(uint32_t a, const void *g) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(a), "l"(g) : "memory"); }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 #endif
 
 struct WState {
   uint32_t ring;                          // this warp's ring: shared-space address of its first byte
-  uint32_t stg;                           // this lane's staging slot
   uint8_t *out;                           // the member's output
   unsigned long long cap;                 // bytes the output may take (capped below 2^32)
   uint32_t pos;                           // output bytes produced so far
@@ -113,91 +100,113 @@ struct WState {
   unsigned long long acc_a, acc_w;        // per lane: sum d and sum i*d over the bytes it flushed (Adler-32)
 };
 
-// A step: the lane's token, where its bytes go, what kind of work its match is.
+// The source words of a far match: E = the word before slot 0 (the head may start there); S[j], S[j+1] feed word slot j.
+struct Src { uint32_t E, S[NW + 2]; };
+
+// A step: the lane's token and where its bytes go (the scan), and — loaded as soon as that is known — the source words
+// of a match older than the ring.
 struct Step {
-  uint32_t lo, hi, nvalid;                // the token; lanes below nvalid have one
+  uint32_t lo, hi;                        // the token (zero for a lane beyond the step's tokens)
   uint32_t p;                             // the token's first output byte
   uint32_t base, total;                   // (uniform) where the step starts, how many bytes it produces
-  uint32_t fl;                            // F_* flags
+  Src f;
 };
-constexpr uint32_t F_READY = 1u, F_FAR = 2u, F_EDGE = 4u, F_PEND = 8u, F_FAIL = 16u;
 
 // The geometry of a ready match: hb head bytes up to the first aligned destination word, then full words, then a tail.
 // Aligned source offset of word slot 0:
 __device__ __forceinline__ uint32_t copy_s0(uint32_t dst, uint32_t src) { return (src & ~3u) + (((src & 3u) + ((0u - dst) & 3u)) & 4u); }
-// ... and where the staging slot of a far source starts in the output (a multiple of 16 that covers the word before slot 0)
-__device__ __forceinline__ uint32_t stage_a0(uint32_t s0) { return s0 >= 4u ? (s0 - 4u) & ~15u : 0u; }
 
-// Offsets by a warp scan, then the classification.
-__device__ __forceinline__ void prepare(Step &q, const WState &w, uint32_t base, uint32_t lo, uint32_t hi, uint32_t nvalid, int lane) {
-  q.lo = lo; q.hi = hi; q.nvalid = nvalid; q.base = base;
-  const bool v = (uint32_t)lane < nvalid;
-  const bool m = v && (hi & T_MATCH);
-  const uint32_t nl = v ? tbzhd::t_nlit(hi) : 0u;
-  const uint32_t n = m ? (hi & 255u) + 3u : 0u;
-  const uint32_t mine = nl + n;
-  uint32_t x = mine;
-#pragma unroll
-  for (int sft = 1; sft < 32; sft <<= 1) {
-    const uint32_t u = __shfl_up_sync(TBZ_FULL, x, sft);
-    if (lane >= sft) x += u;
-  }
-  q.total = __shfl_sync(TBZ_FULL, x, 31);
-  q.p = base + x - mine;
-  const uint32_t dst = q.p + nl;
-  const uint32_t d = ((hi >> 8) & 0x7fffu) + 1u;
-  const uint32_t src = dst - d;
-  const uint32_t end = base + q.total;
-  // output overflow, or a distance that reaches before the start of the output (deflate.lisp:343-345): the sequential kernel reports it
-  const bool fail = (unsigned long long)base + q.total > w.cap || __any_sync(TBZ_FULL, m && d > dst);
-  const uint32_t ring_lo = end > H ? end - H : 0u;
-  const bool far = src < ring_lo;
+// What a step's own lane does with its token: the classification of execute(), computed early (pure arithmetic on the
+// placed step) so that it can be issued between the shuffles of the next step's scan.
+struct Cls {
+  uint32_t nl, n, dst, src, ring_lo;
+  bool m, far, edge, ready, bad;
+};
+__device__ __forceinline__ Cls classify(const Step &q) {
+  Cls c;
+  const uint32_t end = q.base + q.total;
+  c.m = (q.hi & T_MATCH) != 0u;
+  c.nl = tbzhd::t_nlit(q.hi); c.n = (q.hi & 255u) + 3u;
+  const uint32_t d = ((q.hi >> 8) & 0x7fffu) + 1u;
+  c.dst = q.p + c.nl; c.src = c.dst - d;
+  c.bad = c.m && d > c.dst;                          // a distance that reaches before the start of the output (deflate.lisp:343-345)
+  c.ring_lo = end > H ? end - H : 0u;
+  c.far = c.src < c.ring_lo;
   // a token near the ring's end (its bytes, or its source, would wrap) takes the ordered path as a whole
-  const bool edge = v && ((q.p & M) > H - EDGE - 4u || (m && !far && (src & M) > H - EDGE));
-  const bool ready = m && !edge && src + n <= base && n <= NFAST && q.total <= SBMAX;
-  q.fl = (ready ? F_READY : 0u) | (far ? F_FAR : 0u) | (edge ? F_EDGE : 0u) | (m && !ready ? F_PEND : 0u) | (fail ? F_FAIL : 0u);
+  c.edge = (q.p & M) > H - EDGE - 4u || (c.m && !c.far && (c.src & M) > H - EDGE);
+  c.ready = c.m && !c.edge && c.src + c.n <= q.base && c.n <= NFAST;
+  return c;
 }
 
-// The 16-byte pieces of a ready match's far source (older than the ring: the member's output has it) start their way
-// into the lane's staging slot.
+// The next step is placed — offsets by a warp scan — while the current one (already placed) is classified: the five
+// shuffles of the scan depend on each other, the classification is arithmetic that fills their latency.  Then the words
+// of every source of the new step that is older than the ring start their way (the member's output has had them for a
+// long time: see the static_assert on H).  cq == nullptr: nothing to classify (the very first step).
 template <bool AL>
-__device__ __forceinline__ void stage_far(const Step &q, const WState &w) {
-  if ((q.fl & (F_READY | F_FAR | F_FAIL)) == (F_READY | F_FAR)) {
-    const uint32_t dst = q.p + tbzhd::t_nlit(q.hi);
-    const uint32_t src = dst - (((q.hi >> 8) & 0x7fffu) + 1u), n = (q.hi & 255u) + 3u;
-    const uint32_t a0 = stage_a0(copy_s0(dst, src));
+__device__ __forceinline__ void place(Step &q, const WState &w, uint32_t base, uint32_t lo, uint32_t hi, int lane, const Step *cq, Cls &cc) {
+  q.lo = lo; q.hi = hi; q.base = base;
+  const bool m = (hi & T_MATCH) != 0u;
+  const uint32_t nl = tbzhd::t_nlit(hi);
+  const uint32_t n = m ? (hi & 255u) + 3u : 0u;
+  const uint32_t mine = nl + n;
+  uint32_t x = mine, u;
+  u = __shfl_up_sync(TBZ_FULL, x, 1);
+  if (cq) cc = classify(*cq);
+  if (lane >= 1) x += u;
+  u = __shfl_up_sync(TBZ_FULL, x, 2);
+  if (lane >= 2) x += u;
+  u = __shfl_up_sync(TBZ_FULL, x, 4);
+  if (lane >= 4) x += u;
+  u = __shfl_up_sync(TBZ_FULL, x, 8);
+  if (lane >= 8) x += u;
+  u = __shfl_up_sync(TBZ_FULL, x, 16);
+  if (lane >= 16) x += u;
+  q.total = __shfl_sync(TBZ_FULL, x, 31);
+  q.p = base + x - mine;
+  const uint32_t dst = q.p + nl, d = ((hi >> 8) & 0x7fffu) + 1u;
+  const uint32_t end = base + q.total;
+  if (m && d <= dst && end > H && dst - d < end - H && n <= NFAST && (unsigned long long)end <= w.cap) {
+    const uint32_t src = dst - d, s0 = copy_s0(dst, src);
     if (AL) {
+      const uint32_t *gp = reinterpret_cast<const uint32_t *>(w.out + s0);
+      q.f.E = s0 ? __ldcg(gp - 1) : 0u;
 #pragma unroll
-      for (uint32_t i = 0; i < STG / 16; i++) if (a0 + 16u * i < src + n) cp_async16(w.stg + 16u * i, w.out + a0 + 16u * i);
-    } else {                                                           // `out` is not aligned: byte by byte
-      for (uint32_t i = src - a0; i < src + n - a0; i++) sts_low8(w.stg + i, (uint32_t)__ldcg(w.out + a0 + i));
+      for (uint32_t i = 0; i < NW + 2; i++) q.f.S[i] = __ldcg(gp + i);      // (beyond the source, still far below the write position)
+    } else {                                                             // `out` is not aligned: byte by byte
+      q.f.E = 0;
+      if (s0)
+        for (int b = 0; b < 4; b++) q.f.E |= (uint32_t)__ldcg(w.out + s0 - 4 + b) << (8 * b);
+#pragma unroll
+      for (uint32_t i = 0; i < NW + 2; i++) {
+        uint32_t v = 0;
+        for (uint32_t b = 0; b < 4; b++) v |= (uint32_t)__ldcg(w.out + s0 + 4u * i + b) << (8 * b);
+        q.f.S[i] = v;
+      }
     }
   }
-  cp_async_commit();
 }
 
 // One READY match, copied by its own lane: 3 <= n <= NFAST bytes from absolute offset src to dst; the source lies
 // entirely below the current step, so it never overlaps the destination, and neither range comes within EDGE bytes of
-// the end of the ring.  far: the source is older than the ring; the staging slot has it (stage_far).
+// the end of the ring.  far: the source is older than the ring; its words are in f already (place).
 // Straight-line: no data-dependent branch, every shared-memory access at an immediate offset.  Lanes without a ready
-// match run along (act = false): they load unused words from wherever their garbage points inside the warp's memory.
-__device__ __forceinline__ void copy_ready(const WState &w, bool act, bool far, uint32_t dst, uint32_t src, uint32_t n) {
-  const uint32_t ring = w.ring;
+// match run along (act = false): they load unused words from wherever their garbage points inside the warp's ring.
+__device__ __forceinline__ void copy_ready(uint32_t ring, Src &f, bool act, bool far, uint32_t dst, uint32_t src, uint32_t n) {
   const uint32_t hb = (0u - dst) & 3u;               // head bytes up to the first aligned destination word (n >= 3 >= hb)
   const uint32_t as = src & 3u;
   const uint32_t q = as + hb;                        // offset of the first full word's source on the word grid of src
   const uint32_t sh = (q & 3u) * 8u;
   const uint32_t s0 = (src & ~3u) + (q & 4u);        // aligned source offset of word slot 0
   const uint32_t rest = act ? n - hb : 0u;           // bytes in full words and the tail (none for a lane that only runs along)
-  // source words: E = the word before slot 0 (the head may start there); S[j], S[j+1] feed word slot j
-  const uint32_t rp = far ? w.stg + (s0 - stage_a0(s0)) : ring + (s0 & M);
-  uint32_t S[NW + 2];
-  const uint32_t E = lds<uint32_t>(rp - 4u);
+  if (!far) {
+    const uint32_t rp = ring + (s0 & M);
+    f.E = lds<uint32_t>(rp - 4u);
 #pragma unroll
-  for (uint32_t i = 0; i < NW + 2; i++) S[i] = lds<uint32_t>(rp + 4u * i);
+    for (uint32_t i = 0; i < NW + 2; i++) f.S[i] = lds<uint32_t>(rp + 4u * i);
+  }
   // head: stream bytes 0..hb-1 = the bytes at src
   {
-    const uint32_t lo = (q & 4u) ? E : S[0], hi = (q & 4u) ? S[0] : S[1];
+    const uint32_t lo = (q & 4u) ? f.E : f.S[0], hi = (q & 4u) ? f.S[0] : f.S[1];
     const uint32_t hd = __funnelshift_r(lo, hi, as * 8u);
     const uint32_t hp = ring + (dst & M);
     if (act && (hb & 1u)) sts_low8(hp, hd);
@@ -208,7 +217,7 @@ __device__ __forceinline__ void copy_ready(const WState &w, bool act, bool far, 
   uint32_t tw = 0;
 #pragma unroll
   for (uint32_t j = 0; j <= NW; j++) {
-    const uint32_t v = __funnelshift_r(S[j], S[j + 1], sh);
+    const uint32_t v = __funnelshift_r(f.S[j], f.S[j + 1], sh);
     if (j < NW && rest >= 4u * (j + 1u)) sts<uint32_t>(wp + 4u * j, v);
     if (j == 0) tw = v;
     else if (rest >= 4u * j) tw = v;                                   // tw = word slot (rest / 4)
@@ -282,121 +291,103 @@ __device__ __forceinline__ void flush_to(WState &w, uint32_t upto, bool adler, i
   __syncwarp();                     // the stores are ordered before any later read of `out` by another lane
 }
 
-// Execute a prepared step; `nq`: the step after it, whose far sources start their way once this step's straight-line
-// copies have read the staging slots.  Returns false when the member must go to the sequential kernel.  Uniform.
+// Execute a placed and classified step.  Returns false when the member must go to the sequential kernel.  Uniform.
 template <bool AL>
-__device__ __forceinline__ bool execute(WState &w, const Step &q, const Step *nq, bool adler, int lane) {
-  if (q.fl & F_FAIL) { TBZ_LZ_WHY("overflow or distance too far at %u (+%u, cap %llu)\n", q.base, q.total, w.cap); return false; }
+__device__ __forceinline__ bool execute(WState &w, Step &q, const Cls &c, bool adler, int lane) {
   const uint32_t ring = w.ring;
   const uint32_t end = q.base + q.total;
-  const uint32_t nl = (uint32_t)lane < q.nvalid ? tbzhd::t_nlit(q.hi) : 0u;
+  // output overflow, or a distance that reaches too far back: the sequential kernel reports it
+  if (__any_sync(TBZ_FULL, c.bad) || (unsigned long long)end > w.cap) { TBZ_LZ_WHY("overflow or distance too far at %u (+%u, cap %llu)\n", q.base, q.total, w.cap); return false; }
   if (__builtin_expect(q.total <= SBMAX, 1)) {
-    const uint32_t ring_lo = end > H ? end - H : 0u;
-    const uint32_t dst = q.p + nl;
     // literals
     {
-      const uint32_t lp = ring + (q.p & M), nle = (q.fl & F_EDGE) ? 0u : nl;
+      const uint32_t lp = ring + (q.p & M), nle = c.edge ? 0u : c.nl;
       if (nle > 0u) sts_low8(lp, q.lo);
       if (nle > 1u) sts_low8(lp + 1u, q.lo >> 8);
       if (nle > 2u) sts_low8(lp + 2u, q.lo >> 16);
       if (nle > 3u) sts_low8(lp + 3u, q.lo >> 24);
     }
-    cp_async_wait_all();                           // the far sources of this step have arrived ...
+    copy_ready(ring, q.f, c.ready, c.far, c.dst, c.src, c.n);
     __syncwarp();
-    copy_ready(w, (q.fl & F_READY) != 0u, (q.fl & F_FAR) != 0u, dst, dst - (((q.hi >> 8) & 0x7fffu) + 1u), (q.hi & 255u) + 3u);
-    __syncwarp();
-    if (nq) stage_far<AL>(*nq, w);                 // ... and the next step's may use the slots
     // the rest in stream order, by the whole warp
-    uint32_t pm = __ballot_sync(TBZ_FULL, (q.fl & (F_EDGE | F_PEND)) != 0u);
+    uint32_t pm = __ballot_sync(TBZ_FULL, (c.m && !c.ready) || (c.edge && c.nl));
     if (pm) {
-      const uint32_t em = __ballot_sync(TBZ_FULL, (q.fl & F_EDGE) != 0u);
+      const uint32_t em = __ballot_sync(TBZ_FULL, c.edge);
       do {
         const int l = __ffs(pm) - 1;
         pm &= pm - 1u;
         const uint32_t pa = __shfl_sync(TBZ_FULL, q.p, l), ha = __shfl_sync(TBZ_FULL, q.hi, l);
-        if ((em >> l) & 1u) token_warp(w, pa, __shfl_sync(TBZ_FULL, q.lo, l), ha, ring_lo, lane);      // (literals too)
-        else copy_warp(w, pa + tbzhd::t_nlit(ha), (ha & 255u) + 3u, ((ha >> 8) & 0x7fffu) + 1u, ring_lo, lane);
+        if ((em >> l) & 1u) token_warp(w, pa, __shfl_sync(TBZ_FULL, q.lo, l), ha, c.ring_lo, lane);      // (literals too)
+        else copy_warp(w, pa + tbzhd::t_nlit(ha), (ha & 255u) + 3u, ((ha >> 8) & 0x7fffu) + 1u, c.ring_lo, lane);
       } while (pm);
     }
     w.pos = end;
     if (end - w.flushed >= FLUSH) flush_to<AL>(w, w.flushed + ((end - w.flushed) / FLUSH) * FLUSH, adler, lane);
   } else {
     // a step of long matches (RLE, zeros): token by token, so that the ring never runs more than one token ahead of `out`
-    cp_async_wait_all();
-    __syncwarp();
     for (int l = 0; l < 32; l++) {
       const uint32_t pa = __shfl_sync(TBZ_FULL, q.p, l), la = __shfl_sync(TBZ_FULL, q.lo, l), ha = __shfl_sync(TBZ_FULL, q.hi, l);
-      if ((uint32_t)l >= q.nvalid) break;
       const uint32_t e = pa + tbzhd::t_outlen(ha);
+      if (e == pa) continue;                       // (no token in this lane)
       token_warp(w, pa, la, ha, e > H ? e - H : 0u, lane);
       if (e - w.flushed >= FLUSH) flush_to<AL>(w, w.flushed + ((e - w.flushed) / FLUSH) * FLUSH, adler, lane);
     }
     w.pos = end;
-    if (nq) stage_far<AL>(*nq, w);
   }
   return true;
 }
 
-// The member's token stream, step by step: slabs in chain order, the 32 lists of a slab in lane order; a step takes the
-// next 32 tokens wherever the list ends fall.
+// The member's token stream: the blocks of its chain in order, 32 tokens at a time (phase one: huff_decode.cuh).
 struct Cursor {
-  const unsigned char *slabs, *slab;
-  const uint2 *list;
-  uint32_t fc, next_slab, cnt;
-  int j;
-  __device__ __forceinline__ void open(const unsigned char *slabs_, uint32_t first) {
-    slabs = slabs_; slab = nullptr; list = nullptr; cnt = 0; j = 32; next_slab = first; fc = 0;
-  }
-  // the next list that has tokens, in the next slab when this one is done; false at the end of the stream.  Uniform.
-  __device__ __noinline__ bool next_list(int lane) {
-    for (;;) {
-      if (j < 31) {
-        j++;
-        const uint32_t f = __shfl_sync(TBZ_FULL, fc, j);
-        cnt = f >> 16;
-        list = reinterpret_cast<const uint2 *>(slab + SLAB_HDR_BYTES) + (size_t)j * LISTCAP + (f & 0xffffu);
-        if (cnt) return true;
-        continue;
-      }
-      if (next_slab == NO_SLAB) return false;
-      slab = slabs + (size_t)next_slab * SLAB_BYTES;
-      const SlabHdr *h = reinterpret_cast<const SlabHdr *>(slab);
-      next_slab = __ldg(&h->next);
-      fc = __ldg(&h->fc[lane]);
-      j = -1; cnt = 0;
+  const uint4 *heap;
+  const uint2 *tok;
+  uint32_t left, next;
+  __device__ __forceinline__ void open(const uint4 *heap_, uint32_t first) { heap = heap_; tok = nullptr; left = 0; next = first; }
+  // the next step: the lane's token (zero beyond the step's tokens); false at the end of the stream.  Uniform.
+  __device__ __forceinline__ bool step(uint2 &t) {
+    while (left == 0) {
+      if (next == NO_BLOCK) { t = make_uint2(0u, 0u); return false; }
+      const uint4 h = __ldg(heap + next);
+      tok = reinterpret_cast<const uint2 *>(heap + next + 1);
+      left = h.y; next = h.x;
     }
-  }
-  // the next step: the lane's token (zero beyond the step's nvalid <= 32 tokens); false at the end of the stream.  Uniform.
-  __device__ __forceinline__ bool next(uint2 &t, uint32_t &nvalid, int lane) {
-    nvalid = 0; t = make_uint2(0u, 0u);
-    do {
-      if (cnt == 0 && !next_list(lane)) break;
-      const uint32_t take = cnt < 32u - nvalid ? cnt : 32u - nvalid;
-      const uint32_t i = (uint32_t)lane - nvalid;
-      if (i < take) t = __ldg(list + i);
-      list += take; cnt -= take; nvalid += take;
-    } while (nvalid < 32u);
-    return nvalid != 0u;
+    const uint32_t nv = left < 32u ? left : 32u;
+    const uint32_t lane = threadIdx.x & 31u;
+    t = lane < nv ? __ldg(tok + lane) : make_uint2(0u, 0u);
+    tok += nv; left -= nv;
+#ifndef TBZ_EMU
+    if (left > 96u + lane) asm volatile("prefetch.global.L2 [%0];" ::"l"(tok + 96 + lane));   // four steps ahead: the heap is cold in L2
+#endif
+    return true;
   }
 };
 
-// Every step of the stream, software-pipelined: while step k is copied, step k + 1 has its offsets (its far sources
-// start their way half way through step k) and the tokens of step k + 2 are loaded.
+// Every step of the stream, software-pipelined: while step k is copied, step k + 1 has been placed (its far sources
+// are on their way) and the tokens of step k + 2 are loaded.  Two steps per trip, so that no state changes registers.
 template <bool AL>
-__device__ inline bool resolve_stream(WState &w, const P1Rec &rec, const unsigned char *__restrict__ slabs, bool adler, int lane) {
+__device__ inline bool resolve_stream(WState &w, const P1Rec &rec, const uint4 *__restrict__ heap, bool adler, int lane) {
   Cursor cur;
-  cur.open(slabs, rec.first_slab);
-  uint2 t1, t2;
-  uint32_t nv1 = 0, nv2 = 0;
-  Step q, qn;
-  bool have0 = cur.next(t1, nv1, lane);
-  if (have0) { prepare(q, w, 0u, t1.x, t1.y, nv1, lane); stage_far<AL>(q, w); }
-  bool have1 = have0 && cur.next(t1, nv1, lane);
-  while (have0) {
-    const bool have2 = have1 && cur.next(t2, nv2, lane);                   // the tokens two steps ahead travel
-    if (have1) prepare(qn, w, q.base + q.total, t1.x, t1.y, nv1, lane);
-    if (!execute<AL>(w, q, have1 ? &qn : nullptr, adler, lane)) return false;
-    q = qn; have0 = have1; have1 = have2; t1 = t2; nv1 = nv2;
+  cur.open(heap, rec.first_slab);
+  uint2 ta, tb;                                             // the tokens of the next step to place, alternately
+  Step a, b;
+  Cls c;
+  bool more = cur.step(ta);
+  if (more) {
+    place<AL>(a, w, 0u, ta.x, ta.y, lane, nullptr, c);
+    more = cur.step(tb);                                    // the tokens of the step after `a`
+    for (;;) {
+      // `a` is placed; tb holds the tokens of the step after it (if `more`)
+      const bool more2 = more && cur.step(ta);
+      if (more) place<AL>(b, w, a.base + a.total, tb.x, tb.y, lane, &a, c);
+      else c = classify(a);
+      if (!execute<AL>(w, a, c, adler, lane)) return false;
+      if (!more) break;
+      more = more2 && cur.step(tb);
+      if (more2) place<AL>(a, w, b.base + b.total, ta.x, ta.y, lane, &b, c);
+      else c = classify(b);
+      if (!execute<AL>(w, b, c, adler, lane)) return false;
+      if (!more2) break;
+    }
   }
   // what is left in the ring: whole units, then the last partial one byte by byte
   flush_to<AL>(w, w.pos & ~15u, adler, lane);
@@ -411,15 +402,15 @@ __device__ inline bool resolve_stream(WState &w, const P1Rec &rec, const unsigne
 }
 
 // One member, one warp.  Returns false when the caller must queue the member for the sequential kernel.
-__device__ inline bool resolve_member(const DMember &mem, int fmt, const P1Rec &rec, const unsigned char *__restrict__ slabs,
-                                      tbz_result &res, uint32_t ring, uint32_t stg, int lane) {
+__device__ inline bool resolve_member(const DMember &mem, int fmt, const P1Rec &rec, const uint4 *__restrict__ heap,
+                                      tbz_result &res, uint32_t ring, int lane) {
   WState w;
-  w.ring = ring; w.stg = stg; w.out = mem.out;
+  w.ring = ring; w.out = mem.out;
   w.cap = mem.out_cap < 0xffffffffull ? mem.out_cap : 0xffffffffull;
   w.pos = 0; w.flushed = 0; w.acc_a = 0; w.acc_w = 0;
   const bool adler = fmt == TBZ_ZLIB;
   const bool al = (((uintptr_t)mem.out) & 15u) == 0;
-  if (al ? !resolve_stream<true>(w, rec, slabs, adler, lane) : !resolve_stream<false>(w, rec, slabs, adler, lane)) return false;
+  if (al ? !resolve_stream<true>(w, rec, heap, adler, lane) : !resolve_stream<false>(w, rec, heap, adler, lane)) return false;
   const uint32_t pos = w.pos;
   if (rec.out_len != 0xffffffffu && pos != rec.out_len) { TBZ_LZ_WHY("out_len %u != %u\n", pos, rec.out_len); return false; }
   // ---- checksum of the whole member (checksums.lisp:18-62, order-independent form)

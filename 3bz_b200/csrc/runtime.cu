@@ -28,7 +28,7 @@
 // =============================================================================================
 static const size_t kResolveSmem = tbzlz::SMEM_BYTES;
 static const size_t kDecodeSmem = sizeof(tbzhd::WSmem) * tbzhd::WPC;
-static const uint64_t kSlabPoolBytes = 24ull << 30;  // upper bound of the token slab pool per batch (B200: 180 GB)
+static const uint64_t kTokenHeapBytes = 48ull << 30;  // upper bound of the token heap per batch (B200: 180 GB; 2^32 units of 16 bytes at most)
 static const uint64_t kSplitMinBytes = 4ull << 20;   // members at least this large are split across the GPU
 static const uint64_t kSplitChunkBytes =      // compressed bytes per chunk of a split member (TBZ_SPLIT_CHUNK_KB: tuning)
     (getenv("TBZ_SPLIT_CHUNK_KB") ? std::max<uint64_t>(16, strtoull(getenv("TBZ_SPLIT_CHUNK_KB"), nullptr, 10)) : 160ull) << 10;
@@ -118,9 +118,9 @@ struct tbz_batch {
   bool out_direct = false;             // caller's outputs are exactly adjacent: DMA straight into them
   const uint8_t *in_span = nullptr; uint8_t *out_span = nullptr;
   void *d_in = nullptr, *d_out = nullptr, *d_members = nullptr, *d_results = nullptr;
-  void *d_slabs = nullptr, *d_counters = nullptr, *d_todo = nullptr, *d_recs = nullptr;
+  void *d_heap = nullptr, *d_scratch = nullptr, *d_counters = nullptr, *d_todo = nullptr, *d_recs = nullptr;
   int fast_grid = 0, res_grid = 0;
-  uint32_t nslabs = 0;
+  uint32_t heap_units = 0;
   bool launched = false;
   cudaStream_t stream = nullptr;       // the stream this batch lives on
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -348,7 +348,7 @@ extern "C" int32_t tbz_batch_destroy(tbz_batch *b) {
   if (b->ev1) cudaEventDestroy(b->ev1);
   dev_release(ctx, b->d_in); dev_release(ctx, b->d_out);
   dev_release(ctx, b->d_members); dev_release(ctx, b->d_results);
-  dev_release(ctx, b->d_slabs); dev_release(ctx, b->d_counters); dev_release(ctx, b->d_todo); dev_release(ctx, b->d_recs);
+  dev_release(ctx, b->d_heap); dev_release(ctx, b->d_scratch); dev_release(ctx, b->d_counters); dev_release(ctx, b->d_todo); dev_release(ctx, b->d_recs);
   delete b;
   return TBZ_OK;
 }
@@ -375,17 +375,17 @@ extern "C" int32_t tbz_batch_prepare(tbz_ctx *ctx, int32_t format, const tbz_mem
     cudaFuncSetAttribute(k_inflate_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kResolveSmem);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_inflate_resolve, tbzlz::NT, kResolveSmem);
     b->res_grid = (int)std::min<uint64_t>((n + tbzlz::WPC - 1) / tbzlz::WPC, (uint64_t)ctx->sm_count * std::max(1, occ));
-    // token slabs: one per round; a round covers at most ~31 KiB of compressed input and never
-    // crosses a block boundary.  Members that find the pool empty go to the sequential kernel.
-    uint64_t want = 0;
-    // a round covers up to NL * S_MAX bits; blocks end rounds early and a lane that fills its token
-    // list shortens them, hence the factor 2 and the slack
-    const uint64_t round_bytes = (uint64_t)tbzhd::NL * tbzhd::S_MAX / 8;
-    for (uint64_t i = 0; i < n; i++) want += 4 * (m[i].in_len / round_bytes) + 6;
-    const uint64_t slab_bytes = tbzhd::SLAB_BYTES;
-    const uint64_t cap = std::max<uint64_t>(64, kSlabPoolBytes / slab_bytes);
-    b->nslabs = (uint32_t)std::min<uint64_t>(want, cap);
-    PCK(dev_alloc(ctx, (size_t)b->nslabs * slab_bytes, &b->d_slabs));
+    // The token heap: phase one leaves every member's tokens there as contiguous blocks (8 bytes per token; a token
+    // is up to four literals + one match: about one byte per output byte on text, 2.7 at worst).  Sized from what
+    // is known: at most 3 bytes per byte of output capacity, and no more than 48 bytes per compressed byte (a token
+    // costs at least two bits... in practice ~24 bits).  Members that find the heap full go to the sequential kernel.
+    uint64_t want = 4096;
+    for (uint64_t i = 0; i < n; i++) want += std::min<uint64_t>(3 * m[i].out_cap, 48 * m[i].in_len) + 64;
+    want = std::min<uint64_t>(want, kTokenHeapBytes);
+    b->heap_units = (uint32_t)std::min<uint64_t>(want / 16, 0xfffffff0ull);
+    PCK(dev_alloc(ctx, (size_t)b->heap_units * 16, &b->d_heap));
+    // ... and the scratch lists a warp of phase one decodes a round into
+    PCK(dev_alloc(ctx, (size_t)b->fast_grid * tbzhd::WPC * tbzhd::SCRATCH_BYTES, &b->d_scratch));
     PCK(dev_alloc(ctx, 256, &b->d_counters));
     PCK(dev_alloc(ctx, n * 4, &b->d_todo));
     PCK(dev_alloc(ctx, n * sizeof(tbzfast::P1Rec), &b->d_recs));
@@ -722,14 +722,14 @@ static int32_t launch_kernels(tbz_batch *b) {
     CK(ctx, cudaFuncSetAttribute(k_inflate_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDecodeSmem));
     k_inflate_decode<<<b->fast_grid, tbzhd::NT, kDecodeSmem, ctx->stream>>>(
         (const DMember *)b->d_members, n, b->format, (tbzfast::P1Rec *)b->d_recs,
-        (unsigned char *)b->d_slabs, b->nslabs, (uint32_t *)b->d_counters, (uint32_t *)b->d_todo);
+        (unsigned char *)b->d_scratch, (uint4 *)b->d_heap, b->heap_units, (uint32_t *)b->d_counters, (uint32_t *)b->d_todo);
     ctx->launches++;
     CK(ctx, cudaGetLastError());
     if (ctx->ktime) CK(ctx, cudaEventRecord(ctx->kev[1], ctx->stream));
     CK(ctx, cudaFuncSetAttribute(k_inflate_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kResolveSmem));
     k_inflate_resolve<<<b->res_grid, tbzlz::NT, kResolveSmem, ctx->stream>>>(
         (const DMember *)b->d_members, (tbz_result *)b->d_results, n, b->format,
-        (const tbzfast::P1Rec *)b->d_recs, (const unsigned char *)b->d_slabs, (uint32_t *)b->d_counters, (uint32_t *)b->d_todo);
+        (const tbzfast::P1Rec *)b->d_recs, (const uint4 *)b->d_heap, (uint32_t *)b->d_counters, (uint32_t *)b->d_todo);
     ctx->launches++;
     CK(ctx, cudaGetLastError());
     if (b->format == TBZ_GZIP) {   // gzip: CRC-32 of the finished members + trailer compare
@@ -756,7 +756,7 @@ static int32_t launch_kernels(tbz_batch *b) {
       uint32_t cnt[4] = {0, 0, 0, 0};
       cudaMemcpy(cnt, b->d_counters, sizeof cnt, cudaMemcpyDeviceToHost);
       ctx->last_kms[0] = a; ctx->last_kms[1] = c; ctx->last_kms[2] = d;
-      if (!ctx->ktime_quiet) fprintf(stderr, "[tbz] decode %.3f ms, resolve %.3f ms, seq %.3f ms (%u members), %u slabs\n", a, c, d, cnt[1], cnt[2]);
+      if (!ctx->ktime_quiet) fprintf(stderr, "[tbz] decode %.3f ms, resolve %.3f ms, seq %.3f ms (%u members), %u heap units\n", a, c, d, cnt[1], cnt[2]);
     }
     return TBZ_OK;
   }

@@ -17,18 +17,18 @@ extern "C" int emu_inflate_batch(int fmt, const tbz_member *m, uint64_t n, tbz_r
     return 0;
   }
   std::vector<tbzfast::P1Rec> recs(n);
-  const uint64_t round_bytes = (uint64_t)tbzhd::NL * tbzhd::S_MAX / 8;
-  uint64_t want = 0;
-  for (uint64_t i = 0; i < n; i++) want += 4 * (m[i].in_len / round_bytes) + 6;
-  const uint32_t nslabs = (uint32_t)want;
-  std::vector<unsigned char> slabs((size_t)nslabs * tbzhd::SLAB_BYTES + 16);
-  unsigned char *slab0 = (unsigned char *)(((uintptr_t)slabs.data() + 15) & ~(uintptr_t)15);
+  // the token heap: 16-byte units; ~1 token byte per output byte on text, more for short matches
+  uint64_t units = 64;
+  for (uint64_t i = 0; i < n; i++) units += (3 * m[i].out_cap + 4 * m[i].in_len) / 16 + 64;
+  const uint32_t heap_units = (uint32_t)units;
+  std::vector<uint4> heap(heap_units);
   (void)variant;
   const unsigned dec_grid = std::min<unsigned>((nn + tbzhd::WPC - 1) / tbzhd::WPC, 16);
+  std::vector<uint4> scratch((size_t)dec_grid * tbzhd::WPC * tbzhd::SCRATCH_BYTES / 16);
   emu_launch(k_inflate_decode, dim3(dec_grid), dim3(tbzhd::NT), sizeof(tbzhd::WSmem) * tbzhd::WPC,
-             (const DMember *)dm.data(), nn, fmt, recs.data(), slab0, nslabs, counters.data(), todo.data());
+             (const DMember *)dm.data(), nn, fmt, recs.data(), (unsigned char *)scratch.data(), heap.data(), heap_units, counters.data(), todo.data());
   emu_launch(k_inflate_resolve, dim3(std::min<unsigned>((nn + tbzlz::WPC - 1) / tbzlz::WPC, 16)), dim3(tbzlz::NT), tbzlz::SMEM_BYTES,
-             (const DMember *)dm.data(), r, nn, fmt, (const tbzfast::P1Rec *)recs.data(), (const unsigned char *)slab0,
+             (const DMember *)dm.data(), r, nn, fmt, (const tbzfast::P1Rec *)recs.data(), (const uint4 *)heap.data(),
              counters.data(), todo.data());
   if (fmt == TBZ_GZIP)
     emu_launch(tbzcrc::k_member_crc, dim3(std::min<unsigned>(nn, 16)), dim3(tbzcrc::NT), 0,
