@@ -72,17 +72,17 @@ constexpr int NL = 32;                              // decode lanes per member
 constexpr int KLL = 10, KD = TBZ_HD_KD;             // root table bits
 constexpr uint32_t SUBCAP = TBZ_HD_SUBCAP;          // second-level entries a block may need (both codes together)
 constexpr uint32_t LUT_D = 1u << KLL, LUT_SUB = LUT_D + (1u << KD), LUT_N = LUT_SUB + SUBCAP;
-constexpr uint32_t LISTCAP = 512;                   // 64-bit tokens a lane may emit per round (sub-chunk + overrun)
+constexpr uint32_t ITEMCAP = 1024;                  // items a lane may emit per round (sub-chunk + overrun)
 constexpr uint32_t S_MAX = TBZ_HD_SMAX, S_MIN = 256;  // sub-chunk size in bits
-constexpr uint32_t CK_DENSE = 24, CK_EVERY = 16, CK_SPARSE = 24, NCK = CK_DENSE + CK_SPARSE;   // recorded token starts: tokens 0..23 (shared memory: the bits since the token before), then one every CK_EVERY iterations (global scratch: rarely looked at)
+constexpr uint32_t CK_DENSE = 24, CK_SPARSE = 24, NCK = CK_DENSE + CK_SPARSE;   // recorded item starts: items 4 s, s < 24 (shared memory: the bits since the start recorded before), then items 96 + 16 i (global scratch: rarely looked at)
 constexpr uint16_t CK_NONE = 0xffffu, CK_END = 0xfffeu;     // not recorded (yet) / the lane records no more
 static_assert(S_MAX < 0xfffeu, "a recorded token start is a 16-bit offset into the sub-chunk");
 
 // The token heap: 16-byte units handed out by an atomic counter.  A block = one header unit {next block (unit index) or
 // NO_BLOCK, number of tokens, 0, 0} + its tokens; the blocks of a member form a chain in stream order.
 constexpr uint32_t NO_BLOCK = 0xffffffffu;
-constexpr size_t SCRATCH_BYTES = (size_t)NL * LISTCAP * 8 + (size_t)NL * (CK_SPARSE + 1) * 4;   // the per-warp lists a round decodes into + the sparse token starts
-__device__ __forceinline__ uint32_t block_units(uint32_t ntok) { return 1u + (ntok + 1u) / 2u; }
+constexpr size_t SCRATCH_BYTES = (size_t)NL * ITEMCAP * 4 + (size_t)NL * (CK_SPARSE + 1) * 4;   // the per-warp item lists a round decodes into + the sparse item starts
+__device__ __forceinline__ uint32_t block_units(uint32_t ntok) { return 1u + ntok; }
 // A new block of ntok tokens behind block `prev` of the chain (uniform arguments; lane 0 allocates and links).
 // Returns its unit index, or NO_BLOCK when the heap is exhausted.
 __device__ __forceinline__ uint32_t block_alloc(uint4 *heap, uint32_t heap_units, uint32_t *heap_top, uint32_t ntok, uint32_t prev, int lane) {
@@ -98,8 +98,12 @@ __device__ __forceinline__ uint32_t block_alloc(uint4 *heap, uint32_t heap_units
   return __shfl_sync(TBZ_FULL, u, 0);
 }
 
-// ---- 64-bit token: lo = up to four literal bytes (first byte lowest); hi: [7:0] match length - 3, [22:8] distance - 1,
-//      [25:23] number of literals, bit 31 = a match follows the literals
+// ---- item (what one iteration of the decode loop emits, 32 bits): a literal = its byte; two literals = I_LIT2 | second
+//      << 8 | first; a match = I_MATCH | (distance - 1) << 8 | (length - 3)
+constexpr uint32_t I_MATCH = 0x80000000u, I_LIT2 = 0x40000000u;
+// ---- token (what phase two works on, one heap unit): x = up to four literal bytes (first byte lowest); y: [7:0] match
+//      length - 3, [22:8] distance - 1, [25:23] number of literals, bit 31 = a match follows the literals; z = the output
+//      offset of the token's first byte; w = 0
 constexpr uint32_t T_MATCH = 0x80000000u;
 __device__ __forceinline__ uint32_t t_nlit(uint32_t hi) { return (hi >> 23) & 7u; }
 __device__ __forceinline__ uint32_t t_outlen(uint32_t hi) { return t_nlit(hi) + ((hi & T_MATCH) ? (hi & 255u) + 3u : 0u); }
@@ -230,74 +234,50 @@ __device__ inline bool build_sub(uint32_t *lut, uint32_t root, const Canon16 &c,
   return true;
 }
 
-// What a lane needs only at the rare token boundaries where something has to be looked at (a token start to record, a
-// full list, a place where it may synchronise): kept out of the decode loop's registers (the function below is not
-// inlined, so this lives in local memory), as is the code.
+// What a lane needs only while it looks for the place where it synchronises: kept out of the decode loop's registers
+// (the function below is not inlined, so this lives in local memory), as is the code.
 struct Rare {
-  uint32_t cstart, cend, winend, S;                  // the lane's sub-chunk, the end of the round's window, the sub-chunk size
-  uint32_t slot;                                     // the next token start to record (token 0 starts at offset 0)
-  uint32_t lastoff;                                  // offset of the token start recorded last
+  uint32_t winend, S;                                // the end of the round's window, the sub-chunk size
   uint32_t tgt;                                      // the next place where a synchronisation can happen
   uint32_t j, jstart, c, dof;                        // the lane this one is compared with, its sub-chunk start, its recorded start c (dof: offset of start c - 1)
-  uint32_t nx, g_sync;                               // ST_SYNC: synchronised into token g_sync of lane nx
-  uint32_t endp;                                     // where the lane's list ends
+  uint32_t nx, g_sync;                               // ST_SYNC: synchronised into item g_sync of lane nx
 };
-struct RareOut { int st; uint32_t evk, tgt; };
-// k tokens are closed, the next one starts at bit pb (p1: where the reader is).  Returns the lane's new state, the token
-// count of its next event and the next place where it may synchronise.
-__device__ __noinline__ RareOut rare_event(Rare &r, WSmem &sm, uint32_t *gck, int lane, uint32_t k, uint32_t evk, uint32_t pb, uint32_t p1) {
-  int st = ST_RUN;
-  if (k == evk) {
-    if (k + 2u >= LISTCAP) { st = ST_CAP; r.endp = pb; }
-    else if (pb < r.cend && r.slot < NCK) {
-      // inside the own sub-chunk: record where this token starts
-      ck_put(sm, gck, r.slot, lane, pb - r.cstart, k, r.lastoff);
-      r.lastoff = pb - r.cstart;
-      r.slot++;
-      evk = r.slot < CK_DENSE ? r.slot : LISTCAP - 2u;       // (beyond the dense ones: when the iteration count says so)
-    } else evk = LISTCAP - 2u;
-  }
-  if (st == ST_RUN && pb >= r.tgt) {
-    // past the own sub-chunk: does a token of the lane that owns these bits start here?
-    if (r.tgt == r.cend && r.slot < NCK) ck_end(sm, gck, r.slot, lane);
-    if (pb >= r.winend) { st = ST_END; r.endp = p1; }
-    else {
-      while (pb >= r.jstart + r.S) { r.j++; r.jstart += r.S; r.c = 1; r.dof = 0; }
-      const uint32_t j = r.j, rel = pb - r.jstart;
-      uint32_t c = r.c, dof = r.dof;
-      // the first recorded start at or beyond rel: ck = its offset (or "not yet" / "no more"), c its slot
-      uint32_t ck = 0u, ckv = 0u;
-      if (rel) {
-        ck = CK_NONE;
-        while (c < CK_DENSE) {
-          const uint32_t d = sm.ckd[c][j];
-          if (d < 2u) { ck = d ? CK_END : CK_NONE; break; }
-          if (dof + d >= rel) { ck = dof + d; break; }
-          dof += d; c++;
-        }
-        if (c >= CK_DENSE)
-          while (c < NCK && (ck = (ckv = __ldcg(gck + j * (CK_SPARSE + 1) + (c - CK_DENSE))) & 0xffffu) < rel) c++;
-      }
-      r.c = c; r.dof = dof;
-      if (c < NCK && ck == rel) {
-        st = ST_SYNC; r.nx = j; r.g_sync = !rel ? 0u : c < CK_DENSE ? c : ckv >> 16; r.endp = pb;
-      } else if (c < NCK && ck < CK_END) r.tgt = r.jstart + ck;
-      else if (c >= NCK || ck == CK_END) r.tgt = r.jstart + r.S;                  // no more recorded starts in that sub-chunk
-      else r.tgt = pb;                                                            // its owner is not there yet: look again
+// The lane is past its own sub-chunk and about to decode the item that starts at bit p0 >= r.tgt: does an item of the
+// lane that owns these bits start here?  Returns the lane's new state (r.tgt: the next place to look at).
+__device__ __noinline__ int overrun_event(Rare &r, const WSmem &sm, const uint32_t *gck, uint32_t p0) {
+  if (p0 >= r.winend) return ST_END;
+  while (p0 >= r.jstart + r.S) { r.j++; r.jstart += r.S; r.c = 1; r.dof = 0; }
+  const uint32_t j = r.j, rel = p0 - r.jstart;
+  uint32_t c = r.c, dof = r.dof;
+  // the first recorded start at or beyond rel: ck = its offset (or "not yet" / "no more"), c its slot
+  uint32_t ck = 0u, ckv = 0u;
+  if (rel) {
+    ck = CK_NONE;
+    while (c < CK_DENSE) {
+      const uint32_t d = sm.ckd[c][j];
+      if (d < 2u) { ck = d ? CK_END : CK_NONE; break; }
+      if (dof + d >= rel) { ck = dof + d; break; }
+      dof += d; c++;
     }
+    if (c >= CK_DENSE)
+      while (c < NCK && (ck = (ckv = __ldcg(gck + j * (CK_SPARSE + 1) + (c - CK_DENSE))) & 0xffffu) < rel) c++;
   }
-  if (st != ST_RUN && r.slot < NCK) ck_end(sm, gck, r.slot, lane);                // (whatever ended it: no more token starts from this lane)
-  RareOut o; o.st = st; o.evk = evk; o.tgt = r.tgt;
-  return o;
+  r.c = c; r.dof = dof;
+  if (c < NCK && ck == rel) { r.nx = j; r.g_sync = !rel ? 0u : c < CK_DENSE ? 4u * c : ckv >> 16; return ST_SYNC; }
+  if (c < NCK && ck < CK_END) r.tgt = r.jstart + ck;
+  else if (c >= NCK || ck == CK_END) r.tgt = r.jstart + r.S;                    // no more recorded starts in that sub-chunk
+  else r.tgt = p0;                                                              // its owner is not there yet: look again
+  return ST_RUN;
 }
 
 // ------------------------------------------------------------------------------------------------
 // Every block of a member from bit `pos` on, one warp.  Returns true when the token stream is complete (rec filled in),
 // false when the member goes to the sequential kernel.  Every return value is warp-uniform.
 // ------------------------------------------------------------------------------------------------
-__device__ inline bool decode_blocks(const In &in, uint32_t pos, P1Rec &rec, WSmem &sm, uint2 *__restrict__ scratch,
+__device__ inline bool decode_blocks(const In &in, uint32_t pos, P1Rec &rec, WSmem &sm, uint32_t *__restrict__ scratch,
                                      uint4 *__restrict__ heap, uint32_t heap_units, uint32_t *heap_top, int lane) {
   uint32_t first_blk = NO_BLOCK, prev_blk = NO_BLOCK;
+  uint32_t out_base = 0;          // output bytes of the member so far (the offset the next token starts at)
   uint32_t prev_block_bits = 0;   // size of the previous block of this member: predicts this one
   uint32_t s_cap = S_MAX;         // longest sub-chunk a lane's token list has room for (learned when a list fills up)
   bool last = false;
@@ -385,13 +365,14 @@ __device__ inline bool decode_blocks(const In &in, uint32_t pos, P1Rec &rec, WSm
         const uint32_t ntok = (nb + 3u) / 4u;
         const uint32_t blk = block_alloc(heap, heap_units, heap_top, ntok, prev_blk, lane);
         if (blk == NO_BLOCK) { TBZ_HD_WHY("give up"); return false; }
-        uint2 *const tok = reinterpret_cast<uint2 *>(heap + blk + 1);
+        uint4 *const tok = heap + blk + 1;
         for (uint32_t t = lane; t < ntok; t += 32u) {
           const uint32_t a = 4u * t, m = nb - a < 4u ? nb - a : 4u;
           uint32_t wv = peek32(in, (bp + a) * 8u);
           if (m < 4u) wv &= (1u << (8u * m)) - 1u;
-          tok[t] = make_uint2(wv, m << 23);
+          tok[t] = make_uint4(wv, m << 23, out_base + a, 0u);
         }
+        out_base += nb;
         if (first_blk == NO_BLOCK) first_blk = blk;
         prev_blk = blk;
         bp += nb; slen -= nb;
@@ -443,11 +424,11 @@ __device__ inline bool decode_blocks(const In &in, uint32_t pos, P1Rec &rec, WSm
       if (S < S_MIN) S = S_MIN;
       uint32_t winend = P0 + S * NL;
       if (winend > in.end) winend = in.end;
-      uint32_t *const gck = reinterpret_cast<uint32_t *>(scratch + (size_t)NL * LISTCAP);
+      uint32_t *const gck = scratch + (size_t)NL * ITEMCAP;
 #pragma unroll
       for (uint32_t c = 0; c < CK_DENSE; c++) sm.ckd[c][lane] = 0;
       gck[lane * (CK_SPARSE + 1)] = CK_NONE;             // (a sparse slot is set to "not yet" before the one in front of it is filled)
-      uint2 *const list = scratch + (size_t)lane * LISTCAP;
+      uint32_t *const list = scratch + (size_t)lane * ITEMCAP;
       __syncwarp();
 
       const uint32_t *const inw = in.w;
@@ -457,21 +438,21 @@ __device__ inline bool decode_blocks(const In &in, uint32_t pos, P1Rec &rec, WSm
       const uint32_t lastc = (lastw + woff) >> 2;
       // ---- the lane's state
       const uint32_t cstart = P0 + S * lane, cend = cstart + S;
-      uint32_t lb = 0, nl = 0;          // the literals of the open token
-      uint32_t k = 0;                   // tokens closed
-      uint32_t evk = 1;                 // the token count at which something is to be done: a token start to record, a full list
+      uint32_t q0 = 0, q1 = 0, q2 = 0;  // the items of the current group of four that are not stored yet
+      uint32_t nitems = 0;              // items the lane emitted (the iteration count when it stopped)
+      uint32_t lastoff = 0;             // offset of the item start recorded last
+      bool recording = true;            // the lane is inside its own sub-chunk and records item starts
       uint32_t twi = (cend >> 5) + 3u + woff;   // the reader's word index from which on the next place to synchronise may have been reached
+      uint32_t endp = cstart;           // where the lane's list ends
       Rare rare;
-      rare.cstart = cstart; rare.cend = cend; rare.winend = winend; rare.S = S;
-      rare.slot = 1; rare.lastoff = 0; rare.tgt = cend;
+      rare.winend = winend; rare.S = S; rare.tgt = cend;
       rare.j = lane + 1; rare.jstart = cend; rare.c = 1; rare.dof = 0;
-      rare.nx = 0; rare.g_sync = 0; rare.endp = cstart;
+      rare.nx = 0; rare.g_sync = 0;
       // the bit reader: three stream words, a bit offset below 32 between iterations, word wi the next to move up (word
       // indices count from the 16-byte aligned address at or below in.w; the chunk of word wi and the one behind it are
       // in the lane's slots or on their way there); the reader is at bit 32 (wi - 3 - woff) + bo
       uint32_t w0 = 0, w1 = 0, w2 = 0, wi = 3, bo = 0;
       const uint32_t inq = smem_addr(&sm.inq[0][lane]);
-      uint32_t plo = 0, phi = 0;        // a closed token that waits for its neighbour (two tokens per store)
       int st = cstart < winend ? ST_RUN : ST_IDLE;
       if (st == ST_RUN) {
         const uint32_t q = cstart >> 5;
@@ -482,13 +463,42 @@ __device__ inline bool decode_blocks(const In &in, uint32_t pos, P1Rec &rec, WSm
       }
       __syncwarp();
 
-      uint32_t it = 0;                  // iterations of the loop (uniform)
+      uint32_t it = 0;                  // iterations of the loop = items of every lane that still runs (uniform)
 #ifdef TBZ_HD_TIMING
       const long long t_loop0 = clock64();
 #endif
       while (__any_sync(TBZ_FULL, st == ST_RUN)) {
-        // every CK_EVERY iterations: the lanes still inside their own sub-chunk record the start of their next token
-        if ((++it & (CK_EVERY - 1u)) == 0u && evk >= LISTCAP - 2u) evk = k + 1u;       // (what there is to record, if anything, the event decides)
+        const bool was = st == ST_RUN;
+        // ---- every fourth iteration: the lanes inside their own sub-chunk record where this item starts (every 16th
+        // once the dense slots are used up); a full list ends the round for every lane
+        if ((it & 3u) == 0u) {
+          if (it + 8u >= ITEMCAP) { if (st == ST_RUN) { st = ST_CAP; endp = ((wi - 3u - woff) << 5) + bo; } }
+          else if (st == ST_RUN && recording && it) {
+            const uint32_t p0 = ((wi - 3u - woff) << 5) + bo;
+            const bool dense = it < 4u * CK_DENSE;
+            const uint32_t si = (it - 4u * CK_DENSE) >> 4;                        // (sparse index, beyond the dense slots)
+            if (p0 >= cend || (!dense && si >= CK_SPARSE)) {
+              // out of the own sub-chunk (or of slots): no more item starts from this lane
+              recording = false;
+              const uint32_t sl = dense ? it >> 2 : CK_DENSE + ((it - 4u * CK_DENSE + 15u) >> 4);
+              if (sl < NCK) ck_end(sm, gck, sl, lane);
+            } else if (dense || (it & 15u) == 0u) {
+              ck_put(sm, gck, dense ? it >> 2 : CK_DENSE + si, lane, p0 - cstart, it, lastoff);
+              lastoff = p0 - cstart;
+            }
+          }
+        }
+        if (st == ST_RUN) {
+          // ---- past the own sub-chunk: does an item of the lane that owns these bits start here?
+          if (__builtin_expect(wi >= twi, 0)) {
+            const uint32_t p0 = ((wi - 3u - woff) << 5) + bo;
+            if (p0 >= rare.tgt) {
+              st = overrun_event(rare, sm, gck, p0);
+              twi = (rare.tgt >> 5) + 3u + woff;
+              if (st != ST_RUN) endp = p0;
+            }
+          }
+        }
         if (st == ST_RUN) {
           // ---- first symbol: lit/len
           const uint32_t x = __funnelshift_r(w0, w1, bo);
@@ -497,7 +507,7 @@ __device__ inline bool decode_blocks(const In &in, uint32_t pos, P1Rec &rec, WSm
             if (e & K_SUB) e = lut[(e >> 17) + ((x >> KLL) & ~(0xffffffffu << (e & 31u)))];
             if (e & K_STOP) {
               if (e & K_LEN) st = ST_BAD;
-              else { st = ST_EOB; rare.endp = ((wi - 3u - woff) << 5) + bo + (e & 31u); }
+              else { st = ST_EOB; endp = ((wi - 3u - woff) << 5) + bo + (e & 31u); }
             }
           }
           const uint32_t n1 = e_drop(e);
@@ -513,8 +523,7 @@ __device__ inline bool decode_blocks(const In &in, uint32_t pos, P1Rec &rec, WSm
           const uint32_t v1 = e_value(e, x, n1), v2 = e_value(e2, y, n2);
           if (__builtin_expect(ism && (e2 & K_STOP) != 0u && st == ST_RUN, 0)) st = ST_BAD;
           if (st == ST_RUN) {
-            // ---- drop the bits; the words move up by one when the offset passes 32, by two (rarely) when it passes
-            // 64.  Either way what is loaded now is not looked at before a later iteration.
+            // ---- drop the bits; one word moves up when the offset passes 32 (two, rarely)
             bo = o2 + n2;
 #pragma unroll
             for (int twice = 0; twice < 2; twice++) {
@@ -526,41 +535,32 @@ __device__ inline bool decode_blocks(const In &in, uint32_t pos, P1Rec &rec, WSm
                 wi++; bo -= 32u;
               }
             }
-            // ---- the token: a match closes it; literals close it when it would hold more than four
-            const uint32_t cnt = two ? 2u : 1u;
-            const bool close = ism || nl + cnt > 4u;
-            if (close) {
-              const uint32_t th = (nl << 23) | (ism ? T_MATCH | (v2 << 8) | v1 : 0u);
-              if (k & 1u) *reinterpret_cast<uint4 *>(list + (k - 1u)) = make_uint4(plo, phi, lb, th);
-              plo = lb; phi = th;
-            }
-            k += close ? 1u : 0u;
-            lb = close ? 0u : lb; nl = close ? 0u : nl;
-            {
-              const uint32_t keep = (uint32_t)ism - 1u;                   // all ones for literals
-              lb |= (((two ? v2 << 8 : 0u) | v1) << (8u * nl)) & keep;
-              nl += cnt & keep;
-            }
-            // ---- rarely, at a token boundary: a token start to record, a full list, a place where this lane may synchronise
-            if (__builtin_expect(close && (k == evk || wi >= twi), 0)) {
-              const uint32_t p1 = ((wi - 3u - woff) << 5) + bo;
-              const RareOut o = rare_event(rare, sm, gck, lane, k, evk, ism ? p1 : p1 - n1 - n2, p1);
-              st = o.st; evk = o.evk; twi = (o.tgt >> 5) + 3u + woff;
-            }
+            // ---- the item; four of them leave with one store
+            const uint32_t item = (ism ? I_MATCH : two ? I_LIT2 : 0u) | ((ism || two) ? v2 << 8 : 0u) | v1;
+            if ((it & 3u) == 3u) *reinterpret_cast<uint4 *>(list + (it - 3u)) = make_uint4(q0, q1, q2, item);
+            q0 = q1; q1 = q2; q2 = item;
           }
-          if (__builtin_expect(st != ST_RUN && st != ST_SYNC && st != ST_END && st != ST_CAP, 0) && rare.slot < NCK) ck_end(sm, gck, rare.slot, lane);   // (end of block, bad code: no more token starts from this lane)
         }
+        if (__builtin_expect(was && st != ST_RUN, 0)) {
+          // the lane stops in front of this item: the items of its last group that are not stored yet
+          nitems = it;
+          const uint32_t r = it & 3u;
+          if (r > 2u) list[it - 3u] = q0;
+          if (r > 1u) list[it - 2u] = q1;
+          if (r > 0u) list[it - 1u] = q2;
+          if (recording) {                                                     // no more item starts from this lane
+            const uint32_t sl = it < 4u * CK_DENSE ? (it >> 2) + 1u : CK_DENSE + ((it - 4u * CK_DENSE) >> 4) + 1u;
+            if (sl < NCK) ck_end(sm, gck, sl, lane);
+          }
+        }
+        it++;
         __syncwarp();
       }
 #ifdef TBZ_HD_TIMING
       const long long t_loop1 = clock64();
 #endif
-      // ---- the end of the lane's list: literals still waiting close a last token (not after a synchronisation or a
-      // full list: the list ends at a token boundary there and the open literals belong to whoever continues)
-      if (k & 1u) list[k - 1u] = make_uint2(plo, phi);                 // (the last token of an odd count still waits for a neighbour)
-      if ((st == ST_END || st == ST_EOB) && nl) { list[k] = make_uint2(lb, nl << 23); k++; }
       // a lane that decoded past the end of the input has nothing proven to offer (repeated words are read there)
-      const uint32_t endp = rare.endp, nx = rare.nx, g_sync = rare.g_sync;
+      const uint32_t nx = rare.nx, g_sync = rare.g_sync;
       if (st != ST_IDLE && endp > in.end) st = ST_BAD;
       __syncwarp();
       // ---- lanes reachable from lane 0 through "synchronised into" edges are proven
@@ -587,37 +587,82 @@ __device__ inline bool decode_blocks(const In &in, uint32_t pos, P1Rec &rec, WSm
         if (s_cap > S_MAX) s_cap = S_MAX;
         if (s_cap < S_MIN) s_cap = S_MIN;
       }
-      // ---- the proven tokens of the round, lane after lane, become one block of the token heap
+      // ---- the proven items of the round become tokens — up to four literals and the match behind them — in one block
+      // of the token heap: every lane walks its items twice (count tokens and output bytes; then write), the scans over
+      // the lanes in between give every token its place and its output offset.  Both walks are branch-free per item and
+      // read the list in 16-byte groups, four groups in flight (the list is in L2 at best)
       {
-        const uint32_t cnt = proven && k > my_g ? k - my_g : 0u;
-        uint32_t xs = cnt;
+        const uint32_t i0 = my_g, i1 = proven && nitems > my_g ? nitems : my_g;
+        const uint32_t g0 = i0 & ~3u;
+        const uint4 *const lv = reinterpret_cast<const uint4 *>(list);
+        uint32_t ntok = 0, nout = 0;
+        {
+          uint32_t nl = 0;
+          uint4 v[4];
+#pragma unroll
+          for (uint32_t u = 0; u < 4; u++) v[u] = lv[(g0 >> 2) + u];
+          for (uint32_t g = g0; g < i1; g += 16u) {
+#pragma unroll
+            for (uint32_t u = 0; u < 4; u++) {
+              const uint32_t t4[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+              if (g + 16u + 4u * u < i1) v[u] = lv[((g + 16u) >> 2) + u];
+#pragma unroll
+              for (uint32_t e = 0; e < 4; e++) {
+                const uint32_t i = g + 4u * u + e, t = t4[e];
+                const bool valid = i >= i0 && i < i1, ism = (t & I_MATCH) != 0u;
+                const uint32_t c = ism ? 0u : (t >> 30) + 1u;
+                const bool over = nl + c > 4u;
+                ntok += valid && (ism || over) ? 1u : 0u;
+                nout += valid ? (ism ? nl * 0u + (t & 255u) + 3u : c) : 0u;
+                nl = valid ? (ism ? 0u : over ? c : nl + c) : nl;
+              }
+            }
+          }
+          if (nl) ntok++;
+        }
+        uint32_t xt = ntok, xo = nout;
 #pragma unroll
         for (int sft = 1; sft < 32; sft <<= 1) {
-          const uint32_t u = __shfl_up_sync(TBZ_FULL, xs, sft);
-          if (lane >= sft) xs += u;
+          const uint32_t ut = __shfl_up_sync(TBZ_FULL, xt, sft), uo = __shfl_up_sync(TBZ_FULL, xo, sft);
+          if (lane >= sft) { xt += ut; xo += uo; }
         }
-        const uint32_t total = __shfl_sync(TBZ_FULL, xs, 31);
+        const uint32_t total = __shfl_sync(TBZ_FULL, xt, 31), total_out = __shfl_sync(TBZ_FULL, xo, 31);
         if (total) {
           const uint32_t blk = block_alloc(heap, heap_units, heap_top, total, prev_blk, lane);
           if (blk == NO_BLOCK) { TBZ_HD_WHY("give up"); return false; }
-          __syncwarp();                                   // every lane's list is visible to the others from here
-          // list after list, the whole warp on each: coalesced loads and stores, up to eight per lane in flight
-          uint2 *const blk_tok = reinterpret_cast<uint2 *>(heap + blk + 1);
-          for (int L = 0; L < NL; L++) {
-            const uint32_t cntL = __shfl_sync(TBZ_FULL, cnt, L);
-            if (!cntL) continue;
-            const uint2 *src = scratch + (size_t)L * LISTCAP + __shfl_sync(TBZ_FULL, my_g, L);
-            uint2 *dst = blk_tok + (__shfl_sync(TBZ_FULL, xs, L) - cntL);
-            for (uint32_t i0 = lane; i0 < cntL; i0 += 256u) {
-              uint2 a[8];
+          uint4 *dst = heap + blk + 1 + (xt - ntok);
+          uint32_t off = out_base + (xo - nout);
+          uint32_t nl = 0, lb = 0;
+          uint4 v[4];
 #pragma unroll
-              for (uint32_t u = 0; u < 8; u++) if (i0 + 32u * u < cntL) a[u] = __ldcg(src + i0 + 32u * u);
+          for (uint32_t u = 0; u < 4; u++) v[u] = lv[(g0 >> 2) + u];
+          for (uint32_t g = g0; g < i1; g += 16u) {
 #pragma unroll
-              for (uint32_t u = 0; u < 8; u++) if (i0 + 32u * u < cntL) dst[i0 + 32u * u] = a[u];
+            for (uint32_t u = 0; u < 4; u++) {
+              const uint32_t t4[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+              if (g + 16u + 4u * u < i1) v[u] = lv[((g + 16u) >> 2) + u];
+#pragma unroll
+              for (uint32_t e = 0; e < 4; e++) {
+                const uint32_t i = g + 4u * u + e, t = t4[e];
+                const bool valid = i >= i0 && i < i1, ism = (t & I_MATCH) != 0u;
+                const uint32_t c = ism ? 0u : (t >> 30) + 1u;
+                const bool close = valid && (ism || nl + c > 4u);
+                if (close) {
+                  *dst = make_uint4(lb, (nl << 23) | (ism ? T_MATCH | (t & 0x7fffffu) : 0u), off, 0u);
+                  dst++;
+                  off += nl + (ism ? (t & 255u) + 3u : 0u);
+                }
+                lb = close ? 0u : lb; nl = close ? 0u : nl;
+                const uint32_t keep = valid && !ism ? 0xffffffffu : 0u;
+                lb |= ((t & 0xffffu) << (8u * nl)) & keep;
+                nl += c & keep;
+              }
             }
           }
+          if (nl) *dst = make_uint4(lb, nl << 23, off, 0u);
           if (first_blk == NO_BLOCK) first_blk = blk;
           prev_blk = blk;
+          out_base += total_out;
         }
       }
 #ifdef TBZ_HD_TIMING
@@ -627,7 +672,7 @@ __device__ inline bool decode_blocks(const In &in, uint32_t pos, P1Rec &rec, WSm
       }
 #endif
 #if defined(TBZ_EMU) && defined(TBZ_EMU_TRACE)
-      fprintf(stderr, "[hd]   lane %d st %d cstart %u endp %u k %u nx %u g %u proven %d\n", lane, st, cstart, endp, k, nx, g_sync, (int)proven);
+      fprintf(stderr, "[hd]   lane %d st %d cstart %u endp %u k %u nx %u g %u proven %d\n", lane, st, cstart, endp, nitems, nx, g_sync, (int)proven);
       if (lane == 0) fprintf(stderr, "[hd] round P0 %u S %u -> term_st %d pos %u\n", P0, S, term_st, term_pos);
 #endif
       // ---- how did the round end?
@@ -640,7 +685,7 @@ __device__ inline bool decode_blocks(const In &in, uint32_t pos, P1Rec &rec, WSm
   }
   if (lane == 0) {
     rec.first_slab = first_blk;
-    rec.out_len = 0xffffffffu;             // not tracked here: phase two counts (and owns the overflow verdict)
+    rec.out_len = out_base;                // (phase two owns the overflow verdict)
     rec.end_pos = pos;
     rec.status = 1u;
   }
@@ -648,7 +693,7 @@ __device__ inline bool decode_blocks(const In &in, uint32_t pos, P1Rec &rec, WSm
 }
 
 // One member, one warp: wrapper header, then every block.
-__device__ inline bool decode_member(const DMember &mem, int fmt, P1Rec &rec, WSmem &sm, uint2 *__restrict__ scratch,
+__device__ inline bool decode_member(const DMember &mem, int fmt, P1Rec &rec, WSmem &sm, uint32_t *__restrict__ scratch,
                                      uint4 *__restrict__ heap, uint32_t heap_units, uint32_t *heap_top, int lane) {
   In in;
   uint32_t pos;

@@ -40,7 +40,7 @@ k_inflate_decode(const DMember *members, uint32_t n, int fmt, tbzfast::P1Rec *re
   TBZ_DYN_SMEM(smem_raw);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   tbzhd::WSmem &sm = reinterpret_cast<tbzhd::WSmem *>(smem_raw)[warp];
-  uint2 *const scratch = reinterpret_cast<uint2 *>(scratch_all + ((size_t)blockIdx.x * tbzhd::WPC + warp) * tbzhd::SCRATCH_BYTES);
+  uint32_t *const scratch = reinterpret_cast<uint32_t *>(scratch_all + ((size_t)blockIdx.x * tbzhd::WPC + warp) * tbzhd::SCRATCH_BYTES);
   for (;;) {
     uint32_t i = 0;
     if (lane == 0) i = atomicAdd(&counters[0], 1u);

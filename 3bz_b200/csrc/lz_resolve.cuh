@@ -7,9 +7,9 @@
 // text of BASELINE config 2: 4 % of the matches reach back less than 128 bytes, the median distance is 3.8 KB), so a
 // SMALL unit of work has almost no internal dependency.  Here the unit is a step of 32 tokens — one per lane, each
 // `up to four literals + one match` (huff_decode.cuh), about 280 output bytes:
-//   1. the lane's token arrives with one coalesced 8-byte load (issued two steps ahead; phase one leaves a member's
-//      tokens as contiguous blocks, so steps are full); a warp scan of the token lengths gives every token its
-//      output offset
+//   1. the lane's token arrives with one coalesced 16-byte load (issued two steps ahead; phase one leaves a member's
+//      tokens as contiguous blocks, so steps are full) and carries its output offset: phase one, whose lanes walk
+//      their tokens one after the other anyway, counted the bytes')
 //   2. literals are stored; a match whose source lies entirely below the step is READY and is copied by its own lane
 //      with one straight-line, branch-free sequence — aligned 4-byte loads of the source at immediate offsets, one
 //      funnel shift per destination word, 32-bit stores between a <= 3-byte head and tail — the same instructions for
@@ -138,31 +138,20 @@ __device__ __forceinline__ Cls classify(const Step &q) {
   return c;
 }
 
-// The next step is placed — offsets by a warp scan — while the current one (already placed) is classified: the five
-// shuffles of the scan depend on each other, the classification is arithmetic that fills their latency.  Then the words
-// of every source of the new step that is older than the ring start their way (the member's output has had them for a
-// long time: see the static_assert on H).  cq == nullptr: nothing to classify (the very first step).
+// The next step is placed (phase one wrote every token's output offset next to it: no scan) and the current one,
+// already placed, is classified.  Then the words of every source of the new step that is older than the ring start
+// their way (the member's output has had them for a long time: see the static_assert on H).  cq == nullptr: nothing to
+// classify (the very first step).
 template <bool AL>
-__device__ __forceinline__ void place(Step &q, const WState &w, uint32_t base, uint32_t lo, uint32_t hi, int lane, const Step *cq, Cls &cc) {
+__device__ __forceinline__ void place(Step &q, const WState &w, uint32_t base, uint32_t lo, uint32_t hi, uint32_t off, int lane, const Step *cq, Cls &cc) {
   q.lo = lo; q.hi = hi; q.base = base;
   const bool m = (hi & T_MATCH) != 0u;
   const uint32_t nl = tbzhd::t_nlit(hi);
   const uint32_t n = m ? (hi & 255u) + 3u : 0u;
-  const uint32_t mine = nl + n;
-  uint32_t x = mine, u;
-  u = __shfl_up_sync(TBZ_FULL, x, 1);
+  // phase one gave every token its output offset: the step ends where its last token ends
+  q.p = (lo | hi) ? off : base;
+  q.total = __reduce_max_sync(TBZ_FULL, q.p + nl + n) - base;
   if (cq) cc = classify(*cq);
-  if (lane >= 1) x += u;
-  u = __shfl_up_sync(TBZ_FULL, x, 2);
-  if (lane >= 2) x += u;
-  u = __shfl_up_sync(TBZ_FULL, x, 4);
-  if (lane >= 4) x += u;
-  u = __shfl_up_sync(TBZ_FULL, x, 8);
-  if (lane >= 8) x += u;
-  u = __shfl_up_sync(TBZ_FULL, x, 16);
-  if (lane >= 16) x += u;
-  q.total = __shfl_sync(TBZ_FULL, x, 31);
-  q.p = base + x - mine;
   const uint32_t dst = q.p + nl, d = ((hi >> 8) & 0x7fffu) + 1u;
   const uint32_t end = base + q.total;
   if (m && d <= dst && end > H && dst - d < end - H && n <= NFAST && (unsigned long long)end <= w.cap) {
@@ -340,20 +329,20 @@ __device__ __forceinline__ bool execute(WState &w, Step &q, const Cls &c, bool a
 // The member's token stream: the blocks of its chain in order, 32 tokens at a time (phase one: huff_decode.cuh).
 struct Cursor {
   const uint4 *heap;
-  const uint2 *tok;
+  const uint4 *tok;
   uint32_t left, next;
   __device__ __forceinline__ void open(const uint4 *heap_, uint32_t first) { heap = heap_; tok = nullptr; left = 0; next = first; }
   // the next step: the lane's token (zero beyond the step's tokens); false at the end of the stream.  Uniform.
-  __device__ __forceinline__ bool step(uint2 &t) {
+  __device__ __forceinline__ bool step(uint4 &t) {
     while (left == 0) {
-      if (next == NO_BLOCK) { t = make_uint2(0u, 0u); return false; }
+      if (next == NO_BLOCK) { t = make_uint4(0u, 0u, 0u, 0u); return false; }
       const uint4 h = __ldg(heap + next);
-      tok = reinterpret_cast<const uint2 *>(heap + next + 1);
+      tok = heap + next + 1;
       left = h.y; next = h.x;
     }
     const uint32_t nv = left < 32u ? left : 32u;
     const uint32_t lane = threadIdx.x & 31u;
-    t = lane < nv ? __ldg(tok + lane) : make_uint2(0u, 0u);
+    t = lane < nv ? __ldg(tok + lane) : make_uint4(0u, 0u, 0u, 0u);
     tok += nv; left -= nv;
 #ifndef TBZ_EMU
     if (left > 96u + lane) asm volatile("prefetch.global.L2 [%0];" ::"l"(tok + 96 + lane));   // four steps ahead: the heap is cold in L2
@@ -368,22 +357,22 @@ template <bool AL>
 __device__ inline bool resolve_stream(WState &w, const P1Rec &rec, const uint4 *__restrict__ heap, bool adler, int lane) {
   Cursor cur;
   cur.open(heap, rec.first_slab);
-  uint2 ta, tb;                                             // the tokens of the next step to place, alternately
+  uint4 ta, tb;                                             // the tokens of the next step to place, alternately
   Step a, b;
   Cls c;
   bool more = cur.step(ta);
   if (more) {
-    place<AL>(a, w, 0u, ta.x, ta.y, lane, nullptr, c);
+    place<AL>(a, w, 0u, ta.x, ta.y, ta.z, lane, nullptr, c);
     more = cur.step(tb);                                    // the tokens of the step after `a`
     for (;;) {
       // `a` is placed; tb holds the tokens of the step after it (if `more`)
       const bool more2 = more && cur.step(ta);
-      if (more) place<AL>(b, w, a.base + a.total, tb.x, tb.y, lane, &a, c);
+      if (more) place<AL>(b, w, a.base + a.total, tb.x, tb.y, tb.z, lane, &a, c);
       else c = classify(a);
       if (!execute<AL>(w, a, c, adler, lane)) return false;
       if (!more) break;
       more = more2 && cur.step(tb);
-      if (more2) place<AL>(a, w, b.base + b.total, ta.x, ta.y, lane, &b, c);
+      if (more2) place<AL>(a, w, b.base + b.total, ta.x, ta.y, ta.z, lane, &b, c);
       else c = classify(b);
       if (!execute<AL>(w, b, c, adler, lane)) return false;
       if (!more2) break;

@@ -375,12 +375,12 @@ extern "C" int32_t tbz_batch_prepare(tbz_ctx *ctx, int32_t format, const tbz_mem
     cudaFuncSetAttribute(k_inflate_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kResolveSmem);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_inflate_resolve, tbzlz::NT, kResolveSmem);
     b->res_grid = (int)std::min<uint64_t>((n + tbzlz::WPC - 1) / tbzlz::WPC, (uint64_t)ctx->sm_count * std::max(1, occ));
-    // The token heap: phase one leaves every member's tokens there as contiguous blocks (8 bytes per token; a token
-    // is up to four literals + one match: about one byte per output byte on text, 2.7 at worst).  Sized from what
-    // is known: at most 3 bytes per byte of output capacity, and no more than 48 bytes per compressed byte (a token
+    // The token heap: phase one leaves every member's tokens there as contiguous blocks (16 bytes per token; a token
+    // is up to four literals + one match: about two bytes per output byte on text, 5.4 at worst).  Sized from what
+    // is known: at most 6 bytes per byte of output capacity, and no more than 96 bytes per compressed byte (a token
     // costs at least two bits... in practice ~24 bits).  Members that find the heap full go to the sequential kernel.
     uint64_t want = 4096;
-    for (uint64_t i = 0; i < n; i++) want += std::min<uint64_t>(3 * m[i].out_cap, 48 * m[i].in_len) + 64;
+    for (uint64_t i = 0; i < n; i++) want += std::min<uint64_t>(6 * m[i].out_cap, 96 * m[i].in_len) + 64;
     want = std::min<uint64_t>(want, kTokenHeapBytes);
     b->heap_units = (uint32_t)std::min<uint64_t>(want / 16, 0xfffffff0ull);
     PCK(dev_alloc(ctx, (size_t)b->heap_units * 16, &b->d_heap));

@@ -153,6 +153,13 @@ template <class T> static inline uint32_t __match_any_sync(uint32_t mask, T v) {
     }
   });
 }
+static inline uint32_t __reduce_max_sync(uint32_t mask, uint32_t v) {
+  return (uint32_t)emu::collective(emu::OP_BALLOT + 100, mask, v, 0, [](emu::Warp &w, uint64_t *out) {
+    uint64_t r = 0;
+    for (int l = 0; l < 32; l++) if ((w.mask >> l & 1) && w.in[l] > r) r = w.in[l];
+    for (int l = 0; l < 32; l++) out[l] = r;
+  });
+}
 static inline uint32_t __activemask() { return 0xffffffffu; }
 
 // ---- block barriers ------------------------------------------------------------------------------

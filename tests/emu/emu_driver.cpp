@@ -19,7 +19,7 @@ extern "C" int emu_inflate_batch(int fmt, const tbz_member *m, uint64_t n, tbz_r
   std::vector<tbzfast::P1Rec> recs(n);
   // the token heap: 16-byte units; ~1 token byte per output byte on text, more for short matches
   uint64_t units = 64;
-  for (uint64_t i = 0; i < n; i++) units += (3 * m[i].out_cap + 4 * m[i].in_len) / 16 + 64;
+  for (uint64_t i = 0; i < n; i++) units += (6 * m[i].out_cap + 8 * m[i].in_len) / 16 + 64;
   const uint32_t heap_units = (uint32_t)units;
   std::vector<uint4> heap(heap_units);
   (void)variant;
