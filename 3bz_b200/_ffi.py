@@ -28,7 +28,7 @@ SYMBOLS = [
     "tbz_batch_prepare", "tbz_batch_launch", "tbz_batch_finish", "tbz_batch_destroy",
     "tbz_inflate_batch_multi", "tbz_partition",
     "tbz_session_create", "tbz_session_destroy", "tbz_session_set_output",
-    "tbz_session_rebind_output", "tbz_session_replace_output", "tbz_session_decompress", "tbz_session_flags",
+    "tbz_session_rebind_output", "tbz_session_replace_output", "tbz_session_decompress", "tbz_session_flags", "tbz_session_consumed",
     "tbz_gzip_header_parse", "tbz_inflate_gzip_members",
 ]
 
@@ -109,6 +109,7 @@ def lib():
         "tbz_session_replace_output": (i32, [vp, vp, u64]),
         "tbz_session_decompress": (i32, [vp, vp, u64, P(C.c_int64), P(i32)]),
         "tbz_session_flags": (i32, [vp, P(i32), P(i32), P(i32)]),
+        "tbz_session_consumed": (i32, [vp, P(u64)]),
         "tbz_gzip_header_parse": (i32, [vp, u64, P(GzipHeader)]),
         "tbz_inflate_gzip_members": (i32, [vp, vp, u64, vp, u64, P(Result), u64, P(u64), P(u64)]),
     }

@@ -241,7 +241,12 @@ def decompress(context, state):
     if state.output_buffer is None:
         state._set(bytearray(0))               # (make-array 0), deflate.lisp:47
     rc = state.L.tbz_session_decompress(state.h, addr if n else None, n, C.byref(ret), C.byref(verdict))
-    context.offset = context.end               # the session now owns every unread octet
+    # the session owns every unread octet — unless the stream finished inside them: the context then stops just past
+    # the consumed octets (io.lisp:17-58), where trailing data or the next member starts
+    used = C.c_uint64(n)
+    if rc == 0:
+        state.L.tbz_session_consumed(state.h, C.byref(used))
+    context.offset = min(context.end, context.offset + used.value)
     if rc == _ffi.E_STATE:
         raise ThreeBzError("decompress called on a finished or failed state", verdict.value)
     check(rc, state.ctx.h)

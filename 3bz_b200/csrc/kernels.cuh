@@ -5,8 +5,7 @@
 #include "tbz_device.cuh"
 #include "inflate_seq.cuh"
 #include "inflate_decode.cuh"
-#include "huff_decode.cuh"
-#include "lz_resolve.cuh"
+#include "inflate_copy.cuh"
 #include "inflate_crc.cuh"
 
 // =============================================================================================
@@ -30,45 +29,55 @@ k_inflate_seq(const DMember *members, tbz_result *results, uint32_t n, int fmt,
 }
 
 // counters: [0] next member for phase one, [1] members queued for the sequential kernel,
-//           [2] 16-byte units of the token heap handed out, [3] next member for phase two, [4] next member for the gzip CRC kernel
-// Phase one (huff_decode.cuh), persistent CTAs of WPC independent warps: each warp pulls the next member from a
-// global counter and decodes it into blocks of the token heap (through its own scratch lists: SCRATCH_BYTES per warp
-// of the grid); members it cannot prove clean are queued for k_inflate_seq.
-__global__ void __launch_bounds__(tbzhd::NT, TBZ_HD_MINBLOCKS)
-k_inflate_decode(const DMember *members, uint32_t n, int fmt, tbzfast::P1Rec *recs, unsigned char *scratch_all,
-                 uint4 *heap, uint32_t heap_units, uint32_t *counters, uint32_t *todo) {
+//           [2] slabs handed out, [3] next member for phase two, [4] next member for the gzip CRC kernel
+// Phase one, persistent CTAs of WPC independent warps: each warp pulls the next member from a
+// global counter and decodes it into token slabs; members it cannot prove clean are queued for
+// k_inflate_seq.
+__global__ void __launch_bounds__(tbzfast::NT, 8)
+k_inflate_decode(const DMember *members, uint32_t n, int fmt, tbzfast::P1Rec *recs,
+                 uint32_t *slabs, uint32_t nslabs, uint32_t *counters, uint32_t *todo) {
   TBZ_DYN_SMEM(smem_raw);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  tbzhd::WSmem &sm = reinterpret_cast<tbzhd::WSmem *>(smem_raw)[warp];
-  uint32_t *const scratch = reinterpret_cast<uint32_t *>(scratch_all + ((size_t)blockIdx.x * tbzhd::WPC + warp) * tbzhd::SCRATCH_BYTES);
+  tbzfast::WSmem &sm = reinterpret_cast<tbzfast::WSmem *>(smem_raw)[warp];
   for (;;) {
     uint32_t i = 0;
     if (lane == 0) i = atomicAdd(&counters[0], 1u);
     i = __shfl_sync(TBZ_FULL, i, 0);
     if (i >= n) break;
-    const bool ok = tbzhd::decode_member(members[i], fmt, recs[i], sm, scratch, heap, heap_units, &counters[2], lane);
+    const bool ok = tbzfast::decode_member(members[i], fmt, recs[i], sm, slabs, nslabs, &counters[2], lane);
     __syncwarp();
     if (!ok && lane == 0) { recs[i].status = 0; todo[atomicAdd(&counters[1], 1u)] = i; }
   }
 }
 
-// Phase two (lz_resolve.cuh), persistent CTAs of WPC independent warps: ONE WARP per member, a history ring per warp,
-// no CTA barrier.  (The round-1 design — one CTA per member, windows, pointer jumping — and the
-// first round-2 pair live under experiments/ with their numbers in profiles/.)
-__global__ void __launch_bounds__(tbzlz::NT, TBZ_LZ_MINBLOCKS)
+// Phase two, persistent CTAs: one CTA per member resolves the token stream into bytes through a
+// shared-memory window and checks the trailer (inflate_copy.cuh).  The alternatives that were built and
+// measured — byte-parallel rank queries and lock-step lanes (round 1), one warp per member with 64-bit or
+// 16-byte tokens (round 2: inflate_decode2/resolve2, huff_decode/lz_resolve) — live under experiments/ with
+// their numbers in profiles/ and DESIGN.md.
+namespace tbzp2 = tbzcp;
+#ifndef TBZ_P2_MINBLOCKS
+#define TBZ_P2_MINBLOCKS 3
+#endif
+__global__ void __launch_bounds__(tbzp2::NT, TBZ_P2_MINBLOCKS)
 k_inflate_resolve(const DMember *members, tbz_result *results, uint32_t n, int fmt,
-                  const tbzfast::P1Rec *recs, const uint4 *heap, uint32_t *counters, uint32_t *todo) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t ring = tbzlz::smem_base() + tbzlz::PAD + (uint32_t)warp * tbzlz::H;   // shared-space address of this warp's ring
+                  const tbzfast::P1Rec *recs, const uint32_t *slabs, uint32_t *counters, uint32_t *todo) {
+  TBZ_DYN_SMEM(smem_raw);
+  tbzp2::Smem &sm = *reinterpret_cast<tbzp2::Smem *>(smem_raw);
+  const int tid = threadIdx.x;
+  if (fmt == TBZ_GZIP) {
+    crc_table_init(sm.crc_tab, tid, tbzp2::NT);
+    for (uint32_t k = tid; k < tbzp2::WB / 16 + 4; k += tbzp2::NT) sm.x16[k] = crc_x8n(16ull * k);
+  }
   for (;;) {
-    uint32_t i = 0;
-    if (lane == 0) i = atomicAdd(&counters[3], 1u);
-    i = __shfl_sync(TBZ_FULL, i, 0);
+    __syncthreads();
+    if (tid == 0) sm.member = atomicAdd(&counters[3], 1u);
+    __syncthreads();
+    const uint32_t i = sm.member;
     if (i >= n) break;
     if (!recs[i].status) continue;
-    const bool ok = tbzlz::resolve_member(members[i], fmt, recs[i], heap, results[i], ring, lane);
-    __syncwarp();
-    if (!ok && lane == 0) todo[atomicAdd(&counters[1], 1u)] = i;
-    if (ok && lane == 0 && fmt == TBZ_GZIP) const_cast<tbzfast::P1Rec *>(recs)[i].status = tbzcrc::ST_CRC_PENDING;
+    const bool ok = tbzp2::resolve_member(members[i], fmt, recs[i], slabs, results[i], sm, tid);
+    if (!ok && tid == 0) todo[atomicAdd(&counters[1], 1u)] = i;
+    if (ok && tid == 0 && tbzp2::CRC_SEPARATE && fmt == TBZ_GZIP) const_cast<tbzfast::P1Rec *>(recs)[i].status = tbzcrc::ST_CRC_PENDING;
   }
 }

@@ -19,6 +19,7 @@
 #include "inflate_seq.cuh"
 #include "inflate_decode.cuh"
 #include "inflate_resolve.cuh"
+#include "inflate_copy.cuh"
 #include "inflate_crc.cuh"
 #include "kernels.cuh"
 #include "inflate_split.cuh"
@@ -26,9 +27,7 @@
 // =============================================================================================
 // host objects
 // =============================================================================================
-static const size_t kResolveSmem = tbzlz::SMEM_BYTES;
-static const size_t kDecodeSmem = sizeof(tbzhd::WSmem) * tbzhd::WPC;
-static const uint64_t kTokenHeapBytes = 48ull << 30;  // upper bound of the token heap per batch (B200: 180 GB; 2^32 units of 16 bytes at most)
+static const uint64_t kSlabPoolBytes = 24ull << 30;  // upper bound of the token slab pool per batch (B200: 180 GB)
 static const uint64_t kSplitMinBytes = 4ull << 20;   // members at least this large are split across the GPU
 static const uint64_t kSplitChunkBytes =      // compressed bytes per chunk of a split member (TBZ_SPLIT_CHUNK_KB: tuning)
     (getenv("TBZ_SPLIT_CHUNK_KB") ? std::max<uint64_t>(16, strtoull(getenv("TBZ_SPLIT_CHUNK_KB"), nullptr, 10)) : 160ull) << 10;
@@ -116,11 +115,12 @@ struct tbz_batch {
   uint64_t in_total = 0, out_total = 0;
   bool in_direct = false;              // caller's inputs are one dense span: DMA straight from it
   bool out_direct = false;             // caller's outputs are exactly adjacent: DMA straight into them
+  bool copies_issued = false;          // (pipelined path) the D2H copies of the produced bytes are already in the stream
   const uint8_t *in_span = nullptr; uint8_t *out_span = nullptr;
   void *d_in = nullptr, *d_out = nullptr, *d_members = nullptr, *d_results = nullptr;
-  void *d_heap = nullptr, *d_scratch = nullptr, *d_counters = nullptr, *d_todo = nullptr, *d_recs = nullptr;
+  void *d_slabs = nullptr, *d_counters = nullptr, *d_todo = nullptr, *d_recs = nullptr, *d_scratch = nullptr;
   int fast_grid = 0, res_grid = 0;
-  uint32_t heap_units = 0;
+  uint32_t nslabs = 0;
   bool launched = false;
   cudaStream_t stream = nullptr;       // the stream this batch lives on
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -348,7 +348,8 @@ extern "C" int32_t tbz_batch_destroy(tbz_batch *b) {
   if (b->ev1) cudaEventDestroy(b->ev1);
   dev_release(ctx, b->d_in); dev_release(ctx, b->d_out);
   dev_release(ctx, b->d_members); dev_release(ctx, b->d_results);
-  dev_release(ctx, b->d_heap); dev_release(ctx, b->d_scratch); dev_release(ctx, b->d_counters); dev_release(ctx, b->d_todo); dev_release(ctx, b->d_recs);
+  dev_release(ctx, b->d_slabs); dev_release(ctx, b->d_counters); dev_release(ctx, b->d_todo); dev_release(ctx, b->d_recs);
+  dev_release(ctx, b->d_scratch);
   delete b;
   return TBZ_OK;
 }
@@ -369,23 +370,23 @@ extern "C" int32_t tbz_batch_prepare(tbz_ctx *ctx, int32_t format, const tbz_mem
   PCK(dev_alloc(ctx, std::max<uint64_t>(1, n) * sizeof(tbz_result), &b->d_results));
   if (!(flags & TBZ_FLAG_NO_FASTPATH) && n) {
     int occ = 0;
-    cudaFuncSetAttribute(k_inflate_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDecodeSmem);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_inflate_decode, tbzhd::NT, kDecodeSmem);
-    b->fast_grid = (int)std::min<uint64_t>((n + tbzhd::WPC - 1) / tbzhd::WPC, (uint64_t)ctx->sm_count * std::max(1, occ));
-    cudaFuncSetAttribute(k_inflate_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kResolveSmem);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_inflate_resolve, tbzlz::NT, kResolveSmem);
-    b->res_grid = (int)std::min<uint64_t>((n + tbzlz::WPC - 1) / tbzlz::WPC, (uint64_t)ctx->sm_count * std::max(1, occ));
-    // The token heap: phase one leaves every member's tokens there as contiguous blocks (16 bytes per token; a token
-    // is up to four literals + one match: about two bytes per output byte on text, 5.4 at worst).  Sized from what
-    // is known: at most 6 bytes per byte of output capacity, and no more than 96 bytes per compressed byte (a token
-    // costs at least two bits... in practice ~24 bits).  Members that find the heap full go to the sequential kernel.
-    uint64_t want = 4096;
-    for (uint64_t i = 0; i < n; i++) want += std::min<uint64_t>(6 * m[i].out_cap, 96 * m[i].in_len) + 64;
-    want = std::min<uint64_t>(want, kTokenHeapBytes);
-    b->heap_units = (uint32_t)std::min<uint64_t>(want / 16, 0xfffffff0ull);
-    PCK(dev_alloc(ctx, (size_t)b->heap_units * 16, &b->d_heap));
-    // ... and the scratch lists a warp of phase one decodes a round into
-    PCK(dev_alloc(ctx, (size_t)b->fast_grid * tbzhd::WPC * tbzhd::SCRATCH_BYTES, &b->d_scratch));
+    cudaFuncSetAttribute(k_inflate_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(tbzfast::WSmem) * tbzfast::WPC));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_inflate_decode, tbzfast::NT, sizeof(tbzfast::WSmem) * tbzfast::WPC);
+    b->fast_grid = (int)std::min<uint64_t>((n + tbzfast::WPC - 1) / tbzfast::WPC, (uint64_t)ctx->sm_count * std::max(1, occ));
+    cudaFuncSetAttribute(k_inflate_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tbzp2::Smem));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_inflate_resolve, tbzp2::NT, sizeof(tbzp2::Smem));
+    b->res_grid = (int)std::min<uint64_t>(n, (uint64_t)ctx->sm_count * std::max(1, occ));
+    // token slabs: one per round; a round covers at most ~31 KiB of compressed input and never
+    // crosses a block boundary.  Members that find the pool empty go to the sequential kernel.
+    uint64_t want = 0;
+    // a round covers up to NL * S_MAX bits; blocks end rounds early and a lane that fills its token
+    // list shortens them, hence the factor 2 and the slack
+    const uint64_t round_bytes = (uint64_t)tbzfast::NL * tbzfast::S_MAX / 8;
+    for (uint64_t i = 0; i < n; i++) want += 2 * (m[i].in_len / round_bytes) + 4;
+    const uint64_t slab_bytes = (uint64_t)tbzfast::SLAB_WORDS * 4;
+    const uint64_t cap = std::max<uint64_t>(64, kSlabPoolBytes / slab_bytes);
+    b->nslabs = (uint32_t)std::min<uint64_t>(want, cap);
+    PCK(dev_alloc(ctx, (size_t)b->nslabs * slab_bytes, &b->d_slabs));
     PCK(dev_alloc(ctx, 256, &b->d_counters));
     PCK(dev_alloc(ctx, n * 4, &b->d_todo));
     PCK(dev_alloc(ctx, n * sizeof(tbzfast::P1Rec), &b->d_recs));
@@ -403,14 +404,15 @@ extern "C" int32_t tbz_batch_prepare(tbz_ctx *ctx, int32_t format, const tbz_mem
     for (uint64_t i = 0; i < n; i++) {
       in_sum += m[i].in_len;
       if (i + 1 < n) {
-        if (m[i].in + m[i].in_len > m[i + 1].in) in_dense = false;
+        // (one span only when nothing but alignment padding lies between the members: a gap may be memory the
+        // caller never handed over — another allocation, an unmapped page)
+        if (m[i].in + m[i].in_len > m[i + 1].in || (uint64_t)(m[i + 1].in - (m[i].in + m[i].in_len)) >= 16) in_dense = false;
         if (m[i].out + m[i].out_cap != m[i + 1].out) out_adj = false;
       }
     }
     if (in_dense) {
       uint64_t span = (uint64_t)((m[n - 1].in + m[n - 1].in_len) - m[0].in);
-      if (span > in_sum + 64 * n + 4096) in_dense = false;
-      else {
+      {
         b->in_direct = true; b->in_span = m[0].in; b->in_total = span;
         for (uint64_t i = 0; i < n; i++) b->in_off[i] = (uint64_t)(m[i].in - m[0].in);
       }
@@ -719,17 +721,18 @@ static int32_t launch_kernels(tbz_batch *b) {
   if (b->fast_grid) {
     CK(ctx, cudaMemsetAsync(b->d_counters, 0, 256, ctx->stream));
     if (ctx->ktime) CK(ctx, cudaEventRecord(ctx->kev[0], ctx->stream));
-    CK(ctx, cudaFuncSetAttribute(k_inflate_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDecodeSmem));
-    k_inflate_decode<<<b->fast_grid, tbzhd::NT, kDecodeSmem, ctx->stream>>>(
+    const size_t dec_smem = sizeof(tbzfast::WSmem) * tbzfast::WPC;
+    CK(ctx, cudaFuncSetAttribute(k_inflate_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dec_smem));
+    k_inflate_decode<<<b->fast_grid, tbzfast::NT, dec_smem, ctx->stream>>>(
         (const DMember *)b->d_members, n, b->format, (tbzfast::P1Rec *)b->d_recs,
-        (unsigned char *)b->d_scratch, (uint4 *)b->d_heap, b->heap_units, (uint32_t *)b->d_counters, (uint32_t *)b->d_todo);
+        (uint32_t *)b->d_slabs, b->nslabs, (uint32_t *)b->d_counters, (uint32_t *)b->d_todo);
     ctx->launches++;
     CK(ctx, cudaGetLastError());
     if (ctx->ktime) CK(ctx, cudaEventRecord(ctx->kev[1], ctx->stream));
-    CK(ctx, cudaFuncSetAttribute(k_inflate_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kResolveSmem));
-    k_inflate_resolve<<<b->res_grid, tbzlz::NT, kResolveSmem, ctx->stream>>>(
+    CK(ctx, cudaFuncSetAttribute(k_inflate_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tbzp2::Smem)));
+    k_inflate_resolve<<<b->res_grid, tbzp2::NT, sizeof(tbzp2::Smem), ctx->stream>>>(
         (const DMember *)b->d_members, (tbz_result *)b->d_results, n, b->format,
-        (const tbzfast::P1Rec *)b->d_recs, (const uint4 *)b->d_heap, (uint32_t *)b->d_counters, (uint32_t *)b->d_todo);
+        (const tbzfast::P1Rec *)b->d_recs, (const uint32_t *)b->d_slabs, (uint32_t *)b->d_counters, (uint32_t *)b->d_todo);
     ctx->launches++;
     CK(ctx, cudaGetLastError());
     if (b->format == TBZ_GZIP) {   // gzip: CRC-32 of the finished members + trailer compare
@@ -756,7 +759,7 @@ static int32_t launch_kernels(tbz_batch *b) {
       uint32_t cnt[4] = {0, 0, 0, 0};
       cudaMemcpy(cnt, b->d_counters, sizeof cnt, cudaMemcpyDeviceToHost);
       ctx->last_kms[0] = a; ctx->last_kms[1] = c; ctx->last_kms[2] = d;
-      if (!ctx->ktime_quiet) fprintf(stderr, "[tbz] decode %.3f ms, resolve %.3f ms, seq %.3f ms (%u members), %u heap units\n", a, c, d, cnt[1], cnt[2]);
+      if (!ctx->ktime_quiet) fprintf(stderr, "[tbz] decode %.3f ms, resolve %.3f ms, seq %.3f ms (%u members), %u slabs\n", a, c, d, cnt[1], cnt[2]);
     }
     return TBZ_OK;
   }
@@ -816,11 +819,31 @@ extern "C" int32_t tbz_batch_launch(tbz_batch *b) {
     }
   }
   CK(ctx, cudaEventRecord(b->ev1, ctx->stream));
-  if (b->eager_res && b->n) {
+  if (b->eager_res && b->n)
     CK(ctx, cudaMemcpyAsync(b->eager_res, b->d_results, b->n * sizeof(tbz_result), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(ctx, cudaMemcpyAsync(b->out_span, b->d_out, b->out_total, cudaMemcpyDeviceToHost, ctx->stream));
-  }
   b->launched = true;
+  return TBZ_OK;
+}
+
+// Outputs that are exactly adjacent in the caller's memory leave the device straight into it: of every member the
+// bytes it PRODUCED, never its capacity (the reference does not touch an output buffer past the count it returns,
+// api.lisp:35-61, and what lies there on the device is whatever an earlier batch left).  Members that filled their
+// buffers merge with their right neighbour into one copy: a batch of exact-size outputs is one DMA.
+static int32_t copy_out_direct(tbz_batch *b, const tbz_result *res, cudaStream_t st) {
+  tbz_ctx *ctx = b->ctx;
+  uint64_t i = 0;
+  while (i < b->n) {
+    uint64_t j = i, bytes = 0;
+    for (;;) {
+      const uint64_t got = std::min<uint64_t>(res[j].out_len, b->host[j].out_cap);
+      bytes += got;
+      if (got != b->host[j].out_cap || j + 1 == b->n) break;
+      j++;
+    }
+    if (bytes)
+      CK(ctx, cudaMemcpyAsync(b->host[i].out, (const uint8_t *)b->d_out + b->out_off[i], bytes, cudaMemcpyDeviceToHost, st));
+    i = j + 1;
+  }
   return TBZ_OK;
 }
 
@@ -831,14 +854,21 @@ extern "C" int32_t tbz_batch_finish(tbz_batch *b, tbz_result *r) {
   if (!b->launched) return fail(ctx, TBZ_E_STATE, "tbz_batch_finish before tbz_batch_launch");
   if (!b->n) return TBZ_OK;
   cudaStream_t st = b->stream;
-  if (b->eager_res) { CK(ctx, cudaStreamSynchronize(st)); return TBZ_OK; }
+  if (b->eager_res) {                                   // (the pipelined path: results are on their way to pinned memory)
+    CK(ctx, cudaStreamSynchronize(st));
+    if (!b->copies_issued) { int32_t rc = copy_out_direct(b, b->eager_res, st); if (rc) return rc; }
+    CK(ctx, cudaStreamSynchronize(st));
+    return TBZ_OK;
+  }
   std::vector<tbz_result> tmp;
   tbz_result *res = r;
   if (!res) { tmp.resize(b->n); res = tmp.data(); }
   CK(ctx, cudaMemcpyAsync(res, b->d_results, b->n * sizeof(tbz_result), cudaMemcpyDeviceToHost, st));
   if (!b->device_ptrs) {
     if (b->out_direct) {
-      CK(ctx, cudaMemcpyAsync(b->out_span, b->d_out, b->out_total, cudaMemcpyDeviceToHost, st));
+      CK(ctx, cudaStreamSynchronize(st));               // the results say how much every member produced
+      int32_t rc = copy_out_direct(b, res, st);
+      if (rc) return rc;
       CK(ctx, cudaStreamSynchronize(st));
     } else {
       int32_t rc = ensure_stage(ctx, &ctx->stage_out, &ctx->stage_out_cap, b->out_total);
@@ -901,6 +931,16 @@ static int32_t inflate_batch_pipelined(tbz_ctx *ctx, int32_t format, const tbz_m
   }
   ctx->stream = saved;
   float total_ms = 0.f;
+  // part after part: its results arrive, the copies of what it produced go into its stream (they overlap the kernels
+  // of the parts behind it) ...
+  for (uint64_t p = 0; p < parts && !rc && ok; p++) {
+    if (!sub[p] || !sub[p]->launched) continue;
+    cudaError_t e = cudaStreamSynchronize(sub[p]->stream);
+    if (e != cudaSuccess) { rc = fail(ctx, TBZ_E_CUDA, "pipelined results", e); break; }
+    rc = copy_out_direct(sub[p], sub[p]->eager_res, sub[p]->stream);
+    sub[p]->copies_issued = true;
+  }
+  // ... then everything is waited for
   for (uint64_t p = 0; p < parts; p++) {
     if (!sub[p]) continue;
     if (!rc && ok && sub[p]->launched) {
@@ -943,6 +983,36 @@ extern "C" int32_t tbz_inflate_single(tbz_ctx *ctx, int32_t format, const uint8_
   return tbz_inflate_batch(ctx, format, &m, 1, r, flags, device_ms);
 }
 
+// Decode a device-resident input fully into a device buffer that grows until the stream no longer overflows.
+// tail4: the last four octets of the input (host copy; gzip's ISIZE is a sizing hint only: gzip.lisp:95-106 ignores it).
+static int32_t inflate_resident(tbz_ctx *ctx, int32_t format, const void *d_in, uint64_t in_len, const uint8_t *tail4,
+                                void **d_out, uint64_t *d_cap, tbz_result *res) {
+  CK(ctx, cudaSetDevice(ctx->device));
+  uint64_t cap = *d_cap;
+  if (!*d_out) {
+    cap = std::max<uint64_t>(65536, in_len * 4);
+    if (format == TBZ_GZIP && in_len >= 18 && tail4) {
+      uint32_t isz; memcpy(&isz, tail4, 4);
+      if (isz >= cap / 8 && isz <= in_len * 1100 + 65536) cap = (uint64_t)isz + 64;
+    }
+  }
+  int32_t rc;
+  for (;;) {
+    if (!*d_out) {
+      rc = dev_alloc(ctx, cap, d_out);
+      if (rc) return rc;
+      *d_cap = cap;
+    }
+    tbz_member m{(const uint8_t *)d_in, in_len, (uint8_t *)*d_out, *d_cap};
+    rc = tbz_inflate_batch(ctx, format, &m, 1, res, TBZ_FLAG_DEVICE_PTRS, nullptr);
+    if (rc) break;
+    if (res->verdict != TBZ_OUTPUT_OVERFLOW) break;
+    dev_release(ctx, *d_out); *d_out = nullptr;
+    cap = *d_cap * 4;
+  }
+  return rc;
+}
+
 // Decode `in` (host) fully into a device buffer that grows until the stream no longer overflows.
 static int32_t inflate_to_device(tbz_ctx *ctx, int32_t format, const uint8_t *in, uint64_t in_len,
                                  void **d_out, uint64_t *d_cap, tbz_result *res) {
@@ -955,27 +1025,7 @@ static int32_t inflate_to_device(tbz_ctx *ctx, int32_t format, const uint8_t *in
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) { dev_release(ctx, d_in); return fail(ctx, TBZ_E_CUDA, "H2D", e); }
   }
-  uint64_t cap = *d_cap;
-  if (!*d_out) {
-    cap = std::max<uint64_t>(65536, in_len * 4);
-    if (format == TBZ_GZIP && in_len >= 18) {           // ISIZE is only a sizing hint (gzip.lisp:95-106 ignores it)
-      uint32_t isz; memcpy(&isz, in + in_len - 4, 4);
-      if (isz >= cap / 8 && isz <= in_len * 1100 + 65536) cap = (uint64_t)isz + 64;
-    }
-  }
-  for (;;) {
-    if (!*d_out) {
-      rc = dev_alloc(ctx, cap, d_out);
-      if (rc) { dev_release(ctx, d_in); return rc; }
-      *d_cap = cap;
-    }
-    tbz_member m{(const uint8_t *)d_in, in_len, (uint8_t *)*d_out, *d_cap};
-    rc = tbz_inflate_batch(ctx, format, &m, 1, res, TBZ_FLAG_DEVICE_PTRS, nullptr);
-    if (rc) break;
-    if (res->verdict != TBZ_OUTPUT_OVERFLOW) break;
-    dev_release(ctx, *d_out); *d_out = nullptr;
-    cap = *d_cap * 4;
-  }
+  rc = inflate_resident(ctx, format, d_in, in_len, in_len >= 4 ? in + in_len - 4 : nullptr, d_out, d_cap, res);
   dev_release(ctx, d_in);
   return rc;
 }
@@ -1058,8 +1108,10 @@ extern "C" int32_t tbz_inflate_batch_multi(tbz_ctx *const *ctxs, int32_t g, int3
 struct tbz_session {
   tbz_ctx *ctx;
   int format;
-  std::vector<uint8_t> input;     // every octet handed over so far
-  bool decoded = false;           // d_out/total reflect `input`
+  void *d_in = nullptr; uint64_t in_cap = 0, in_len = 0;   // every octet handed over so far, on the device: a call uploads only its own
+  uint8_t tail[4] = {0, 0, 0, 0}; // the last four of them (gzip ISIZE: a sizing hint)
+  uint64_t last_n = 0;            // octets of the last call
+  bool decoded = false;           // d_out/total reflect the input
   void *d_out = nullptr; uint64_t d_cap = 0;
   tbz_result total{};
   uint64_t served = 0;            // decoded bytes already delivered
@@ -1078,6 +1130,7 @@ extern "C" int32_t tbz_session_create(tbz_ctx *ctx, int32_t format, tbz_session 
 extern "C" int32_t tbz_session_destroy(tbz_session *s) {
   if (!s) return TBZ_OK;
   dev_release(s->ctx, s->d_out);
+  dev_release(s->ctx, s->d_in);
   delete s;
   return TBZ_OK;
 }
@@ -1105,6 +1158,16 @@ extern "C" int32_t tbz_session_flags(tbz_session *s, int32_t *fin, int32_t *unde
   return TBZ_OK;
 }
 
+extern "C" int32_t tbz_session_consumed(tbz_session *s, uint64_t *n) {
+  if (!s || !n) return TBZ_E_ARG;
+  *n = s->last_n;
+  if (s->finished && s->decoded) {
+    const uint64_t before = s->in_len - s->last_n;                    // octets of the earlier calls
+    *n = s->total.in_used > before ? std::min<uint64_t>(s->total.in_used - before, s->last_n) : 0;
+  }
+  return TBZ_OK;
+}
+
 extern "C" int32_t tbz_session_decompress(tbz_session *s, const uint8_t *in, uint64_t n,
                                           int64_t *ret, int32_t *verdict) {
   if (!s || !ret || !verdict || (n && !in)) return TBZ_E_ARG;
@@ -1112,9 +1175,30 @@ extern "C" int32_t tbz_session_decompress(tbz_session *s, const uint8_t *in, uin
   if (s->error) { *ret = -1; *verdict = s->error; return TBZ_E_STATE; }
   if (s->finished) { *ret = -1; *verdict = TBZ_FINISHED; return TBZ_E_STATE; }   // ecase on :done (gzip.lisp:279-286)
   s->underrun = false;                       // deflate.lisp:102-103
-  if (n) { s->input.insert(s->input.end(), in, in + n); s->decoded = false; }
+  s->last_n = n;
+  if (n) {
+    // the new octets join the ones already on the device (the buffer doubles when it is full)
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (s->in_len + n + 16 > s->in_cap) {
+      const uint64_t cap = std::max<uint64_t>(std::max<uint64_t>(65536, 2 * s->in_cap), s->in_len + n + 16);
+      void *d = nullptr;
+      int32_t rc = dev_alloc(ctx, cap, &d);
+      if (rc) return rc;
+      if (s->in_len) CK(ctx, cudaMemcpyAsync(d, s->d_in, s->in_len, cudaMemcpyDeviceToDevice, ctx->stream));
+      CK(ctx, cudaStreamSynchronize(ctx->stream));
+      dev_release(ctx, s->d_in);
+      s->d_in = d; s->in_cap = cap;
+    }
+    cudaError_t e = cudaMemcpyAsync((uint8_t *)s->d_in + s->in_len, in, n, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) return fail(ctx, TBZ_E_CUDA, "session H2D", e);
+    for (uint64_t i = 0; i < 4; i++) s->tail[i] = i + n >= 4 ? in[n - 4 + i] : s->tail[i + n];   // (shift in the new octets)
+    s->in_len += n;
+    s->decoded = false;
+  }
   if (!s->decoded) {
-    int32_t rc = inflate_to_device(ctx, s->format, s->input.data(), s->input.size(), &s->d_out, &s->d_cap, &s->total);
+    if (!s->d_in) { int32_t rc = dev_alloc(ctx, 65536, &s->d_in); if (rc) return rc; s->in_cap = 65536; }
+    int32_t rc = inflate_resident(ctx, s->format, s->d_in, s->in_len, s->in_len >= 4 ? s->tail : nullptr, &s->d_out, &s->d_cap, &s->total);
     if (rc) return rc;
     s->decoded = true;
   }
@@ -1211,15 +1295,36 @@ extern "C" int32_t tbz_inflate_gzip_members(tbz_ctx *ctx, const uint8_t *in, uin
                                             uint64_t out_cap, tbz_result *r, uint64_t max_members,
                                             uint64_t *n_members, uint64_t *in_used) {
   if (!ctx || !r || !n_members || (in_len && !in) || (out_cap && !out)) return fail(ctx, TBZ_E_ARG, "tbz_inflate_gzip_members: bad argument");
-  uint64_t ip = 0, op = 0, k = 0;
-  while (k < max_members && ip < in_len) {
-    int32_t rc = tbz_inflate_single(ctx, TBZ_GZIP, in + ip, in_len - ip, out + op, out_cap - op, &r[k], 0, nullptr);
-    if (rc != TBZ_OK) return rc;
+  // the input goes to the device once, the members are decoded there one after the other (a member's length is only
+  // known once it is decoded), and what they produced comes back with one copy
+  CK(ctx, cudaSetDevice(ctx->device));
+  void *d_in = nullptr, *d_out = nullptr;
+  int32_t rc = dev_alloc(ctx, in_len + 16, &d_in);
+  if (!rc) rc = dev_alloc(ctx, out_cap + 16, &d_out);
+  if (rc) { dev_release(ctx, d_in); return rc; }
+  uint64_t ip = 0, op = 0, k = 0, produced = 0;
+  if (in_len) {
+    cudaError_t e = cudaMemcpyAsync(d_in, in, in_len, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) rc = fail(ctx, TBZ_E_CUDA, "H2D", e);
+  }
+  while (!rc && k < max_members && ip < in_len) {
+    tbz_member m{(const uint8_t *)d_in + ip, in_len - ip, (uint8_t *)d_out + op, out_cap - op};
+    rc = tbz_inflate_batch(ctx, TBZ_GZIP, &m, 1, &r[k], TBZ_FLAG_DEVICE_PTRS, nullptr);
+    if (rc != TBZ_OK) break;
     k++;
+    produced = op + std::min<uint64_t>(r[k - 1].out_len, out_cap - op);   // (a member that did not finish leaves what it produced)
     if (r[k - 1].verdict != TBZ_FINISHED) break;
     ip += r[k - 1].in_used;
     op += r[k - 1].out_len;
   }
+  if (!rc && produced) {
+    cudaError_t e = cudaMemcpyAsync(out, d_out, produced, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) rc = fail(ctx, TBZ_E_CUDA, "D2H", e);
+  }
+  dev_release(ctx, d_in); dev_release(ctx, d_out);
+  if (rc) return rc;
   *n_members = k;
   if (in_used) *in_used = ip;
   return TBZ_OK;

@@ -138,7 +138,7 @@ def run_reference(args, rank, world, out=sys.stdout):
         return
     n, size, fmt, seed0 = WORKLOADS[args.workload]
     cores = os.cpu_count() or 1
-    sample = min(n, args.ref_sample)
+    sample = min(n, args.ref_sample or n)
     ms = make_members(sample, size, fmt, seed0, cores)
     comps = [c for _, c in ms]
     for _ in range(max(1, min(args.warmup, 1))):
@@ -151,7 +151,8 @@ def run_reference(args, rank, world, out=sys.stdout):
     line = {"impl": "reference", "metric": METRIC, "value": gbs, "unit": "GB/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": args.workload, "members_per_step": sample, "member_bytes": size, "format": fmt,
+            "config": {"workload": args.workload, "members_per_gpu": n, "members_per_step": sample, "member_bytes": size,
+                       "format": fmt, "level": 6,
                        "note": "3bz/SBCL unavailable in image; oracle port (C restatement of 3bz) on host cores"},
             "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": cores, "kind": "port",
                              "sample": "%d of %d members per step" % (sample, n)},
@@ -179,7 +180,8 @@ def _main(real_stdout):
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="zlib64k", choices=sorted(WORKLOADS))
     ap.add_argument("--members", type=int, default=0, help="override members per GPU (testing)")
-    ap.add_argument("--ref-sample", type=int, default=1024)
+    ap.add_argument("--ref-sample", type=int, default=0, help="members per step of the reference arm (0 = all of the workload)")
+    ap.add_argument("--no-also", action="store_true", help="headline workload only (skip the gzip1m / gzip1g records)")
     ap.add_argument("--cpu-sample", type=int, default=512)
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--flags", type=int, default=0)
@@ -204,16 +206,50 @@ def _main(real_stdout):
             dist.barrier()
         torch.cuda.synchronize()
 
-    n, size, fmt, seed0 = WORKLOADS[args.workload]
-    if args.members:
+    ctx = t.Ctx(dev)
+    env = dict(L=L, ffi=_ffi, ctx=ctx, dev=dev, rank=rank, world=world, barrier=barrier, args=args,
+               torch=torch, dist=dist if world > 1 else None)
+    head = run_workload(env, args.workload, headline=True)
+    also = {}
+    if args.workload == "zlib64k" and not args.no_also and not args.members:
+        # BASELINE.json configs[3] (1 MiB gzip members, the batch API, every N) and configs[2] (one 1 GiB gzip member,
+        # speculative split decode; one GPU only): device-timed, every member verified
+        also["gzip1m"] = run_workload(env, "gzip1m", headline=False)
+        if world == 1:
+            also["gzip1g"] = run_workload(env, "gzip1g", headline=False)
+    ctx.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        if also:
+            head["also"] = also
+        print(json.dumps(head), file=real_stdout, flush=True)
+
+
+def run_workload(env, workload, headline):
+    """One workload on this rank's GPU: device-timed throughput over `tbz_batch_launch` (all ranks, max over ranks),
+    every member verified; the headline workload adds the end-to-end leg, a sustained leg, the roofline and the CPU
+    baseline.  Returns the JSON object (rank 0) or None."""
+    L, _ffi, ctx, args = env["L"], env["ffi"], env["ctx"], env["args"]
+    rank, world, barrier, torch, dist = env["rank"], env["world"], env["barrier"], env["torch"], env["dist"]
+    n, size, fmt, seed0 = WORKLOADS[workload]
+    if args.members and headline:
         n = args.members
     threads = max(1, (os.cpu_count() or 1) // max(1, world))
-    ms = make_members(n, size, fmt, seed0 + rank * n, threads)
-    comps = [c for _, c in ms]
+    # gzip1m: the members of one GPU are replicas of a bounded number of unique ones (generating 8 GiB of level-6
+    # gzip per rank would take minutes of host time); every replica has its own compressed copy and output in HBM
+    unique = n if (headline or n <= 1) else min(n, max(128, (1024 if workload == "gzip1m" else n) // world))
+    steps = args.steps if headline else max(3, min(args.steps, 5))
+    warmup = args.warmup if headline else 3
+    ms = make_members(unique, size, fmt, seed0 + rank * n, threads)
+    comps_u = [c for _, c in ms]
+    comps = [comps_u[i % unique] for i in range(n)]
     C_total = sum(len(c) for c in comps)
     U_total = n * size
+    ck = zlib.adler32 if fmt == "zlib" else zlib.crc32
+    want_ck = [ck(p) for p, _ in ms]
 
-    ctx = t.Ctx(dev)
     # ---- pinned host arenas: inputs dense, outputs adjacent (the engine DMAs straight from/to them)
     in_off, o = [], 0
     for c in comps:
@@ -222,48 +258,62 @@ def _main(real_stdout):
     in_span = o
     h_in, h_out = C.c_void_p(), C.c_void_p()
     _ffi.check(L.tbz_host_alloc(in_span + 64, C.byref(h_in)))
-    _ffi.check(L.tbz_host_alloc(U_total + 64, C.byref(h_out)))
     for c, off in zip(comps, in_off):
         C.memmove(h_in.value + off, c, len(c))
-    # ---- device-resident copies for the device-timed metric
     d_in, d_out = C.c_void_p(), C.c_void_p()
     _ffi.check(L.tbz_device_alloc(ctx.h, in_span + 64, C.byref(d_in)), ctx.h)
     _ffi.check(L.tbz_device_alloc(ctx.h, U_total + 64, C.byref(d_out)), ctx.h)
     _ffi.check(L.tbz_memcpy_h2d(ctx.h, d_in, h_in, in_span), ctx.h)
-    hm = (_ffi.Member * n)()
     dm = (_ffi.Member * n)()
     for i, c in enumerate(comps):
-        hm[i] = _ffi.Member(h_in.value + in_off[i], len(c), h_out.value + i * size, size)
         dm[i] = _ffi.Member(d_in.value + in_off[i], len(c), d_out.value + i * size, size)
     res = (_ffi.Result * n)()
 
     batch = C.c_void_p()
     _ffi.check(L.tbz_batch_prepare(ctx.h, _ffi.fmt_code(fmt), dm, n, _ffi.FLAG_DEVICE_PTRS | args.flags, C.byref(batch)), ctx.h)
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         _ffi.check(L.tbz_batch_launch(batch), ctx.h)
     _ffi.check(L.tbz_ctx_synchronize(ctx.h), ctx.h)
 
-    sampler = ClockSampler(dev)
+    sampler = ClockSampler(env["dev"])
     sampler.start()
     time.sleep(0.25)
     l0 = ctx.launches()
     barrier()
     _ffi.check(L.tbz_ctx_timer_start(ctx.h), ctx.h)
-    for _ in range(args.steps):
+    for _ in range(steps):
         _ffi.check(L.tbz_batch_launch(batch), ctx.h)
     ms_total = C.c_float()
     _ffi.check(L.tbz_ctx_timer_stop(ctx.h, C.byref(ms_total)), ctx.h)
     barrier()
     launches = ctx.launches() - l0
     dev_ms = ms_total.value
+    clocks = sampler.stop()
     _ffi.check(L.tbz_batch_finish(batch, res), ctx.h)
-    bad = [i for i in range(n) if res[i].verdict != 0 or res[i].out_len != size]
-    assert not bad, "members not finished: %r" % bad[:8]
-    # full verification of the device-resident result: Adler/CRC verdicts are computed on device
-    # from the produced bytes; compare them with libz's checksum of the original text
-    ck = zlib.adler32 if fmt == "zlib" else zlib.crc32
-    for i in (0, n // 2, n - 1):
-        assert res[i].checksum == ck(ms[i][0]), "checksum mismatch on member %d" % i
+
+    # ---- verification, outside the timed region: every member's verdict, size and checksum (Adler-32 / CRC-32 are
+    # computed on the device from the produced bytes; compared here with libz's checksum of the original text), and
+    # the produced bytes themselves: all of them for the headline workload, a sample of the members otherwise
+    bad = [i for i in range(n) if res[i].verdict != 0 or res[i].out_len != size or res[i].checksum != want_ck[i % unique]]
+    assert not bad, "members not finished / checksum mismatch: %r" % bad[:8]
+    check = range(n) if headline else sorted(set(list(range(0, n, max(1, n // 16))) + [n - 1]))
+    hb = C.create_string_buffer(size) if size <= (64 << 20) else None
+    nbytes = 0
+    if hb is not None:
+        for i in check:
+            _ffi.check(L.tbz_memcpy_d2h(ctx.h, hb, C.c_void_p(d_out.value + i * size), size), ctx.h)
+            assert hb.raw == ms[i % unique][0], "output mismatch on member %d" % i
+            nbytes += size
+    else:                                              # one huge member: compare in 64 MiB pieces
+        piece = 64 << 20
+        hb = C.create_string_buffer(piece)
+        for o in range(0, size, piece):
+            m = min(piece, size - o)
+            _ffi.check(L.tbz_memcpy_d2h(ctx.h, hb, C.c_void_p(d_out.value + o), m), ctx.h)
+            assert hb.raw[:m] == ms[0][0][o:o + m], "output mismatch at offset %d" % o
+            nbytes += m
+    verification = {"members_verdict_size_checksum": n, "bytes_compared": nbytes, "ok": True,
+                    "paths": sorted(set(int(res[i].path) for i in range(n)))}
 
     # ---- per-kernel times of the same launch (CUDA events between the kernels), three extra launches
     kms = [[], [], []]
@@ -278,85 +328,111 @@ def _main(real_stdout):
     kernel_ms = {"k_inflate_decode": statistics.median(kms[0]), "k_inflate_resolve": statistics.median(kms[1]),
                  "k_inflate_seq": statistics.median(kms[2])}
 
-    # ---- end to end through the public C-ABI call with HOST buffers
-    e2e_t = []
-    for k in range(args.e2e_steps + 1):
+    sustained = None
+    e2e_step, e2e_ok = None, None
+    if headline:
+        # ---- sustained: at least two seconds of back-to-back launches, with its own clock samples
+        sampler = ClockSampler(env["dev"])
+        sampler.start()
         barrier()
-        t0 = time.perf_counter()
-        _ffi.check(L.tbz_inflate_batch(ctx.h, _ffi.fmt_code(fmt), hm, n, res, args.flags, None), ctx.h)
-        dt = time.perf_counter() - t0
-        if k:
-            e2e_t.append(dt)
-    clocks = sampler.stop()
-    got = C.string_at(h_out.value + (n - 1) * size, size)
-    assert got == ms[n - 1][0], "e2e output mismatch"
-    assert all(res[i].verdict == 0 for i in range(n))
-    e2e_step = sum(e2e_t) / len(e2e_t)
+        per = max(1e-4, dev_ms / steps * 1e-3)
+        k_sus = int(min(20000, max(steps, 2.2 / per)))
+        _ffi.check(L.tbz_ctx_timer_start(ctx.h), ctx.h)
+        for _ in range(k_sus):
+            _ffi.check(L.tbz_batch_launch(batch), ctx.h)
+        _ffi.check(L.tbz_ctx_timer_stop(ctx.h, C.byref(ms_total)), ctx.h)
+        barrier()
+        sus_ms = ms_total.value
+        sustained = {"steps": k_sus, "seconds": sus_ms * 1e-3, "ms_per_step": sus_ms / k_sus, "clocks": sampler.stop()}
+        # ---- end to end through the public C-ABI call with HOST buffers
+        _ffi.check(L.tbz_host_alloc(U_total + 64, C.byref(h_out)))
+        hm = (_ffi.Member * n)()
+        for i, c in enumerate(comps):
+            hm[i] = _ffi.Member(h_in.value + in_off[i], len(c), h_out.value + i * size, size)
+        e2e_t = []
+        for k in range(args.e2e_steps + 1):
+            barrier()
+            t0 = time.perf_counter()
+            _ffi.check(L.tbz_inflate_batch(ctx.h, _ffi.fmt_code(fmt), hm, n, res, args.flags, None), ctx.h)
+            dt = time.perf_counter() - t0
+            if k:
+                e2e_t.append(dt)
+        assert all(res[i].verdict == 0 and res[i].out_len == size and res[i].checksum == want_ck[i % unique] for i in range(n))
+        for i in range(n):                                  # every byte of the last end-to-end step
+            assert C.string_at(h_out.value + i * size, size) == ms[i % unique][0], "e2e output mismatch on member %d" % i
+        e2e_ok = True
+        e2e_step = sum(e2e_t) / len(e2e_t)
 
     # ---- max over ranks
     if world > 1:
-        tt = torch.tensor([dev_ms, e2e_step], device="cuda", dtype=torch.float64)
+        vals = [dev_ms, e2e_step or 0.0, sustained["ms_per_step"] if sustained else 0.0]
+        tt = torch.tensor(vals, device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)        # t.shard.reduce_max is the same reduction on CPU tensors (gloo test)
-        dev_ms, e2e_step = float(tt[0]), float(tt[1])
+        dev_ms = float(tt[0])
+        if headline:
+            e2e_step = float(tt[1]); sustained["ms_per_step"] = float(tt[2])
 
     line = None
     if rank == 0:
-        ms_per_step = dev_ms / args.steps
+        ms_per_step = dev_ms / steps
         value = world * U_total / (ms_per_step * 1e-3) / 1e9
-        # roofline of the dominant kernel: algorithmic bytes C + U + B per launch
+        # roofline: algorithmic bytes C + U + B per launch; B from the oracle's count on a sample
         cores = os.cpu_count() or 1
-        sample = min(n, args.cpu_sample)
-        _, b_sample = oracle_pass(comps[:sample], fmt, size, cores)            # warm
-        cpu_t, b_sample = oracle_pass(comps[:sample], fmt, size, cores)
+        sample = min(unique, args.cpu_sample if headline else 8)
+        if headline:
+            oracle_pass(comps_u[:sample], fmt, size, cores)                       # warm
+        cpu_t, b_sample = oracle_pass(comps_u[:sample], fmt, size, cores)
         B_total = sum(b_sample) * n / sample
+        peak, how = peaks()
+        achieved = (C_total + U_total + B_total) / (ms_per_step * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": recorded_traffic(workload),
+                    "peak_source": how, "frac_of_8000": achieved / 8000.0,
+                    "algorithmic_bytes_per_launch": C_total + U_total + B_total,
+                    "kernel_ms": ms_per_step, "kernels_ms": kernel_ms,
+                    "note": "achieved = (C + U + B) of one launch of the hot path / its CUDA-event time; traffic = ncu "
+                            "dram bytes of the dominant kernel (profiles/traffic.json)"}
+        config = {"workload": workload, "members_per_gpu": n, "unique_members_per_gpu": unique, "member_bytes": size,
+                  "format": fmt, "level": 6, "compressed_bytes_per_gpu": C_total,
+                  "l2": "working set %d MiB per step > 126 MB L2, no flush needed" % ((C_total + U_total) >> 20),
+                  "parallelism": "members sharded over %d GPU(s), no collective" % world}
+        if not headline:
+            return {"value": value, "unit": "GB/s", "ms_per_step": ms_per_step, "steps": steps, "warmup": warmup,
+                    "config": config, "clocks": clocks, "roofline": roofline, "verification": verification,
+                    "gpu_launches": launches}
+        roofline["per_kernel"] = {
+            "k_inflate_decode": {"algorithmic_bytes": C_total, "achieved": C_total / (kernel_ms["k_inflate_decode"] * 1e-3) / 1e9,
+                                 "note": "compressed bytes in (token scratch is not algorithmic)"},
+            "k_inflate_resolve": {"algorithmic_bytes": U_total + B_total,
+                                  "achieved": (U_total + B_total) / (kernel_ms["k_inflate_resolve"] * 1e-3) / 1e9,
+                                  "note": "decompressed bytes out + back-reference bytes read: the dominant kernel"}}
         # second stand-in named by SURVEY.md 8d: system libz `inflate` on the same sample and threads
         wb = {"deflate": -15, "zlib": 15, "gzip": 31}[fmt]
         with ThreadPoolExecutor(cores) as ex:
             t0 = time.perf_counter()
-            outs = list(ex.map(lambda cdata: len(zlib.decompress(cdata, wb)), comps[:sample]))
+            outs = list(ex.map(lambda cdata: len(zlib.decompress(cdata, wb)), comps_u[:sample]))
             libz_t = time.perf_counter() - t0
         assert all(o == size for o in outs)
-        peak, how = peaks()
-        achieved = (C_total + U_total + B_total) / (ms_per_step * 1e-3) / 1e9
-        line = {"metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                "config": {"workload": args.workload, "members_per_gpu": n, "member_bytes": size, "format": fmt,
-                           "level": 6, "compressed_bytes_per_gpu": C_total,
-                           "l2": "working set %d MiB per step > 126 MB L2, no flush needed" % ((C_total + U_total) >> 20),
-                           "parallelism": "members sharded over %d GPU(s), no collective" % world},
-                "clocks": clocks,
+        sustained["value"] = world * U_total / (sustained["ms_per_step"] * 1e-3) / 1e9
+        verification["e2e_bytes_compared"] = U_total if e2e_ok else 0
+        line = {"impl": "ours", "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": steps,
+                "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config, "clocks": clocks,
+                "sustained": sustained,
                 "e2e": {"value": world * U_total / e2e_step / 1e9, "unit": "GB/s",
                         "h2d_bytes_per_step": in_span + n * 32, "d2h_bytes_per_step": U_total + n * 32,
                         "ms_per_step": e2e_step * 1e3, "api": "tbz_inflate_batch, pinned host buffers"},
-                "gpu_launches": launches,
-                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                             "frac": achieved / peak, "traffic": recorded_traffic(args.workload),
-                             "peak_source": how, "frac_of_8000": achieved / 8000.0,
-                             "algorithmic_bytes_per_launch": C_total + U_total + B_total,
-                             "kernel_ms": ms_per_step,
-                             "kernels_ms": kernel_ms,
-                             "per_kernel": {
-                                 "k_inflate_decode": {"algorithmic_bytes": C_total, "achieved": C_total / (kernel_ms["k_inflate_decode"] * 1e-3) / 1e9,
-                                                      "note": "compressed bytes in (token scratch is not algorithmic)"},
-                                 "k_inflate_resolve": {"algorithmic_bytes": U_total + B_total,
-                                                       "achieved": (U_total + B_total) / (kernel_ms["k_inflate_resolve"] * 1e-3) / 1e9,
-                                                       "note": "decompressed bytes out + back-reference bytes read: the dominant kernel"}},
-                             "note": "achieved = (C + U + B) of one launch of the hot path (decode + resolve kernels) / its "
-                                     "CUDA-event time; traffic = ncu dram bytes of the dominant kernel (k_inflate_resolve)"},
+                "gpu_launches": launches, "verification": verification, "roofline": roofline,
                 "cpu_baseline": {"value": sample * size / cpu_t / 1e9, "unit": "GB/s", "cores": cores, "kind": "port",
                                  "sample": "%d of %d members, one pass, %d threads" % (sample, n, cores),
                                  "libz": {"value": sample * size / libz_t / 1e9, "unit": "GB/s",
                                           "what": "system libz inflate (python zlib, GIL released) on the same sample and threads"}}}
     L.tbz_batch_destroy(batch)
     L.tbz_device_free(ctx.h, d_in); L.tbz_device_free(ctx.h, d_out)
-    L.tbz_host_free(h_in); L.tbz_host_free(h_out)
-    ctx.close()
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
-    if line:
-        print(json.dumps(line), file=real_stdout, flush=True)
+    L.tbz_host_free(h_in)
+    if h_out.value:
+        L.tbz_host_free(h_out)
+    return line
 
 
 if __name__ == "__main__":

@@ -171,6 +171,10 @@ int32_t tbz_session_decompress(tbz_session *s, const uint8_t *in, uint64_t n,
                                int64_t *ret, int32_t *verdict);
 int32_t tbz_session_flags(tbz_session *s, int32_t *finished, int32_t *input_underrun,
                           int32_t *output_overflow);
+/* How many of the octets handed over by the LAST tbz_session_decompress call the stream consumed: all of them
+ * unless it finished inside them — the reference leaves the context's offset just past the consumed octets
+ * (io.lisp:17-58; %resync-file-stream, io-common.lisp:60-63, seeks the stream there). */
+int32_t tbz_session_consumed(tbz_session *s, uint64_t *n);
 
 /* ---- gzip member metadata: the gzip-state slots flags / extra / name / comment / operating-system /
  * mtime/unix / compression-level that decompress-gzip fills while it reads the header

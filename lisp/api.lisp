@@ -47,8 +47,14 @@
        (lambda (pin n)
          (cffi:with-foreign-objects ((ret :int64) (verdict :int32))
            (let ((rc (tbz-session-decompress (%session state) pin n ret verdict)))
-             ;; the session now owns every unread octet: the context is consumed to its end
-             (setf (cb-offset (boxes context)) (cb-end (boxes context)))
+             ;; the session owns every unread octet -- unless the stream finished inside them: the context
+             ;; then stops just past the consumed octets (io.lisp:17-58), where %resync-file-stream seeks
+             (let ((b (boxes context)))
+               (if (zerop rc)
+                   (cffi:with-foreign-object (used :uint64)
+                     (tbz-session-consumed (%session state) used)
+                     (setf (cb-offset b) (min (cb-end b) (+ (cb-offset b) (cffi:mem-ref used :uint64)))))
+                   (setf (cb-offset b) (cb-end b))))
              (when (= rc +tbz-e-state+) (error "decompress called on a finished or failed state"))
              (check rc)
              (let ((v (cffi:mem-ref verdict :int32)))

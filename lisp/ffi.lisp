@@ -44,6 +44,7 @@
   (session :pointer) (in :pointer) (n :uint64) (ret :pointer) (verdict :pointer))
 (cffi:defcfun "tbz_session_flags" :int32
   (session :pointer) (finished :pointer) (underrun :pointer) (overflow :pointer))
+(cffi:defcfun "tbz_session_consumed" :int32 (session :pointer) (n :pointer))
 
 (defvar *device* 0 "CUDA device the engine context of this thread is created on.")
 (defvar *ctx* nil "tbz_ctx of the current thread (a ctx is single-owner; bind per thread).")

@@ -17,19 +17,20 @@ extern "C" int emu_inflate_batch(int fmt, const tbz_member *m, uint64_t n, tbz_r
     return 0;
   }
   std::vector<tbzfast::P1Rec> recs(n);
-  // the token heap: 16-byte units; ~1 token byte per output byte on text, more for short matches
-  uint64_t units = 64;
-  for (uint64_t i = 0; i < n; i++) units += (6 * m[i].out_cap + 8 * m[i].in_len) / 16 + 64;
-  const uint32_t heap_units = (uint32_t)units;
-  std::vector<uint4> heap(heap_units);
+  const uint64_t round_bytes = (uint64_t)tbzfast::NL * tbzfast::S_MAX / 8;
+  uint64_t want = 0;
+  for (uint64_t i = 0; i < n; i++) want += 2 * (m[i].in_len / round_bytes) + 4;
+  const uint32_t nslabs = (uint32_t)want;
+  std::vector<uint32_t> slabs((size_t)nslabs * tbzfast::SLAB_WORDS);
   (void)variant;
-  const unsigned dec_grid = std::min<unsigned>((nn + tbzhd::WPC - 1) / tbzhd::WPC, 16);
-  std::vector<uint4> scratch((size_t)dec_grid * tbzhd::WPC * tbzhd::SCRATCH_BYTES / 16);
-  emu_launch(k_inflate_decode, dim3(dec_grid), dim3(tbzhd::NT), sizeof(tbzhd::WSmem) * tbzhd::WPC,
-             (const DMember *)dm.data(), nn, fmt, recs.data(), (unsigned char *)scratch.data(), heap.data(), heap_units, counters.data(), todo.data());
-  emu_launch(k_inflate_resolve, dim3(std::min<unsigned>((nn + tbzlz::WPC - 1) / tbzlz::WPC, 16)), dim3(tbzlz::NT), tbzlz::SMEM_BYTES,
-             (const DMember *)dm.data(), r, nn, fmt, (const tbzfast::P1Rec *)recs.data(), (const uint4 *)heap.data(),
-             counters.data(), todo.data());
+  {
+    const unsigned dec_grid = std::min<unsigned>((nn + tbzfast::WPC - 1) / tbzfast::WPC, 16);
+    emu_launch(k_inflate_decode, dim3(dec_grid), dim3(tbzfast::NT), sizeof(tbzfast::WSmem) * tbzfast::WPC,
+               (const DMember *)dm.data(), nn, fmt, recs.data(), slabs.data(), nslabs, counters.data(), todo.data());
+    emu_launch(k_inflate_resolve, dim3(std::min<unsigned>(nn, 16)), dim3(tbzp2::NT), sizeof(tbzp2::Smem),
+               (const DMember *)dm.data(), r, nn, fmt, (const tbzfast::P1Rec *)recs.data(), (const uint32_t *)slabs.data(),
+               counters.data(), todo.data());
+  }
   if (fmt == TBZ_GZIP)
     emu_launch(tbzcrc::k_member_crc, dim3(std::min<unsigned>(nn, 16)), dim3(tbzcrc::NT), 0,
                (const DMember *)dm.data(), r, nn, (const tbzfast::P1Rec *)recs.data(), counters.data(), todo.data());

@@ -410,3 +410,31 @@ def test_octet_stream_context(engine, ctx, tmp_path):
             assert n == len(plain) and engine.finished(st) and bytes(st.output_buffer[:n]) == plain
     with pytest.raises(engine.ThreeBzError):
         engine.make_octet_stream_context(object())
+
+
+def test_output_tail_is_untouched(engine, ctx):
+    """the bytes of an output buffer past the returned count are the caller's (api.lisp:35-61 never writes them):
+    oversized, pre-filled buffers — one member (every decompress-vector :output call), adjacent members (the direct
+    DMA path), and a batch large enough for the pipelined path"""
+    import ctypes as C
+    from threebz_b200 import _ffi
+    L = _ffi.lib()
+    for n, size in ((1, 5000), (7, 3000), (600, 60000)):
+        ms = datagen.members(n, size, 7000, "zlib")
+        cap = size + 1000 + 17
+        blob = b"".join(c for _, c in ms)
+        inbuf = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+        outbuf = (C.c_uint8 * (cap * n))()
+        C.memset(outbuf, 0xA5, cap * n)
+        marr = (_ffi.Member * n)()
+        io = 0
+        for i, (p, c) in enumerate(ms):
+            marr[i] = _ffi.Member(C.addressof(inbuf) + io, len(c), C.addressof(outbuf) + i * cap, cap)
+            io += len(c)
+        rarr = (_ffi.Result * n)()
+        _ffi.check(L.tbz_inflate_batch(ctx.h, _ffi.fmt_code("zlib"), marr, n, rarr, 0, None), ctx.h)
+        raw = bytes(outbuf)
+        for i, (p, c) in enumerate(ms):
+            assert rarr[i].verdict == 0 and rarr[i].out_len == size
+            assert raw[i * cap:i * cap + size] == p, (n, i)
+            assert raw[i * cap + size:(i + 1) * cap] == b"\xa5" * (cap - size), ("tail overwritten", n, i)
