@@ -3,7 +3,7 @@
 Import with importlib.import_module("3bz_b200") (the name starts with a digit, like the reference's
 package `3bz`), or through the `threebz_b200` alias module at the repo root.
 """
-from .api import (ThreeBzError, Ctx, default_ctx, decompress, decompress_vector, decompress_batch,  # noqa: F401
+from .api import (ThreeBzError, Ctx, default_ctx, device_count, decompress, decompress_vector, decompress_batch,  # noqa: F401
                   with_octet_pointer, make_octet_vector_context, make_octet_stream_context,
                   make_octet_pointer_context, make_deflate_state, make_zlib_state, make_gzip_state,
                   finished, input_underrun, output_overflow, replace_output_buffer,

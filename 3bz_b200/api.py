@@ -371,10 +371,18 @@ def decompress_gzip_members(compressed, output, max_members=1 << 20, ctx=None):
     return [(r.out_len, r.in_used, r.checksum, r.verdict) for r in res[:nm.value]], used.value
 
 
-def decompress_batch(members, format="zlib", capacities=None, ctx=None, flags=0):
+def device_count():
+    n = C.c_int32()
+    check(lib().tbz_device_count(C.byref(n)))
+    return n.value
+
+
+def decompress_batch(members, format="zlib", capacities=None, ctx=None, flags=0, ctxs=None):
     """members: sequence of octet vectors; capacities: per-member output size (int or sequence).
+    ctxs: several engine contexts (one per GPU): the members are partitioned over them on the host
+    (tbz_inflate_batch_multi: one thread, context and stream per device, no collective).
     Returns a list of (buffer, count, verdict_code); a bad member never poisons the batch."""
-    ctx = ctx or default_ctx()
+    ctx = ctx or (ctxs[0] if ctxs else default_ctx())
     L = lib()
     n = len(members)
     if capacities is None:
@@ -389,5 +397,9 @@ def decompress_batch(members, format="zlib", capacities=None, ctx=None, flags=0)
         keep += [k1, k2]
         marr[i] = _ffi.Member(a1, len(m), a2, len(o))
     rarr = (_ffi.Result * max(1, n))()
-    check(L.tbz_inflate_batch(ctx.h, fmt_code(format), marr, n, rarr, flags, None), ctx.h)
+    if ctxs and len(ctxs) > 1:
+        hs = (C.c_void_p * len(ctxs))(*[c.h for c in ctxs])
+        check(L.tbz_inflate_batch_multi(hs, len(ctxs), fmt_code(format), marr, n, rarr, flags, None), ctx.h)
+    else:
+        check(L.tbz_inflate_batch(ctx.h, fmt_code(format), marr, n, rarr, flags, None), ctx.h)
     return [(outs[i], rarr[i].out_len, rarr[i].verdict) for i in range(n)]

@@ -489,17 +489,27 @@ static int32_t split_inflate(tbz_ctx *ctx, int fmt, const DMember &m, tbz_result
     fprintf(stderr, "[tbz split] %-10s %8.3f ms\n", name, std::chrono::duration<double, std::milli>(t - t_prev).count());
     t_prev = t;
   };
-  // ---- wrapper header, on the host (zlib.lisp:108-126, gzip.lisp:113-177 without optional fields)
-  uint8_t head[16] = {0};
-  CK(ctx, cudaMemcpyAsync(head, m.in, 16, cudaMemcpyDeviceToHost, st));
-  CK(ctx, cudaStreamSynchronize(st));
+  // ---- wrapper header, on the host (zlib.lisp:108-126; gzip.lisp:113-260 with FEXTRA / FNAME / FCOMMENT / FHCRC:
+  // `gzip file` always writes a name).  Anything but a clean header leaves the member to the sequential kernel,
+  // which owns the verdicts.
   uint64_t hdr_bytes = 0;
   if (fmt == TBZ_ZLIB) {
+    uint8_t head[2] = {0, 0};
+    CK(ctx, cudaMemcpyAsync(head, m.in, 2, cudaMemcpyDeviceToHost, st));
+    CK(ctx, cudaStreamSynchronize(st));
     if ((head[0] * 256 + head[1]) % 31 || (head[0] & 15) != 8 || (head[0] >> 4) > 7 || (head[1] & 32)) return TBZ_OK;
     hdr_bytes = 2;
   } else if (fmt == TBZ_GZIP) {
-    if (head[0] != 0x1f || head[1] != 0x8b || head[2] != 8 || head[3] != 0) return TBZ_OK;
-    hdr_bytes = 10;
+    std::vector<uint8_t> head;
+    for (uint64_t take = 4096;; take = 140000) {        // (FEXTRA holds up to 65535 octets; names and comments are short)
+      head.resize((size_t)std::min<uint64_t>(take, m.in_len));
+      CK(ctx, cudaMemcpyAsync(head.data(), m.in, head.size(), cudaMemcpyDeviceToHost, st));
+      CK(ctx, cudaStreamSynchronize(st));
+      tbz_gzip_header h;
+      if (tbz_gzip_header_parse(head.data(), head.size(), &h) != TBZ_OK) return TBZ_OK;
+      if (h.verdict == TBZ_FINISHED) { hdr_bytes = h.header_len; break; }
+      if (h.verdict != TBZ_INPUT_UNDERRUN || take != 4096 || head.size() == m.in_len) return TBZ_OK;
+    }
   }
   const uint64_t trailer = fmt == TBZ_ZLIB ? 4 : fmt == TBZ_GZIP ? 8 : 0;
   if (m.in_len < hdr_bytes + trailer + 64 || m.in_len >= (1ull << 40) || m.out_cap >= (1ull << 32)) return TBZ_OK;

@@ -211,6 +211,11 @@ def _main(real_stdout):
                torch=torch, dist=dist if world > 1 else None)
     head = run_workload(env, args.workload, headline=True)
     also = {}
+    if world > 1 and not args.no_also:
+        barrier()
+        if rank == 0:
+            also["batch_multi"] = run_batch_multi(env, args.workload)
+        barrier()
     if args.workload == "zlib64k" and not args.no_also and not args.members:
         # BASELINE.json configs[3] (1 MiB gzip members, the batch API, every N) and configs[2] (one 1 GiB gzip member,
         # speculative split decode; one GPU only): device-timed, every member verified
@@ -225,6 +230,53 @@ def _main(real_stdout):
         if also:
             head["also"] = also
         print(json.dumps(head), file=real_stdout, flush=True)
+
+
+def run_batch_multi(env, workload):
+    """tbz_inflate_batch_multi, the product's own multi-GPU entry point, driven by ONE process (rank 0, the other
+    ranks wait): the members of the workload — as many as all GPUs of this run take together — in pinned host
+    memory, partitioned over one engine context per GPU on the host, every result verified."""
+    L, _ffi, args, world = env["L"], env["ffi"], env["args"], env["world"]
+    import threebz_b200 as t
+    n1, size, fmt, seed0 = WORKLOADS[workload]
+    unique = n1
+    n = n1 * world
+    ms = make_members(unique, size, fmt, seed0, os.cpu_count() or 1)
+    ck = zlib.adler32 if fmt == "zlib" else zlib.crc32
+    want_ck = [ck(p) for p, _ in ms]
+    comps = [ms[i % unique][1] for i in range(n)]
+    in_off, o = [], 0
+    for c in comps:
+        in_off.append(o)
+        o += len(c)
+    h_in, h_out = C.c_void_p(), C.c_void_p()
+    _ffi.check(L.tbz_host_alloc(o + 64, C.byref(h_in)))
+    _ffi.check(L.tbz_host_alloc(n * size + 64, C.byref(h_out)))
+    for c, off in zip(comps, in_off):
+        C.memmove(h_in.value + off, c, len(c))
+    hm = (_ffi.Member * n)()
+    for i, c in enumerate(comps):
+        hm[i] = _ffi.Member(h_in.value + in_off[i], len(c), h_out.value + i * size, size)
+    res = (_ffi.Result * n)()
+    ctxs = [t.Ctx(d) for d in range(world)]
+    hs = (C.c_void_p * world)(*[c.h for c in ctxs])
+    times = []
+    for k in range(4):
+        t0 = time.perf_counter()
+        _ffi.check(L.tbz_inflate_batch_multi(hs, world, _ffi.fmt_code(fmt), hm, n, res, args.flags, None), ctxs[0].h)
+        if k:
+            times.append(time.perf_counter() - t0)
+    bad = [i for i in range(n) if res[i].verdict != 0 or res[i].out_len != size or res[i].checksum != want_ck[i % unique]]
+    assert not bad, "batch_multi: members not finished / checksum mismatch: %r" % bad[:8]
+    for i in range(0, n, max(1, n // 64)):
+        assert C.string_at(h_out.value + i * size, size) == ms[i % unique][0], "batch_multi output mismatch on member %d" % i
+    for c in ctxs:
+        c.close()
+    L.tbz_host_free(h_in); L.tbz_host_free(h_out)
+    step = sum(times) / len(times)
+    return {"api": "tbz_inflate_batch_multi, one process, %d engine contexts, pinned host buffers" % world,
+            "members": n, "value": n * size / step / 1e9, "unit": "GB/s (end to end: H2D + kernels + D2H)",
+            "ms_per_step": step * 1e3, "verified_members": n}
 
 
 def run_workload(env, workload, headline):
@@ -329,7 +381,7 @@ def run_workload(env, workload, headline):
                  "k_inflate_seq": statistics.median(kms[2])}
 
     sustained = None
-    e2e_step, e2e_ok = None, None
+    e2e_step, e2e_ok, ceiling_step = None, None, None
     if headline:
         # ---- sustained: at least two seconds of back-to-back launches, with its own clock samples
         sampler = ClockSampler(env["dev"])
@@ -357,6 +409,26 @@ def run_workload(env, workload, headline):
             dt = time.perf_counter() - t0
             if k:
                 e2e_t.append(dt)
+        # the ceiling of this leg: the same bytes moved by plain copies — H2D of the inputs and D2H of the outputs at
+        # once, every rank at the same time (the ranks of a box share its host memory and PCIe root)
+        ceil_t = []
+        s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+        th_in = torch.empty(in_span, dtype=torch.uint8).pin_memory()
+        th_out = torch.empty(U_total, dtype=torch.uint8).pin_memory()
+        td_in = torch.empty(in_span, dtype=torch.uint8, device="cuda")
+        td_out = torch.empty(U_total, dtype=torch.uint8, device="cuda")
+        for k in range(4):
+            barrier()
+            t0 = time.perf_counter()
+            with torch.cuda.stream(s_in):
+                td_in.copy_(th_in, non_blocking=True)
+            with torch.cuda.stream(s_out):
+                th_out.copy_(td_out, non_blocking=True)
+            s_in.synchronize(); s_out.synchronize()
+            if k:
+                ceil_t.append(time.perf_counter() - t0)
+        del th_in, th_out, td_in, td_out
+        ceiling_step = min(ceil_t)
         assert all(res[i].verdict == 0 and res[i].out_len == size and res[i].checksum == want_ck[i % unique] for i in range(n))
         for i in range(n):                                  # every byte of the last end-to-end step
             assert C.string_at(h_out.value + i * size, size) == ms[i % unique][0], "e2e output mismatch on member %d" % i
@@ -365,12 +437,12 @@ def run_workload(env, workload, headline):
 
     # ---- max over ranks
     if world > 1:
-        vals = [dev_ms, e2e_step or 0.0, sustained["ms_per_step"] if sustained else 0.0]
+        vals = [dev_ms, e2e_step or 0.0, sustained["ms_per_step"] if sustained else 0.0, ceiling_step or 0.0]
         tt = torch.tensor(vals, device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)        # t.shard.reduce_max is the same reduction on CPU tensors (gloo test)
         dev_ms = float(tt[0])
         if headline:
-            e2e_step = float(tt[1]); sustained["ms_per_step"] = float(tt[2])
+            e2e_step = float(tt[1]); sustained["ms_per_step"] = float(tt[2]); ceiling_step = float(tt[3])
 
     line = None
     if rank == 0:
@@ -421,7 +493,9 @@ def run_workload(env, workload, headline):
                 "sustained": sustained,
                 "e2e": {"value": world * U_total / e2e_step / 1e9, "unit": "GB/s",
                         "h2d_bytes_per_step": in_span + n * 32, "d2h_bytes_per_step": U_total + n * 32,
-                        "ms_per_step": e2e_step * 1e3, "api": "tbz_inflate_batch, pinned host buffers"},
+                        "ms_per_step": e2e_step * 1e3, "api": "tbz_inflate_batch, pinned host buffers",
+                        "ceiling_gbs": world * U_total / ceiling_step / 1e9,
+                        "ceiling": "the same bytes as plain pinned copies, H2D and D2H at once, all ranks at the same time (max over ranks)"},
                 "gpu_launches": launches, "verification": verification, "roofline": roofline,
                 "cpu_baseline": {"value": sample * size / cpu_t / 1e9, "unit": "GB/s", "cores": cores, "kind": "port",
                                  "sample": "%d of %d members, one pass, %d threads" % (sample, n, cores),

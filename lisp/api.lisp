@@ -104,33 +104,73 @@
                        (values b n)))
                 (tbz-free p))))))))
 
-(defun decompress-batch (members &key (format :zlib) capacities)
+;;; one engine context per device for the multi-GPU batch entry point
+(defvar *device-ctxs* (make-hash-table) "device index -> tbz_ctx of this thread")
+(defun device-ctx (device)
+  (or (gethash device *device-ctxs*)
+      (setf (gethash device *device-ctxs*)
+            (if (eql device *device*)
+                (ctx)
+                (cffi:with-foreign-object (c :pointer)
+                  (check (tbz-ctx-create device 0 c))
+                  (cffi:mem-ref c :pointer))))))
+
+(defun decompress-batch (members &key (format :zlib) capacities devices)
   "NEW: many independent members in one engine call.  MEMBERS: sequence of octet-vectors;
-CAPACITIES: per-member output size (one integer or a sequence).  Returns a list of
-\(buffer count verdict) — verdict :finished / :input-underrun / :output-overflow or the engine's
-name for the place where the reference would have signalled.  A bad member never poisons the batch."
-  (let* ((n (length members))
+CAPACITIES: per-member output size (one integer or a sequence); DEVICES: list of CUDA device indices to
+shard the members over (host-side partition, tbz_inflate_batch_multi) -- default: this thread's device.
+Returns a list of (buffer count verdict) -- verdict :finished / :input-underrun / :output-overflow or the
+engine's name for the place where the reference would have signalled.  A bad member never poisons the batch.
+The members travel through two pinned arenas (inputs back to back, outputs back to back): the engine then
+DMAs straight from and to them, and only one Lisp vector is pinned at a time however long the batch is."
+  (let* ((ins (coerce members 'list))
+         (n (length ins))
          (caps (if (integerp capacities) (make-list n :initial-element capacities) (coerce capacities 'list)))
-         (outs (mapcar (lambda (c) (make-array c :element-type 'octet)) caps)))
-    (cffi:with-foreign-objects ((m '(:struct tbz-member) (max 1 n)) (r '(:struct tbz-result) (max 1 n)))
-      (labels ((pin (i ins os)
-                 (if ins
-                     (cffi:with-pointer-to-vector-data (pi (car ins))
-                       (cffi:with-pointer-to-vector-data (po (car os))
-                         (let ((e (cffi:mem-aptr m '(:struct tbz-member) i)))
-                           (setf (cffi:foreign-slot-value e '(:struct tbz-member) 'in) pi
-                                 (cffi:foreign-slot-value e '(:struct tbz-member) 'in-len) (length (car ins))
-                                 (cffi:foreign-slot-value e '(:struct tbz-member) 'out) po
-                                 (cffi:foreign-slot-value e '(:struct tbz-member) 'out-cap) (length (car os))))
-                         (pin (1+ i) (cdr ins) (cdr os))))
-                     (check (tbz-inflate-batch (ctx) (format-code format) m n r 0 (cffi:null-pointer))))))
-        (pin 0 (coerce members 'list) outs))
-      (loop for i below n for o in outs
-            for e = (cffi:mem-aptr r '(:struct tbz-result) i)
-            for v = (cffi:foreign-slot-value e '(:struct tbz-result) 'verdict)
-            collect (list o (cffi:foreign-slot-value e '(:struct tbz-result) 'out-len)
-                          (case v (0 :finished) (1 :input-underrun) (2 :output-overflow)
-                            (t (tbz-verdict-name v))))))))
+         (outs (mapcar (lambda (c) (make-array c :element-type 'octet)) caps))
+         (in-total (reduce #'+ ins :key #'length))
+         (out-total (reduce #'+ caps)))
+    (cffi:with-foreign-objects ((m '(:struct tbz-member) (max 1 n)) (r '(:struct tbz-result) (max 1 n))
+                                (ph-in :pointer) (ph-out :pointer))
+      (check (tbz-host-alloc (max 1 in-total) ph-in))
+      (let ((h-in (cffi:mem-ref ph-in :pointer)) (h-out (cffi:null-pointer)))
+        (unwind-protect
+             (progn
+               (check (tbz-host-alloc (max 1 out-total) ph-out))
+               (setf h-out (cffi:mem-ref ph-out :pointer))
+               (loop with io = 0 and oo = 0
+                     for i from 0 for v in ins for c in caps
+                     for e = (cffi:mem-aptr m '(:struct tbz-member) i)
+                     do (cffi:with-pointer-to-vector-data (p-in v)
+                          (cffi:foreign-funcall "memcpy" :pointer (cffi:inc-pointer h-in io) :pointer p-in
+                                                         :size (length v) :pointer))
+                        (setf (cffi:foreign-slot-value e '(:struct tbz-member) 'in) (cffi:inc-pointer h-in io)
+                              (cffi:foreign-slot-value e '(:struct tbz-member) 'in-len) (length v)
+                              (cffi:foreign-slot-value e '(:struct tbz-member) 'out) (cffi:inc-pointer h-out oo)
+                              (cffi:foreign-slot-value e '(:struct tbz-member) 'out-cap) c)
+                        (incf io (length v)) (incf oo c))
+               (if (and devices (rest devices))
+                   (let ((g (length devices)))
+                     (cffi:with-foreign-object (cs :pointer g)
+                       (loop for d in devices for k from 0
+                             do (setf (cffi:mem-aref cs :pointer k) (device-ctx d)))
+                       (check (tbz-inflate-batch-multi cs g (format-code format) m n r 0 (cffi:null-pointer)))))
+                   (check (tbz-inflate-batch (if devices (device-ctx (first devices)) (ctx))
+                                             (format-code format) m n r 0 (cffi:null-pointer))))
+               (loop with oo = 0
+                     for i from 0 for o in outs for c in caps
+                     for e = (cffi:mem-aptr r '(:struct tbz-result) i)
+                     for v = (cffi:foreign-slot-value e '(:struct tbz-result) 'verdict)
+                     for got = (min c (cffi:foreign-slot-value e '(:struct tbz-result) 'out-len))
+                     do (when (plusp got)
+                          (cffi:with-pointer-to-vector-data (p-out o)
+                            (cffi:foreign-funcall "memcpy" :pointer p-out :pointer (cffi:inc-pointer h-out oo)
+                                                           :size got :pointer)))
+                        (incf oo c)
+                     collect (list o (cffi:foreign-slot-value e '(:struct tbz-result) 'out-len)
+                                   (case v (0 :finished) (1 :input-underrun) (2 :output-overflow)
+                                     (t (tbz-verdict-name v))))))
+          (tbz-host-free h-in)
+          (unless (cffi:null-pointer-p h-out) (tbz-host-free h-out)))))))
 
 (defun gzip-header (octets &key (start 0) (end (length octets)))
   "The slots DECOMPRESS-GZIP fills from a member header in the reference's GZIP-STATE
@@ -170,9 +210,9 @@ incomplete (the reference's input-underrun); header errors signal like the refer
 all concatenated members into OUTPUT.  Returns (values list-of-(count in-used crc32 verdict) octets-consumed)."
   (let ((n (min max-members (1+ (floor (length octets) 18)))))
     (cffi:with-foreign-objects ((r '(:struct tbz-result) n) (nm :uint64) (used :uint64))
-      (cffi:with-pointer-to-vector-data (pi octets)
-        (cffi:with-pointer-to-vector-data (po output)
-          (check (tbz-inflate-gzip-members (ctx) pi (length octets) po (length output) r n nm used))))
+      (cffi:with-pointer-to-vector-data (p-in octets)
+        (cffi:with-pointer-to-vector-data (p-out output)
+          (check (tbz-inflate-gzip-members (ctx) p-in (length octets) p-out (length output) r n nm used))))
       (values (loop for i below (cffi:mem-ref nm :uint64)
                     for e = (cffi:mem-aptr r '(:struct tbz-result) i)
                     collect (list (cffi:foreign-slot-value e '(:struct tbz-result) 'out-len)

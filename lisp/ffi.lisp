@@ -29,6 +29,12 @@
 (cffi:defcfun "tbz_inflate_batch" :int32
   (ctx :pointer) (format :int32) (members :pointer) (n :uint64) (results :pointer)
   (flags :uint32) (device-ms :pointer))
+(cffi:defcfun "tbz_inflate_batch_multi" :int32
+  (ctxs :pointer) (g :int32) (format :int32) (members :pointer) (n :uint64) (results :pointer)
+  (flags :uint32) (device-ms-per-gpu :pointer))
+(cffi:defcfun "tbz_device_count" :int32 (n :pointer))
+(cffi:defcfun "tbz_host_alloc" :int32 (n :uint64) (p :pointer))
+(cffi:defcfun "tbz_host_free" :int32 (p :pointer))
 (cffi:defcfun "tbz_inflate_single" :int32
   (ctx :pointer) (format :int32) (in :pointer) (in-len :uint64) (out :pointer) (out-cap :uint64)
   (result :pointer) (flags :uint32) (device-ms :pointer))

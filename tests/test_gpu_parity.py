@@ -244,6 +244,46 @@ def test_chunked_input_sessions(engine, ctx, oracle):
         assert engine.finished(est) and bytes(est.output_buffer[:got]) == ref
 
 
+def test_chunked_input_three_octets_at_a_time(engine, ctx, oracle):
+    """test-chunked-input.lisp:27-44: the fixture fed in 3-octet pieces; every call's return value and flags are the
+    oracle's.  (The session keeps what it was given on the device and uploads only the new octets.)"""
+    import time
+    raw, meta = cases.test_deflated()
+    payload = raw[8:]
+    t0 = time.time()
+    ost = oracle.State("deflate", output_size=22728)
+    est = engine.make_deflate_state(output_buffer=bytearray(22728))
+    calls = 0
+    for o in range(0, len(payload), 3):
+        piece = payload[o:o + 3]
+        want = ost.decompress(ost.make_context(piece))
+        got = engine.decompress(engine.make_octet_vector_context(piece), est)
+        calls += 1
+        assert got == want, (o, got, want)
+        assert (engine.finished(est), engine.input_underrun(est), engine.output_overflow(est)) == \
+               (ost.finished, ost.input_underrun, ost.output_overflow), o
+        if ost.finished:
+            break
+    assert ost.finished and bytes(est.output_buffer[:got]) == ost.output(want)
+    assert time.time() - t0 < 10.0, "chunked input must stay cheap (%d calls took %.1f s)" % (calls, time.time() - t0)
+
+
+def test_context_stops_behind_the_stream(engine, ctx, oracle):
+    """the context's offset after a stream finished is just past its last octet (io.lisp:17-58): trailing data or the
+    next member starts there"""
+    p1, c1 = datagen.member(30000, 11, "gzip")
+    p2, c2 = datagen.member(20000, 12, "gzip")
+    data = c1 + c2 + b"tail"
+    ectx = engine.make_octet_vector_context(data)
+    est = engine.make_gzip_state(output_buffer=bytearray(40000))
+    n = engine.decompress(ectx, est)
+    assert engine.finished(est) and bytes(est.output_buffer[:n]) == p1
+    assert ectx.offset == len(c1), (ectx.offset, len(c1))
+    est2 = engine.make_gzip_state(output_buffer=bytearray(40000))
+    n2 = engine.decompress(ectx, est2)
+    assert engine.finished(est2) and bytes(est2.output_buffer[:n2]) == p2 and ectx.offset == len(c1) + len(c2)
+
+
 def test_decompress_batch_api(engine, ctx):
     ms = datagen.members(8, 20000, 300, "zlib")
     ins = [c for _, c in ms]
@@ -282,6 +322,14 @@ def test_split_single_member(engine, ctx, oracle):
         # the same stream with the split disabled: identical result record
         got2, _ = run_batch(ctx, fmt, [comp], len(plain), flags=4)
         assert got2[0]["path"] != 2 and got2[0]["out"] == g["out"] and got2[0]["checksum"] == g["checksum"]
+    # a gzip header with optional fields (`gzip file` always writes a name; gzip.lisp:178-260): still the split path
+    for kw in ({"extra": None, "comment": None, "hcrc": False}, {}, {"extra": b"x" * 5000, "hcrc": False}):
+        comp = cases.gzip_with_header_fields(plain, **kw)
+        got, _ = run_batch(ctx, "gzip", [comp], len(plain))
+        g = got[0]
+        assert g["path"] == 2, ("a gzip member with header fields must take the split path", kw)
+        assert g["verdict"] == 0 and g["out_len"] == len(plain) and g["checksum"] == zlib.crc32(plain) and g["in_used"] == len(comp)
+        assert hashlib.sha256(g["out"]).digest() == hashlib.sha256(plain).digest()
     # damage in the middle, a wrong trailer, a truncated stream, too small a buffer: verdict and bytes as the oracle's
     comp = datagen.compress(plain[: 6 << 20], "gzip")
     n = 6 << 20
@@ -438,3 +486,26 @@ def test_output_tail_is_untouched(engine, ctx):
             assert rarr[i].verdict == 0 and rarr[i].out_len == size
             assert raw[i * cap:i * cap + size] == p, (n, i)
             assert raw[i * cap + size:(i + 1) * cap] == b"\xa5" * (cap - size), ("tail overwritten", n, i)
+
+
+def test_batch_multi_partitions_over_contexts(engine, ctx, oracle):
+    """tbz_inflate_batch_multi, the product's host-side partitioner: members of mixed sizes and formats'
+    verdicts are spread over several engine contexts — one per GPU where the box has several, two contexts on the one
+    GPU otherwise (the partitioning, the per-device threads and the gathering of results are the same code) — and every
+    result equals the oracle's, in the caller's order."""
+    ng = engine.device_count()
+    ctxs = [engine.Ctx(d) for d in range(min(ng, 4))] if ng > 1 else [engine.Ctx(0), engine.Ctx(0)]
+    rnd = random.Random(3)
+    ms = [datagen.member(rnd.choice((3000, 20000, 65536, 200000)), 900 + i, "zlib") for i in range(70)]
+    comps = [c for _, c in ms]
+    comps[5] = comps[5][: len(comps[5]) // 2]                      # truncated
+    bad = bytearray(comps[9]); bad[len(bad) // 2] ^= 0x10; comps[9] = bytes(bad)
+    caps = [len(p) for p, _ in ms]
+    caps[11] -= 100                                               # too small an output
+    res = engine.decompress_batch(comps, "zlib", caps, ctxs=ctxs)
+    for i, (buf, count, verdict) in enumerate(res):
+        want = oracle.decompress_vector(comps[i], "zlib", out_cap=caps[i])
+        assert verdict == want["verdict"] and count == want["out_len"], (i, verdict, want["verdict"])
+        assert bytes(buf[:count]) == want["out"], i
+    for c in ctxs:
+        c.close()
