@@ -186,6 +186,7 @@ __device__ inline void crc_window(Smem &sm, const uint8_t *buf, uint32_t a, uint
 struct RState {
   uint32_t pos;                           // output bytes produced so far (window base)
   uint32_t flushed;                       // output bytes already stored to global memory
+  uint32_t cap;                           // bytes the output may take (phase one does not count them)
   unsigned long long acc_a, acc_w;        // per thread: Adler sum d, sum i*d over the bytes it flushed
 };
 
@@ -332,6 +333,7 @@ __device__ inline uint32_t resolve_window(uint8_t *__restrict__ out, int fmt, co
   }
   if (sm.fail) return 0xffffffffu;
   const uint32_t wsize = sm.wsize;
+  if ((unsigned long long)rs.pos + wsize > rs.cap) return 0xffffffffu;     // output overflow: the sequential kernel reports it
   // ---- 3. the ready queue: one job per thread and step; the pending queue becomes bytes with pointers
   {                                                     // the next window's tokens travel while this one is copied
     const uint32_t fn = f + nused;
@@ -511,9 +513,10 @@ __device__ inline bool resolve_member(const DMember &mem, int fmt, const P1Rec &
   const int lane = tid & 31, warp = tid >> 5;
   RState rs;
   rs.pos = 0; rs.flushed = 0; rs.acc_a = 0; rs.acc_w = 0;
+  rs.cap = mem.out_cap < 0xffffffffull ? (uint32_t)mem.out_cap : 0xffffffffu;
   if (!resolve_stream(mem.out, fmt, rec, slabs, rs, sm, tid)) return false;
   const uint32_t pos = rs.pos;
-  if (pos != rec.out_len) return false;
+  if (rec.out_len != 0xffffffffu && pos != rec.out_len) return false;
   unsigned long long acc_a = rs.acc_a, acc_w = rs.acc_w;
   // ---- checksum of the whole member
   uint32_t ck = 0;

@@ -5,6 +5,7 @@
 #include "tbz_device.cuh"
 #include "inflate_seq.cuh"
 #include "inflate_decode.cuh"
+#include "huff_decode.cuh"
 #include "inflate_copy.cuh"
 #include "inflate_crc.cuh"
 
@@ -28,23 +29,35 @@ k_inflate_seq(const DMember *members, tbz_result *results, uint32_t n, int fmt,
   tbzseq::inflate_member(members[i], fmt, results[i], sm[warp], crc_tab, lane);
 }
 
+// A session's member (sessions: decompress / replace-output-buffer with chunked input), one warp: resumes at the
+// last block boundary an earlier call reached and leaves the new one behind (tbzseq::Resume, device-resident).
+__global__ void __launch_bounds__(32)
+k_inflate_session(DMember member, int fmt, tbz_result *result, tbzseq::Resume *rs) {
+  __shared__ tbzseq::WarpSmem sm;
+  __shared__ uint32_t crc_tab[256];
+  crc_table_init(crc_tab, threadIdx.x, blockDim.x);
+  __syncthreads();
+  tbzseq::inflate_member(member, fmt, *result, sm, crc_tab, threadIdx.x & 31, rs);
+}
+
 // counters: [0] next member for phase one, [1] members queued for the sequential kernel,
 //           [2] slabs handed out, [3] next member for phase two, [4] next member for the gzip CRC kernel
-// Phase one, persistent CTAs of WPC independent warps: each warp pulls the next member from a
-// global counter and decodes it into token slabs; members it cannot prove clean are queued for
-// k_inflate_seq.
-__global__ void __launch_bounds__(tbzfast::NT, 8)
+// Phase one (huff_decode.cuh), persistent CTAs of WPC independent warps: each warp pulls the next member from a
+// global counter and decodes it into token slabs; members it cannot prove clean are queued for k_inflate_seq.
+// scratch: tbzhd::SCRATCH_BYTES per warp of the grid.
+__global__ void __launch_bounds__(tbzhd::NT, TBZ_HD_MINBLOCKS)
 k_inflate_decode(const DMember *members, uint32_t n, int fmt, tbzfast::P1Rec *recs,
-                 uint32_t *slabs, uint32_t nslabs, uint32_t *counters, uint32_t *todo) {
+                 uint32_t *slabs, uint32_t nslabs, uint32_t *counters, uint32_t *todo, unsigned char *scratch) {
   TBZ_DYN_SMEM(smem_raw);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  tbzfast::WSmem &sm = reinterpret_cast<tbzfast::WSmem *>(smem_raw)[warp];
+  tbzhd::WSmem &sm = reinterpret_cast<tbzhd::WSmem *>(smem_raw)[warp];
+  uint32_t *const gck = reinterpret_cast<uint32_t *>(scratch + ((size_t)blockIdx.x * tbzhd::WPC + warp) * tbzhd::SCRATCH_BYTES);
   for (;;) {
     uint32_t i = 0;
     if (lane == 0) i = atomicAdd(&counters[0], 1u);
     i = __shfl_sync(TBZ_FULL, i, 0);
     if (i >= n) break;
-    const bool ok = tbzfast::decode_member(members[i], fmt, recs[i], sm, slabs, nslabs, &counters[2], lane);
+    const bool ok = tbzhd::decode_member(members[i], fmt, recs[i], sm, gck, slabs, nslabs, &counters[2], lane);
     __syncwarp();
     if (!ok && lane == 0) { recs[i].status = 0; todo[atomicAdd(&counters[1], 1u)] = i; }
   }

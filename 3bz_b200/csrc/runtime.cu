@@ -370,9 +370,9 @@ extern "C" int32_t tbz_batch_prepare(tbz_ctx *ctx, int32_t format, const tbz_mem
   PCK(dev_alloc(ctx, std::max<uint64_t>(1, n) * sizeof(tbz_result), &b->d_results));
   if (!(flags & TBZ_FLAG_NO_FASTPATH) && n) {
     int occ = 0;
-    cudaFuncSetAttribute(k_inflate_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(tbzfast::WSmem) * tbzfast::WPC));
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_inflate_decode, tbzfast::NT, sizeof(tbzfast::WSmem) * tbzfast::WPC);
-    b->fast_grid = (int)std::min<uint64_t>((n + tbzfast::WPC - 1) / tbzfast::WPC, (uint64_t)ctx->sm_count * std::max(1, occ));
+    cudaFuncSetAttribute(k_inflate_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(tbzhd::WSmem) * tbzhd::WPC));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_inflate_decode, tbzhd::NT, sizeof(tbzhd::WSmem) * tbzhd::WPC);
+    b->fast_grid = (int)std::min<uint64_t>((n + tbzhd::WPC - 1) / tbzhd::WPC, (uint64_t)ctx->sm_count * std::max(1, occ));
     cudaFuncSetAttribute(k_inflate_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tbzp2::Smem));
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_inflate_resolve, tbzp2::NT, sizeof(tbzp2::Smem));
     b->res_grid = (int)std::min<uint64_t>(n, (uint64_t)ctx->sm_count * std::max(1, occ));
@@ -387,6 +387,7 @@ extern "C" int32_t tbz_batch_prepare(tbz_ctx *ctx, int32_t format, const tbz_mem
     const uint64_t cap = std::max<uint64_t>(64, kSlabPoolBytes / slab_bytes);
     b->nslabs = (uint32_t)std::min<uint64_t>(want, cap);
     PCK(dev_alloc(ctx, (size_t)b->nslabs * slab_bytes, &b->d_slabs));
+    PCK(dev_alloc(ctx, (size_t)b->fast_grid * tbzhd::WPC * tbzhd::SCRATCH_BYTES, &b->d_scratch));
     PCK(dev_alloc(ctx, 256, &b->d_counters));
     PCK(dev_alloc(ctx, n * 4, &b->d_todo));
     PCK(dev_alloc(ctx, n * sizeof(tbzfast::P1Rec), &b->d_recs));
@@ -731,11 +732,11 @@ static int32_t launch_kernels(tbz_batch *b) {
   if (b->fast_grid) {
     CK(ctx, cudaMemsetAsync(b->d_counters, 0, 256, ctx->stream));
     if (ctx->ktime) CK(ctx, cudaEventRecord(ctx->kev[0], ctx->stream));
-    const size_t dec_smem = sizeof(tbzfast::WSmem) * tbzfast::WPC;
+    const size_t dec_smem = sizeof(tbzhd::WSmem) * tbzhd::WPC;
     CK(ctx, cudaFuncSetAttribute(k_inflate_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dec_smem));
-    k_inflate_decode<<<b->fast_grid, tbzfast::NT, dec_smem, ctx->stream>>>(
+    k_inflate_decode<<<b->fast_grid, tbzhd::NT, dec_smem, ctx->stream>>>(
         (const DMember *)b->d_members, n, b->format, (tbzfast::P1Rec *)b->d_recs,
-        (uint32_t *)b->d_slabs, b->nslabs, (uint32_t *)b->d_counters, (uint32_t *)b->d_todo);
+        (uint32_t *)b->d_slabs, b->nslabs, (uint32_t *)b->d_counters, (uint32_t *)b->d_todo, (unsigned char *)b->d_scratch);
     ctx->launches++;
     CK(ctx, cudaGetLastError());
     if (ctx->ktime) CK(ctx, cudaEventRecord(ctx->kev[1], ctx->stream));
@@ -1088,14 +1089,37 @@ extern "C" int32_t tbz_inflate_batch_multi(tbz_ctx *const *ctxs, int32_t g, int3
   if (!ctxs || g <= 0 || (n && (!m || !r))) return TBZ_E_ARG;
   if (flags & TBZ_FLAG_DEVICE_PTRS) return fail(ctxs[0], TBZ_E_ARG, "tbz_inflate_batch_multi takes host members");
   std::vector<uint64_t> lens(n);
-  for (uint64_t i = 0; i < n; i++) lens[i] = m[i].in_len;
+  uint64_t total = 0, biggest = 0;
+  for (uint64_t i = 0; i < n; i++) { lens[i] = m[i].in_len; total += lens[i] + 1; biggest = std::max(biggest, lens[i] + 1); }
+  std::vector<int32_t> rcs(g, TBZ_OK);
+  std::vector<std::thread> th;
+  // Members of similar size (the common batch): consecutive ranges of equal compressed size.  A range keeps what the
+  // caller's layout offers — dense inputs, adjacent outputs: the engine then DMAs straight from and to the caller's
+  // memory, in pipelined parts — which a size-sorted assignment scatters.
+  if (n >= (uint64_t)g && biggest * (uint64_t)g * 8 <= total) {
+    std::vector<uint64_t> cut(g + 1, n);
+    cut[0] = 0;
+    uint64_t acc = 0; int d = 1;
+    for (uint64_t i = 0; i < n && d < g; i++) {
+      acc += lens[i] + 1;
+      if (acc * g >= total * d) cut[d++] = i + 1;
+    }
+    for (int dd = 0; dd < g; dd++)
+      th.emplace_back([&, dd] {
+        float ms = 0.f;
+        const uint64_t lo = cut[dd], hi = cut[dd + 1];
+        if (hi > lo) rcs[dd] = tbz_inflate_batch(ctxs[dd], format, m + lo, hi - lo, r + lo, flags, &ms);
+        if (device_ms_per_gpu) device_ms_per_gpu[dd] = ms;
+      });
+    for (auto &t : th) t.join();
+    for (int dd = 0; dd < g; dd++) if (rcs[dd]) return rcs[dd];
+    return TBZ_OK;
+  }
   std::vector<int32_t> owner(n);
   int32_t rc = tbz_partition(lens.data(), n, g, owner.data());
   if (rc) return rc;
   std::vector<std::vector<uint64_t>> part(g);
   for (uint64_t i = 0; i < n; i++) part[owner[i]].push_back(i);
-  std::vector<int32_t> rcs(g, TBZ_OK);
-  std::vector<std::thread> th;
   for (int d = 0; d < g; d++)
     th.emplace_back([&, d] {
       std::vector<tbz_member> mm(part[d].size());
@@ -1121,6 +1145,8 @@ struct tbz_session {
   void *d_in = nullptr; uint64_t in_cap = 0, in_len = 0;   // every octet handed over so far, on the device: a call uploads only its own
   uint8_t tail[4] = {0, 0, 0, 0}; // the last four of them (gzip ISIZE: a sizing hint)
   uint64_t last_n = 0;            // octets of the last call
+  bool resumable = false;         // the caller feeds pieces: calls resume at block boundaries (k_inflate_session)
+  void *d_rs = nullptr, *d_res = nullptr;   // tbzseq::Resume and the result record of the resumable kernel
   bool decoded = false;           // d_out/total reflect the input
   void *d_out = nullptr; uint64_t d_cap = 0;
   tbz_result total{};
@@ -1141,6 +1167,7 @@ extern "C" int32_t tbz_session_destroy(tbz_session *s) {
   if (!s) return TBZ_OK;
   dev_release(s->ctx, s->d_out);
   dev_release(s->ctx, s->d_in);
+  dev_release(s->ctx, s->d_rs); dev_release(s->ctx, s->d_res);
   delete s;
   return TBZ_OK;
 }
@@ -1165,6 +1192,46 @@ extern "C" int32_t tbz_session_flags(tbz_session *s, int32_t *fin, int32_t *unde
   if (fin) *fin = s->finished;
   if (under) *under = s->underrun;
   if (over) *over = s->overflow;
+  return TBZ_OK;
+}
+
+// A call of a session that is fed in pieces: one warp decodes from the last block boundary an earlier call reached
+// (deflate.lisp:65-88,114-137 saves its whole state machine instead) over everything that has arrived since, into the
+// session's device buffer (the window of the blocks before it is there), and leaves the new boundary and the running
+// checksum behind.  The cost of a call is the block it is in plus the new octets, not the stream so far.
+static int32_t session_resume(tbz_session *s) {
+  tbz_ctx *ctx = s->ctx;
+  CK(ctx, cudaSetDevice(ctx->device));
+  int32_t rc;
+  if (!s->d_rs) {
+    rc = dev_alloc(ctx, 256, &s->d_rs);
+    if (!rc) rc = dev_alloc(ctx, 256, &s->d_res);
+    if (rc) return rc;
+    CK(ctx, cudaMemsetAsync(s->d_rs, 0, 256, ctx->stream));
+  }
+  if (!s->d_out) {
+    s->d_cap = std::max<uint64_t>(1 << 20, s->in_len * 4);
+    rc = dev_alloc(ctx, s->d_cap, &s->d_out);
+    if (rc) return rc;
+  }
+  for (;;) {
+    DMember m{(const uint8_t *)s->d_in, s->in_len, (uint8_t *)s->d_out, s->d_cap};
+    k_inflate_session<<<1, 32, 0, ctx->stream>>>(m, s->format, (tbz_result *)s->d_res, (tbzseq::Resume *)s->d_rs);
+    ctx->launches++;
+    CK(ctx, cudaGetLastError());
+    CK(ctx, cudaMemcpyAsync(&s->total, s->d_res, sizeof(tbz_result), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (s->total.verdict != TBZ_OUTPUT_OVERFLOW) break;
+    // the session's own buffer is full (not the caller's): a larger one, the bytes so far stay (they are the window)
+    void *d = nullptr;
+    const uint64_t cap = s->d_cap * 4;
+    rc = dev_alloc(ctx, cap, &d);
+    if (rc) return rc;
+    CK(ctx, cudaMemcpyAsync(d, s->d_out, s->d_cap, cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    dev_release(ctx, s->d_out);
+    s->d_out = d; s->d_cap = cap;
+  }
   return TBZ_OK;
 }
 
@@ -1208,8 +1275,17 @@ extern "C" int32_t tbz_session_decompress(tbz_session *s, const uint8_t *in, uin
   }
   if (!s->decoded) {
     if (!s->d_in) { int32_t rc = dev_alloc(ctx, 65536, &s->d_in); if (rc) return rc; s->in_cap = 65536; }
-    int32_t rc = inflate_resident(ctx, s->format, s->d_in, s->in_len, s->in_len >= 4 ? s->tail : nullptr, &s->d_out, &s->d_cap, &s->total);
-    if (rc) return rc;
+    int32_t rc;
+    if (!s->resumable) {
+      // the first look at the stream: the whole engine (fast kernels, split decode).  A stream that is complete —
+      // the usual call: a context over all of it — is done here.
+      rc = inflate_resident(ctx, s->format, s->d_in, s->in_len, s->in_len >= 4 ? s->tail : nullptr, &s->d_out, &s->d_cap, &s->total);
+      if (rc) return rc;
+      if (s->total.verdict == TBZ_INPUT_UNDERRUN) s->resumable = true;   // pieces: from the next call on, resume at block boundaries
+    } else {
+      rc = session_resume(s);
+      if (rc) return rc;
+    }
     s->decoded = true;
   }
   uint64_t room = s->cap - s->off, left = s->total.out_len - s->served;

@@ -24,9 +24,10 @@ extern "C" int emu_inflate_batch(int fmt, const tbz_member *m, uint64_t n, tbz_r
   std::vector<uint32_t> slabs((size_t)nslabs * tbzfast::SLAB_WORDS);
   (void)variant;
   {
-    const unsigned dec_grid = std::min<unsigned>((nn + tbzfast::WPC - 1) / tbzfast::WPC, 16);
-    emu_launch(k_inflate_decode, dim3(dec_grid), dim3(tbzfast::NT), sizeof(tbzfast::WSmem) * tbzfast::WPC,
-               (const DMember *)dm.data(), nn, fmt, recs.data(), slabs.data(), nslabs, counters.data(), todo.data());
+    const unsigned dec_grid = std::min<unsigned>((nn + tbzhd::WPC - 1) / tbzhd::WPC, 16);
+    std::vector<unsigned char> scratch((size_t)dec_grid * tbzhd::WPC * tbzhd::SCRATCH_BYTES + 16);
+    emu_launch(k_inflate_decode, dim3(dec_grid), dim3(tbzhd::NT), sizeof(tbzhd::WSmem) * tbzhd::WPC,
+               (const DMember *)dm.data(), nn, fmt, recs.data(), slabs.data(), nslabs, counters.data(), todo.data(), scratch.data());
     emu_launch(k_inflate_resolve, dim3(std::min<unsigned>(nn, 16)), dim3(tbzp2::NT), sizeof(tbzp2::Smem),
                (const DMember *)dm.data(), r, nn, fmt, (const tbzfast::P1Rec *)recs.data(), (const uint32_t *)slabs.data(),
                counters.data(), todo.data());

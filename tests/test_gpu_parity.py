@@ -268,6 +268,30 @@ def test_chunked_input_three_octets_at_a_time(engine, ctx, oracle):
     assert time.time() - t0 < 10.0, "chunked input must stay cheap (%d calls took %.1f s)" % (calls, time.time() - t0)
 
 
+@pytest.mark.parametrize("fmt", ["gzip", "zlib", "deflate"])
+def test_chunked_input_resumes_at_block_boundaries(engine, ctx, oracle, fmt):
+    """a stream of many blocks fed in 16 KiB pieces: every call's return value and flags are the oracle's, and a call
+    costs the block it is in, not the stream so far (the session resumes at the last block boundary it reached;
+    deflate.lisp:65-88,114-137 saves its whole state instead)"""
+    import time
+    plain = datagen.text(6 << 20, 21)
+    comp = datagen.compress(plain, fmt)
+    ost = oracle.State(fmt, output_size=len(plain) + 10)
+    est = {"deflate": engine.make_deflate_state, "zlib": engine.make_zlib_state,
+           "gzip": engine.make_gzip_state}[fmt](output_buffer=bytearray(len(plain) + 10))
+    t0 = time.time()
+    got = want = 0
+    for o in range(0, len(comp), 16384):
+        piece = comp[o:o + 16384]
+        want = ost.decompress(ost.make_context(piece))
+        got = engine.decompress(engine.make_octet_vector_context(piece), est)
+        assert got == want, (o, got, want)
+        assert (engine.finished(est), engine.input_underrun(est), engine.output_overflow(est)) == \
+               (ost.finished, ost.input_underrun, ost.output_overflow), o
+    assert ost.finished and got == len(plain) and bytes(est.output_buffer[:got]) == plain
+    assert time.time() - t0 < 30.0, "%.1f s" % (time.time() - t0)
+
+
 def test_context_stops_behind_the_stream(engine, ctx, oracle):
     """the context's offset after a stream finished is just past its last octet (io.lisp:17-58): trailing data or the
     next member starts there"""
@@ -507,5 +531,10 @@ def test_batch_multi_partitions_over_contexts(engine, ctx, oracle):
         want = oracle.decompress_vector(comps[i], "zlib", out_cap=caps[i])
         assert verdict == want["verdict"] and count == want["out_len"], (i, verdict, want["verdict"])
         assert bytes(buf[:count]) == want["out"], i
+    # members of similar size: consecutive ranges (the direct-DMA, pipelined path per device)
+    ms = datagen.members(1200, 30000, 4000, "zlib")
+    res = engine.decompress_batch([c for _, c in ms], "zlib", 30000, ctxs=ctxs)
+    for i, (buf, count, verdict) in enumerate(res):
+        assert verdict == 0 and count == 30000 and bytes(buf) == ms[i][0], i
     for c in ctxs:
         c.close()
