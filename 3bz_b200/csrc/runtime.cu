@@ -123,7 +123,7 @@ struct tbz_batch {
   uint32_t nslabs = 0;
   bool launched = false;
   cudaStream_t stream = nullptr;       // the stream this batch lives on
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_res = nullptr;   // kernels start / end; (pipelined path) results in pinned memory
   tbz_result *eager_res = nullptr;     // pipelined sub-batch: results and outputs are copied back right behind the kernels
   std::vector<DMember> dm;             // device view of the members (kept alive for the asynchronous upload)
   std::vector<std::pair<uint64_t, DMember>> big;   // members decoded by the split path (index, device view)
@@ -346,6 +346,7 @@ extern "C" int32_t tbz_batch_destroy(tbz_batch *b) {
   if (b->launched || b->n) cudaStreamSynchronize(b->stream);
   if (b->ev0) cudaEventDestroy(b->ev0);
   if (b->ev1) cudaEventDestroy(b->ev1);
+  if (b->ev_res) cudaEventDestroy(b->ev_res);
   dev_release(ctx, b->d_in); dev_release(ctx, b->d_out);
   dev_release(ctx, b->d_members); dev_release(ctx, b->d_results);
   dev_release(ctx, b->d_slabs); dev_release(ctx, b->d_counters); dev_release(ctx, b->d_todo); dev_release(ctx, b->d_recs);
@@ -363,6 +364,7 @@ extern "C" int32_t tbz_batch_prepare(tbz_ctx *ctx, int32_t format, const tbz_mem
   b->ctx = ctx; b->format = format; b->flags = flags; b->n = n;
   b->stream = ctx->stream;
   CK(ctx, cudaEventCreate(&b->ev0)); CK(ctx, cudaEventCreate(&b->ev1));
+  CK(ctx, cudaEventCreateWithFlags(&b->ev_res, cudaEventDisableTiming));
   b->device_ptrs = (flags & TBZ_FLAG_DEVICE_PTRS) != 0;
   int32_t rc;
 #define PCK(x) do { rc = (x); if (rc != TBZ_OK) { tbz_batch_destroy(b); return rc; } } while (0)
@@ -747,8 +749,9 @@ static int32_t launch_kernels(tbz_batch *b) {
     ctx->launches++;
     CK(ctx, cudaGetLastError());
     if (b->format == TBZ_GZIP) {   // gzip: CRC-32 of the finished members + trailer compare
-      const int crc_grid = (int)std::min<uint64_t>(n, (uint64_t)ctx->sm_count * 6);
-      tbzcrc::k_member_crc<<<crc_grid, tbzcrc::NT, 0, ctx->stream>>>(
+      const int crc_grid = (int)std::min<uint64_t>(n, (uint64_t)ctx->sm_count);
+      CK(ctx, cudaFuncSetAttribute(tbzcrc::k_member_crc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tbzcrc::SMEM_BYTES));
+      tbzcrc::k_member_crc<<<crc_grid, tbzcrc::NT, tbzcrc::SMEM_BYTES, ctx->stream>>>(
           (const DMember *)b->d_members, (tbz_result *)b->d_results, n, (const tbzfast::P1Rec *)b->d_recs,
           (uint32_t *)b->d_counters, (uint32_t *)b->d_todo);
       ctx->launches++;
@@ -830,8 +833,10 @@ extern "C" int32_t tbz_batch_launch(tbz_batch *b) {
     }
   }
   CK(ctx, cudaEventRecord(b->ev1, ctx->stream));
-  if (b->eager_res && b->n)
+  if (b->eager_res && b->n) {
     CK(ctx, cudaMemcpyAsync(b->eager_res, b->d_results, b->n * sizeof(tbz_result), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaEventRecord(b->ev_res, ctx->stream));
+  }
   b->launched = true;
   return TBZ_OK;
 }
@@ -921,8 +926,10 @@ static int32_t inflate_batch_pipelined(tbz_ctx *ctx, int32_t format, const tbz_m
     bytes += m[i].in_len + m[i].out_cap;
   }
   if (bytes < (32ull << 20)) return TBZ_OK;
-  static const uint64_t max_parts = getenv("TBZ_PIPE_PARTS") ? strtoull(getenv("TBZ_PIPE_PARTS"), nullptr, 10) : 12;
-  static const uint64_t npipe = std::min<uint64_t>(tbz_ctx::kPipeStreams, getenv("TBZ_PIPE_STREAMS") ? std::max<uint64_t>(1, strtoull(getenv("TBZ_PIPE_STREAMS"), nullptr, 10)) : 6);
+  // (measured, config 2 on one B200, r2aa: parts x streams 4x3 42.9 GB/s, 8x3 43.4, 12x3 41.1, 12x6 37.4, 24x6 37.1
+  //  against 54.1 for the same bytes as plain copies: few, large DMAs)
+  static const uint64_t max_parts = getenv("TBZ_PIPE_PARTS") ? strtoull(getenv("TBZ_PIPE_PARTS"), nullptr, 10) : 8;
+  static const uint64_t npipe = std::min<uint64_t>(tbz_ctx::kPipeStreams - 2, getenv("TBZ_PIPE_STREAMS") ? std::max<uint64_t>(1, strtoull(getenv("TBZ_PIPE_STREAMS"), nullptr, 10)) : 3);
   const uint64_t parts = std::min<uint64_t>(max_parts, std::max<uint64_t>(2, n / 256));
   std::vector<tbz_batch *> sub(parts, nullptr);
   {
@@ -944,12 +951,17 @@ static int32_t inflate_batch_pipelined(tbz_ctx *ctx, int32_t format, const tbz_m
   float total_ms = 0.f;
   // part after part: its results arrive, the copies of what it produced go into its stream (they overlap the kernels
   // of the parts behind it) ...
+  // (the copies get streams of their own: a part's stream already holds the kernels of the part queued behind it)
   for (uint64_t p = 0; p < parts && !rc && ok; p++) {
     if (!sub[p] || !sub[p]->launched) continue;
-    cudaError_t e = cudaStreamSynchronize(sub[p]->stream);
+    cudaError_t e = cudaEventSynchronize(sub[p]->ev_res);
     if (e != cudaSuccess) { rc = fail(ctx, TBZ_E_CUDA, "pipelined results", e); break; }
-    rc = copy_out_direct(sub[p], sub[p]->eager_res, sub[p]->stream);
+    rc = copy_out_direct(sub[p], sub[p]->eager_res, ctx->pstream[tbz_ctx::kPipeStreams - 1 - (p & 1)]);
     sub[p]->copies_issued = true;
+  }
+  for (int k = 0; k < 2; k++) {
+    cudaError_t e = cudaStreamSynchronize(ctx->pstream[tbz_ctx::kPipeStreams - 1 - k]);
+    if (e != cudaSuccess && !rc) rc = fail(ctx, TBZ_E_CUDA, "pipelined D2H", e);
   }
   // ... then everything is waited for
   for (uint64_t p = 0; p < parts; p++) {

@@ -33,7 +33,7 @@ extern "C" int emu_inflate_batch(int fmt, const tbz_member *m, uint64_t n, tbz_r
                counters.data(), todo.data());
   }
   if (fmt == TBZ_GZIP)
-    emu_launch(tbzcrc::k_member_crc, dim3(std::min<unsigned>(nn, 16)), dim3(tbzcrc::NT), 0,
+    emu_launch(tbzcrc::k_member_crc, dim3(std::min<unsigned>(nn, 4)), dim3(tbzcrc::NT), tbzcrc::SMEM_BYTES,
                (const DMember *)dm.data(), r, nn, (const tbzfast::P1Rec *)recs.data(), counters.data(), todo.data());
   if (!(variant & 2))          // (variant bit 1: leave the members the fast kernels gave up on as they are, for debugging)
     emu_launch(k_inflate_seq, dim3((nn + SEQ_WARPS - 1) / SEQ_WARPS), dim3(SEQ_WARPS * 32), 0,
