@@ -454,9 +454,11 @@ __device__ inline bool decode_blocks(const In &in, uint32_t pos, P1Rec &rec, WSm
         const uint32_t q = cstart >> 5;
         w0 = __ldg(inw + min(q, lastw)); w1 = __ldg(inw + min(q + 1u, lastw)); w2 = __ldg(inw + min(q + 2u, lastw));
         wi = q + 3u + woff; bo = cstart & 31u;
+        // the chunk of word wi, and — unless that word is its first: then the loop asks when it gets there — the next
         cp_async16(inq + ((wi & 4u) << 7), inb + min(wi >> 2, lastc)); cp_async_commit();
-        cp_async16(inq + ((~wi & 4u) << 7), inb + min((wi >> 2) + 1u, lastc)); cp_async_commit();
+        if (wi & 3u) { cp_async16(inq + ((~wi & 4u) << 7), inb + min((wi >> 2) + 1u, lastc)); cp_async_commit(); }
       }
+      cp_async_wait<0>();               // (the first words are needed right away; the lists' first stores wait for nothing)
       __syncwarp();
 
       uint32_t it = 0;                  // iterations of the loop = items of every lane that still runs (uniform)
@@ -524,10 +526,12 @@ __device__ inline bool decode_blocks(const In &in, uint32_t pos, P1Rec &rec, WSm
 #pragma unroll
             for (int twice = 0; twice < 2; twice++) {
               if (twice == 0 ? __builtin_expect(bo >= 64u, 0) : bo >= 32u) {
-                const uint32_t slot = inq + ((wi & 4u) << 7);
-                cp_async_wait<1>();                                    // (all but the newest chunk have landed)
-                w0 = w1; w1 = w2; w2 = lds32(slot + ((wi & 3u) << 2));
-                if ((wi & 3u) == 3u) { cp_async16(slot, inb + min((wi >> 2) + 2u, lastc)); cp_async_commit(); }   // the slot is free: the chunk after next
+                // entering a chunk: it was asked for a chunk ago and has landed (nothing else is on its way); the other
+                // slot — its words were moved up and used — takes the chunk behind this one
+                const bool first = (wi & 3u) == 0u;
+                if (first) cp_async_wait<0>();
+                w0 = w1; w1 = w2; w2 = lds32(inq + ((wi & 4u) << 7) + ((wi & 3u) << 2));
+                if (first) { cp_async16(inq + ((~wi & 4u) << 7), inb + min((wi >> 2) + 1u, lastc)); cp_async_commit(); }
                 wi++; bo -= 32u;
               }
             }
@@ -552,6 +556,7 @@ __device__ inline bool decode_blocks(const In &in, uint32_t pos, P1Rec &rec, WSm
         it++;
         __syncwarp();
       }
+      cp_async_wait<0>();               // nothing may still be on its way into the slots: the next header builds its tables there
 #ifdef TBZ_HD_TIMING
       const long long t_loop1 = clock64();
 #endif

@@ -96,6 +96,28 @@ struct Smem {
   uint32_t crc;
 };
 
+// val[] is read by some threads while others advance it (pointer jumping, step 4): these accesses are CTA-scope
+// acquire loads and release stores — a byte is copied only after its source's val reads FINAL, and FINAL is
+// released after the byte was written — so the one intended concurrent access of the kernel is a data-race-free
+// one in the PTX memory model, not an ordering that `volatile` happens to give.
+#ifdef TBZ_EMU
+__device__ __forceinline__ uint32_t ld_acquire_u16(const uint16_t *p) { return *reinterpret_cast<const volatile uint16_t *>(p); }
+__device__ __forceinline__ void st_release_u16(uint16_t *p, uint32_t v) { *reinterpret_cast<volatile uint16_t *>(p) = (uint16_t)v; }
+__device__ __forceinline__ void st_relaxed_u16(uint16_t *p, uint32_t v) { *reinterpret_cast<volatile uint16_t *>(p) = (uint16_t)v; }
+#else
+__device__ __forceinline__ uint32_t ld_acquire_u16(const uint16_t *p) {
+  uint16_t v;
+  asm volatile("ld.acquire.cta.shared.u16 %0, [%1];" : "=h"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u16(uint16_t *p, uint32_t v) {
+  asm volatile("st.release.cta.shared.u16 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "h"((uint16_t)v) : "memory");
+}
+__device__ __forceinline__ void st_relaxed_u16(uint16_t *p, uint32_t v) {     // (a pointer moves on: it publishes no data)
+  asm volatile("st.relaxed.cta.shared.u16 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "h"((uint16_t)v) : "memory");
+}
+#endif
+
 __device__ __forceinline__ uint32_t tok_len(uint32_t t) { return (t & TOK_MATCH) ? (t & 255u) + 3u : 1u + ((t >> 30) & 1u); }
 
 // Final history: the ring in shared memory, or (GHIST) the member's own output in global memory, read
@@ -368,19 +390,18 @@ __device__ inline uint32_t resolve_window(uint8_t *__restrict__ out, int fmt, co
       int unresolved = 0;
       for (uint32_t i = tid; i < nb; i += NT) {
         const uint32_t r = sm.pbytes[i];
-        volatile uint16_t *vp = reinterpret_cast<volatile uint16_t *>(&sm.val[r]);
-        const uint32_t s2 = *vp;
+        uint16_t *vp = &sm.val[r];
+        const uint32_t s2 = ld_acquire_u16(vp);
         if (s2 != V_FINAL) {
           uint32_t sp = s2;
-          uint32_t vs = *reinterpret_cast<volatile uint16_t *>(&sm.val[sp]);
+          uint32_t vs = ld_acquire_u16(&sm.val[sp]);
 #pragma unroll
           for (int hop = 1; hop < PJ_HOPS; hop++)         // several hops per level: fewer levels, fewer barriers
-            if (vs != V_FINAL) { sp = vs; vs = *reinterpret_cast<volatile uint16_t *>(&sm.val[sp]); }
+            if (vs != V_FINAL) { sp = vs; vs = ld_acquire_u16(&sm.val[sp]); }
           if (vs == V_FINAL) {
-            buf[wb + r] = *reinterpret_cast<volatile uint8_t *>(&buf[wb + sp]);
-            __threadfence_block();
-            *vp = (uint16_t)V_FINAL;
-          } else { *vp = (uint16_t)vs; unresolved = 1; }   // equal bytes: adopt the source's pointer
+            buf[wb + r] = *reinterpret_cast<volatile uint8_t *>(&buf[wb + sp]);   // (ordered behind the acquire that read FINAL)
+            st_release_u16(vp, V_FINAL);                                           // the byte first, then FINAL
+          } else { st_relaxed_u16(vp, vs); unresolved = 1; }   // equal bytes: adopt the source's pointer
         }
       }
       if (!__syncthreads_or(unresolved)) break;
