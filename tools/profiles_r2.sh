@@ -1,0 +1,55 @@
+#!/bin/bash
+# here (no GPU): turns gpurun_out/<tag>* of tools/final_r2.sh into the tracked summaries under profiles/
+tag=${1:-r2g2}
+P=profiles
+cp gpurun_out/${tag}_bench_default.json $P/r2_bench_default.json
+cp gpurun_out/${tag}_bench_reference.json $P/r2_bench_reference.json
+[ -e gpurun_out/r2v_bench_2gpu.json ] && cp gpurun_out/r2v_bench_2gpu.json $P/r2_bench_2gpu.json
+cp gpurun_out/${tag}_launches.csv $P/r2_launches.csv
+cp gpurun_out/${tag}_launches_gzip1m.csv $P/r2_launches_gzip1m.csv
+{
+  echo "# ncu --set full --clock-control none, config 2 (4096 x 64 KiB zlib), one launch of each hot kernel (gpurun_out/${tag}.ncu-rep)"
+  python tools/ncusum.py ${tag} 2>&1
+  echo
+  echo "# stall reasons per issued instruction, pipe utilisation"
+  ncu -i gpurun_out/${tag}.ncu-rep --page raw --csv 2>/dev/null | python -c "
+import csv,sys
+rows=list(csv.reader(sys.stdin)); h=rows[0]
+ks=[k for k in h if 'issue_stalled' in k and 'per_issue_active' in k and 'not_issued' not in k]
+for k in ks+['sm__cycles_active.avg','sm__cycles_elapsed.max','l1tex__t_sector_hit_rate.pct','lts__t_sector_hit_rate.pct','l1tex__throughput.avg.pct_of_peak_sustained_active','sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active','sm__inst_executed_pipe_lsu.sum']:
+    if k in h:
+        i=h.index(k); print(k.replace('smsp__average_warps_issue_stalled_','stall ').replace('_per_issue_active.ratio',''), ' | '.join(r[i][:12] for r in rows[2:]))
+"
+} > $P/r2_ncu_summary.txt
+{
+  echo "# k_inflate_resolve (inflate_copy.cuh): hottest lines"
+  python profiles/hotlines.py gpurun_out/${tag}.ncu-rep 3bz_b200/libthreebz_cuda.so k_inflate_resolve 28 2>&1 | cut -c1-200
+  echo
+  echo "# k_inflate_decode (huff_decode.cuh): hottest lines"
+  python profiles/hotlines.py gpurun_out/${tag}.ncu-rep 3bz_b200/libthreebz_cuda.so k_inflate_decode 32 2>&1 | cut -c1-200
+} > $P/r2_hotlines.txt
+{
+  echo "# cuobjdump -sass 3bz_b200/libthreebz_cuda.so, k_inflate_decode: the input of every decode lane arrives through cp.async"
+  echo "# (LDGSTS.E.BYPASS.128 = cp.async.cg.shared.global 16 bytes; LDGDEPBAR = commit_group; DEPBAR.LE SB0 = wait_group)"
+  cuobjdump -sass 3bz_b200/libthreebz_cuda.so 2>/dev/null | awk '/Function : /{f=(index($0,"k_inflate_decodePK")>0)} f' | grep -E "LDGSTS|LDGDEPBAR|DEPBAR" | sed 's/ *\/\* 0x[0-9a-f]* \*\///'
+  echo
+  echo "# the refill of the decode loop (huff_decode.cuh: 'entering a chunk'):"
+  cuobjdump -sass 3bz_b200/libthreebz_cuda.so 2>/dev/null | awk '/Function : /{f=(index($0,"k_inflate_decodePK")>0)} f' | grep -B14 -A6 "LDGSTS" | sed 's/ *\/\* 0x[0-9a-f]* \*\///' | sed -n '60,110p'
+  echo
+  echo "# instruction mix of the library's kernels (no UTMA*/UBLKCP: nothing here moves tiles; LDGSTS is the one async copy)"
+  for k in k_inflate_decodePK k_inflate_resolvePK k_member_crc k_inflate_seq; do
+    printf "%-22s " $k; cuobjdump -sass 3bz_b200/libthreebz_cuda.so 2>/dev/null | awk -v k=$k '/Function : /{f=(index($0,k)>0)} f' | grep -oE "^\s+/\*[0-9a-f]+\*/\s+(@!?U?P[0-9T] )?[A-Z0-9_.]+" | awk '{print $NF}' | sed 's/\..*//' | sort | uniq -c | sort -rn | head -8 | awk '{printf "%s %s  ", $2, $1}'; echo
+  done
+} > $P/r2_sass_ldgsts.txt
+{
+  echo "# same-box A/B runs of round 2 (tools/sweep.sh: every library variant on the bench workload, per-kernel CUDA-event times)"
+  for f in r2n r2p r2q r2r r2s r2x; do [ -e gpurun_out/${f}_sweep.log ] && { echo "## $f"; grep -E "^==|^\[tbz\]" gpurun_out/${f}_sweep.log; }; done
+  echo "## r2aa: e2e pipeline geometry (parts x streams -> GB/s, ms per step, ceiling)"; grep "^parts" /tmp/r2aa.out 2>/dev/null
+} > $P/r2_experiments.txt
+{
+  echo "# compute-sanitizer over the parity tests (config2_subset, config4_members, edge_mix [, truncation, corruption])"
+  echo "## racecheck --racecheck-report analysis: the only lines reported are the acquire / release accesses of pointer jumping (inflate_copy.cuh step 4; DESIGN.md 9)"
+  grep -E "Race reported|RACECHECK SUMMARY|passed" gpurun_out/r2ab_racecheck.txt | sed 's/=========//' | cut -c1-170 | sort | uniq -c | sort -rn
+  echo "## memcheck"; tail -3 gpurun_out/r2ab_memcheck.txt
+} > $P/r2_sanitizer.txt
+ls -la $P | grep r2_
