@@ -70,7 +70,7 @@ k_inflate_decode(const DMember *members, uint32_t n, int fmt, tbzfast::P1Rec *re
 // their numbers in profiles/ and DESIGN.md.
 namespace tbzp2 = tbzcp;
 #ifndef TBZ_P2_MINBLOCKS
-#define TBZ_P2_MINBLOCKS 3
+#define TBZ_P2_MINBLOCKS (tbzp2::PJ ? 3 : 4)
 #endif
 __global__ void __launch_bounds__(tbzp2::NT, TBZ_P2_MINBLOCKS)
 k_inflate_resolve(const DMember *members, tbz_result *results, uint32_t n, int fmt,
@@ -78,7 +78,7 @@ k_inflate_resolve(const DMember *members, tbz_result *results, uint32_t n, int f
   TBZ_DYN_SMEM(smem_raw);
   tbzp2::Smem &sm = *reinterpret_cast<tbzp2::Smem *>(smem_raw);
   const int tid = threadIdx.x;
-  if (fmt == TBZ_GZIP) {
+  if (fmt == TBZ_GZIP && !tbzp2::CRC_SEPARATE) {
     crc_table_init(sm.crc_tab, tid, tbzp2::NT);
     for (uint32_t k = tid; k < tbzp2::WB / 16 + 4; k += tbzp2::NT) sm.x16[k] = crc_x8n(16ull * k);
   }

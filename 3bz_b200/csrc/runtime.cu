@@ -666,28 +666,31 @@ static int32_t split_inflate(tbz_ctx *ctx, int fmt, const DMember &m, tbz_result
   uint32_t ck = 0;
   uint8_t tr[8] = {0};
   if (trailer) {
-    const uint64_t nseg = (total + tbzsplit::CSEG - 1) / tbzsplit::CSEG;
+    // gzip: the CTA-per-span CRC of the batched path (inflate_crc.cuh) over 1 MiB pieces; zlib: sums per 4 KiB segment
+    const uint64_t seg_bytes = fmt == TBZ_GZIP ? (1ull << 20) : (uint64_t)tbzsplit::CSEG;
+    const uint64_t nseg = (total + seg_bytes - 1) / seg_bytes;
     SRC(dev_alloc(ctx, (size_t)std::max<uint64_t>(1, nseg) * 8, &d_parts));
     if (nseg) {
-      tbzsplit::k_split_checksum<<<(uint32_t)((nseg + 255) / 256), 256, 0, st>>>(m.out, total, fmt, (uint32_t *)d_parts);
+      if (fmt == TBZ_GZIP) {
+        SCK(cudaFuncSetAttribute(tbzcrc::k_span_crc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tbzcrc::SMEM_BYTES));
+        tbzcrc::k_span_crc<<<(uint32_t)std::min<uint64_t>(nseg, (uint64_t)ctx->sm_count), tbzcrc::NT, tbzcrc::SMEM_BYTES, st>>>(
+            m.out, total, (uint32_t)seg_bytes, (uint32_t *)d_parts);
+      } else {
+        tbzsplit::k_split_checksum<<<(uint32_t)((nseg + 255) / 256), 256, 0, st>>>(m.out, total, fmt, (uint32_t *)d_parts);
+      }
       ctx->launches++;
     }
     std::vector<uint32_t> parts(2 * std::max<uint64_t>(1, nseg));
-    SCK(cudaMemcpyAsync(parts.data(), d_parts, (size_t)nseg * 8, cudaMemcpyDeviceToHost, st));
+    SCK(cudaMemcpyAsync(parts.data(), d_parts, (size_t)nseg * (fmt == TBZ_GZIP ? 4 : 8), cudaMemcpyDeviceToHost, st));
     SCK(cudaMemcpyAsync(tr, (const uint8_t *)words + trailer_byte, trailer, cudaMemcpyDeviceToHost, st));
     SCK(cudaStreamSynchronize(st));
     if (fmt == TBZ_GZIP) {
-      // crc(A || B) = crc(A) * x^(8 |B|) + crc(B); multiplying by the constant of a full segment is linear: four byte tables
-      const uint32_t xs = crc_x8n_h(tbzsplit::CSEG);
-      std::vector<uint32_t> mt(4 * 256);
-      for (int bsel = 0; bsel < 4; bsel++)
-        for (uint32_t v = 0; v < 256; v++) mt[bsel * 256 + v] = crc_mulmod_h(v << (8 * bsel), xs);
+      // crc(A || B) = crc(A) * x^(8 |B|) + crc(B)
+      const uint32_t xs = crc_x8n_h(seg_bytes);
       uint32_t c = 0;
       for (uint64_t s2 = 0; s2 < nseg; s2++) {
-        const uint64_t len = std::min<uint64_t>(tbzsplit::CSEG, total - s2 * tbzsplit::CSEG);
-        if (len == tbzsplit::CSEG) c = mt[c & 255] ^ mt[256 + ((c >> 8) & 255)] ^ mt[512 + ((c >> 16) & 255)] ^ mt[768 + (c >> 24)];
-        else c = crc_mulmod_h(crc_x8n_h(len), c);
-        c ^= parts[2 * s2];
+        const uint64_t len = std::min<uint64_t>(seg_bytes, total - s2 * seg_bytes);
+        c = crc_mulmod_h(len == seg_bytes ? xs : crc_x8n_h(len), c) ^ parts[s2];
       }
       ck = c;
     } else {

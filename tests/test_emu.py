@@ -113,3 +113,27 @@ def test_emu_long_distances_and_lengths():
         comp = datagen.compress(plain, "zlib", level=level)
         got, nseq = emuutil.run_batch("zlib", [comp], [len(plain)])
         assert nseq == 0 and got[0]["out"] == plain and got[0]["path"] == 1
+
+
+@pytest.mark.parametrize("out_mis", [0, 1, 7, 15])
+def test_emu_gzip_crc_span_geometry(out_mis):
+    """k_member_crc (inflate_crc.cuh): lengths around every boundary of its segment geometry (NT = 1024 threads, 64-byte
+    runs, the 16-byte alignment offset, the last segment on thread 0), at several output misalignments; mixed lengths in
+    one launch, so the cached weights are recomputed between members."""
+    lens = [0, 1, 2, 15, 16, 17, 63, 64, 65, 127, 1023, 1024, 1025, 4095, 65535, 65536, 65537, 65536 + 64, 65600 - out_mis,
+            70001, 2 * 65536 - 1, 200000, 65536, 65536, 1]
+    text = datagen.text(max(lens), 4242)
+    plain = [text[:n] for n in lens]
+    comp = [datagen.compress(p, "gzip") for p in plain]
+    got, nseq = emuutil.run_batch("gzip", comp, [len(p) for p in plain], out_mis=out_mis)
+    assert nseq == 0
+    for p, c, g in zip(plain, comp, got):
+        assert g["verdict"] == 0 and g["out"] == p and g["checksum"] == zlib.crc32(p) and g["path"] == 1, len(p)
+    # a damaged CRC goes to the sequential kernel, which reports it like the oracle
+    bad = [bytearray(c) for c in comp[5:12]]
+    for b in bad:
+        b[-6] ^= 0x40
+    got, nseq = emuutil.run_batch("gzip", [bytes(b) for b in bad], [len(p) for p in plain[5:12]], out_mis=out_mis)
+    assert nseq == len(bad)
+    for b, p, g in zip(bad, plain[5:12], got):
+        compare(g, o3bz.decompress_vector(bytes(b), "gzip", out_cap=len(p)), ("bad crc", len(p)))
