@@ -237,33 +237,44 @@ k_tail_write(const Chunk *__restrict__ chunks, const uint16_t *__restrict__ map,
   }
 }
 
-// every symbol becomes a byte, eight per thread and step (16-byte loads, 8-byte stores).  The tails are
-// final already and come out the same again.  offs[k] = output offset of chunk k, offs[nchunks] = total.
+// every symbol becomes a byte, sixteen per thread and step (two 16-byte loads in flight, one 16-byte store).  The
+// tails are final already and come out the same again: a marker's byte is read through L1 (the only concurrent
+// writes to those addresses store the value they hold).  offs[k] = output offset of chunk k, offs[nchunks] = total.
 __global__ void __launch_bounds__(256)
 k_split_translate(const uint64_t *__restrict__ offs, uint32_t nchunks, const uint16_t *__restrict__ sym, uint8_t *out, uint64_t total) {
-  const uint64_t nunits = (total + 7) / 8;
+  const uint64_t nunits = (total + 15) / 16;
   // every block takes one contiguous range of units, so a thread stays inside one chunk for many
   // steps and the chunk lookup is two cached loads instead of a binary search
   const uint64_t per_block = (nunits + gridDim.x - 1) / gridDim.x;
   const uint64_t u_end = per_block * (blockIdx.x + 1) < nunits ? per_block * (blockIdx.x + 1) : nunits;
+  const bool vec = (((uintptr_t)out) & 15) == 0;
   uint32_t k = 0xffffffffu;
   for (uint64_t u = per_block * blockIdx.x + threadIdx.x; u < u_end; u += blockDim.x) {
-    const uint64_t a0 = u * 8;
+    const uint64_t a0 = u * 16;
     if (k == 0xffffffffu || a0 < offs[k] || a0 >= offs[k + 1]) {
       k = 0;                                             // last chunk with offs[k] <= a0
       for (uint32_t stp = 1u << 15; stp; stp >>= 1)
         if (k + stp < nchunks && offs[k + stp] <= a0) k += stp;
     }
     uint64_t start = offs[k], next = offs[k + 1];
-    if (a0 + 8 <= total && a0 + 8 <= next) {
-      const uint4 v = *reinterpret_cast<const uint4 *>(sym + a0);
-      uint32_t s[8] = {v.x & 0xffffu, v.x >> 16, v.y & 0xffffu, v.y >> 16, v.z & 0xffffu, v.z >> 16, v.w & 0xffffu, v.w >> 16};
+    if (vec && a0 + 16 <= total && a0 + 16 <= next) {
+      const uint4 v0 = __ldcs(reinterpret_cast<const uint4 *>(sym + a0)), v1 = __ldcs(reinterpret_cast<const uint4 *>(sym + a0 + 8));
+      uint32_t s[16] = {v0.x & 0xffffu, v0.x >> 16, v0.y & 0xffffu, v0.y >> 16, v0.z & 0xffffu, v0.z >> 16, v0.w & 0xffffu, v0.w >> 16,
+                        v1.x & 0xffffu, v1.x >> 16, v1.y & 0xffffu, v1.y >> 16, v1.z & 0xffffu, v1.z >> 16, v1.w & 0xffffu, v1.w >> 16};
+      const uint8_t *const win = out + (start - 32768);
+      if ((v0.x | v0.y | v0.z | v0.w | v1.x | v1.y | v1.z | v1.w) & (tbzres::SYM_MARK | (tbzres::SYM_MARK << 16))) {
 #pragma unroll
-      for (int j = 0; j < 8; j++)
-        if (s[j] & tbzres::SYM_MARK) s[j] = *reinterpret_cast<const volatile uint8_t *>(out + (start - 32768 + (s[j] & 0x7fffu)));
-      *reinterpret_cast<uint2 *>(out + a0) = make_uint2(s[0] | (s[1] << 8) | (s[2] << 16) | (s[3] << 24), s[4] | (s[5] << 8) | (s[6] << 16) | (s[7] << 24));
+        for (int j = 0; j < 16; j++)
+          if (s[j] & tbzres::SYM_MARK) s[j] = win[s[j] & 0x7fffu];
+      }
+      uint4 o;
+      o.x = s[0] | (s[1] << 8) | (s[2] << 16) | (s[3] << 24);
+      o.y = s[4] | (s[5] << 8) | (s[6] << 16) | (s[7] << 24);
+      o.z = s[8] | (s[9] << 8) | (s[10] << 16) | (s[11] << 24);
+      o.w = s[12] | (s[13] << 8) | (s[14] << 16) | (s[15] << 24);
+      *reinterpret_cast<uint4 *>(out + a0) = o;
     } else {
-      for (uint64_t a = a0; a < a0 + 8 && a < total; a++) {
+      for (uint64_t a = a0; a < a0 + 16 && a < total; a++) {
         while (a >= next) { k++; start = next; next = offs[k + 1]; }
         const uint32_t sv = sym[a];
         out[a] = (sv & tbzres::SYM_MARK) ? *reinterpret_cast<const volatile uint8_t *>(out + (start - 32768 + (sv & 0x7fffu))) : (uint8_t)sv;

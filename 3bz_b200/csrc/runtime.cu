@@ -933,7 +933,19 @@ static int32_t inflate_batch_pipelined(tbz_ctx *ctx, int32_t format, const tbz_m
   //  against 54.1 for the same bytes as plain copies: few, large DMAs)
   static const uint64_t max_parts = getenv("TBZ_PIPE_PARTS") ? strtoull(getenv("TBZ_PIPE_PARTS"), nullptr, 10) : 8;
   static const uint64_t npipe = std::min<uint64_t>(tbz_ctx::kPipeStreams - 2, getenv("TBZ_PIPE_STREAMS") ? std::max<uint64_t>(1, strtoull(getenv("TBZ_PIPE_STREAMS"), nullptr, 10)) : 3);
-  const uint64_t parts = std::min<uint64_t>(max_parts, std::max<uint64_t>(2, n / 256));
+  // The first output byte can leave only after one part has been uploaded, decoded (a member's decode latency is the
+  // same ~0.5 ms whatever the part's size) and resolved, and from then on the D2H engine is the bottleneck: the first
+  // parts are small (a sixteenth of the batch each), so that the wait in front of the first DMA holds little work
+  static const uint64_t first_div = getenv("TBZ_PIPE_FIRST") ? strtoull(getenv("TBZ_PIPE_FIRST"), nullptr, 10) : 16;
+  std::vector<uint64_t> cut;                            // part p = members [cut[p], cut[p + 1])
+  {
+    const uint64_t eq = std::min<uint64_t>(max_parts, std::max<uint64_t>(2, n / 256));
+    cut.push_back(0);
+    uint64_t at = 0;
+    if (first_div > eq && n / first_div >= 128) { at = n / first_div; cut.push_back(at); at *= 2; cut.push_back(at); }
+    for (uint64_t p = 1; p <= eq; p++) cut.push_back(at + (n - at) * p / eq);
+  }
+  const uint64_t parts = cut.size() - 1;
   std::vector<tbz_batch *> sub(parts, nullptr);
   {
     int32_t src = ensure_stage(ctx, &ctx->stage_res, &ctx->stage_res_cap, n * sizeof(tbz_result));
@@ -944,7 +956,7 @@ static int32_t inflate_batch_pipelined(tbz_ctx *ctx, int32_t format, const tbz_m
   int32_t rc = TBZ_OK;
   bool ok = true;
   for (uint64_t p = 0; p < parts && !rc; p++) {
-    const uint64_t lo = n * p / parts, hi = n * (p + 1) / parts;
+    const uint64_t lo = cut[p], hi = cut[p + 1];
     ctx->stream = ctx->pstream[p % npipe];
     rc = tbz_batch_prepare(ctx, format, m + lo, hi - lo, flags, &sub[p]);
     if (!rc && !(sub[p]->in_direct && sub[p]->out_direct)) { ok = false; break; }
