@@ -44,6 +44,13 @@ for k in ks+['sm__cycles_active.avg','sm__cycles_elapsed.max','l1tex__t_sector_h
 {
   echo "# same-box A/B runs of round 2 (tools/sweep.sh: every library variant on the bench workload, per-kernel CUDA-event times)"
   for f in r2n r2p r2q r2r r2s r2x; do [ -e gpurun_out/${f}_sweep.log ] && { echo "## $f"; grep -E "^==|^\[tbz\]" gpurun_out/${f}_sweep.log; }; done
+  echo "## phase two, third session of round 2 (variants of inflate_copy.cuh; var_rN = N token rounds over the pending queue before pointer jumping,"
+  echo "## nopj = token rounds only, 47 KB and 4 CTAs/SM; w3072t3 = 3 072-byte windows of 768 tokens, 4 CTAs/SM; tNNN = NNN threads per CTA)"
+  echo "## r2j: the round variants ran at 2 CTAs/SM (77 KB of shared memory: one CTA fewer) - kept as the occupancy data point"
+  for f in r2j r2k2 r2l r2z; do [ -e gpurun_out/${f}_sweep.log ] && { echo "## $f"; grep -E "^==|^\[tbz\]" gpurun_out/${f}_sweep.log; }; done
+  echo "## r2m: e2e with two small leading parts (TBZ_PIPE_FIRST = divisor; 0 = equal parts), split decode stages after the translate / CRC changes"
+  cat gpurun_out/r2m_e2e.log gpurun_out/r2m_split.log 2>/dev/null
+  echo "## r2i: split decode stages before (1 GiB gzip member)"; grep "tbz split" gpurun_out/r2i_gzip1g.err 2>/dev/null | tail -7
   echo "## r2aa: e2e pipeline geometry (parts x streams -> GB/s, ms per step, ceiling)"; grep "^parts" /tmp/r2aa.out 2>/dev/null
 } > $P/r2_experiments.txt
 {
