@@ -698,6 +698,10 @@ __device__ inline uint32_t find_block_start(const In &in, uint32_t from, uint32_
         uint32_t pp = q + 17 + 3 * ncl;
         int idx = 0, lastlen = 0xff;
         const int total = hlit + hdist;
+        // Kraft sums of the two codes as their lengths arrive (units of 2^-15): a code that is over-subscribed after a
+        // few lengths cannot become complete any more, and that is how nearly every false candidate ends — after a
+        // handful of symbols instead of all ~300 (the same verdict the completeness test below would give)
+        uint32_t kr_ll = 0, kr_d = 0;
         while (idx < total) {
           const uint32_t w = peek32(in, pp);
           const uint32_t r = sm.h.lut_cl[w & 127];
@@ -712,6 +716,12 @@ __device__ inline uint32_t find_block_start(const In &in, uint32_t from, uint32_
           else { rep = (sym == 17 ? 3 : 11) + extra; val = 0; lastlen = 0; }
           if (idx + rep > total) { err = 1; break; }
           for (int k = 0; k < rep; k++) sm.h.lens[32 + idx + k] = (uint8_t)val;
+          if (val) {
+            const int in_ll = idx + rep <= hlit ? rep : idx < hlit ? hlit - idx : 0;   // (a run may cross from one code into the other)
+            kr_ll += (uint32_t)in_ll * (32768u >> val);
+            kr_d += (uint32_t)(rep - in_ll) * (32768u >> val);
+            if (kr_ll > 32768u || kr_d > 32768u) { err = 1; break; }
+          }
           idx += rep;
         }
         if (!err && sm.h.lens[32 + 256] == 0) err = 1;      // a block must be able to end

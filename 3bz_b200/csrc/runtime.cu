@@ -30,7 +30,7 @@
 static const uint64_t kSlabPoolBytes = 24ull << 30;  // upper bound of the token slab pool per batch (B200: 180 GB)
 static const uint64_t kSplitMinBytes = 4ull << 20;   // members at least this large are split across the GPU
 static const uint64_t kSplitChunkBytes =      // compressed bytes per chunk of a split member (TBZ_SPLIT_CHUNK_KB: tuning)
-    (getenv("TBZ_SPLIT_CHUNK_KB") ? std::max<uint64_t>(16, strtoull(getenv("TBZ_SPLIT_CHUNK_KB"), nullptr, 10)) : 160ull) << 10;
+    (getenv("TBZ_SPLIT_CHUNK_KB") ? std::max<uint64_t>(16, strtoull(getenv("TBZ_SPLIT_CHUNK_KB"), nullptr, 10)) : 224ull) << 10;
 
 struct DevBlock { void *p; size_t size; bool used; };
 
@@ -520,7 +520,20 @@ static int32_t split_inflate(tbz_ctx *ctx, int fmt, const DMember &m, tbz_result
   const uint32_t *words = (const uint32_t *)(m.in - mis);
   const uint64_t end_bit = (mis + m.in_len) * 8;
   const uint64_t body_bit = (mis + hdr_bytes) * 8;
-  const uint64_t chunk_bits = kSplitChunkBytes * 8;
+  // Chunk size (measured on a 1 GiB gzip member, r2u: 160 / 224 / 256 / 320 / 384 KiB -> 17.8 / 15.9 / 19.5 / 16.0 / 23.1 ms):
+  // the block-start search costs per chunk, the decode's latency grows with the chunk, and the symbolic resolve runs
+  // two CTAs per SM over chunks of equal size, so its time goes in whole waves — a large member gets a chunk count that
+  // is a multiple of one wave (2 x SMs)
+  uint64_t chunk_bytes = kSplitChunkBytes;
+  {
+    const uint64_t wave = 2ull * (uint64_t)ctx->sm_count, body = m.in_len - hdr_bytes;
+    uint64_t nc = body / chunk_bytes;
+    if (!getenv("TBZ_SPLIT_CHUNK_KB") && nc >= 3 * wave) {
+      nc = (nc + wave / 2) / wave * wave;
+      chunk_bytes = ((body + nc - 1) / nc + 63) & ~63ull;
+    }
+  }
+  const uint64_t chunk_bits = chunk_bytes * 8;
   const uint32_t nchunks = (uint32_t)((end_bit - body_bit + chunk_bits - 1) / chunk_bits);
   if (nchunks < 4) return TBZ_OK;
 
