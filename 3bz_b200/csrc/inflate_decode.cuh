@@ -640,14 +640,104 @@ __device__ inline bool decode_member(const DMember &mem, int fmt, P1Rec &rec, WS
 // ------------------------------------------------------------------------------------------------
 // Split decode of one large member (pugz-style): where does the first dynamic block at or after
 // bit `from` start?  32 candidate bit positions per step, one per lane: block type, HLIT / HDIST
-// range and completeness of the code-length code are tested by every lane for its own candidate;
-// the few survivors are validated by the whole warp (code lengths decode without error, lit/len
-// and distance codes complete, end-of-block coded).  Returns the bit position or 0xffffffff.  A
-// false positive is caught later: the previous chunk's decoder must land exactly on this bit.
+// range and completeness of the code-length code are tested by every lane for its own candidate.
+// The survivors (2 - 3 per 4 096 bits of text) are queued and validated TOGETHER, one per lane
+// (validate_starts): the code lengths decode without error, the lit/len code is complete, the distance
+// code complete or a lone code, end-of-block coded.  Until the third session of round 2 every survivor was
+// validated on its own, its ~300 code lengths decoded by one lane: 45 % of k_split_find's instructions at
+// one active thread (profiles/r2_split_ncu.txt).  Returns the bit position or 0xffffffff.  A false positive is
+// caught later: the previous chunk's decoder must land exactly on this bit.
 // ------------------------------------------------------------------------------------------------
+constexpr uint32_t FIND_KRAFT_BYTES = 1024, FIND_LUT_BYTES = 128 * 32, FIND_QUEUE = 64;
+static_assert(sizeof(WSmem) >= FIND_KRAFT_BYTES + FIND_LUT_BYTES + 2 * FIND_QUEUE * 4, "the search's tables live in the decoder's shared memory");
+
+// queue[0, n), n <= 32, ascending: the first one that is a valid dynamic-block header, or 0xffffffff.
+// lutb: [128][32] bytes, entry e of lane l at lutb[32 e + l]: symbol | code length << 5 of the code-length code.
+__device__ inline uint32_t validate_starts(const In &in, const uint32_t *queue, uint32_t n, uint8_t *lutb, int lane) {
+  const bool act = (uint32_t)lane < n;
+  const uint32_t q = act ? queue[lane] : 0u;
+  uint32_t total = 0, hlit = 0, pp = 0;
+  unsigned long long clp = 0;                   // the code-length code's lengths, 3 bits per symbol
+  unsigned long long cntp = 0;                  // symbols per length, 8 bits per length
+  if (act) {
+    const uint32_t v = peek32(in, q + 3);
+    hlit = (v & 31u) + 257u;
+    const uint32_t hdist = ((v >> 5) & 31u) + 1u, ncl = ((v >> 10) & 15u) + 4u;
+    total = hlit + hdist;
+    const unsigned long long bits = (unsigned long long)peek32(in, q + 17) | ((unsigned long long)peek32(in, q + 49) << 32);
+#pragma unroll
+    for (int i = 0; i < 19; i++) {
+      const uint32_t l = (uint32_t)i < ncl ? (uint32_t)(bits >> (3 * i)) & 7u : 0u;
+      clp |= (unsigned long long)l << (3 * c_clen_order[i]);
+      cntp += 1ull << (8 * l);
+    }
+    pp = q + 17u + 3u * ncl;
+  }
+  unsigned long long nxp = 0;                   // next canonical code per length, 8 bits per length
+  {
+    uint32_t code = 0;
+#pragma unroll
+    for (int L = 1; L <= 7; L++) {
+      code = (code + (L > 1 ? (uint32_t)(cntp >> (8 * (L - 1))) & 0xffu : 0u)) << 1;
+      nxp |= (unsigned long long)(code & 0xffu) << (8 * L);
+    }
+  }
+  // ---- every lane's own 7-bit table (the code is complete: the filter checked its Kraft sum)
+#pragma unroll 1
+  for (int sym = 0; sym < 19; sym++) {
+    const uint32_t l = act ? (uint32_t)(clp >> (3 * sym)) & 7u : 0u;
+    const uint32_t c = (uint32_t)(nxp >> (8 * l)) & 0xffu;
+    if (l) nxp += 1ull << (8 * l);
+    uint32_t e = l ? __brev(c) >> (32u - l) : 128u;
+    const uint32_t fills = __reduce_max_sync(TBZ_FULL, l ? 128u >> l : 0u);
+    for (uint32_t it = 0; it < fills; it++) {
+      if (e < 128u) { lutb[32u * e + lane] = (uint8_t)(sym | (l << 5)); e += 1u << l; }
+    }
+  }
+  __syncwarp();
+  // ---- the code lengths of the two codes, with their Kraft sums (units of 2^-15) as they arrive
+  uint32_t idx = 0, last = 0xffu, kr_ll = 0, kr_d = 0, ndist = 0, dlen1 = 0, eob = 0;
+  bool run = act, err = false;
+  while (__any_sync(TBZ_FULL, run)) {
+    if (run) {
+      const uint32_t w = peek32(in, pp);
+      const uint32_t ent = lutb[32u * (w & 127u) + lane];
+      const uint32_t L = ent >> 5, sym = ent & 31u;
+      const uint32_t xb = sym < 16u ? 0u : sym == 16u ? 2u : sym == 17u ? 3u : 7u;
+      const uint32_t extra = (w >> L) & ((1u << xb) - 1u);
+      uint32_t rep, val;
+      if (sym < 16u) { rep = 1u; val = sym; last = sym; }
+      else if (sym == 16u) { if (last >= 16u) err = true; rep = 3u + extra; val = last & 15u; }
+      else { rep = (sym == 17u ? 3u : 11u) + extra; val = 0u; last = 0u; }
+      if (L == 0u || pp + L + xb > in.end || idx + rep > total) err = true;
+      pp += L + xb;
+      if (val && !err) {
+        const uint32_t in_ll = idx + rep <= hlit ? rep : idx < hlit ? hlit - idx : 0u;   // (a run may cross from one code into the other)
+        kr_ll += in_ll * (32768u >> val);
+        kr_d += (rep - in_ll) * (32768u >> val);
+        if (rep > in_ll) { ndist += rep - in_ll; dlen1 = val; }
+        if (idx <= 256u && 256u < idx + rep) eob = val;
+        if (kr_ll > 32768u || kr_d > 32768u) err = true;           // over-subscribed: cannot become complete any more
+      }
+      idx += rep;
+      if (err || idx >= total) run = false;
+    }
+  }
+  // a block must be able to end; lit/len complete; distances complete, or a lone code (what libz writes for literal-only blocks), or none
+  const bool valid = act && !err && idx == total && eob != 0u && kr_ll == 32768u &&
+                     (kr_d == 32768u || ndist == 0u || (ndist == 1u && dlen1 < 11u));
+  const uint32_t m = __ballot_sync(TBZ_FULL, valid);
+  __syncwarp();
+  return m ? queue[__ffs(m) - 1] : 0xffffffffu;
+}
+
 __device__ inline uint32_t find_block_start(const In &in, uint32_t from, uint32_t to, WSmem &sm, int lane) {
-  // Kraft sums of three 3-bit code lengths at a time (the root table's memory is free during a search)
-  uint16_t *const kraft = sm.lut_ll;
+  uint8_t *const raw = reinterpret_cast<uint8_t *>(&sm);
+  // Kraft sums of three 3-bit code lengths at a time (the decoder's tables are free during a search)
+  uint16_t *const kraft = reinterpret_cast<uint16_t *>(raw);
+  uint8_t *const lutb = raw + FIND_KRAFT_BYTES;
+  uint32_t *const queue = reinterpret_cast<uint32_t *>(raw + FIND_KRAFT_BYTES + FIND_LUT_BYTES);   // survivors of both tests
+  uint32_t *const q1 = queue + FIND_QUEUE;                                                         // survivors of the first
   __syncwarp();
   for (uint32_t x = lane; x < 512u; x += 32u) {
     uint32_t sum3 = 0;
@@ -656,15 +746,29 @@ __device__ inline uint32_t find_block_start(const In &in, uint32_t from, uint32_
     kraft[x] = (uint16_t)sum3;
   }
   __syncwarp();
-  for (uint32_t base = from; base < to; base += 32) {
-    const uint32_t p = base + lane;
-    bool cand = p < to && p + 17 + 12 <= in.end;
-    uint32_t h = 0;
-    if (cand) {
-      h = peek32(in, p);
-      cand = ((h >> 1) & 3) == 2 && ((h >> 3) & 31) <= 29 && ((h >> 8) & 31) <= 29;
+  uint32_t qn = 0, q1n = 0;                            // queued candidates (uniform)
+  for (uint32_t base = from; base < to || q1n; base += 32) {
+    // ---- first test, every lane its own bit position: block type, HLIT and HDIST in range (22 % pass)
+    if (base < to) {
+      const uint32_t p = base + lane;
+      bool c1 = p < to && p + 17 + 12 <= in.end;
+      if (c1) {
+        const uint32_t h = peek32(in, p);
+        c1 = ((h >> 1) & 3) == 2 && ((h >> 3) & 31) <= 29 && ((h >> 8) & 31) <= 29;
+      }
+      const uint32_t m1 = __ballot_sync(TBZ_FULL, c1);
+      if (c1) q1[q1n + __popc(m1 & ((1u << lane) - 1u))] = p;
+      q1n += __popc(m1);
+      __syncwarp();
+      if (q1n < 32u && base + 32u < to) continue;      // (collect a warp's worth of them for the second test)
     }
-    if (cand) {                                        // Kraft sum of the code-length code: 3 ncl <= 57 bits
+    // ---- second test, one queued position per lane: the Kraft sum of the code-length code, 3 ncl <= 57 bits
+    const uint32_t take = min(32u, q1n);
+    bool cand = (uint32_t)lane < take;
+    const uint32_t p = cand ? q1[lane] : 0u;
+    const uint32_t moved = (uint32_t)lane + 32u < q1n ? q1[lane + 32u] : 0u;
+    if (cand) {
+      const uint32_t h = peek32(in, p);
       const uint32_t ncl = ((h >> 13) & 15) + 4, nb = 3u * ncl, q = p + 17;
       uint32_t lo = peek32(in, q), hi = peek32(in, q + 32);
       if (nb < 32u) { lo &= (1u << nb) - 1u; hi = 0u; } else hi &= (1u << (nb - 32u)) - 1u;
@@ -673,77 +777,27 @@ __device__ inline uint32_t find_block_start(const In &in, uint32_t from, uint32_
                            kraft[(hi >> 22) & 511u];
       cand = sum == 128u && p + 17 + nb <= in.end;
     }
-    uint32_t m = __ballot_sync(TBZ_FULL, cand);
-    while (m) {                                        // full validation, one survivor at a time
-      const int src = __ffs(m) - 1;
-      m &= m - 1;
-      const uint32_t q = base + src;
-      const uint32_t v = peek32(in, q + 3);
-      const int hlit = (v & 31) + 257, hdist = ((v >> 5) & 31) + 1, ncl = ((v >> 10) & 15) + 4;
+    __syncwarp();
+    if ((uint32_t)lane + 32u < q1n) q1[lane] = moved;  // what the queue holds beyond this batch moves to its front
+    q1n -= take;
+    const uint32_t m = __ballot_sync(TBZ_FULL, cand);
+    if (m) {
+      if (cand) queue[qn + __popc(m & ((1u << lane) - 1u))] = p;
+      qn += __popc(m);
       __syncwarp();
-      if (lane < 19) sm.h.lens[lane] = 0;
-      __syncwarp();
-      if (lane < ncl) sm.h.lens[c_clen_order[lane]] = peek32(in, q + 17 + 3 * lane) & 7;
-      __syncwarp();
-      if (warp_canon(sm.h.lens, 19, sm.h.c_cl, sm.h.sorted_cl, sm.h.run, lane)) continue;
-      for (int e = lane; e < 128; e += 32) {
-        const uint32_t r = canon_lookup(sm.h.c_cl, sm.h.sorted_cl, (uint32_t)e, 1, 7);
-        const uint32_t sym = r >> 4;
-        const uint32_t xb = sym < 16 ? 0 : sym == 16 ? 2 : sym == 17 ? 3 : 7;
-        sm.h.lut_cl[e] = r ? ((r & 15) | (xb << 4) | (sym << 8)) : 0;
-      }
-      __syncwarp();
-      int err = 0;
-      if (lane == 0) {
-        uint32_t pp = q + 17 + 3 * ncl;
-        int idx = 0, lastlen = 0xff;
-        const int total = hlit + hdist;
-        // Kraft sums of the two codes as their lengths arrive (units of 2^-15): a code that is over-subscribed after a
-        // few lengths cannot become complete any more, and that is how nearly every false candidate ends — after a
-        // handful of symbols instead of all ~300 (the same verdict the completeness test below would give)
-        uint32_t kr_ll = 0, kr_d = 0;
-        while (idx < total) {
-          const uint32_t w = peek32(in, pp);
-          const uint32_t r = sm.h.lut_cl[w & 127];
-          if (!r) { err = 1; break; }
-          const uint32_t L = r & 15, xb = (r >> 4) & 15, sym = r >> 8;
-          if (pp + L + xb > in.end) { err = 1; break; }
-          pp += L + xb;
-          const uint32_t extra = (w >> L) & ((1u << xb) - 1);
-          int rep, val;
-          if (sym < 16) { rep = 1; val = (int)sym; lastlen = (int)sym; }
-          else if (sym == 16) { if (lastlen >= 16) { err = 1; break; } rep = 3 + extra; val = lastlen; }
-          else { rep = (sym == 17 ? 3 : 11) + extra; val = 0; lastlen = 0; }
-          if (idx + rep > total) { err = 1; break; }
-          for (int k = 0; k < rep; k++) sm.h.lens[32 + idx + k] = (uint8_t)val;
-          if (val) {
-            const int in_ll = idx + rep <= hlit ? rep : idx < hlit ? hlit - idx : 0;   // (a run may cross from one code into the other)
-            kr_ll += (uint32_t)in_ll * (32768u >> val);
-            kr_d += (uint32_t)(rep - in_ll) * (32768u >> val);
-            if (kr_ll > 32768u || kr_d > 32768u) { err = 1; break; }
-          }
-          idx += rep;
+      if (qn > FIND_QUEUE - 32u) {                     // (rare: the queue could not take another batch's survivors)
+        for (uint32_t k = 0; k < qn; k += 32u) {
+          const uint32_t r = validate_starts(in, queue + k, min(32u, qn - k), lutb, lane);
+          if (r != 0xffffffffu) return r;
         }
-        if (!err && sm.h.lens[32 + 256] == 0) err = 1;      // a block must be able to end
+        qn = 0;
       }
-      err = __shfl_sync(TBZ_FULL, err, 0);
-      if (err) continue;
-      __syncwarp();
-      // both codes complete (a lone distance code is what libz writes for literal-only blocks)
-      if (warp_canon(sm.h.lens + 32, hlit, sm.c_ll, sm.sorted_ll, sm.h.run, lane)) continue;
-      {
-        uint32_t k = 0;
-        for (int L = 1; L <= 15; L++) k += (uint32_t)sm.c_ll.count[L] << (15 - L);
-        if (k != 32768u) continue;
-      }
-      if (warp_canon(sm.h.lens + 32 + hlit, hdist, sm.c_d, sm.sorted_d, sm.h.run, lane)) continue;
-      {
-        uint32_t k = 0;
-        for (int L = 1; L <= 15; L++) k += (uint32_t)sm.c_d.count[L] << (15 - L);
-        if (k != 32768u && sm.c_d.nsyms > 1) continue;
-      }
-      return q;
     }
+    __syncwarp();
+  }
+  for (uint32_t k = 0; k < qn; k += 32u) {
+    const uint32_t r = validate_starts(in, queue + k, min(32u, qn - k), lutb, lane);
+    if (r != 0xffffffffu) return r;
   }
   return 0xffffffffu;
 }

@@ -100,11 +100,13 @@ k_split_decode(const uint32_t *words, uint64_t end_bit, Chunk *chunks, const uin
     const uint64_t base = ch.start_bit - rel;
     tbzfast::StopList sl;
     sl.starts = cands; sl.n = ncands; sl.next = ch.pad + 1u; sl.base = base;
+    const long long t0 = clock64();
     const bool ok = tbzfast::decode_blocks(in, rel, sl.rel(sl.next), 0xffffffffull, ch.rec, sm, slabs, nslabs, &counters[2], lane, &sl);
     __syncwarp();
     if (lane == 0) {
       if (!ok) ch.rec.status = 0;
       ch.land_bit = ok ? base + ch.rec.end_pos : NONE64;
+      ch.pad = (uint32_t)((clock64() - t0) >> 10);      // (TBZ_KTIME: the chunk's decode time in 1 024-cycle units; the candidate index is used up)
     }
   }
 }

@@ -520,19 +520,12 @@ static int32_t split_inflate(tbz_ctx *ctx, int fmt, const DMember &m, tbz_result
   const uint32_t *words = (const uint32_t *)(m.in - mis);
   const uint64_t end_bit = (mis + m.in_len) * 8;
   const uint64_t body_bit = (mis + hdr_bytes) * 8;
-  // Chunk size (measured on a 1 GiB gzip member, r2u: 160 / 224 / 256 / 320 / 384 KiB -> 17.8 / 15.9 / 19.5 / 16.0 / 23.1 ms):
-  // the block-start search costs per chunk, the decode's latency grows with the chunk, and the symbolic resolve runs
-  // two CTAs per SM over chunks of equal size, so its time goes in whole waves — a large member gets a chunk count that
-  // is a multiple of one wave (2 x SMs)
-  uint64_t chunk_bytes = kSplitChunkBytes;
-  {
-    const uint64_t wave = 2ull * (uint64_t)ctx->sm_count, body = m.in_len - hdr_bytes;
-    uint64_t nc = body / chunk_bytes;
-    if (!getenv("TBZ_SPLIT_CHUNK_KB") && nc >= 3 * wave) {
-      nc = (nc + wave / 2) / wave * wave;
-      chunk_bytes = ((body + nc - 1) / nc + 63) & ~63ull;
-    }
-  }
+  // Chunk size, measured on a 1 GiB gzip member (r2u, r2w2, r2x2: 160 / 192 / 224 / 256 / 288 / 320 / 384 KiB ->
+  // 17.1 / 18.4 / 15.4 / 19.0 / 20.3 / 16.0 / 23.1 ms): the block-start search costs per chunk and the decode's latency
+  // grows with the chunk (one warp per chunk, one wave).  The scatter is one chunk: where the search's first hit in a
+  // chunk is a false positive (about one chunk in a thousand), the chunk in front of it decodes twice as far and
+  // the kernel waits for it (TBZ_KTIME=1 prints the slowest chunks).
+  const uint64_t chunk_bytes = kSplitChunkBytes;
   const uint64_t chunk_bits = chunk_bytes * 8;
   const uint32_t nchunks = (uint32_t)((end_bit - body_bit + chunk_bits - 1) / chunk_bits);
   if (nchunks < 4) return TBZ_OK;
@@ -610,6 +603,18 @@ static int32_t split_inflate(tbz_ctx *ctx, int fmt, const DMember &m, tbz_result
       auto it = std::lower_bound(cands.begin() + v + 1, cands.end(), (unsigned long long)c.land_bit);
       if (it == cands.end() || *it != c.land_bit) { cleanup(); return TBZ_OK; }
       v = (size_t)(it - cands.begin());
+    }
+    if (ctx->ktime && !ctx->ktime_quiet) {            // which chunks held the kernel up
+      std::vector<uint32_t> by(chain.begin(), chain.end());
+      std::sort(by.begin(), by.end(), [&](uint32_t a, uint32_t b) { return ch[a].pad > ch[b].pad; });
+      for (size_t k = 0; k < std::min<size_t>(4, by.size()); k++) {
+        const Chunk &c = ch[by[k]];
+        fprintf(stderr, "[tbz split]   slowest decode: chunk %u, %.0f kcycles, %.0f KiB in, %u bytes out\n", by[k], c.pad * 1.024,
+                (double)(c.land_bit - c.start_bit) / 8192.0, c.rec.out_len);
+      }
+      const Chunk &c = ch[by[by.size() / 2]];
+      fprintf(stderr, "[tbz split]   median decode: chunk %u, %.0f kcycles, %.0f KiB in, %u bytes out\n", by[by.size() / 2], c.pad * 1.024,
+              (double)(c.land_bit - c.start_bit) / 8192.0, c.rec.out_len);
     }
     valid.swap(chain);
   }
