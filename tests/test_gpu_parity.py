@@ -154,6 +154,28 @@ def test_config4_members(ctx, oracle):
         assert g["path"] == 1
 
 
+@pytest.mark.gpu
+def test_gzip_crc_span_geometry(ctx, oracle):
+    """k_member_crc (inflate_crc.cuh): member lengths around every boundary of its segment geometry (1 024 threads, 64-byte
+    runs, the last segment on thread 0), packed back to back so that the device outputs start at every alignment, mixed
+    lengths in one launch (the cached weights are recomputed between members), and CRCs that disagree with the trailer."""
+    lens = [0, 1, 2, 15, 16, 17, 63, 64, 65, 127, 1023, 1024, 1025, 4095, 65535, 65536, 65537, 65536 + 64, 65599,
+            70001, 2 * 65536 - 1, 200000, 65536, 65536, 1, 1 << 20, (1 << 20) + 1, (1 << 20) - 1, 3 << 20, 1234567]
+    text = datagen.text(max(lens), 4242)
+    plain = [text[:n] for n in lens]
+    comp = [datagen.compress(p, "gzip") for p in plain]
+    for flags in (0,):
+        got, _ = run_batch(ctx, "gzip", comp, [len(p) for p in plain], flags=flags)
+        for p, g in zip(plain, got):
+            assert g["verdict"] == 0 and g["out"] == p and g["checksum"] == zlib.crc32(p) and g["path"] == 1, len(p)
+    bad = [bytearray(c) for c in comp[5:]]
+    for b in bad:
+        b[-6] ^= 0x40
+    got, _ = run_batch(ctx, "gzip", [bytes(b) for b in bad], [len(p) for p in plain[5:]])
+    for b, p, g in zip(bad, plain[5:], got):
+        compare(g, oracle.decompress_vector(bytes(b), "gzip", out_cap=len(p)), ("bad crc", len(p)))
+
+
 def test_gzip_header_fields(ctx, oracle):
     plain = datagen.text(5000, 5)
     variants = [cases.gzip_with_header_fields(plain),
