@@ -51,6 +51,12 @@ for k in ks+['sm__cycles_active.avg','sm__cycles_elapsed.max','l1tex__t_sector_h
   echo "## r2m: e2e with two small leading parts (TBZ_PIPE_FIRST = divisor; 0 = equal parts), split decode stages after the translate / CRC changes"
   cat gpurun_out/r2m_e2e.log gpurun_out/r2m_split.log 2>/dev/null
   echo "## r2i: split decode stages before (1 GiB gzip member)"; grep "tbz split" gpurun_out/r2i_gzip1g.err 2>/dev/null | tail -7
+  echo "## r2t2: Kraft early exit in the block-start validation; 16 Ki / 8 Ki-symbol ring with far sources from global memory (not kept); chunk sweep"
+  cat gpurun_out/r2t2_stages.log gpurun_out/r2t2_split.log 2>/dev/null
+  echo "## r2u: chunk-size sweep, 1 GiB and 256 MiB members"; cat gpurun_out/r2u_split.log 2>/dev/null
+  echo "## r2v2: block-start search with lane-parallel validation (same chunks found)"; cat gpurun_out/r2v2_stages.log 2>/dev/null
+  echo "## r2w2: stage times per chunk size"; cat gpurun_out/r2w2_stages.log 2>/dev/null
+  echo "## r2x2: + first-filter compaction; the slowest chunks of the decode (a chunk behind a false-positive start decodes twice as far)"; cat gpurun_out/r2x2_stages.log 2>/dev/null
   echo "## r2aa: e2e pipeline geometry (parts x streams -> GB/s, ms per step, ceiling)"; grep "^parts" /tmp/r2aa.out 2>/dev/null
 } > $P/r2_experiments.txt
 {
