@@ -4,7 +4,7 @@ tag=${1:-r2g2}
 P=profiles
 cp gpurun_out/${tag}_bench_default.json $P/r2_bench_default.json
 cp gpurun_out/${tag}_bench_reference.json $P/r2_bench_reference.json
-[ -e gpurun_out/r2v_bench_2gpu.json ] && cp gpurun_out/r2v_bench_2gpu.json $P/r2_bench_2gpu.json
+[ -e gpurun_out/${tag}_bench_2gpu.json ] && cp gpurun_out/${tag}_bench_2gpu.json $P/r2_bench_2gpu.json; [ -e gpurun_out/${tag}_bench_8gpu.json ] && cp gpurun_out/${tag}_bench_8gpu.json $P/r2_bench_8gpu.json
 cp gpurun_out/${tag}_launches.csv $P/r2_launches.csv
 cp gpurun_out/${tag}_launches_gzip1m.csv $P/r2_launches_gzip1m.csv
 {
