@@ -696,7 +696,7 @@ __device__ inline uint32_t validate_starts(const In &in, const uint32_t *queue, 
   }
   __syncwarp();
   // ---- the code lengths of the two codes, with their Kraft sums (units of 2^-15) as they arrive
-  uint32_t idx = 0, last = 0xffu, kr_ll = 0, kr_d = 0, ndist = 0, dlen1 = 0, eob = 0;
+  uint32_t idx = 0, last = 0xffu, kr_ll = 0, kr_d = 0, ndist = 0, dlen1 = 0, eob = 0, nlen = 0;
   bool run = act, err = false;
   while (__any_sync(TBZ_FULL, run)) {
     if (run) {
@@ -716,6 +716,7 @@ __device__ inline uint32_t validate_starts(const In &in, const uint32_t *queue, 
         kr_ll += in_ll * (32768u >> val);
         kr_d += (rep - in_ll) * (32768u >> val);
         if (rep > in_ll) { ndist += rep - in_ll; dlen1 = val; }
+        if (idx + in_ll > 257u) nlen += idx + in_ll - max(idx, 257u);       // length symbols (257 ...) that have a code
         if (idx <= 256u && 256u < idx + rep) eob = val;
         if (kr_ll > 32768u || kr_d > 32768u) err = true;           // over-subscribed: cannot become complete any more
       }
@@ -723,9 +724,12 @@ __device__ inline uint32_t validate_starts(const In &in, const uint32_t *queue, 
       if (err || idx >= total) run = false;
     }
   }
-  // a block must be able to end; lit/len complete; distances complete, or a lone code (what libz writes for literal-only blocks), or none
+  // A block must be able to end; lit/len complete; distances complete — or, what an encoder may write for a block with
+  // one distance or none: a lone 1-bit code, or no code at all in a block whose lit/len code has no length symbols.
+  // (The distance test is where the false positives of the search get through — five on a 1 GiB member before this
+  // rule, HDIST 1 .. 7 each, gpurun_out/r2fp.log; everything the search rejects wrongly only costs parallelism.)
   const bool valid = act && !err && idx == total && eob != 0u && kr_ll == 32768u &&
-                     (kr_d == 32768u || ndist == 0u || (ndist == 1u && dlen1 < 11u));
+                     (kr_d == 32768u || (ndist == 1u && dlen1 == 1u) || (ndist == 0u && nlen == 0u));
   const uint32_t m = __ballot_sync(TBZ_FULL, valid);
   __syncwarp();
   return m ? queue[__ffs(m) - 1] : 0xffffffffu;
@@ -754,7 +758,8 @@ __device__ inline uint32_t find_block_start(const In &in, uint32_t from, uint32_
       bool c1 = p < to && p + 17 + 12 <= in.end;
       if (c1) {
         const uint32_t h = peek32(in, p);
-        c1 = ((h >> 1) & 3) == 2 && ((h >> 3) & 31) <= 29 && ((h >> 8) & 31) <= 29;
+        // (not the final block: there is one per stream, at its end, and half of the false positives claim to be it)
+        c1 = (h & 7u) == 4u && ((h >> 3) & 31) <= 29 && ((h >> 8) & 31) <= 29;
       }
       const uint32_t m1 = __ballot_sync(TBZ_FULL, c1);
       if (c1) q1[q1n + __popc(m1 & ((1u << lane) - 1u))] = p;

@@ -35,7 +35,10 @@ using tbzfast::SlabHdr;
 using tbzfast::TOKCAP;
 using tbzfast::TOK_MATCH;
 
-constexpr int NT = 256;
+#ifndef TBZ_RES_NT
+#define TBZ_RES_NT 256
+#endif
+constexpr int NT = TBZ_RES_NT;
 constexpr int NWARP = NT / 32;
 constexpr uint32_t HIST = 32768u, HMASK = HIST - 1u;
 constexpr bool CRC_SEPARATE = false;    // CRC-32 inside the kernel
@@ -43,7 +46,11 @@ constexpr bool CRC_SEPARATE = false;    // CRC-32 inside the kernel
 #define TBZ_RES_TPT 4
 #endif
 constexpr int TPT = TBZ_RES_TPT;         // tokens per thread and window
-constexpr uint32_t WB = 1024u * TPT;     // window bytes (including the <= 3 bytes of alignment lead-in)
+#ifndef TBZ_RES_WB
+#define TBZ_RES_WB (1024 * TBZ_RES_TPT)
+#endif
+constexpr uint32_t WB = TBZ_RES_WB;      // window bytes (including the <= 3 bytes of alignment lead-in)
+static_assert(WB % 1024u == 0 && WB <= 8192u, "rank directory: 32 lanes x WB / 1024 bitmap words");
 constexpr uint32_t WT = TPT * NT;        // window tokens
 constexpr uint32_t V_FINAL = 0xffffu;
 

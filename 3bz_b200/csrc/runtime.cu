@@ -615,6 +615,21 @@ static int32_t split_inflate(tbz_ctx *ctx, int fmt, const DMember &m, tbz_result
       const Chunk &c = ch[by[by.size() / 2]];
       fprintf(stderr, "[tbz split]   median decode: chunk %u, %.0f kcycles, %.0f KiB in, %u bytes out\n", by[by.size() / 2], c.pad * 1.024,
               (double)(c.land_bit - c.start_bit) / 8192.0, c.rec.out_len);
+      // the candidates nobody landed on (false positives of the search): what their headers claim
+      size_t ci = 0, shown = 0;
+      for (uint32_t vc : valid) {
+        if (ci < chain.size() && chain[ci] == vc) { ci++; continue; }
+        if (shown++ >= 8) break;
+        const uint64_t bit = ch[vc].start_bit;
+        uint8_t raw[16] = {0};
+        cudaMemcpy(raw, (const uint8_t *)words + (bit >> 3), 12, cudaMemcpyDeviceToHost);
+        unsigned long long w = 0;
+        for (int k = 7; k >= 0; k--) w = (w << 8) | raw[k];
+        w >>= (bit & 7);
+        fprintf(stderr, "[tbz split]   dropped candidate: chunk %u at bit %llu (+%llu in its chunk): final %llu hlit %llu hdist %llu hclen %llu, decode status %u\n",
+                vc, (unsigned long long)bit, (unsigned long long)(bit - (body_bit + chunk_bits * vc)), w & 1, ((w >> 3) & 31) + 257,
+                ((w >> 8) & 31) + 1, ((w >> 13) & 15) + 4, ch[vc].rec.status);
+      }
     }
     valid.swap(chain);
   }
