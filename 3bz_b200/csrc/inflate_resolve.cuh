@@ -35,19 +35,22 @@ using tbzfast::SlabHdr;
 using tbzfast::TOKCAP;
 using tbzfast::TOK_MATCH;
 
+// 512 threads, two tokens each, 4 096-element windows: the kernel's only instance resolves 16-bit symbols with a 64 KB
+// ring (110 KB: two CTAs per SM), and with 256 threads per CTA those were 16 warps per SM at IPC 1.7 with a quarter of the
+// stall samples at barriers; 32 warps: 7.45 -> 6.10 ms per GiB (384 threads x 3 tokens: 6.94; gpurun_out/r2rv.log)
 #ifndef TBZ_RES_NT
-#define TBZ_RES_NT 256
+#define TBZ_RES_NT 512
 #endif
 constexpr int NT = TBZ_RES_NT;
 constexpr int NWARP = NT / 32;
 constexpr uint32_t HIST = 32768u, HMASK = HIST - 1u;
 constexpr bool CRC_SEPARATE = false;    // CRC-32 inside the kernel
 #ifndef TBZ_RES_TPT
-#define TBZ_RES_TPT 4
+#define TBZ_RES_TPT 2
 #endif
 constexpr int TPT = TBZ_RES_TPT;         // tokens per thread and window
 #ifndef TBZ_RES_WB
-#define TBZ_RES_WB (1024 * TBZ_RES_TPT)
+#define TBZ_RES_WB 4096
 #endif
 constexpr uint32_t WB = TBZ_RES_WB;      // window bytes (including the <= 3 bytes of alignment lead-in)
 static_assert(WB % 1024u == 0 && WB <= 8192u, "rank directory: 32 lanes x WB / 1024 bitmap words");
