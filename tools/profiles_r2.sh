@@ -57,6 +57,9 @@ for k in ks+['sm__cycles_active.avg','sm__cycles_elapsed.max','l1tex__t_sector_h
   echo "## r2v2: block-start search with lane-parallel validation (same chunks found)"; cat gpurun_out/r2v2_stages.log 2>/dev/null
   echo "## r2w2: stage times per chunk size"; cat gpurun_out/r2w2_stages.log 2>/dev/null
   echo "## r2x2: + first-filter compaction; the slowest chunks of the decode (a chunk behind a false-positive start decodes twice as far)"; cat gpurun_out/r2x2_stages.log 2>/dev/null
+  echo "## r2fp: the false positives of the block-start search (same bit positions at every chunk size)"; cat gpurun_out/r2fp.log 2>/dev/null
+  echo "## r2fp2: BFINAL = 0 candidates only, stricter distance-code rule: no false positive left, times smooth in the chunk size"; cat gpurun_out/r2fp2.log 2>/dev/null
+  echo "## r2rv / r2rv2 / r2rv3: symbolic resolve, threads per CTA (res512 = 512 x 2 tokens became the default after r2rv)"; cat gpurun_out/r2rv.log gpurun_out/r2rv2.log gpurun_out/r2rv3.log 2>/dev/null
   echo "## r2aa: e2e pipeline geometry (parts x streams -> GB/s, ms per step, ceiling)"; grep "^parts" /tmp/r2aa.out 2>/dev/null
 } > $P/r2_experiments.txt
 {
