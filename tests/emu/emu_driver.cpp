@@ -1,6 +1,7 @@
 // emu_driver.cpp — runs the batched kernel sequence of runtime.cu::launch_kernels under the SIMT
 // emulator (tests/emu/cuda_emu.h).  TEST INFRASTRUCTURE ONLY: built and loaded by tests/test_emu.py.
 #include <cuda_runtime.h>
+#include <cstring>
 #include <vector>
 #include "kernels.cuh"
 
@@ -39,4 +40,24 @@ extern "C" int emu_inflate_batch(int fmt, const tbz_member *m, uint64_t n, tbz_r
     emu_launch(k_inflate_seq, dim3((nn + SEQ_WARPS - 1) / SEQ_WARPS), dim3(SEQ_WARPS * 32), 0,
                (const DMember *)dm.data(), r, nn, fmt, (const uint32_t *)todo.data(), (const uint32_t *)counters.data() + 1);
   return (int)counters[1];     // members that took the sequential kernel
+}
+
+// The block-start search of the split decode (tbzfast::find_block_start), one warp: first dynamic-block start in bits
+// [from, to) of the stream `data` (4-byte aligned copy, `nbytes` long); 0xffffffff = none.
+__global__ void k_emu_find(const uint32_t *words, uint32_t nbits, uint32_t from, uint32_t to, uint32_t *result) {
+  TBZ_DYN_SMEM(smem_raw);
+  tbzfast::WSmem &sm = *reinterpret_cast<tbzfast::WSmem *>(smem_raw);
+  tbzfast::In in;
+  in.w = words; in.pos0 = 0; in.end = nbits; in.nwords = (nbits + 31) >> 5;
+  const uint32_t r = tbzfast::find_block_start(in, from, to, sm, threadIdx.x & 31);
+  if (threadIdx.x == 0) *result = r;
+}
+
+extern "C" uint32_t emu_find_block_start(const uint8_t *data, uint64_t nbytes, uint32_t from, uint32_t to) {
+  emu_os_threads = 1;
+  std::vector<uint32_t> words((nbytes + 3) / 4 + 2, 0);
+  memcpy(words.data(), data, nbytes);
+  uint32_t result = 0;
+  emu_launch(k_emu_find, dim3(1), dim3(32), sizeof(tbzfast::WSmem), (const uint32_t *)words.data(), (uint32_t)(nbytes * 8), from, to, &result);
+  return result;
 }

@@ -32,6 +32,8 @@ def lib():
         _lib = C.CDLL(build())
         _lib.emu_inflate_batch.argtypes = [C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_int, C.c_int]
         _lib.emu_inflate_batch.restype = C.c_int
+        _lib.emu_find_block_start.argtypes = [C.c_char_p, C.c_uint64, C.c_uint32, C.c_uint32]
+        _lib.emu_find_block_start.restype = C.c_uint32
     return _lib
 
 
@@ -63,3 +65,10 @@ def run_batch(fmt, inputs, caps, flags=0, threads=None, in_mis=0, out_mis=0, var
                     "out": C.string_at(obase + ooff[i], r.out_len),
                     "raw": C.string_at(obase + ooff[i], caps[i])})     # the whole buffer (debugging a member that fell back)
     return res, nseq
+
+
+def find_block_start(data, from_bit, to_bit):
+    """tbzfast::find_block_start (the split decode's search) on the emulator: first dynamic-block start in bits
+    [from_bit, to_bit) of the raw deflate stream `data`, or None."""
+    r = lib().emu_find_block_start(data, len(data), from_bit, to_bit)
+    return None if r == 0xffffffff else r

@@ -137,3 +137,37 @@ def test_emu_gzip_crc_span_geometry(out_mis):
     assert nseq == len(bad)
     for b, p, g in zip(bad, plain[5:12], got):
         compare(g, o3bz.decompress_vector(bytes(b), "gzip", out_cap=len(p)), ("bad crc", len(p)))
+
+
+def test_emu_block_start_search():
+    """The split decode's block-start search (inflate_decode.cuh find_block_start: two filters, survivors validated one
+    per lane).  Ground truth without a bit-level parser: a Z_FULL_FLUSH ends the stream on a byte boundary behind an
+    empty stored block, so the next block starts at a known bit; on text it is a dynamic block."""
+    text = datagen.text(600000, 31337)
+    co = zlib.compressobj(6, zlib.DEFLATED, -15)
+    pieces, starts, pos = [], [], 0
+    for k in range(6):
+        starts.append(pos * 8)                       # a block starts here (the first one, or the one behind a flush)
+        d = co.compress(text[k * 100000:(k + 1) * 100000]) + (co.flush(zlib.Z_FULL_FLUSH) if k < 5 else co.flush())
+        pieces.append(d)
+        pos += len(d)
+    raw = b"".join(pieces)
+    assert zlib.decompress(raw, -15) == text
+    for k in range(1, 5):
+        s = starts[k]
+        assert (raw[s // 8] & 7) == 4, "not a non-final dynamic block: the test's assumption about libz is off"
+        # searched from the start itself, from inside the flush marker in front of it, and from far in front of it: libz
+        # cuts 100 000 bytes of text into several blocks, so the hit from far away is some earlier real start
+        assert emuutil.find_block_start(raw, s, s + 4096) == s
+        assert emuutil.find_block_start(raw, s - 30, s + 4096) == s
+        far = emuutil.find_block_start(raw, starts[k - 1] + 1, s + 64)
+        assert far is not None and starts[k - 1] < far <= s
+        # nothing between a start and the end of its header
+        assert emuutil.find_block_start(raw, s + 1, s + 200) is None
+    # the last piece: its first block starts behind the flush; the stream's final block is never reported (BFINAL = 1)
+    s = starts[5]
+    first = emuutil.find_block_start(raw, s, len(raw) * 8)
+    assert first == s or (raw[s // 8] & 1) == 1
+    # random bits: no hit
+    rnd = datagen.random_bytes(1 << 16, 99)
+    assert emuutil.find_block_start(rnd, 0, len(rnd) * 8 - 64) is None
