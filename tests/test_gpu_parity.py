@@ -509,11 +509,12 @@ def test_octet_stream_context(engine, ctx, tmp_path):
 def test_output_tail_is_untouched(engine, ctx):
     """the bytes of an output buffer past the returned count are the caller's (api.lisp:35-61 never writes them):
     oversized, pre-filled buffers — one member (every decompress-vector :output call), adjacent members (the direct
-    DMA path), and a batch large enough for the pipelined path"""
+    DMA path), a batch large enough for the pipelined path, and one large enough for its small leading parts (>= 2 048
+    members)"""
     import ctypes as C
     from threebz_b200 import _ffi
     L = _ffi.lib()
-    for n, size in ((1, 5000), (7, 3000), (600, 60000)):
+    for n, size in ((1, 5000), (7, 3000), (600, 60000), (2304, 16000)):
         ms = datagen.members(n, size, 7000, "zlib")
         cap = size + 1000 + 17
         blob = b"".join(c for _, c in ms)
