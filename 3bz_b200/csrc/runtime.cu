@@ -763,6 +763,12 @@ static int32_t split_inflate(tbz_ctx *ctx, int fmt, const DMember &m, tbz_result
   return TBZ_OK;
 }
 
+// a sub-batch's result records, device -> mapped pinned host memory (see tbz_batch_launch)
+static __global__ void k_results_to_host(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, uint32_t words) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < words) dst[i] = src[i];
+}
+
 static int32_t launch_kernels(tbz_batch *b) {
   tbz_ctx *ctx = b->ctx;
   if (!b->n) return TBZ_OK;
@@ -870,7 +876,19 @@ extern "C" int32_t tbz_batch_launch(tbz_batch *b) {
   }
   CK(ctx, cudaEventRecord(b->ev1, ctx->stream));
   if (b->eager_res && b->n) {
-    CK(ctx, cudaMemcpyAsync(b->eager_res, b->d_results, b->n * sizeof(tbz_result), cudaMemcpyDeviceToHost, ctx->stream));
+    // The result records go to the host's pinned memory by a kernel's stores, not through a copy engine: as a DMA they
+    // queued behind the 30 MB output copies of the parts in front (0.5 ms each), and the kernels of the next part on
+    // this stream waited with them (TBZ_PIPE_TRACE=1 shows the timeline)
+    static const bool by_dma = getenv("TBZ_PIPE_RESULTS_DMA") != nullptr;
+    void *host_dev = nullptr;
+    if (!by_dma && cudaHostGetDevicePointer(&host_dev, b->eager_res, 0) == cudaSuccess && host_dev) {
+      const uint32_t words = (uint32_t)(b->n * sizeof(tbz_result) / 4);
+      k_results_to_host<<<(words + 255) / 256, 256, 0, ctx->stream>>>((const uint32_t *)b->d_results, (uint32_t *)host_dev, words);
+      ctx->launches++;
+    } else {
+      cudaGetLastError();
+      CK(ctx, cudaMemcpyAsync(b->eager_res, b->d_results, b->n * sizeof(tbz_result), cudaMemcpyDeviceToHost, ctx->stream));
+    }
     CK(ctx, cudaEventRecord(b->ev_res, ctx->stream));
   }
   b->launched = true;
@@ -988,6 +1006,9 @@ static int32_t inflate_batch_pipelined(tbz_ctx *ctx, int32_t format, const tbz_m
   cudaStream_t saved = ctx->stream;
   int32_t rc = TBZ_OK;
   bool ok = true;
+  static const bool trace = getenv("TBZ_PIPE_TRACE") != nullptr;   // the host's timeline of the pipeline (TBZ_KTIME would add its own syncs)
+  const auto t_begin = std::chrono::steady_clock::now();
+  auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
   for (uint64_t p = 0; p < parts && !rc; p++) {
     const uint64_t lo = cut[p], hi = cut[p + 1];
     ctx->stream = ctx->pstream[p % npipe];
@@ -996,6 +1017,7 @@ static int32_t inflate_batch_pipelined(tbz_ctx *ctx, int32_t format, const tbz_m
     if (!rc) { sub[p]->eager_res = pinned + lo; rc = tbz_batch_launch(sub[p]); }
   }
   ctx->stream = saved;
+  if (trace) fprintf(stderr, "[tbz pipe] %llu parts prepared and launched at %.3f ms\n", (unsigned long long)parts, since());
   float total_ms = 0.f;
   // part after part: its results arrive, the copies of what it produced go into its stream (they overlap the kernels
   // of the parts behind it) ...
@@ -1004,13 +1026,17 @@ static int32_t inflate_batch_pipelined(tbz_ctx *ctx, int32_t format, const tbz_m
     if (!sub[p] || !sub[p]->launched) continue;
     cudaError_t e = cudaEventSynchronize(sub[p]->ev_res);
     if (e != cudaSuccess) { rc = fail(ctx, TBZ_E_CUDA, "pipelined results", e); break; }
+    const double t_res = trace ? since() : 0.0;
     rc = copy_out_direct(sub[p], sub[p]->eager_res, ctx->pstream[tbz_ctx::kPipeStreams - 1 - (p & 1)]);
     sub[p]->copies_issued = true;
+    if (trace) fprintf(stderr, "[tbz pipe]   part %llu (%llu members): results at %.3f ms, its D2H issued at %.3f ms\n", (unsigned long long)p,
+                       (unsigned long long)(cut[p + 1] - cut[p]), t_res, since());
   }
   for (int k = 0; k < 2; k++) {
     cudaError_t e = cudaStreamSynchronize(ctx->pstream[tbz_ctx::kPipeStreams - 1 - k]);
     if (e != cudaSuccess && !rc) rc = fail(ctx, TBZ_E_CUDA, "pipelined D2H", e);
   }
+  if (trace) fprintf(stderr, "[tbz pipe] all D2H done at %.3f ms\n", since());
   // ... then everything is waited for
   for (uint64_t p = 0; p < parts; p++) {
     if (!sub[p]) continue;
@@ -1026,6 +1052,7 @@ static int32_t inflate_batch_pipelined(tbz_ctx *ctx, int32_t format, const tbz_m
   if (!ok) return TBZ_OK;                              // (sub-batches already launched rewrote nothing the one-piece path will not rewrite)
   memcpy(r, pinned, n * sizeof(tbz_result));
   if (device_ms) *device_ms = total_ms;
+  if (trace) fprintf(stderr, "[tbz pipe] finished at %.3f ms\n", since());
   *done = true;
   return TBZ_OK;
 }
