@@ -70,7 +70,7 @@ k_inflate_decode(const DMember *members, uint32_t n, int fmt, tbzfast::P1Rec *re
 // their numbers in profiles/ and DESIGN.md.
 namespace tbzp2 = tbzcp;
 #ifndef TBZ_P2_MINBLOCKS
-#define TBZ_P2_MINBLOCKS (tbzp2::PJ ? 3 : 4)
+#define TBZ_P2_MINBLOCKS 3
 #endif
 __global__ void __launch_bounds__(tbzp2::NT, TBZ_P2_MINBLOCKS)
 k_inflate_resolve(const DMember *members, tbz_result *results, uint32_t n, int fmt,

@@ -1,3 +1,11 @@
+// experiments/inflate_copy_token_rounds.cuh — inflate_copy.cuh (phase two of the batched path) with the variants of the
+// third session of round 2, all parity-green under the emulator and on the GPU, all measured SLOWER than the shipped
+// kernel (profiles/r2_experiments.txt: r2j, r2k2, r2l, r2z):
+//   -DTBZ_CP_ROUNDS=N   N token rounds over the pending queue (a bitmap of pending bytes; a pending match whose source bits
+//                       are clear is copied like a ready one) before pointer jumping takes what is left
+//   -DTBZ_CP_PJ=0       token rounds only: no byte pointers, 47 KB of shared memory, 4 CTAs per SM
+//   -DTBZ_CP_NT=...     threads per CTA (with -DTBZ_CP_TPT=...)
+// To build a library with it: copy it over 3bz_b200/csrc/inflate_copy.cuh and pass the macros through tools/variants.py.
 // inflate_copy.cuh — phase two of the batched fast path for byte members: LZ77 resolution of a
 // token stream (deflate.lisp:244-359 `copy-history`), one thread per token.
 //
@@ -27,6 +35,18 @@
 #include "tbz_device.cuh"
 #include "inflate_decode.cuh"
 
+#if defined(TBZ_EMU) && defined(TBZ_CP_STATS)
+#include <atomic>
+#include <cstdio>
+namespace tbzcp_stats {
+struct S { std::atomic<unsigned long long> tok[8], byt[8]; ~S() { for (int i = 0; i < 8; i++) if (tok[i]) fprintf(stderr, "[cp stats] slot %d: %llu tokens %llu bytes\n", i, (unsigned long long)tok[i], (unsigned long long)byt[i]); } };
+static S g;
+}
+#define TBZ_CP_STAT(slot, n) do { tbzcp_stats::g.tok[(slot) & 7]++; tbzcp_stats::g.byt[(slot) & 7] += (n); } while (0)
+#else
+#define TBZ_CP_STAT(slot, n) do { } while (0)
+#endif
+
 namespace tbzcp {
 
 using tbzfast::NL;
@@ -38,7 +58,10 @@ using tbzfast::SlabHdr;
 using tbzfast::TOKCAP;
 using tbzfast::TOK_MATCH;
 
-constexpr int NT = 256;
+#ifndef TBZ_CP_NT
+#define TBZ_CP_NT 256
+#endif
+constexpr int NT = TBZ_CP_NT;
 constexpr int NWARP = NT / 32;
 #ifndef TBZ_CP_TPT
 #define TBZ_CP_TPT 4
@@ -60,6 +83,20 @@ constexpr uint32_t V_FINAL = 0xffffu;
 #define TBZ_CP_HOPS 4
 #endif
 constexpr int PJ_HOPS = TBZ_CP_HOPS;           // pointer hops per level of the pending-byte resolution
+#ifndef TBZ_CP_ROUNDS
+#define TBZ_CP_ROUNDS 0
+#endif
+constexpr int TOK_ROUNDS = TBZ_CP_ROUNDS;      // token rounds over the pending queue before what is left goes to pointer jumping
+#ifndef TBZ_CP_PJ
+#define TBZ_CP_PJ 1
+#endif
+#ifndef TBZ_CP_MAXROUNDS
+#define TBZ_CP_MAXROUNDS 48
+#endif
+constexpr bool PJ = TBZ_CP_PJ != 0;            // false: token rounds until nothing is pending (no byte pointers: 47 KB of shared memory,
+                                               // 4 CTAs per SM); a window that needs more than MAXROUNDS sends the member to the sequential kernel
+constexpr int MAXROUNDS = TBZ_CP_MAXROUNDS;
+static_assert(PJ || TOK_ROUNDS > 0, "something has to resolve the pending matches");
 constexpr int CRC_UPT = TBZ_CP_CRC_UPT;
 #ifndef TBZ_CP_CRC_SEPARATE
 #define TBZ_CP_CRC_SEPARATE 1
@@ -76,16 +113,18 @@ struct Smem {
   alignas(16) uint8_t ring[GHIST ? 16 : HIST]; // final history: absolute output offset p lives at ring[p & HMASK]
   alignas(16) uint8_t win[16 + WCAP + 16];     // the window: offset r (absolute pos + r) lives at win[(pos & 15) + r], so that
                                                // 16-byte units of the output are 16-byte units here
-  alignas(16) uint16_t val[WCAP];              // per window byte: V_FINAL, or the window offset of an equal byte
-  uint16_t pbytes[WCAP];                       // the bytes of the pending matches
+  alignas(16) uint16_t val[PJ ? WCAP : 8];     // per window byte: V_FINAL, or the window offset of an equal byte
+  uint16_t pbytes[PJ ? WCAP : 8];              // the bytes of the pending matches
   uint16_t tokoff[WT < 1024u ? 1026u : WT + 2u]; // window offset of every token; [tokens used] = window size (>= 2 KiB: CRC scratch)
   uint32_t jobs[WT];                           // ready matches from [0] up, pending from [WT - 1] down: token | (distance - 1) << 10
-  uint16_t pq[WT];                             // per pending match: where its bytes start in pbytes
+  uint16_t pq[TOK_ROUNDS ? 2 : WT];            // per pending match: where its bytes start in pbytes (token rounds: handed out by nleft)
   uint32_t nready, npk;                        // npk: pending matches | their bytes << 16
+  uint32_t pend[WCAP / 32 + 1];                // one bit per window byte: it belongs to a pending match that is not copied yet
+  uint32_t nleft;                              // bytes of the pending matches the token rounds left (they go to pointer jumping)
   uint32_t hdr[SLAB_HDR_WORDS];
   uint32_t segstart[NL + 1];                   // flat index of the first token of every list of the current slab
   uint32_t segptr[NL];                         // word offset of that token in the slab
-  uint32_t crc_tab[CRC_SEPARATE ? 1 : 256];    // (only when the CRC is computed here)
+  uint32_t crc_tab[CRC_SEPARATE ? 1 : 256];
   uint32_t x16[CRC_SEPARATE ? 1 : WCAP / 16 + 4];   // x^(8 * 16 k) mod P: shifts a CRC over k 16-byte units
   uint32_t crcw[NWARP];
   uint32_t wscan[NWARP], wscan2[NWARP];
@@ -130,13 +169,40 @@ struct Hist {
     if (GHIST) { return wi < lim ? __ldcg(reinterpret_cast<const uint32_t *>(out - ((uintptr_t)out & 3u)) + wi) : 0u; }
     return reinterpret_cast<const uint32_t *>(ring)[wi & (HMASK >> 2)];
   }
+  __device__ __forceinline__ uint32_t grid() const { return GHIST ? (uint32_t)((uintptr_t)out & 3u) : 0u; }   // offset of byte 0 on the word grid
 };
+
+// The window itself as a copy source (token rounds over the pending queue): offsets are indices into win[].
+struct WinSrc {
+  const uint8_t *win;
+  __device__ __forceinline__ uint32_t byte(uint32_t p) const { return win[p]; }
+  __device__ __forceinline__ uint32_t word(uint32_t wi, uint32_t) const { return reinterpret_cast<const uint32_t *>(win)[wi]; }
+  __device__ __forceinline__ uint32_t grid() const { return 0u; }
+};
+
+// The pending bitmap: bit r = window byte r belongs to a pending match whose bytes do not exist yet.
+template <class F> __device__ __forceinline__ void bits_each(uint32_t a, uint32_t n, F f) {
+  const uint32_t end = a + n;
+  do {
+    const uint32_t b = a & 31u, take = min(32u - b, end - a);
+    f(a >> 5, (0xffffffffu >> (32u - take)) << b);
+    a += take;
+  } while (a < end);
+}
+__device__ __forceinline__ void bits_set(uint32_t *bm, uint32_t a, uint32_t n) { bits_each(a, n, [&](uint32_t w, uint32_t m) { atomicOr(&bm[w], m); }); }
+__device__ __forceinline__ void bits_clear(uint32_t *bm, uint32_t a, uint32_t n) { bits_each(a, n, [&](uint32_t w, uint32_t m) { atomicAnd(&bm[w], ~m); }); }
+__device__ __forceinline__ bool bits_any(const uint32_t *bm, uint32_t a, uint32_t n) {
+  uint32_t any = 0;
+  bits_each(a, n, [&](uint32_t w, uint32_t m) { any |= *reinterpret_cast<const volatile uint32_t *>(&bm[w]) & m; });
+  return any != 0u;
+}
 
 // One match whose source is final history: n bytes from history offset src to win[dst, dst+n).
 // Straight-line for n <= 19: byte moves up to the first aligned destination word and after the last
 // one, in between one aligned word load per 4 source bytes and a funnel shift.  lim: (GHIST) number of
 // history words that may be read (nothing beyond the bytes produced so far).
-__device__ __forceinline__ void copy_hist(uint8_t *win, uint32_t dst, const Hist &h, uint32_t src, uint32_t n, uint32_t lim) {
+template <class H>
+__device__ __forceinline__ void copy_hist(uint8_t *win, uint32_t dst, const H &h, uint32_t src, uint32_t n, uint32_t lim) {
   const uint32_t dend = dst + n;
   uint32_t hb = (0u - dst) & 3u;                         // bytes up to the first aligned destination word
   if (hb > n) hb = n;
@@ -144,7 +210,7 @@ __device__ __forceinline__ void copy_hist(uint8_t *win, uint32_t dst, const Hist
   for (uint32_t b = 0; b < 3; b++)
     if (b < hb) win[dst + b] = (uint8_t)h.byte(src + b);
   uint32_t p = dst + hb;                                 // aligned (or the end)
-  const uint32_t sa = src + hb + (GHIST ? (uint32_t)((uintptr_t)h.out & 3u) : 0u);   // offset on the history's word grid
+  const uint32_t sa = src + hb + h.grid();                // offset on the source's word grid
   const uint32_t sh = (sa & 3u) * 8u;
   uint32_t wi = sa >> 2;
   uint32_t lo = h.word(wi, lim);
@@ -267,8 +333,9 @@ __device__ inline uint32_t resolve_window(uint8_t *__restrict__ out, int fmt, co
     if (lane >= sft) x += u;
   }
   if (lane == 31) sm.wscan[warp] = x;
-  if (tid == 0) { sm.nready = 0; sm.npk = 0; }
-  for (uint32_t i = tid; i < WCAP / 8u; i += NT)        // (the previous window's levels ended at a barrier)
+  if (tid == 0) { sm.nready = 0; sm.npk = 0; sm.nleft = 0; }
+  if (TOK_ROUNDS) for (uint32_t i = tid; i < WCAP / 32u + 1u; i += NT) sm.pend[i] = 0u;
+  if (PJ) for (uint32_t i = tid; i < WCAP / 8u; i += NT)        // (the previous window's levels ended at a barrier)
     reinterpret_cast<uint4 *>(sm.val)[i] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
   __syncthreads();
   Hist hist;
@@ -318,7 +385,7 @@ __device__ inline uint32_t resolve_window(uint8_t *__restrict__ out, int fmt, co
         const uint32_t d = ((t >> 8) & 0x7fffu) + 1u;
         const uint32_t reach = d < ln[q] ? d : ln[q];    // source bytes that are not the token's own output
         if (d >= st[q] + reach) rmask |= 1u << q;        // entirely below the window
-        else { pmask |= 1u << q; pb += ln[q]; }
+        else { pmask |= 1u << q; pb += ln[q]; if (TOK_ROUNDS) bits_set(sm.pend, st[q], ln[q]); }
       }
     }
   }
@@ -343,7 +410,7 @@ __device__ inline uint32_t resolve_window(uint8_t *__restrict__ out, int fmt, co
     for (int q = 0; q < TPT; q++) {
       const uint32_t job = (tid * TPT + q) | (((tk[q] >> 8) & 0x7fffu) << 10);
       if (rmask & (1u << q)) sm.jobs[ri++] = job;
-      if (pmask & (1u << q)) { sm.jobs[WT - 1u - pi] = job; sm.pq[pi] = (uint16_t)qb; pi++; qb += ln[q]; }
+      if (pmask & (1u << q)) { sm.jobs[WT - 1u - pi] = job; if (!TOK_ROUNDS) sm.pq[pi] = (uint16_t)qb; pi++; qb += ln[q]; }
     }
   }
   __syncthreads();
@@ -368,12 +435,55 @@ __device__ inline uint32_t resolve_window(uint8_t *__restrict__ out, int fmt, co
       const uint32_t job = sm.jobs[j], idx = job & 1023u;
       const uint32_t o = sm.tokoff[idx], d = (job >> 10) + 1u, n_ = sm.tokoff[idx + 1] - o;
       copy_hist(buf, wb + o, hist, pos + o - d, d < n_ ? d : n_, hlim);
+      TBZ_CP_STAT(6, n_);
       for (uint32_t k = d; k < n_; k++) buf[wb + o + k] = buf[wb + o + k - d];   // (first token of the window only) its own period
     }
-    for (uint32_t j = tid; j < np; j += NT) {
-      const uint32_t job = sm.jobs[WT - 1u - j], idx = job & 1023u, d = (job >> 10) + 1u;
+    if (TOK_ROUNDS) {
+      // ---- 3b. token rounds: a pending match whose source bytes all exist by now (literals, ready matches, pending
+      // matches of an earlier round: no bit of the pending bitmap over its source) is copied like a ready one, from the
+      // window; its bits are cleared behind a fence, so a match that finds them clear may read the bytes.  On text a
+      // window's dependency chains are two or three tokens deep; what TOK_ROUNDS rounds leave (long chains: runs)
+      // becomes bytes with pointers as before
+      const WinSrc wsrc{buf};
+      __syncthreads();                                  // literals and ready matches are in the window
+      for (int round = 0; !PJ || round < TOK_ROUNDS; round++) {
+        int left = 0;
+        for (uint32_t j = tid; j < np; j += NT) {
+          const uint32_t job = sm.jobs[WT - 1u - j];
+          if (job >> 31) continue;                      // copied in an earlier round
+          const uint32_t idx = job & 1023u, d = ((job >> 10) & 0x7fffu) + 1u;
+          const uint32_t s0 = sm.tokoff[idx], n_ = sm.tokoff[idx + 1] - s0;
+          const uint32_t m = d < n_ ? d : n_;           // source bytes that are not the token's own output
+          if (s0 < d) {                                 // its source begins below the window (rare)
+            if (PJ) continue;                           // bytes with pointers
+            const uint32_t inwin = s0 + m > d ? s0 + m - d : 0u;
+            if (inwin && bits_any(sm.pend, 0u, inwin)) { left = 1; continue; }
+            __threadfence_block();
+            for (uint32_t k = 0; k < n_; k++) {
+              const uint32_t r = s0 + k;
+              buf[wb + r] = r < d ? (uint8_t)hist.byte(pos + r - d) : buf[wb + r - d];
+            }
+          } else {
+            if (bits_any(sm.pend, s0 - d, m)) { left = 1; continue; }
+            __threadfence_block();
+            copy_hist(buf, wb + s0, wsrc, wb + s0 - d, m, 0u);
+            for (uint32_t k = d; k < n_; k++) buf[wb + s0 + k] = buf[wb + s0 + k - d];   // its own period
+          }
+          __threadfence_block();
+          bits_clear(sm.pend, s0, n_);
+          sm.jobs[WT - 1u - j] = job | 0x80000000u;
+          TBZ_CP_STAT(round, n_);
+        }
+        if (!__syncthreads_or(left)) break;
+        if (!PJ && round + 1 >= MAXROUNDS) return 0xffffffffu;   // (uniform) a chain this deep: the sequential kernel copies in order
+      }
+    }
+    if (PJ) for (uint32_t j = tid; j < np; j += NT) {
+      const uint32_t job = sm.jobs[WT - 1u - j], idx = job & 1023u, d = ((job >> 10) & 0x7fffu) + 1u;
+      if (job >> 31) continue;
       const uint32_t s0 = sm.tokoff[idx], n_ = sm.tokoff[idx + 1] - s0;
-      uint16_t *qp = sm.pbytes + sm.pq[j];
+      uint16_t *qp = sm.pbytes + (TOK_ROUNDS ? atomicAdd(&sm.nleft, n_) : (uint32_t)sm.pq[j]);
+      TBZ_CP_STAT(7, n_);
       for (uint32_t k = 0; k < n_; k++) {
         const uint32_t r = s0 + k;
         qp[k] = (uint16_t)r;
@@ -382,10 +492,10 @@ __device__ inline uint32_t resolve_window(uint8_t *__restrict__ out, int fmt, co
       }
     }
   }
-  __syncthreads();
   // ---- 4. pointer jumping over the pending bytes
-  {
-    const uint32_t nb = sm.npk >> 16;
+  if (PJ) {
+    __syncthreads();
+    const uint32_t nb = TOK_ROUNDS ? sm.nleft : sm.npk >> 16;
     for (;;) {
       int unresolved = 0;
       for (uint32_t i = tid; i < nb; i += NT) {
