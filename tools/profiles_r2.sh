@@ -4,7 +4,7 @@ tag=${1:-r2g2}
 P=profiles
 cp gpurun_out/${tag}_bench_default.json $P/r2_bench_default.json
 cp gpurun_out/${tag}_bench_reference.json $P/r2_bench_reference.json
-[ -e gpurun_out/${tag}_bench_2gpu.json ] && cp gpurun_out/${tag}_bench_2gpu.json $P/r2_bench_2gpu.json; [ -e gpurun_out/${tag}_bench_8gpu.json ] && cp gpurun_out/${tag}_bench_8gpu.json $P/r2_bench_8gpu.json
+[ -e gpurun_out/${tag}_bench_2gpu.json ] && cp gpurun_out/${tag}_bench_2gpu.json $P/r2_bench_2gpu.json; [ -e gpurun_out/${tag}_bench_8gpu.json ] && cp gpurun_out/${tag}_bench_8gpu.json $P/r2_bench_8gpu.json; true
 cp gpurun_out/${tag}_launches.csv $P/r2_launches.csv
 cp gpurun_out/${tag}_launches_gzip1m.csv $P/r2_launches_gzip1m.csv
 {
@@ -59,6 +59,8 @@ for k in ks+['sm__cycles_active.avg','sm__cycles_elapsed.max','l1tex__t_sector_h
   echo "## r2x2: + first-filter compaction; the slowest chunks of the decode (a chunk behind a false-positive start decodes twice as far)"; cat gpurun_out/r2x2_stages.log 2>/dev/null
   echo "## r2fp: the false positives of the block-start search (same bit positions at every chunk size)"; cat gpurun_out/r2fp.log 2>/dev/null
   echo "## r2fp2: BFINAL = 0 candidates only, stricter distance-code rule: no false positive left, times smooth in the chunk size"; cat gpurun_out/r2fp2.log 2>/dev/null
+  echo "## r2ds: sub-chunk size of the split decode's phase one (default 4000 bits)"; cat gpurun_out/r2ds.log 2>/dev/null
+  echo "## r2pipe: e2e pipeline, result records by kernel stores (default) against a DMA; streams; the host timeline"; cat gpurun_out/r2pipe.log 2>/dev/null
   echo "## r2rv / r2rv2 / r2rv3: symbolic resolve, threads per CTA (res512 = 512 x 2 tokens became the default after r2rv)"; cat gpurun_out/r2rv.log gpurun_out/r2rv2.log gpurun_out/r2rv3.log 2>/dev/null
   echo "## r2aa: e2e pipeline geometry (parts x streams -> GB/s, ms per step, ceiling)"; grep "^parts" /tmp/r2aa.out 2>/dev/null
 } > $P/r2_experiments.txt
