@@ -17,7 +17,8 @@
 //                        chunks, log2(chunks) rounds, every round fully parallel).  k_split_tails is the
 //                        sequential form of the same step (one CTA walks the chunks), kept for comparison
 //   K4 k_split_translate every other symbol becomes a byte, all chunks in parallel
-//   K5 k_split_checksum  CRC-32 / Adler-32 partials per 4 KiB segment; the host combines them
+//   K5 checksum          gzip: tbzcrc::k_span_crc (CRC-32 of 1 MiB pieces); zlib: k_split_adler (Adler-32 sums per
+//                        64 KiB segment); the host combines the partials
 #pragma once
 #include "tbz_device.cuh"
 #include "inflate_decode.cuh"
@@ -26,7 +27,6 @@
 namespace tbzsplit {
 
 constexpr uint64_t NONE64 = ~0ull;
-constexpr uint32_t CSEG = 4096;          // checksum segment bytes
 
 struct Chunk {                           // host fills start/stop, the kernels fill the rest
   uint64_t start_bit;                    // absolute bit (from the member's 4-byte aligned base) of a block start
@@ -285,50 +285,42 @@ k_split_translate(const uint64_t *__restrict__ offs, uint32_t nchunks, const uin
   }
 }
 
-// parts[2 * seg] = CRC-32 of the segment (gzip) or sum of its bytes (zlib); parts[2 * seg + 1] = unused / sum (n - i) d_i
-// One thread per 4 KiB segment, 16-byte loads.
+// Adler-32 partials of the output (zlib members; gzip goes through tbzcrc::k_span_crc): one WARP per 64 KiB segment,
+// coalesced 16-byte loads, dp4a sums.  parts[2 seg] = sum of the segment's bytes, parts[2 seg + 1] = sum (m - j) d_j
+// (m = the segment's length, j = offset in it), both mod 65521; the host chains the segments
+// (s2 += m s1 + parts[1]; s1 += parts[0]).  Round 1 ran one THREAD per 4 KiB segment (every lane its own 4 KiB stride).
+constexpr uint32_t ASEG = 65536;
 __global__ void __launch_bounds__(256)
-k_split_checksum(const uint8_t *__restrict__ out, uint64_t n, int fmt, uint32_t *parts) {
-  __shared__ uint32_t tab[256];
-  crc_table_init(tab, threadIdx.x, blockDim.x);
-  __syncthreads();
-  const uint64_t seg = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const uint64_t lo = seg * CSEG;
+k_split_adler(const uint8_t *__restrict__ out, uint64_t n, uint32_t *parts) {
+  const int lane = threadIdx.x & 31;
+  const uint64_t seg = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const uint64_t lo = seg * ASEG;
   if (lo >= n) return;
-  const uint64_t hi = lo + CSEG < n ? lo + CSEG : n;
-  const bool vec = (((uintptr_t)(out + lo)) & 15) == 0;
+  const uint64_t hi = lo + ASEG < n ? lo + ASEG : n;
+  const uint32_t m = (uint32_t)(hi - lo);
+  unsigned long long a = 0, w = 0;
   uint64_t i = lo;
-  if (fmt == TBZ_GZIP) {
-    uint32_t c = 0xffffffffu;
-    if (vec)
-      for (; i + 16 <= hi; i += 16) {
-        const uint4 v = *reinterpret_cast<const uint4 *>(out + i);
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int q = 0; q < 4; q++)
-#pragma unroll
-          for (int b = 0; b < 4; b++) c = (c >> 8) ^ tab[(c ^ (w[q] >> (8 * b))) & 0xff];
-      }
-    for (; i < hi; i++) c = (c >> 8) ^ tab[(c ^ out[i]) & 0xff];
-    parts[2 * seg] = c ^ 0xffffffffu;
-    parts[2 * seg + 1] = 0;
-  } else {
-    uint32_t a = 0, w = 0;
-    const uint32_t m = (uint32_t)(hi - lo);
-    if (vec)
-      for (; i + 16 <= hi; i += 16) {
-        const uint4 v = *reinterpret_cast<const uint4 *>(out + i);
-        uint32_t sd = __dp4a(v.x, 0x01010101u, 0u); sd = __dp4a(v.y, 0x01010101u, sd);
-        sd = __dp4a(v.z, 0x01010101u, sd); sd = __dp4a(v.w, 0x01010101u, sd);
-        uint32_t wj = __dp4a(v.x, 0x03020100u, 0u); wj = __dp4a(v.y, 0x07060504u, wj);
-        wj = __dp4a(v.z, 0x0b0a0908u, wj); wj = __dp4a(v.w, 0x0f0e0d0cu, wj);
-        a += sd;
-        w += (m - (uint32_t)(i - lo)) * sd - wj;       // sum (m - j) d_j over the unit
-      }
-    for (; i < hi; i++) { const uint32_t d = out[i]; a += d; w += (m - (uint32_t)(i - lo)) * d; }
-    parts[2 * seg] = a;
-    parts[2 * seg + 1] = w;
+  if ((((uintptr_t)(out + lo)) & 15) == 0) {
+    const uint64_t vend = lo + (m & ~15u);
+    for (uint64_t p = lo + 16u * lane; p < vend; p += 512u) {
+      const uint4 v = __ldcs(reinterpret_cast<const uint4 *>(out + p));
+      uint32_t sd = __dp4a(v.x, 0x01010101u, 0u); sd = __dp4a(v.y, 0x01010101u, sd);
+      sd = __dp4a(v.z, 0x01010101u, sd); sd = __dp4a(v.w, 0x01010101u, sd);
+      uint32_t wj = __dp4a(v.x, 0x03020100u, 0u); wj = __dp4a(v.y, 0x07060504u, wj);
+      wj = __dp4a(v.z, 0x0b0a0908u, wj); wj = __dp4a(v.w, 0x0f0e0d0cu, wj);
+      a += sd;
+      w += (unsigned long long)(m - (uint32_t)(p - lo)) * sd - wj;       // sum (m - j) d_j over the unit
+    }
+    i = vend;
   }
+  for (uint64_t p = i + lane; p < hi; p += 32) {                         // what 16-byte loads cannot take
+    const uint32_t d = out[p];
+    a += d; w += (unsigned long long)(m - (uint32_t)(p - lo)) * d;
+  }
+  a %= TBZ_ADLER_MOD; w %= TBZ_ADLER_MOD;
+#pragma unroll
+  for (int sft = 16; sft; sft >>= 1) { a += __shfl_xor_sync(TBZ_FULL, a, sft); w += __shfl_xor_sync(TBZ_FULL, w, sft); }
+  if (lane == 0) { parts[2 * seg] = (uint32_t)(a % TBZ_ADLER_MOD); parts[2 * seg + 1] = (uint32_t)(w % TBZ_ADLER_MOD); }
 }
 
 }  // namespace tbzsplit

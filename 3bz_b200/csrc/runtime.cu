@@ -699,8 +699,8 @@ static int32_t split_inflate(tbz_ctx *ctx, int fmt, const DMember &m, tbz_result
   uint32_t ck = 0;
   uint8_t tr[8] = {0};
   if (trailer) {
-    // gzip: the CTA-per-span CRC of the batched path (inflate_crc.cuh) over 1 MiB pieces; zlib: sums per 4 KiB segment
-    const uint64_t seg_bytes = fmt == TBZ_GZIP ? (1ull << 20) : (uint64_t)tbzsplit::CSEG;
+    // gzip: the CTA-per-span CRC of the batched path (inflate_crc.cuh) over 1 MiB pieces; zlib: sums per 64 KiB segment
+    const uint64_t seg_bytes = fmt == TBZ_GZIP ? (1ull << 20) : (uint64_t)tbzsplit::ASEG;
     const uint64_t nseg = (total + seg_bytes - 1) / seg_bytes;
     SRC(dev_alloc(ctx, (size_t)std::max<uint64_t>(1, nseg) * 8, &d_parts));
     if (nseg) {
@@ -709,7 +709,7 @@ static int32_t split_inflate(tbz_ctx *ctx, int fmt, const DMember &m, tbz_result
         tbzcrc::k_span_crc<<<(uint32_t)std::min<uint64_t>(nseg, (uint64_t)ctx->sm_count), tbzcrc::NT, tbzcrc::SMEM_BYTES, st>>>(
             m.out, total, (uint32_t)seg_bytes, (uint32_t *)d_parts);
       } else {
-        tbzsplit::k_split_checksum<<<(uint32_t)((nseg + 255) / 256), 256, 0, st>>>(m.out, total, fmt, (uint32_t *)d_parts);
+        tbzsplit::k_split_adler<<<(uint32_t)((nseg + 7) / 8), 256, 0, st>>>(m.out, total, (uint32_t *)d_parts);
       }
       ctx->launches++;
     }
@@ -729,7 +729,7 @@ static int32_t split_inflate(tbz_ctx *ctx, int fmt, const DMember &m, tbz_result
     } else {
       uint64_t s1 = 1, s2v = 0;
       for (uint64_t s = 0; s < nseg; s++) {
-        const uint64_t len = std::min<uint64_t>(tbzsplit::CSEG, total - s * tbzsplit::CSEG);
+        const uint64_t len = std::min<uint64_t>(seg_bytes, total - s * seg_bytes);
         s2v = (s2v + len * s1 + parts[2 * s + 1]) % TBZ_ADLER_MOD;
         s1 = (s1 + parts[2 * s]) % TBZ_ADLER_MOD;
       }
