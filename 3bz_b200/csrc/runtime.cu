@@ -525,7 +525,11 @@ static int32_t split_inflate(tbz_ctx *ctx, int fmt, const DMember &m, tbz_result
   // grows with the chunk (one warp per chunk, one wave).  The scatter is one chunk: where the search's first hit in a
   // chunk is a false positive (about one chunk in a thousand), the chunk in front of it decodes twice as far and
   // the kernel waits for it (TBZ_KTIME=1 prints the slowest chunks).
-  const uint64_t chunk_bytes = kSplitChunkBytes;
+  // Smaller members get smaller chunks — about a thousand of them, not below 64 KiB (256 MiB member, r2c256: 64 / 96 / 128 /
+  // 160 / 224 KiB -> 5.85 / 5.49 / 5.63 / 5.72 / 6.50 ms: with few chunks the decode's latency is all there is)
+  uint64_t chunk_bytes = kSplitChunkBytes;
+  if (!getenv("TBZ_SPLIT_CHUNK_KB"))
+    chunk_bytes = std::min<uint64_t>(kSplitChunkBytes, std::max<uint64_t>(64ull << 10, ((m.in_len - hdr_bytes) / 1000 + 63) & ~63ull));
   const uint64_t chunk_bits = chunk_bytes * 8;
   const uint32_t nchunks = (uint32_t)((end_bit - body_bit + chunk_bits - 1) / chunk_bits);
   if (nchunks < 4) return TBZ_OK;
