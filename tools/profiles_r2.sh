@@ -69,5 +69,6 @@ for k in ks+['sm__cycles_active.avg','sm__cycles_elapsed.max','l1tex__t_sector_h
   echo "## racecheck --racecheck-report analysis: the only lines reported are the acquire / release accesses of pointer jumping (inflate_copy.cuh step 4; DESIGN.md 9)"
   grep -E "Race reported|RACECHECK SUMMARY|passed" gpurun_out/r2ab_racecheck.txt | sed 's/=========//' | cut -c1-170 | sort | uniq -c | sort -rn
   echo "## memcheck"; tail -3 gpurun_out/r2ab_memcheck.txt
+  echo "## memcheck over the third session's code (tools/experiments/memcheck_r2.py: split decode of a gzip and a zlib member, CRC kernel on mixed lengths, pipelined batch of 2 304 members)"; tail -3 gpurun_out/r2_memcheck2.txt
 } > $P/r2_sanitizer.txt
 ls -la $P | grep r2_
