@@ -214,17 +214,28 @@ k_tail_init(const Chunk *__restrict__ chunks, const uint16_t *__restrict__ sym, 
     mv[j] = (uint16_t)s;
   }
 }
-// out[v] = in[v] o in[v - stride]: markers of map v are looked up in the map `stride` chunks back
+// out[v] = in[v] o in[v - stride]: markers of map v are looked up in the map `stride` chunks back.  Eight entries per
+// thread (one 16-byte load and store; the lookups are 2-byte gathers in a 64 KB map: L1 / L2).
 __global__ void __launch_bounds__(256)
 k_tail_compose(const uint16_t *__restrict__ in, uint16_t *__restrict__ outm, uint32_t stride) {
   const uint32_t v = blockIdx.x;
   const uint16_t *mv = in + (size_t)v * TAILW;
   uint16_t *ov = outm + (size_t)v * TAILW;
   const uint16_t *pv = v >= stride ? in + (size_t)(v - stride) * TAILW : nullptr;
-  for (uint32_t j = blockIdx.y * 1024u + threadIdx.x; j < blockIdx.y * 1024u + 1024u; j += 256u) {
-    uint32_t s = mv[j];
-    if (pv && (s & tbzres::SYM_MARK)) s = pv[s & 0x7fffu];
-    ov[j] = (uint16_t)s;
+  for (uint32_t j = (blockIdx.y * 256u + threadIdx.x) * 8u; j < TAILW; j += gridDim.y * 256u * 8u) {
+    uint4 q = *reinterpret_cast<const uint4 *>(mv + j);
+    if (pv && ((q.x | q.y | q.z | q.w) & (tbzres::SYM_MARK | (tbzres::SYM_MARK << 16)))) {
+      uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        uint32_t lo = w[k] & 0xffffu, hi = w[k] >> 16;
+        if (lo & tbzres::SYM_MARK) lo = pv[lo & 0x7fffu];
+        if (hi & tbzres::SYM_MARK) hi = pv[hi & 0x7fffu];
+        w[k] = lo | (hi << 16);
+      }
+      q = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    *reinterpret_cast<uint4 *>(ov + j) = q;
   }
 }
 // the final windows go to the output: chunk v owns [max(end - 32768, start), end)

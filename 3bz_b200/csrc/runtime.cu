@@ -675,7 +675,7 @@ static int32_t split_inflate(tbz_ctx *ctx, int fmt, const DMember &m, tbz_result
       tbzsplit::k_tail_init<<<grid, 256, 0, st>>>((const Chunk *)d_chunks, (const uint16_t *)d_sym, ma);
       ctx->launches++;
       for (uint32_t stride = 1; stride < nv; stride <<= 1) {
-        tbzsplit::k_tail_compose<<<grid, 256, 0, st>>>(ma, mb, stride);
+        tbzsplit::k_tail_compose<<<dim3(nv, tbzsplit::TAILW / 2048), 256, 0, st>>>(ma, mb, stride);
         ctx->launches++;
         std::swap(ma, mb);
       }
