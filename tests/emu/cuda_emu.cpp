@@ -55,7 +55,7 @@ static void run_block(Block *b, unsigned bx, dim3 grid, dim3 block, size_t smem,
   g_blk = b;
   const unsigned n = block.x * block.y * block.z;
   b->nthreads = n;
-  b->bidx = dim3(bx, 0, 0); b->bdim = block; b->gdim = grid;
+  b->bidx = dim3(bx % grid.x, bx / grid.x, 0); b->bdim = block; b->gdim = grid;
   b->body = body;
   if (b->fibers.size() < n) b->fibers.resize(n);
   b->warps.assign((n + 31) / 32, Warp());
@@ -80,7 +80,7 @@ static void run_block(Block *b, unsigned bx, dim3 grid, dim3 block, size_t smem,
       if (f.done) continue;
       b->cur = t;
       threadIdx = EmuIdx{t % block.x, (t / block.x) % block.y, t / (block.x * block.y)};
-      blockIdx = EmuIdx{bx, 0, 0};
+      blockIdx = EmuIdx{bx % grid.x, bx / grid.x, 0};
       blockDim = EmuIdx{block.x, block.y, block.z};
       gridDim = EmuIdx{grid.x, grid.y, grid.z};
       swapcontext(&b->sched, &f.ctx);
@@ -95,18 +95,19 @@ static void run_block(Block *b, unsigned bx, dim3 grid, dim3 block, size_t smem,
 }
 
 void launch_impl(dim3 grid, dim3 block, size_t smem, const std::function<void()> &body, int os_threads) {
-  if (grid.y != 1 || grid.z != 1) { fprintf(stderr, "[cuda_emu] only 1-D grids\n"); abort(); }
+  if (grid.z != 1) { fprintf(stderr, "[cuda_emu] only 1-D and 2-D grids\n"); abort(); }
+  const unsigned nblocks = grid.x * grid.y;
   std::atomic<unsigned> next{0};
   auto worker = [&]() {
     Block *b = new Block();
     for (;;) {
       const unsigned bx = next.fetch_add(1);
-      if (bx >= grid.x) break;
+      if (bx >= nblocks) break;
       run_block(b, bx, grid, block, smem, body);
     }
     delete b;
   };
-  const int nt = (int)std::min<unsigned>((unsigned)std::max(1, os_threads), grid.x);
+  const int nt = (int)std::min<unsigned>((unsigned)std::max(1, os_threads), nblocks);
   if (nt <= 1) { worker(); return; }
   std::vector<std::thread> th;
   for (int i = 0; i < nt; i++) th.emplace_back(worker);

@@ -194,6 +194,8 @@ static inline uint32_t __byte_perm(uint32_t x, uint32_t y, uint32_t s) {
 }
 template <class T> static inline T __ldg(const T *p) { return *p; }
 template <class T> static inline T __ldcg(const T *p) { return *p; }
+template <class T> static inline T __ldcs(const T *p) { return *p; }
+static inline long long clock64() { return 0; }
 template <class T> static inline T __ldca(const T *p) { return *p; }
 static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
 

@@ -4,6 +4,7 @@
 #include <cstring>
 #include <vector>
 #include "kernels.cuh"
+#include "inflate_split.cuh"
 
 extern "C" int emu_inflate_batch(int fmt, const tbz_member *m, uint64_t n, tbz_result *r, uint32_t flags, int os_threads, int variant) {
   emu_os_threads = os_threads > 0 ? os_threads : 1;
@@ -60,4 +61,30 @@ extern "C" uint32_t emu_find_block_start(const uint8_t *data, uint64_t nbytes, u
   uint32_t result = 0;
   emu_launch(k_emu_find, dim3(1), dim3(32), sizeof(tbzfast::WSmem), (const uint32_t *)words.data(), (uint32_t)(nbytes * 8), from, to, &result);
   return result;
+}
+
+// ---- kernels of the split decode of one large member that do not need a whole member to be tested ----------------
+// Adler-32 of data[0, n) from k_split_adler's per-segment sums, chained as runtime.cu does
+extern "C" uint32_t emu_split_adler(const uint8_t *data, uint64_t n) {
+  emu_os_threads = 1;
+  const uint64_t nseg = (n + tbzsplit::ASEG - 1) / tbzsplit::ASEG;
+  std::vector<uint32_t> parts(2 * std::max<uint64_t>(1, nseg), 0);
+  if (nseg) emu_launch(tbzsplit::k_split_adler, dim3((unsigned)((nseg + 7) / 8)), dim3(256), 0, data, n, parts.data());
+  uint64_t s1 = 1, s2 = 0;
+  for (uint64_t s = 0; s < nseg; s++) {
+    const uint64_t len = std::min<uint64_t>(tbzsplit::ASEG, n - s * tbzsplit::ASEG);
+    s2 = (s2 + len * s1 + parts[2 * s + 1]) % TBZ_ADLER_MOD;
+    s1 = (s1 + parts[2 * s]) % TBZ_ADLER_MOD;
+  }
+  return (uint32_t)(s1 | (s2 << 16));
+}
+// out[v] = in[v] o in[v - stride] over nv maps of 32 Ki entries (k_tail_compose)
+extern "C" void emu_tail_compose(const uint16_t *in, uint16_t *out, uint32_t nv, uint32_t stride) {
+  emu_os_threads = 1;
+  emu_launch(tbzsplit::k_tail_compose, dim3(nv, tbzsplit::TAILW / 2048), dim3(256), 0, in, out, stride);
+}
+// symbols -> bytes (k_split_translate); offs[nchunks + 1], out holds the final tails already
+extern "C" void emu_split_translate(const uint64_t *offs, uint32_t nchunks, const uint16_t *sym, uint8_t *out, uint64_t total, uint32_t grid) {
+  emu_os_threads = 1;
+  emu_launch(tbzsplit::k_split_translate, dim3(grid), dim3(256), 0, offs, nchunks, sym, out, total);
 }

@@ -34,6 +34,12 @@ def lib():
         _lib.emu_inflate_batch.restype = C.c_int
         _lib.emu_find_block_start.argtypes = [C.c_char_p, C.c_uint64, C.c_uint32, C.c_uint32]
         _lib.emu_find_block_start.restype = C.c_uint32
+        _lib.emu_split_adler.argtypes = [C.c_void_p, C.c_uint64]
+        _lib.emu_split_adler.restype = C.c_uint32
+        _lib.emu_tail_compose.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
+        _lib.emu_tail_compose.restype = None
+        _lib.emu_split_translate.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32]
+        _lib.emu_split_translate.restype = None
     return _lib
 
 
@@ -72,3 +78,41 @@ def find_block_start(data, from_bit, to_bit):
     [from_bit, to_bit) of the raw deflate stream `data`, or None."""
     r = lib().emu_find_block_start(data, len(data), from_bit, to_bit)
     return None if r == 0xffffffff else r
+
+
+def _aligned(nbytes, mis=0):
+    """(keep-alive buffer, address) of nbytes at a 64-byte aligned address + mis"""
+    buf = (C.c_uint8 * (nbytes + 128))()
+    return buf, ((C.addressof(buf) + 63) & ~63) + mis
+
+
+def split_adler(data, mis=0):
+    """Adler-32 through k_split_adler (the split decode's zlib checksum), data placed at a 64-byte aligned address + mis"""
+    keep, a = _aligned(max(1, len(data)), mis)
+    C.memmove(a, data, len(data))
+    return lib().emu_split_adler(a, len(data))
+
+
+def tail_compose(maps, stride):
+    """k_tail_compose over a (nv, 32768) uint16 numpy array; returns the composed array"""
+    import numpy as np
+    nv = maps.shape[0]
+    kin, ain = _aligned(maps.nbytes)
+    kout, aout = _aligned(maps.nbytes)
+    C.memmove(ain, maps.ctypes.data, maps.nbytes)
+    lib().emu_tail_compose(ain, aout, nv, stride)
+    return np.frombuffer(C.string_at(aout, maps.nbytes), dtype=np.uint16).reshape(maps.shape).copy()
+
+
+def split_translate(offs, sym, out, grid=3, mis=0):
+    """k_split_translate: offs (chunk output offsets + total), sym (uint16 numpy), out (bytearray holding the final
+    tails); returns the translated bytes"""
+    import numpy as np
+    total = int(offs[-1])
+    o = np.asarray(offs, dtype=np.uint64)
+    ks, asym = _aligned(sym.nbytes + 64)
+    C.memmove(asym, sym.ctypes.data, sym.nbytes)
+    ko, aout = _aligned(total + 64, mis)
+    C.memmove(aout, bytes(out), total)
+    lib().emu_split_translate(o.ctypes.data, len(offs) - 1, asym, aout, total, grid)
+    return C.string_at(aout, total)

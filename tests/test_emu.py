@@ -171,3 +171,54 @@ def test_emu_block_start_search():
     # random bits: no hit
     rnd = datagen.random_bytes(1 << 16, 99)
     assert emuutil.find_block_start(rnd, 0, len(rnd) * 8 - 64) is None
+
+
+def test_emu_split_adler():
+    """k_split_adler (zlib members of the split decode): 64 KiB segments, 16-byte loads, every alignment class"""
+    data = datagen.random_bytes(300001, 5) + bytes(70000) + b"\xff" * 70000
+    for n in (0, 1, 15, 16, 17, 65535, 65536, 65537, 131072, 200000, len(data)):
+        for mis in (0, 1, 8, 15):
+            assert emuutil.split_adler(data[:n], mis) == zlib.adler32(data[:n]), (n, mis)
+
+
+def test_emu_tail_compose_and_translate():
+    """k_tail_compose (markers of map v looked up in map v - stride) and k_split_translate (symbols to bytes; a marker is a
+    byte of the 32 KiB in front of its chunk) against numpy"""
+    import numpy as np
+    rng = np.random.default_rng(7)
+    MARK = 0x8000
+    nv = 5
+    maps = rng.integers(0, 256, size=(nv, 32768), dtype=np.uint16)
+    mark = rng.random((nv, 32768)) < 0.3
+    maps[mark] = MARK | rng.integers(0, 32768, size=int(mark.sum()), dtype=np.uint16)
+    for stride in (1, 2, 4):
+        want = maps.copy()
+        for v in range(stride, nv):
+            m = (maps[v] & MARK) != 0
+            want[v][m] = maps[v - stride][maps[v][m] & 0x7fff]
+        assert np.array_equal(emuutil.tail_compose(maps, stride), want), stride
+    # translate: three chunks behind 40 000 bytes of known output; the tails (last 32 KiB of a chunk) are final already
+    sizes = [40000, 50001, 33000, 70017]
+    offs = np.cumsum([0] + sizes)
+    total = int(offs[-1])
+    final = rng.integers(0, 256, size=total, dtype=np.uint8)
+    # markers of chunk k sit in front of its own tail and point into the 32 KiB in front of the chunk — the tail of
+    # chunk k - 1, which is final (literal bytes) before the translation starts
+    out = bytearray(total)
+    sym = final.astype(np.uint16)
+    final2 = final.copy()
+    for k in range(1, len(sizes)):
+        a, b = int(offs[k]), int(offs[k + 1])
+        body = np.arange(a, max(a, b - 32768))           # the part of the chunk in front of its own tail
+        if body.size:
+            pos = rng.choice(body, size=body.size // 3, replace=False)
+            idx = rng.integers(0, 32768, size=pos.size)
+            sym[pos] = MARK | idx
+            final2[pos] = final2[a - 32768 + idx]        # (the window in front of chunk k is a final tail: literal bytes)
+    for k in range(len(sizes)):
+        a, b = int(offs[k]), int(offs[k + 1])
+        t0 = max(a, b - 32768)
+        out[t0:b] = final2[t0:b].tobytes()               # k_tail_write's work
+    for mis in (0, 3):
+        got = emuutil.split_translate(offs, sym, out, grid=3, mis=mis)
+        assert got == final2.tobytes(), mis
